@@ -1,0 +1,14 @@
+"""dril_b200 — B200-native PPO rollout-and-update hot path of DRiL.jl behind the reference's API.
+
+Everything computes in libdril_b200.so (hand-written CUDA, sm_100a). This package is only the
+host-side mirror of the reference interface; importing it without the built library or using
+it without a CUDA device raises (no CPU fallback)."""
+from ._lib import DrilError, IterStats, NormCfg, PPOHyper, load  # noqa: F401
+from .spaces import Box, Discrete  # noqa: F401
+from .core import (Context, CudaBatchedEnv, DevicePolicy, NormalizeConfig, RolloutBuffer, gae_raw)  # noqa: F401
+from .api import (AbstractCallback, AbstractTrainingLogger, ActorCriticLayer, Agent, BroadcastedParallelEnv,  # noqa: F401
+                  ContinuousActorCriticLayer, DictLogger, DiscreteActorCriticLayer, MonitorWrapperEnv,
+                  MultiThreadedParallelEnv, NeuralPolicy, NormalizeWrapperEnv, NormWrapperPolicy, NoTrainingLogger, PPO,
+                  collect_rollout, evaluate_agent, extract_policy, get_action_and_values, get_hparams,
+                  load_policy_params_and_state, predict_actions, predict_values, save_policy_params_and_state,
+                  steps_taken, to_env, train)

@@ -1,0 +1,1389 @@
+// libdril_b200.so — C ABI implementation (include/dril_b200.h): handles, launch logic,
+// host<->device staging.  All compute is in the kernels of rollout.cuh / gae.cuh / update.cuh.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "gae.cuh"
+#include "rollout.cuh"
+#include "update.cuh"
+
+#define DRIL_SMEM_MAX 232448  // 227 KB opt-in per CTA on sm_100
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void dril_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* dril_last_error(void) { return g_err; }
+extern "C" int32_t dril_version(void) { return 100; }
+extern "C" int32_t dril_device_count(int32_t* count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        dril_set_error("no usable CUDA device (%s); libdril_b200 has no CPU fallback", cudaGetErrorString(e));
+        if (count) *count = 0;
+        return DRIL_ERR_CUDA;
+    }
+    if (count) *count = n;
+    return DRIL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// NCCL through dlopen (no link-time dependency: single-GPU use never touches it)
+// ---------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(nccl_comm*, int, nccl_uid, int) = nullptr;
+    int (*CommDestroy)(nccl_comm) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int32_t nccl_load() {
+    if (g_nccl.lib) return DRIL_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) { dril_set_error("cannot dlopen libnccl.so.2: %s", dlerror()); return DRIL_ERR_NCCL; }
+    g_nccl.GetUniqueId = (int (*)(nccl_uid*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(nccl_comm*, int, nccl_uid, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(nccl_comm))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) {
+        dril_set_error("libnccl is missing required symbols");
+        return DRIL_ERR_NCCL;
+    }
+    return DRIL_OK;
+}
+#define DRIL_NCCL(expr)                                                                              \
+    do {                                                                                             \
+        int _r = (expr);                                                                             \
+        if (_r != 0) {                                                                               \
+            dril_set_error("NCCL error %d (%s) at %s:%d", _r,                                        \
+                           g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?", __FILE__, __LINE__); \
+            return DRIL_ERR_NCCL;                                                                    \
+        }                                                                                            \
+    } while (0)
+enum { NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+// ---------------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------------
+struct ProfSpan { int kind; cudaEvent_t a, b; };
+
+struct dril_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t seed = 0;
+    int sm_count = 0;
+    int64_t launches = 0;
+    bool profiling = false;
+    double prof_ms[DRIL_K_COUNT] = {0};
+    int64_t prof_n[DRIL_K_COUNT] = {0};
+    std::vector<ProfSpan> spans;
+    std::vector<cudaEvent_t> free_events;
+    nccl_comm comm = nullptr;
+    int rank = 0, nranks = 1;
+    cudaEvent_t user_ev[16] = {nullptr};
+    void* l2_scratch = nullptr;
+    size_t l2_bytes = 0;
+};
+
+struct dril_buffer {
+    dril_ctx* ctx;
+    BufDev d;
+    int act_elems;  // per-sample action elements
+};
+
+struct dril_env {
+    dril_ctx* ctx;
+    EnvDev d;
+    dril_buffer* compat = nullptr;   // 1-step buffer for the act!/observe compatibility path
+    void* compat_actions = nullptr;  // device staging
+    float* compat_obs = nullptr;     // device [n][D]
+    MonitorRing ring;
+    int max_blocks = 0;
+    int64_t total_episodes = 0;
+    PolicyDesc nopolicy;             // zeroed descriptor for policy-less launches
+};
+
+struct dril_policy {
+    dril_ctx* ctx;
+    PolicyDesc pd;
+    float *flat = nullptr, *pack = nullptr, *m = nullptr, *v = nullptr, *g = nullptr, *gpart = nullptr;
+    int *flat2pack = nullptr, *flat2packT = nullptr, *flat2g = nullptr;
+    long long* step = nullptr;
+    double *iter_acc = nullptr, *ev_acc = nullptr, *mbstats = nullptr, *adv_partial = nullptr;
+    int* stop_flag = nullptr;
+    int gpart_ctas = 0;
+    int mbstats_cap = 0;
+    uint64_t seed = 0;
+    uint32_t step_index = 0;
+    // last iteration bookkeeping
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    dril_env* last_env = nullptr;
+    dril_buffer* last_buf = nullptr;
+    float last_lr = 0.f;
+    int64_t last_steps = 0;
+    // scratch for the host-pointer entry points
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+// ---------------------------------------------------------------------------------------
+// launch bookkeeping / profiling
+// ---------------------------------------------------------------------------------------
+struct Span {
+    dril_ctx* c;
+    int kind;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Span(dril_ctx* c_, int kind_) : c(c_), kind(kind_) {
+        c->launches += 1;
+        if (c->profiling) {
+            a = take(); b = take();
+            cudaEventRecord(a, c->stream);
+        }
+    }
+    cudaEvent_t take() {
+        if (!c->free_events.empty()) { cudaEvent_t e = c->free_events.back(); c->free_events.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    ~Span() {
+        if (c->profiling) {
+            cudaEventRecord(b, c->stream);
+            c->spans.push_back({kind, a, b});
+        }
+    }
+};
+static void flush_spans(dril_ctx* c) {
+    if (c->spans.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto& s : c->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { c->prof_ms[s.kind] += ms; c->prof_n[s.kind] += 1; }
+        c->free_events.push_back(s.a); c->free_events.push_back(s.b);
+    }
+    c->spans.clear();
+}
+
+template <typename T>
+static int32_t dmalloc(T** p, size_t n) {
+    DRIL_CUDA(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    return DRIL_OK;
+}
+static int32_t ensure_scratch(dril_policy* p, size_t bytes) {
+    if (p->scratch_bytes >= bytes) return DRIL_OK;
+    if (p->scratch) cudaFree(p->scratch);
+    p->scratch = nullptr; p->scratch_bytes = 0;
+    DRIL_CUDA(cudaMalloc(&p->scratch, bytes));
+    p->scratch_bytes = bytes;
+    return DRIL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+extern "C" int32_t dril_ctx_create(int32_t device, uint64_t seed, dril_ctx** out) {
+    DRIL_REQUIRE(out, "out is NULL");
+    int32_t n = 0;
+    DRIL_TRY(dril_device_count(&n));
+    DRIL_REQUIRE(device >= 0 && device < n, "device %d out of range (%d devices)", device, n);
+    DRIL_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    DRIL_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        dril_set_error("device %d is sm_%d%d; libdril_b200 is built for sm_100a only", device, prop.major, prop.minor);
+        return DRIL_ERR_UNSUPPORTED;
+    }
+    dril_ctx* c = new dril_ctx();
+    c->device = device;
+    c->seed = seed;
+    c->sm_count = prop.multiProcessorCount;
+    DRIL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    DRIL_CUDA(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
+    DRIL_CUDA(cudaFuncSetAttribute(policy_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
+    DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
+    *out = c;
+    return DRIL_OK;
+}
+extern "C" int32_t dril_ctx_destroy(dril_ctx* c) {
+    if (!c) return DRIL_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    flush_spans(c);
+    for (auto e : c->free_events) cudaEventDestroy(e);
+    for (auto e : c->user_ev) if (e) cudaEventDestroy(e);
+    if (c->l2_scratch) cudaFree(c->l2_scratch);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return DRIL_OK;
+}
+extern "C" int32_t dril_ctx_synchronize(dril_ctx* c) {
+    DRIL_REQUIRE(c, "ctx is NULL");
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_ctx_launch_count(dril_ctx* c, int64_t* launches) {
+    DRIL_REQUIRE(c && launches, "NULL argument");
+    *launches = c->launches;
+    return DRIL_OK;
+}
+extern "C" int32_t dril_ctx_set_profiling(dril_ctx* c, int32_t on) {
+    DRIL_REQUIRE(c, "ctx is NULL");
+    flush_spans(c);
+    c->profiling = on != 0;
+    return DRIL_OK;
+}
+extern "C" int32_t dril_ctx_reset_profile(dril_ctx* c) {
+    DRIL_REQUIRE(c, "ctx is NULL");
+    flush_spans(c);
+    for (int i = 0; i < DRIL_K_COUNT; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+    return DRIL_OK;
+}
+extern "C" int32_t dril_ctx_get_profile(dril_ctx* c, int32_t kind, double* total_ms, int64_t* launches) {
+    DRIL_REQUIRE(c && kind >= 0 && kind < DRIL_K_COUNT, "bad profile kind %d", kind);
+    flush_spans(c);
+    if (total_ms) *total_ms = c->prof_ms[kind];
+    if (launches) *launches = c->prof_n[kind];
+    return DRIL_OK;
+}
+extern "C" int32_t dril_ctx_event_record(dril_ctx* c, int32_t slot) {
+    DRIL_REQUIRE(c && slot >= 0 && slot < 16, "bad event slot");
+    DRIL_CUDA(cudaSetDevice(c->device));
+    if (!c->user_ev[slot]) DRIL_CUDA(cudaEventCreate(&c->user_ev[slot]));
+    DRIL_CUDA(cudaEventRecord(c->user_ev[slot], c->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_ctx_event_elapsed_ms(dril_ctx* c, int32_t a, int32_t b, float* ms) {
+    DRIL_REQUIRE(c && ms && a >= 0 && a < 16 && b >= 0 && b < 16 && c->user_ev[a] && c->user_ev[b], "bad event slots");
+    DRIL_CUDA(cudaEventSynchronize(c->user_ev[b]));
+    DRIL_CUDA(cudaEventElapsedTime(ms, c->user_ev[a], c->user_ev[b]));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_ctx_flush_l2(dril_ctx* c) {
+    DRIL_REQUIRE(c, "ctx is NULL");
+    DRIL_CUDA(cudaSetDevice(c->device));
+    if (!c->l2_scratch) {
+        c->l2_bytes = (size_t)256 << 20;   // > 126 MB L2
+        DRIL_CUDA(cudaMalloc(&c->l2_scratch, c->l2_bytes));
+    }
+    DRIL_CUDA(cudaMemsetAsync(c->l2_scratch, 0, c->l2_bytes, c->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_ctx_sm_count(dril_ctx* c, int32_t* sms) {
+    DRIL_REQUIRE(c && sms, "NULL argument");
+    *sms = c->sm_count;
+    return DRIL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// comm
+// ---------------------------------------------------------------------------------------
+extern "C" int32_t dril_comm_unique_id(uint8_t id_out[128]) {
+    DRIL_TRY(nccl_load());
+    nccl_uid id;
+    DRIL_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, 128);
+    return DRIL_OK;
+}
+extern "C" int32_t dril_comm_init(dril_ctx* c, int32_t rank, int32_t nranks, const uint8_t id[128]) {
+    DRIL_REQUIRE(c && id && nranks >= 1 && rank >= 0 && rank < nranks, "bad comm arguments");
+    DRIL_TRY(nccl_load());
+    DRIL_CUDA(cudaSetDevice(c->device));
+    nccl_uid uid;
+    memcpy(&uid, id, 128);
+    DRIL_NCCL(g_nccl.CommInitRank(&c->comm, nranks, uid, rank));
+    c->rank = rank; c->nranks = nranks;
+    return DRIL_OK;
+}
+extern "C" int32_t dril_comm_destroy(dril_ctx* c) {
+    DRIL_REQUIRE(c, "ctx is NULL");
+    if (c->comm) { cudaStreamSynchronize(c->stream); g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
+    c->rank = 0; c->nranks = 1;
+    return DRIL_OK;
+}
+static int32_t allreduce_sum(dril_ctx* c, void* buf, size_t count, bool is_double) {
+    if (!c->comm || c->nranks == 1) return DRIL_OK;
+    Span sp(c, DRIL_K_ALLREDUCE);
+    DRIL_NCCL(g_nccl.AllReduce(buf, buf, count, is_double ? NCCL_FLOAT64 : NCCL_FLOAT32, NCCL_SUM, c->comm, c->stream));
+    return DRIL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// buffer
+// ---------------------------------------------------------------------------------------
+extern "C" int32_t dril_buffer_create(dril_ctx* c, int64_t T, int64_t N, int32_t obs_dim, int32_t act_kind,
+                                      int32_t act_dim, dril_buffer** out) {
+    DRIL_REQUIRE(c && out && T >= 1 && N >= 1 && obs_dim >= 1 && obs_dim <= DRIL_MAX_OBS_DIM, "bad buffer arguments");
+    DRIL_REQUIRE(act_kind == DRIL_ACT_DISCRETE || (act_kind == DRIL_ACT_CONTINUOUS && act_dim >= 1 && act_dim <= DRIL_MAX_ACT_DIM),
+                 "bad action space");
+    DRIL_CUDA(cudaSetDevice(c->device));
+    dril_buffer* b = new dril_buffer();
+    b->ctx = c;
+    memset(&b->d, 0, sizeof(b->d));
+    b->d.T = T; b->d.N = N; b->d.obs_dim = obs_dim; b->d.act_kind = act_kind;
+    b->d.act_dim = act_kind == DRIL_ACT_DISCRETE ? 1 : act_dim;
+    b->act_elems = b->d.act_dim;
+    size_t tn = (size_t)T * N;
+    DRIL_TRY(dmalloc(&b->d.obs, tn * obs_dim));
+    DRIL_CUDA(cudaMalloc(&b->d.actions, tn * b->act_elems * 4));
+    DRIL_TRY(dmalloc(&b->d.rewards, tn)); DRIL_TRY(dmalloc(&b->d.values, tn)); DRIL_TRY(dmalloc(&b->d.logprobs, tn));
+    DRIL_TRY(dmalloc(&b->d.advantages, tn)); DRIL_TRY(dmalloc(&b->d.returns, tn)); DRIL_TRY(dmalloc(&b->d.boot, tn));
+    DRIL_TRY(dmalloc(&b->d.last_values, (size_t)N)); DRIL_TRY(dmalloc(&b->d.episode_r, tn));
+    DRIL_TRY(dmalloc(&b->d.episode_l, tn)); DRIL_TRY(dmalloc(&b->d.flags, tn)); DRIL_TRY(dmalloc(&b->d.done_count, (size_t)T));
+    // reset!(rollout_buffer) zero-fills (rollout_buffer.jl:35-44)
+    DRIL_CUDA(cudaMemsetAsync(b->d.obs, 0, tn * obs_dim * 4, c->stream));
+    DRIL_CUDA(cudaMemsetAsync(b->d.actions, 0, tn * b->act_elems * 4, c->stream));
+    float* fz[] = {b->d.rewards, b->d.values, b->d.logprobs, b->d.advantages, b->d.returns, b->d.boot, b->d.episode_r};
+    for (float* p : fz) DRIL_CUDA(cudaMemsetAsync(p, 0, tn * 4, c->stream));
+    DRIL_CUDA(cudaMemsetAsync(b->d.last_values, 0, (size_t)N * 4, c->stream));
+    DRIL_CUDA(cudaMemsetAsync(b->d.episode_l, 0, tn * 4, c->stream));
+    DRIL_CUDA(cudaMemsetAsync(b->d.flags, 0, tn, c->stream));
+    DRIL_CUDA(cudaMemsetAsync(b->d.done_count, 0, (size_t)T * 4, c->stream));
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    *out = b;
+    return DRIL_OK;
+}
+extern "C" int32_t dril_buffer_destroy(dril_buffer* b) {
+    if (!b) return DRIL_OK;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    void* ps[] = {b->d.obs, b->d.actions, b->d.rewards, b->d.values, b->d.logprobs, b->d.advantages, b->d.returns,
+                  b->d.boot, b->d.last_values, b->d.episode_r, b->d.episode_l, b->d.flags, b->d.done_count};
+    for (void* p : ps) cudaFree(p);
+    delete b;
+    return DRIL_OK;
+}
+static int32_t buffer_field(dril_buffer* b, int32_t field, void** ptr, int64_t* bytes) {
+    size_t tn = (size_t)b->d.T * b->d.N;
+    switch (field) {
+        case DRIL_BUF_OBS: *ptr = b->d.obs; *bytes = tn * b->d.obs_dim * 4; break;
+        case DRIL_BUF_ACTIONS: *ptr = b->d.actions; *bytes = tn * b->act_elems * 4; break;
+        case DRIL_BUF_REWARDS: *ptr = b->d.rewards; *bytes = tn * 4; break;
+        case DRIL_BUF_VALUES: *ptr = b->d.values; *bytes = tn * 4; break;
+        case DRIL_BUF_LOGPROBS: *ptr = b->d.logprobs; *bytes = tn * 4; break;
+        case DRIL_BUF_ADVANTAGES: *ptr = b->d.advantages; *bytes = tn * 4; break;
+        case DRIL_BUF_RETURNS: *ptr = b->d.returns; *bytes = tn * 4; break;
+        case DRIL_BUF_FLAGS: *ptr = b->d.flags; *bytes = tn; break;
+        case DRIL_BUF_BOOT: *ptr = b->d.boot; *bytes = tn * 4; break;
+        case DRIL_BUF_LAST_VALUES: *ptr = b->d.last_values; *bytes = (size_t)b->d.N * 4; break;
+        case DRIL_BUF_EPISODE_R: *ptr = b->d.episode_r; *bytes = tn * 4; break;
+        case DRIL_BUF_EPISODE_L: *ptr = b->d.episode_l; *bytes = tn * 4; break;
+        default: dril_set_error("unknown buffer field %d", field); return DRIL_ERR_INVALID;
+    }
+    return DRIL_OK;
+}
+extern "C" int32_t dril_buffer_field_bytes(dril_buffer* b, int32_t field, int64_t* bytes) {
+    DRIL_REQUIRE(b && bytes, "NULL argument");
+    void* p;
+    return buffer_field(b, field, &p, bytes);
+}
+extern "C" int32_t dril_buffer_download(dril_buffer* b, int32_t field, void* dst, int64_t bytes) {
+    DRIL_REQUIRE(b && dst, "NULL argument");
+    void* p; int64_t nb;
+    DRIL_TRY(buffer_field(b, field, &p, &nb));
+    DRIL_REQUIRE(bytes == nb, "field %d is %lld bytes, caller passed %lld", field, (long long)nb, (long long)bytes);
+    DRIL_CUDA(cudaSetDevice(b->ctx->device));
+    DRIL_CUDA(cudaMemcpyAsync(dst, p, nb, cudaMemcpyDeviceToHost, b->ctx->stream));
+    DRIL_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_buffer_upload(dril_buffer* b, int32_t field, const void* src, int64_t bytes) {
+    DRIL_REQUIRE(b && src, "NULL argument");
+    void* p; int64_t nb;
+    DRIL_TRY(buffer_field(b, field, &p, &nb));
+    DRIL_REQUIRE(bytes == nb, "field %d is %lld bytes, caller passed %lld", field, (long long)nb, (long long)bytes);
+    DRIL_CUDA(cudaSetDevice(b->ctx->device));
+    DRIL_CUDA(cudaMemcpyAsync(p, src, nb, cudaMemcpyHostToDevice, b->ctx->stream));
+    DRIL_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    return DRIL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// policy
+// ---------------------------------------------------------------------------------------
+static inline int pad4(int x) { return (x + 3) & ~3; }
+
+extern "C" int32_t dril_policy_create(dril_ctx* c, int32_t obs_dim, int32_t n_hidden, const int32_t* hidden,
+                                      int32_t act_kind, int32_t act_n, int32_t act_start, const float* act_low,
+                                      const float* act_high, dril_policy** out) {
+    DRIL_REQUIRE(c && out, "NULL argument");
+    DRIL_REQUIRE(obs_dim >= 1 && obs_dim <= DRIL_MAX_OBS_DIM, "obs_dim %d out of range", obs_dim);
+    DRIL_REQUIRE(n_hidden >= 0 && n_hidden <= DRIL_MAX_HIDDEN_LAYERS, "n_hidden %d out of range", n_hidden);
+    DRIL_REQUIRE(act_kind == DRIL_ACT_DISCRETE || act_kind == DRIL_ACT_CONTINUOUS, "bad act_kind");
+    DRIL_REQUIRE(act_n >= 1 && (act_kind == DRIL_ACT_DISCRETE ? act_n <= 1024 : act_n <= DRIL_MAX_ACT_DIM), "act_n %d out of range", act_n);
+    for (int i = 0; i < n_hidden; ++i) DRIL_REQUIRE(hidden[i] >= 1 && hidden[i] <= 1024, "hidden dim out of range");
+    DRIL_CUDA(cudaSetDevice(c->device));
+    dril_policy* p = new dril_policy();
+    p->ctx = c;
+    p->seed = c->seed;
+    PolicyDesc& pd = p->pd;
+    memset(&pd, 0, sizeof(pd));
+    pd.obs_dim = obs_dim; pd.obs_dim_p = pad4(obs_dim);
+    pd.act_kind = act_kind; pd.act_n = act_n; pd.act_start = act_start;
+    // layer shapes (layers/layer_helpers.jl:27-57): empty hidden_dims -> single Dense(in -> 1)
+    pd.n_layers = n_hidden == 0 ? 1 : n_hidden + 1;
+    int flat_off = 0, pack_off = 0;
+    pd.max_np = 4;
+    for (int net = 0; net < 2; ++net) {
+        for (int l = 0; l < pd.n_layers; ++l) {
+            LayerDesc& L = pd.L[net][l];
+            L.K = l == 0 ? obs_dim : hidden[l - 1];
+            if (n_hidden == 0) L.N = 1;
+            else L.N = l < n_hidden ? hidden[l] : (net == 0 ? act_n : 1);
+            L.Kp = pad4(L.K); L.Np = pad4(L.N);
+            L.w_off = flat_off; flat_off += L.K * L.N;
+            L.b_off = flat_off; flat_off += L.N;
+            L.pw_off = pack_off; pack_off += L.Kp * L.Np;
+            L.pb_off = pack_off; pack_off += L.Np;
+            pd.max_np = std::max(pd.max_np, L.Np);
+        }
+    }
+    if (n_hidden == 0) DRIL_REQUIRE(act_kind == DRIL_ACT_DISCRETE ? act_n == 1 : act_n == 1,
+                                    "hidden_dims=[] gives a Dense(in->1) actor (layer_helpers.jl:33); act_n must be 1");
+    pd.pack_fwd = pack_off;
+    for (int net = 0; net < 2; ++net)
+        for (int l = 0; l < pd.n_layers; ++l) { pd.L[net][l].pwt_off = pack_off; pack_off += pd.L[net][l].Kp * pd.L[net][l].Np; }
+    pd.pack_total = pack_off;
+    pd.log_std_off = -1;
+    if (act_kind == DRIL_ACT_CONTINUOUS) { pd.log_std_off = flat_off; flat_off += act_n; }
+    pd.n_params = flat_off;
+    pd.gpack = pd.pack_fwd + pad4(act_n) + 8;
+    for (int j = 0; j < DRIL_MAX_ACT_DIM; ++j) {
+        pd.act_low[j] = (act_kind == DRIL_ACT_CONTINUOUS && act_low && j < act_n) ? act_low[j] : -INFINITY;
+        pd.act_high[j] = (act_kind == DRIL_ACT_CONTINUOUS && act_high && j < act_n) ? act_high[j] : INFINITY;
+    }
+    // index maps flat -> packed W, packed Wt, packed gradient
+    std::vector<int> f2p(pd.n_params, -1), f2t(pd.n_params, -1), f2g(pd.n_params, -1);
+    for (int net = 0; net < 2; ++net)
+        for (int l = 0; l < pd.n_layers; ++l) {
+            const LayerDesc& L = pd.L[net][l];
+            for (int k = 0; k < L.K; ++k)
+                for (int n = 0; n < L.N; ++n) {
+                    int f = L.w_off + k * L.N + n;   // Lux (out,in) column-major == [in][out]
+                    f2p[f] = L.pw_off + k * L.Np + n;
+                    f2t[f] = L.pwt_off + n * L.Kp + k;
+                    f2g[f] = f2p[f];
+                }
+            for (int n = 0; n < L.N; ++n) { f2p[L.b_off + n] = L.pb_off + n; f2g[L.b_off + n] = L.pb_off + n; }
+        }
+    if (act_kind == DRIL_ACT_CONTINUOUS)
+        for (int j = 0; j < act_n; ++j) f2g[pd.log_std_off + j] = pd.pack_fwd + j;
+    size_t np = pd.n_params;
+    DRIL_TRY(dmalloc(&p->flat, np)); DRIL_TRY(dmalloc(&p->m, np)); DRIL_TRY(dmalloc(&p->v, np));
+    DRIL_TRY(dmalloc(&p->g, np + 8)); DRIL_TRY(dmalloc(&p->pack, (size_t)pd.pack_total));
+    DRIL_TRY(dmalloc(&p->flat2pack, np)); DRIL_TRY(dmalloc(&p->flat2packT, np)); DRIL_TRY(dmalloc(&p->flat2g, np));
+    DRIL_TRY(dmalloc(&p->step, 1)); DRIL_TRY(dmalloc(&p->iter_acc, ITER_ACC_N)); DRIL_TRY(dmalloc(&p->ev_acc, 4));
+    DRIL_TRY(dmalloc(&p->stop_flag, 1));
+    p->gpart_ctas = c->sm_count * 2;
+    DRIL_TRY(dmalloc(&p->gpart, (size_t)p->gpart_ctas * pd.gpack));
+    DRIL_CUDA(cudaMemcpy(p->flat2pack, f2p.data(), np * 4, cudaMemcpyHostToDevice));
+    DRIL_CUDA(cudaMemcpy(p->flat2packT, f2t.data(), np * 4, cudaMemcpyHostToDevice));
+    DRIL_CUDA(cudaMemcpy(p->flat2g, f2g.data(), np * 4, cudaMemcpyHostToDevice));
+    DRIL_CUDA(cudaMemset(p->flat, 0, np * 4)); DRIL_CUDA(cudaMemset(p->m, 0, np * 4)); DRIL_CUDA(cudaMemset(p->v, 0, np * 4));
+    DRIL_CUDA(cudaMemset(p->g, 0, (np + 8) * 4)); DRIL_CUDA(cudaMemset(p->pack, 0, (size_t)pd.pack_total * 4));
+    DRIL_CUDA(cudaMemset(p->step, 0, 8)); DRIL_CUDA(cudaMemset(p->iter_acc, 0, ITER_ACC_N * 8));
+    DRIL_CUDA(cudaMemset(p->ev_acc, 0, 32)); DRIL_CUDA(cudaMemset(p->stop_flag, 0, 4));
+    DRIL_CUDA(cudaMemset(p->gpart, 0, (size_t)p->gpart_ctas * pd.gpack * 4));
+    for (int i = 0; i < 3; ++i) DRIL_CUDA(cudaEventCreate(&p->ev[i]));
+    *out = p;
+    return DRIL_OK;
+}
+extern "C" int32_t dril_policy_destroy(dril_policy* p) {
+    if (!p) return DRIL_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    void* ps[] = {p->flat, p->pack, p->m, p->v, p->g, p->gpart, p->flat2pack, p->flat2packT, p->flat2g, p->step,
+                  p->iter_acc, p->ev_acc, p->mbstats, p->adv_partial, p->stop_flag, p->scratch};
+    for (void* q : ps) if (q) cudaFree(q);
+    for (int i = 0; i < 3; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+    delete p;
+    return DRIL_OK;
+}
+extern "C" int32_t dril_policy_num_params(dril_policy* p, int64_t* n) {
+    DRIL_REQUIRE(p && n, "NULL argument");
+    *n = p->pd.n_params;
+    return DRIL_OK;
+}
+static int32_t repack(dril_policy* p) {
+    Span sp(p->ctx, DRIL_K_POLICY);
+    int n = p->pd.n_params;
+    repack_kernel<<<(n + 255) / 256, 256, 0, p->ctx->stream>>>(p->flat, p->pack, p->flat2pack, p->flat2packT, n);
+    DRIL_CUDA(cudaGetLastError());
+    return DRIL_OK;
+}
+extern "C" int32_t dril_policy_set_params(dril_policy* p, const float* flat, int64_t n) {
+    DRIL_REQUIRE(p && flat, "NULL argument");
+    DRIL_REQUIRE(n == p->pd.n_params, "expected %d parameters, got %lld", p->pd.n_params, (long long)n);
+    DRIL_CUDA(cudaSetDevice(p->ctx->device));
+    DRIL_CUDA(cudaMemcpyAsync(p->flat, flat, n * 4, cudaMemcpyHostToDevice, p->ctx->stream));
+    DRIL_TRY(repack(p));
+    DRIL_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_policy_get_params(dril_policy* p, float* flat, int64_t n) {
+    DRIL_REQUIRE(p && flat, "NULL argument");
+    DRIL_REQUIRE(n == p->pd.n_params, "expected %d parameters, got %lld", p->pd.n_params, (long long)n);
+    DRIL_CUDA(cudaSetDevice(p->ctx->device));
+    DRIL_CUDA(cudaMemcpyAsync(flat, p->flat, n * 4, cudaMemcpyDeviceToHost, p->ctx->stream));
+    DRIL_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_policy_get_opt_state(dril_policy* p, float* m, float* v, int64_t n, int64_t* step) {
+    DRIL_REQUIRE(p && m && v && step, "NULL argument");
+    DRIL_REQUIRE(n == p->pd.n_params, "expected %d parameters, got %lld", p->pd.n_params, (long long)n);
+    DRIL_CUDA(cudaSetDevice(p->ctx->device));
+    long long s = 0;
+    DRIL_CUDA(cudaMemcpyAsync(m, p->m, n * 4, cudaMemcpyDeviceToHost, p->ctx->stream));
+    DRIL_CUDA(cudaMemcpyAsync(v, p->v, n * 4, cudaMemcpyDeviceToHost, p->ctx->stream));
+    DRIL_CUDA(cudaMemcpyAsync(&s, p->step, 8, cudaMemcpyDeviceToHost, p->ctx->stream));
+    DRIL_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    *step = s;
+    return DRIL_OK;
+}
+extern "C" int32_t dril_policy_set_opt_state(dril_policy* p, const float* m, const float* v, int64_t n, int64_t step) {
+    DRIL_REQUIRE(p && m && v, "NULL argument");
+    DRIL_REQUIRE(n == p->pd.n_params, "expected %d parameters, got %lld", p->pd.n_params, (long long)n);
+    DRIL_CUDA(cudaSetDevice(p->ctx->device));
+    long long s = step;
+    DRIL_CUDA(cudaMemcpyAsync(p->m, m, n * 4, cudaMemcpyHostToDevice, p->ctx->stream));
+    DRIL_CUDA(cudaMemcpyAsync(p->v, v, n * 4, cudaMemcpyHostToDevice, p->ctx->stream));
+    DRIL_CUDA(cudaMemcpyAsync(p->step, &s, 8, cudaMemcpyHostToDevice, p->ctx->stream));
+    DRIL_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_policy_seed(dril_policy* p, uint64_t seed, uint64_t step_index) {
+    DRIL_REQUIRE(p, "NULL argument");
+    p->seed = seed;
+    p->step_index = (uint32_t)step_index;
+    return DRIL_OK;
+}
+
+// tile width / weight placement for the stand-alone layer application
+static int32_t launch_apply(dril_policy* p, ApplyArgs& a) {
+    dril_ctx* c = p->ctx;
+    const PolicyDesc& pd = p->pd;
+    int M4 = 64;
+    auto bytes = [&](int m4, bool ws) {
+        int ld = m4 + 4;
+        return ((size_t)(ws ? pd.pack_fwd : 0) + (size_t)pd.obs_dim_p * ld + (size_t)4 * pd.max_np * ld) * 4;
+    };
+    bool ws = true;
+    while (M4 > 4 && bytes(M4, true) > DRIL_SMEM_MAX && bytes(M4, false) > DRIL_SMEM_MAX) M4 -= 4;
+    if (bytes(M4, true) > DRIL_SMEM_MAX) ws = false;
+    if (bytes(M4, ws) > DRIL_SMEM_MAX) { dril_set_error("network too wide for shared memory"); return DRIL_ERR_UNSUPPORTED; }
+    while (M4 > 4 && (a.B + M4 - 1) / M4 < c->sm_count && M4 > (a.B + c->sm_count - 1) / c->sm_count) M4 -= 4;
+    a.M4 = M4; a.weights_smem = ws;
+    a.pd = pd; a.pack = p->pack; a.flat = p->flat; a.pseed = p->seed;
+    long long tiles = (a.B + M4 - 1) / M4;
+    int grid = (int)std::min<long long>(tiles, (long long)c->sm_count * 4);
+    Span sp(c, DRIL_K_POLICY);
+    policy_apply_kernel<<<grid, DRIL_THREADS, bytes(M4, ws), c->stream>>>(a);
+    DRIL_CUDA(cudaGetLastError());
+    return DRIL_OK;
+}
+
+// host actions (int64 | float) -> device int32 | float
+static int32_t stage_actions(dril_ctx* c, int act_kind, int act_n, const void* host, int64_t count, void* dev) {
+    if (act_kind == DRIL_ACT_DISCRETE) {
+        std::vector<int> tmp((size_t)count);
+        const int64_t* src = (const int64_t*)host;
+        for (int64_t i = 0; i < count; ++i) tmp[i] = (int)src[i];
+        DRIL_CUDA(cudaMemcpyAsync(dev, tmp.data(), count * 4, cudaMemcpyHostToDevice, c->stream));
+        DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+        DRIL_CUDA(cudaMemcpyAsync(dev, host, count * act_n * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    return DRIL_OK;
+}
+static int32_t unstage_actions(dril_ctx* c, int act_kind, int act_n, const void* dev, int64_t count, void* host) {
+    if (act_kind == DRIL_ACT_DISCRETE) {
+        std::vector<int> tmp((size_t)count);
+        DRIL_CUDA(cudaMemcpyAsync(tmp.data(), dev, count * 4, cudaMemcpyDeviceToHost, c->stream));
+        DRIL_CUDA(cudaStreamSynchronize(c->stream));
+        int64_t* dst = (int64_t*)host;
+        for (int64_t i = 0; i < count; ++i) dst[i] = tmp[i];
+    } else {
+        DRIL_CUDA(cudaMemcpyAsync(host, dev, count * act_n * 4, cudaMemcpyDeviceToHost, c->stream));
+        DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return DRIL_OK;
+}
+
+static int32_t policy_apply_host(dril_policy* p, int mode, const float* obs, const void* actions_in, int64_t B,
+                                 const int64_t* gids, void* actions_out, float* values, float* logprobs, float* entropy) {
+    DRIL_REQUIRE(p && obs && B >= 1, "bad arguments");
+    dril_ctx* c = p->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    const PolicyDesc& pd = p->pd;
+    const int ae = pd.act_kind == DRIL_ACT_DISCRETE ? 1 : pd.act_n;
+    size_t o_obs = 0, o_act = o_obs + (size_t)B * pd.obs_dim * 4, o_val = o_act + (size_t)B * ae * 4,
+           o_lp = o_val + (size_t)B * 4, o_ent = o_lp + (size_t)B * 4, o_gid = (o_ent + (size_t)B * 4 + 7) & ~(size_t)7,
+           total = o_gid + (size_t)B * 8;
+    DRIL_TRY(ensure_scratch(p, total));
+    char* s = (char*)p->scratch;
+    DRIL_CUDA(cudaMemcpyAsync(s + o_obs, obs, (size_t)B * pd.obs_dim * 4, cudaMemcpyHostToDevice, c->stream));
+    if (mode == 2) { DRIL_REQUIRE(actions_in, "actions is NULL"); DRIL_TRY(stage_actions(c, pd.act_kind, pd.act_n, actions_in, B, s + o_act)); }
+    if (gids) DRIL_CUDA(cudaMemcpyAsync(s + o_gid, gids, (size_t)B * 8, cudaMemcpyHostToDevice, c->stream));
+    ApplyArgs a;
+    memset(&a, 0, sizeof(a));
+    a.obs = (const float*)(s + o_obs);
+    a.actions_in = mode == 2 ? (s + o_act) : nullptr;
+    a.actions_out = (mode == 0 || mode == 1) ? (s + o_act) : nullptr;
+    a.gids = gids ? (const long long*)(s + o_gid) : nullptr;
+    a.values = (float*)(s + o_val);
+    a.logprobs = mode != 3 ? (float*)(s + o_lp) : nullptr;
+    a.entropy = mode == 2 ? (float*)(s + o_ent) : nullptr;
+    a.B = B; a.mode = mode; a.step = p->step_index;
+    DRIL_TRY(launch_apply(p, a));
+    if (mode == 0) p->step_index += 1;
+    if (values) DRIL_CUDA(cudaMemcpyAsync(values, s + o_val, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (logprobs && mode != 3) DRIL_CUDA(cudaMemcpyAsync(logprobs, s + o_lp, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (entropy && mode == 2) DRIL_CUDA(cudaMemcpyAsync(entropy, s + o_ent, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (actions_out && (mode == 0 || mode == 1)) DRIL_TRY(unstage_actions(c, pd.act_kind, pd.act_n, s + o_act, B, actions_out));
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_policy_forward(dril_policy* p, const float* obs, int64_t B, int32_t deterministic,
+                                       const int64_t* env_gids, void* actions, float* values, float* logprobs) {
+    return policy_apply_host(p, deterministic ? 1 : 0, obs, nullptr, B, env_gids, actions, values, logprobs, nullptr);
+}
+extern "C" int32_t dril_policy_evaluate(dril_policy* p, const float* obs, const void* actions, int64_t B,
+                                        float* values, float* logprobs, float* entropy) {
+    return policy_apply_host(p, 2, obs, actions, B, nullptr, nullptr, values, logprobs, entropy);
+}
+extern "C" int32_t dril_policy_predict_values(dril_policy* p, const float* obs, int64_t B, float* values) {
+    return policy_apply_host(p, 3, obs, nullptr, B, nullptr, nullptr, values, nullptr, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------
+// env
+// ---------------------------------------------------------------------------------------
+extern "C" int32_t dril_env_create(dril_ctx* c, int32_t kind, int64_t n_envs, int32_t max_steps, int32_t obs_dim,
+                                   int32_t act_start, int64_t gid_offset, const dril_norm_cfg* norm,
+                                   int32_t monitor_window, dril_env** out) {
+    DRIL_REQUIRE(c && out && n_envs >= 1, "bad env arguments");
+    DRIL_REQUIRE(kind >= DRIL_ENV_CARTPOLE && kind <= DRIL_ENV_SYNTHETIC, "unknown env kind %d", kind);
+    DRIL_REQUIRE(n_envs + gid_offset < (1ll << 32), "global env ids must fit 32 bits");
+    DRIL_CUDA(cudaSetDevice(c->device));
+    dril_env* e = new dril_env();
+    e->ctx = c;
+    EnvDev& d = e->d;
+    memset(&d, 0, sizeof(d));
+    memset(&e->nopolicy, 0, sizeof(e->nopolicy));
+    d.kind = kind; d.n_envs = n_envs; d.gid_offset = gid_offset; d.seed = c->seed; d.act_start = act_start;
+    if (kind == DRIL_ENV_CARTPOLE) { d.obs_dim = 4; d.state_dim = 4; d.act_dim = 0; d.max_steps = max_steps > 0 ? max_steps : 500; }
+    else if (kind == DRIL_ENV_PENDULUM) { d.obs_dim = 3; d.state_dim = 2; d.act_dim = 1; d.max_steps = max_steps > 0 ? max_steps : 200; }
+    else {
+        DRIL_REQUIRE(obs_dim >= 1 && obs_dim <= DRIL_MAX_OBS_DIM, "synthetic obs_dim %d out of range", obs_dim);
+        d.obs_dim = obs_dim; d.state_dim = 0; d.act_dim = 0; d.max_steps = max_steps > 0 ? max_steps : 500;
+    }
+    size_t n = (size_t)n_envs;
+    DRIL_TRY(dmalloc(&d.state, n * std::max(d.state_dim, 1))); DRIL_TRY(dmalloc(&d.steps, n));
+    DRIL_TRY(dmalloc(&d.episode, n)); DRIL_TRY(dmalloc(&d.life, n));
+    DRIL_TRY(dmalloc(&d.tobs, n * d.obs_dim)); DRIL_TRY(dmalloc(&d.old_obs, n * d.obs_dim)); DRIL_TRY(dmalloc(&d.old_rewards, n));
+    DRIL_CUDA(cudaMemset(d.state, 0, n * std::max(d.state_dim, 1) * 4)); DRIL_CUDA(cudaMemset(d.steps, 0, n * 4));
+    DRIL_CUDA(cudaMemset(d.episode, 0, n * 4)); DRIL_CUDA(cudaMemset(d.life, 0, n * 4));
+    DRIL_CUDA(cudaMemset(d.tobs, 0, n * d.obs_dim * 4)); DRIL_CUDA(cudaMemset(d.old_obs, 0, n * d.obs_dim * 4));
+    DRIL_CUDA(cudaMemset(d.old_rewards, 0, n * 4));
+    d.monitor = monitor_window > 0 ? monitor_window : 0;
+    DRIL_TRY(dmalloc(&d.ep_ret, n)); DRIL_TRY(dmalloc(&d.ep_len, n)); DRIL_TRY(dmalloc(&d.roll_sums, 2)); DRIL_TRY(dmalloc(&d.roll_eps, 1));
+    DRIL_CUDA(cudaMemset(d.ep_ret, 0, n * 4)); DRIL_CUDA(cudaMemset(d.ep_len, 0, n * 4));
+    DRIL_CUDA(cudaMemset(d.roll_sums, 0, 16)); DRIL_CUDA(cudaMemset(d.roll_eps, 0, 8));
+    int w = std::max(d.monitor, 1);
+    e->ring.window = w;
+    DRIL_TRY(dmalloc(&e->ring.ret, (size_t)w)); DRIL_TRY(dmalloc(&e->ring.len, (size_t)w)); DRIL_TRY(dmalloc(&e->ring.head, 1));
+    DRIL_CUDA(cudaMemset(e->ring.ret, 0, w * 4)); DRIL_CUDA(cudaMemset(e->ring.len, 0, w * 4)); DRIL_CUDA(cudaMemset(e->ring.head, 0, 8));
+    d.normalize = norm ? 1 : 0;
+    if (norm) {
+        d.training = norm->training; d.norm_obs = norm->norm_obs; d.norm_reward = norm->norm_reward;
+        d.clip_obs = norm->clip_obs; d.clip_reward = norm->clip_reward; d.ngamma = norm->gamma; d.eps = norm->epsilon;
+    }
+    e->max_blocks = c->sm_count * 8;
+    DRIL_TRY(dmalloc(&d.ret, n)); DRIL_TRY(dmalloc(&d.obs_mean, (size_t)d.obs_dim)); DRIL_TRY(dmalloc(&d.obs_var, (size_t)d.obs_dim));
+    DRIL_TRY(dmalloc(&d.ret_stats, 2)); DRIL_TRY(dmalloc(&d.counts, 2));
+    DRIL_TRY(dmalloc(&d.partials, (size_t)2 * e->max_blocks * (2 * d.obs_dim + 2)));
+    DRIL_CUDA(cudaMemset(d.ret, 0, n * 4));
+    {   // RunningMeanStd init: mean 0, var 1, count 0 (normalizeWrapperEnv.jl:13-15)
+        std::vector<float> ones((size_t)d.obs_dim, 1.0f);
+        float rs[2] = {0.f, 1.f};
+        DRIL_CUDA(cudaMemset(d.obs_mean, 0, d.obs_dim * 4));
+        DRIL_CUDA(cudaMemcpy(d.obs_var, ones.data(), d.obs_dim * 4, cudaMemcpyHostToDevice));
+        DRIL_CUDA(cudaMemcpy(d.ret_stats, rs, 8, cudaMemcpyHostToDevice));
+        DRIL_CUDA(cudaMemset(d.counts, 0, 16));
+    }
+    DRIL_TRY(dril_buffer_create(c, 1, n_envs, d.obs_dim, d.act_dim == 0 ? DRIL_ACT_DISCRETE : DRIL_ACT_CONTINUOUS,
+                                std::max(d.act_dim, 1), &e->compat));
+    DRIL_CUDA(cudaMalloc(&e->compat_actions, n * std::max(d.act_dim, 1) * 4));
+    DRIL_TRY(dmalloc(&e->compat_obs, n * d.obs_dim));
+    *out = e;
+    DRIL_TRY(dril_env_reset(e));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_env_destroy(dril_env* e) {
+    if (!e) return DRIL_OK;
+    cudaSetDevice(e->ctx->device);
+    cudaStreamSynchronize(e->ctx->stream);
+    EnvDev& d = e->d;
+    void* ps[] = {d.state, d.steps, d.episode, d.life, d.tobs, d.old_obs, d.old_rewards, d.ep_ret, d.ep_len, d.roll_sums,
+                  d.roll_eps, d.ret, d.obs_mean, d.obs_var, d.ret_stats, d.counts, d.partials, e->ring.ret, e->ring.len,
+                  e->ring.head, e->compat_actions, e->compat_obs};
+    for (void* p : ps) if (p) cudaFree(p);
+    dril_buffer_destroy(e->compat);
+    delete e;
+    return DRIL_OK;
+}
+extern "C" int32_t dril_env_seed(dril_env* e, uint64_t seed) {
+    DRIL_REQUIRE(e, "NULL argument");
+    DRIL_CUDA(cudaSetDevice(e->ctx->device));
+    e->d.seed = seed;
+    DRIL_CUDA(cudaMemsetAsync(e->d.episode, 0, (size_t)e->d.n_envs * 4, e->ctx->stream));
+    DRIL_CUDA(cudaMemsetAsync(e->d.life, 0, (size_t)e->d.n_envs * 4, e->ctx->stream));
+    DRIL_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_env_reset(dril_env* e) {
+    DRIL_REQUIRE(e, "NULL argument");
+    dril_ctx* c = e->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    {
+        Span sp(c, DRIL_K_ENV);
+        env_reset_kernel<<<(unsigned)((e->d.n_envs + 255) / 256), 256, 0, c->stream>>>(e->d);
+        DRIL_CUDA(cudaGetLastError());
+    }
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_env_num_envs(dril_env* e, int64_t* n) {
+    DRIL_REQUIRE(e && n, "NULL argument");
+    *n = e->d.n_envs;
+    return DRIL_OK;
+}
+
+// Launch the rollout engine. policy may be NULL (compat paths).
+static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const void* forced_dev, float* obs_out_dev,
+                              int T, int base_flags) {
+    dril_ctx* c = e->ctx;
+    RolloutArgs a;
+    memset(&a, 0, sizeof(a));
+    a.env = e->d; a.buf = b->d;
+    const bool has_policy = p != nullptr;
+    a.pd = has_policy ? p->pd : e->nopolicy;
+    a.pack = has_policy ? p->pack : nullptr;
+    a.flat = has_policy ? p->flat : nullptr;
+    a.forced = forced_dev; a.obs_out = obs_out_dev;
+    a.pseed = has_policy ? p->seed : 0; a.step0 = has_policy ? p->step_index : 0;
+    a.T = T;
+    int flags = base_flags | (has_policy ? RO_HAS_POLICY : 0);
+    const EnvDev& d = e->d;
+    const bool upd = d.normalize && d.training && (d.norm_obs || d.norm_reward);
+    if (upd) flags |= RO_GRID_SYNC;
+    const long long N = d.n_envs;
+    // tile width: fill the SMs, at most 64 envs per tile, shrink until shared memory fits
+    int M4 = (int)std::min<long long>(64, ((N + c->sm_count - 1) / c->sm_count + 3) & ~3ll);
+    M4 = std::max(M4, 4);
+    bool ws = has_policy;
+    auto total = [&](int m4, bool w) { return rollout_smem_layout(a.pd, d.obs_dim, d.act_dim, m4, w, has_policy).total; };
+    while (M4 > 4 && total(M4, ws) > DRIL_SMEM_MAX && total(M4, false) > DRIL_SMEM_MAX) M4 -= 4;
+    if (total(M4, ws) > DRIL_SMEM_MAX) ws = false;
+    if (total(M4, ws) > DRIL_SMEM_MAX) { dril_set_error("network too wide for the rollout kernel's shared memory"); return DRIL_ERR_UNSUPPORTED; }
+    // weights that leave no room for a reasonable tile are streamed from L2 instead
+    if (ws && M4 < 32 && N >= 32ll * c->sm_count && total(64, false) <= DRIL_SMEM_MAX) { ws = false; M4 = 64; }
+    if (ws) flags |= RO_WEIGHTS_SMEM;
+    a.M4 = M4; a.flags = flags;
+    a.n_tiles = (int)((N + M4 - 1) / M4);
+    size_t smem = total(M4, ws);
+    int grid = a.n_tiles;
+    Span sp(c, has_policy ? DRIL_K_ROLLOUT : DRIL_K_ENV);
+    if (flags & RO_GRID_SYNC) {
+        int per_sm = 0;
+        DRIL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kernel, DRIL_THREADS, smem));
+        DRIL_REQUIRE(per_sm >= 1, "rollout kernel does not fit on an SM");
+        grid = std::min(grid, std::min(per_sm * c->sm_count, e->max_blocks));
+        void* args[] = {(void*)&a};
+        DRIL_CUDA(cudaLaunchCooperativeKernel((void*)rollout_kernel, dim3(grid), dim3(DRIL_THREADS), args, smem, c->stream));
+    } else {
+        rollout_kernel<<<grid, DRIL_THREADS, smem, c->stream>>>(a);
+        DRIL_CUDA(cudaGetLastError());
+    }
+    return DRIL_OK;
+}
+
+static int32_t launch_monitor_finalize(dril_env* e, dril_buffer* b) {
+    if (!e->d.monitor) return DRIL_OK;
+    Span sp(e->ctx, DRIL_K_MONITOR);
+    monitor_finalize_kernel<<<1, 1024, 0, e->ctx->stream>>>(e->ring, b->d.flags, b->d.episode_r, b->d.episode_l,
+                                                            b->d.done_count, b->d.T, b->d.N);
+    DRIL_CUDA(cudaGetLastError());
+    return DRIL_OK;
+}
+
+extern "C" int32_t dril_env_observe(dril_env* e, float* obs_out) {
+    DRIL_REQUIRE(e && obs_out, "NULL argument");
+    dril_ctx* c = e->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    DRIL_TRY(launch_rollout(e, nullptr, e->compat, nullptr, e->compat_obs, 0, RO_INITIAL_OBSERVE | RO_WRITE_OBS_OUT));
+    DRIL_CUDA(cudaMemcpyAsync(obs_out, e->compat_obs, (size_t)e->d.n_envs * e->d.obs_dim * 4, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    return DRIL_OK;
+}
+
+extern "C" int32_t dril_env_step(dril_env* e, const void* actions, float* rewards, uint8_t* terminated, uint8_t* truncated,
+                                 float* terminal_obs, float* episode_r, int64_t* episode_l) {
+    DRIL_REQUIRE(e && actions && rewards && terminated && truncated, "NULL argument");
+    dril_ctx* c = e->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    const EnvDev& d = e->d;
+    const int64_t N = d.n_envs;
+    DRIL_TRY(stage_actions(c, d.act_dim == 0 ? DRIL_ACT_DISCRETE : DRIL_ACT_CONTINUOUS, d.act_dim, actions, N, e->compat_actions));
+    DRIL_CUDA(cudaMemsetAsync(e->compat->d.done_count, 0, 4, c->stream));
+    DRIL_CUDA(cudaMemsetAsync(d.roll_sums, 0, 16, c->stream));
+    DRIL_CUDA(cudaMemsetAsync(d.roll_eps, 0, 8, c->stream));
+    DRIL_TRY(launch_rollout(e, nullptr, e->compat, e->compat_actions, nullptr, 1, 0));
+    DRIL_TRY(launch_monitor_finalize(e, e->compat));
+    std::vector<uint8_t> flags((size_t)N);
+    DRIL_CUDA(cudaMemcpyAsync(rewards, e->compat->d.rewards, N * 4, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaMemcpyAsync(flags.data(), e->compat->d.flags, N, cudaMemcpyDeviceToHost, c->stream));
+    if (terminal_obs) DRIL_CUDA(cudaMemcpyAsync(terminal_obs, d.tobs, (size_t)N * d.obs_dim * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (episode_r) DRIL_CUDA(cudaMemcpyAsync(episode_r, e->compat->d.episode_r, N * 4, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<int> el;
+    if (episode_l) { el.resize((size_t)N); DRIL_CUDA(cudaMemcpyAsync(el.data(), e->compat->d.episode_l, N * 4, cudaMemcpyDeviceToHost, c->stream)); }
+    unsigned long long eps = 0;
+    DRIL_CUDA(cudaMemcpyAsync(&eps, d.roll_eps, 8, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    e->total_episodes += (int64_t)eps;
+    for (int64_t i = 0; i < N; ++i) {
+        terminated[i] = flags[i] & 1; truncated[i] = (flags[i] >> 1) & 1;
+        if (episode_l) episode_l[i] = (flags[i] & 3) ? el[i] : 0;
+        if (episode_r && !(flags[i] & 3)) episode_r[i] = 0.f;
+    }
+    return DRIL_OK;
+}
+
+extern "C" int32_t dril_env_get_state(dril_env* e, float* state, int32_t* steps) {
+    DRIL_REQUIRE(e, "NULL argument");
+    dril_ctx* c = e->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    if (state && e->d.state_dim) DRIL_CUDA(cudaMemcpyAsync(state, e->d.state, (size_t)e->d.n_envs * e->d.state_dim * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (steps) DRIL_CUDA(cudaMemcpyAsync(steps, e->d.steps, (size_t)e->d.n_envs * 4, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_env_set_state(dril_env* e, const float* state, const int32_t* steps) {
+    DRIL_REQUIRE(e, "NULL argument");
+    dril_ctx* c = e->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    if (state && e->d.state_dim) DRIL_CUDA(cudaMemcpyAsync(e->d.state, state, (size_t)e->d.n_envs * e->d.state_dim * 4, cudaMemcpyHostToDevice, c->stream));
+    if (steps) DRIL_CUDA(cudaMemcpyAsync(e->d.steps, steps, (size_t)e->d.n_envs * 4, cudaMemcpyHostToDevice, c->stream));
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_env_get_norm_stats(dril_env* e, float* obs_mean, float* obs_var, int64_t* obs_count,
+                                           float* ret_mean, float* ret_var, int64_t* ret_count) {
+    DRIL_REQUIRE(e, "NULL argument");
+    DRIL_REQUIRE(e->d.normalize, "env has no NormalizeWrapperEnv");
+    dril_ctx* c = e->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    float rs[2]; long long cnt[2];
+    if (obs_mean) DRIL_CUDA(cudaMemcpyAsync(obs_mean, e->d.obs_mean, e->d.obs_dim * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (obs_var) DRIL_CUDA(cudaMemcpyAsync(obs_var, e->d.obs_var, e->d.obs_dim * 4, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaMemcpyAsync(rs, e->d.ret_stats, 8, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaMemcpyAsync(cnt, e->d.counts, 16, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    if (ret_mean) *ret_mean = rs[0];
+    if (ret_var) *ret_var = rs[1];
+    if (obs_count) *obs_count = cnt[0];
+    if (ret_count) *ret_count = cnt[1];
+    return DRIL_OK;
+}
+extern "C" int32_t dril_env_set_norm_stats(dril_env* e, const float* obs_mean, const float* obs_var, int64_t obs_count,
+                                           float ret_mean, float ret_var, int64_t ret_count) {
+    DRIL_REQUIRE(e && obs_mean && obs_var, "NULL argument");
+    DRIL_REQUIRE(e->d.normalize, "env has no NormalizeWrapperEnv");
+    dril_ctx* c = e->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    float rs[2] = {ret_mean, ret_var}; long long cnt[2] = {obs_count, ret_count};
+    DRIL_CUDA(cudaMemcpyAsync(e->d.obs_mean, obs_mean, e->d.obs_dim * 4, cudaMemcpyHostToDevice, c->stream));
+    DRIL_CUDA(cudaMemcpyAsync(e->d.obs_var, obs_var, e->d.obs_dim * 4, cudaMemcpyHostToDevice, c->stream));
+    DRIL_CUDA(cudaMemcpyAsync(e->d.ret_stats, rs, 8, cudaMemcpyHostToDevice, c->stream));
+    DRIL_CUDA(cudaMemcpyAsync(e->d.counts, cnt, 16, cudaMemcpyHostToDevice, c->stream));
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_env_set_training(dril_env* e, int32_t training) {
+    DRIL_REQUIRE(e, "NULL argument");
+    e->d.training = training ? 1 : 0;
+    return DRIL_OK;
+}
+extern "C" int32_t dril_env_get_original(dril_env* e, float* obs_out, float* rewards_out) {
+    DRIL_REQUIRE(e, "NULL argument");
+    dril_ctx* c = e->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    if (obs_out) DRIL_CUDA(cudaMemcpyAsync(obs_out, e->d.old_obs, (size_t)e->d.n_envs * e->d.obs_dim * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (rewards_out) DRIL_CUDA(cudaMemcpyAsync(rewards_out, e->d.old_rewards, (size_t)e->d.n_envs * 4, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_env_monitor_stats(dril_env* e, float* ep_rew_mean, float* ep_len_mean, int64_t* n_in_window,
+                                          int64_t* total_episodes) {
+    DRIL_REQUIRE(e, "NULL argument");
+    DRIL_REQUIRE(e->d.monitor, "env has no MonitorWrapperEnv");
+    dril_ctx* c = e->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    int w = e->ring.window;
+    std::vector<float> r((size_t)w); std::vector<int> l((size_t)w);
+    long long head = 0;
+    DRIL_CUDA(cudaMemcpyAsync(r.data(), e->ring.ret, w * 4, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaMemcpyAsync(l.data(), e->ring.len, w * 4, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaMemcpyAsync(&head, e->ring.head, 8, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    long long cnt = std::min<long long>(head, w);
+    float sr = 0.f; double sl = 0;
+    for (long long i = 0; i < cnt; ++i) { sr += r[i]; sl += l[i]; }   // mean(::CircularBuffer{Float32})
+    if (ep_rew_mean) *ep_rew_mean = cnt ? sr / (float)cnt : NAN;
+    if (ep_len_mean) *ep_len_mean = cnt ? (float)(sl / (double)cnt) : NAN;
+    if (n_in_window) *n_in_window = cnt;
+    if (total_episodes) *total_episodes = e->total_episodes;
+    return DRIL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// rollout / GAE
+// ---------------------------------------------------------------------------------------
+static int32_t check_compat(dril_env* e, dril_policy* p, dril_buffer* b) {
+    DRIL_REQUIRE(e && p && b, "NULL argument");
+    DRIL_REQUIRE(e->ctx == p->ctx && e->ctx == b->ctx, "env, policy and buffer must share a ctx");
+    DRIL_REQUIRE(b->d.N == e->d.n_envs, "buffer has %lld envs, env has %lld", b->d.N, e->d.n_envs);
+    DRIL_REQUIRE(b->d.obs_dim == e->d.obs_dim && p->pd.obs_dim == e->d.obs_dim, "obs_dim mismatch");
+    DRIL_REQUIRE(b->d.act_kind == p->pd.act_kind, "action kind mismatch between buffer and policy");
+    if (p->pd.act_kind == DRIL_ACT_CONTINUOUS) DRIL_REQUIRE(b->d.act_dim == p->pd.act_n, "act_dim mismatch");
+    if (e->d.kind == DRIL_ENV_CARTPOLE) DRIL_REQUIRE(p->pd.act_kind == DRIL_ACT_DISCRETE && p->pd.act_n == 2, "CartPole needs Discrete(2)");
+    if (e->d.kind == DRIL_ENV_PENDULUM) DRIL_REQUIRE(p->pd.act_kind == DRIL_ACT_CONTINUOUS && p->pd.act_n == 1, "Pendulum needs Box (1,)");
+    return DRIL_OK;
+}
+
+static int32_t rollout_async(dril_env* e, dril_policy* p, dril_buffer* b, const void* forced_dev) {
+    dril_ctx* c = e->ctx;
+    DRIL_CUDA(cudaMemsetAsync(b->d.done_count, 0, (size_t)b->d.T * 4, c->stream));
+    DRIL_CUDA(cudaMemsetAsync(e->d.roll_sums, 0, 16, c->stream));
+    DRIL_CUDA(cudaMemsetAsync(e->d.roll_eps, 0, 8, c->stream));
+    DRIL_TRY(launch_rollout(e, p, b, forced_dev, nullptr, (int)b->d.T, RO_INITIAL_OBSERVE | RO_FOLD_NEXT_OBSERVE));
+    p->step_index += (uint32_t)b->d.T;
+    return DRIL_OK;
+}
+
+extern "C" int32_t dril_rollout_collect(dril_env* e, dril_policy* p, dril_buffer* b, const void* forced_actions, float* fps_out) {
+    DRIL_TRY(check_compat(e, p, b));
+    dril_ctx* c = e->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    void* forced_dev = nullptr;
+    if (forced_actions) {
+        size_t cnt = (size_t)b->d.T * b->d.N;
+        DRIL_TRY(ensure_scratch(p, cnt * b->act_elems * 4));
+        DRIL_TRY(stage_actions(c, b->d.act_kind, b->d.act_dim, forced_actions, cnt, p->scratch));
+        forced_dev = p->scratch;
+    }
+    DRIL_CUDA(cudaEventRecord(p->ev[0], c->stream));
+    DRIL_TRY(rollout_async(e, p, b, forced_dev));
+    DRIL_CUDA(cudaEventRecord(p->ev[1], c->stream));
+    DRIL_TRY(launch_monitor_finalize(e, b));
+    unsigned long long eps = 0;
+    DRIL_CUDA(cudaMemcpyAsync(&eps, e->d.roll_eps, 8, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    e->total_episodes += (int64_t)eps;
+    float ms = 0.f;
+    DRIL_CUDA(cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]));
+    if (fps_out) *fps_out = (float)((double)b->d.T * b->d.N / (ms * 1e-3));
+    return DRIL_OK;
+}
+
+static int32_t gae_async(dril_ctx* c, const BufDev& d, float gamma, float lambda) {
+    Span sp(c, DRIL_K_GAE);
+    gae_kernel<<<(unsigned)((d.N + 255) / 256), 256, 0, c->stream>>>(d.rewards, d.values, d.flags, d.boot, d.last_values,
+                                                                    d.advantages, d.returns, d.T, d.N, gamma, lambda);
+    DRIL_CUDA(cudaGetLastError());
+    return DRIL_OK;
+}
+extern "C" int32_t dril_gae(dril_buffer* b, float gamma, float lambda) {
+    DRIL_REQUIRE(b, "NULL argument");
+    DRIL_CUDA(cudaSetDevice(b->ctx->device));
+    DRIL_TRY(gae_async(b->ctx, b->d, gamma, lambda));
+    DRIL_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_gae_raw(dril_ctx* c, const float* rewards, const float* values, const uint8_t* terminated,
+                                const uint8_t* truncated, const float* boot, const float* last_values, int64_t T, int64_t N,
+                                float gamma, float lambda, float* advantages, float* returns) {
+    DRIL_REQUIRE(c && rewards && values && terminated && truncated && boot && last_values && advantages && returns, "NULL argument");
+    DRIL_REQUIRE(T >= 1 && N >= 1, "empty buffer");
+    dril_buffer* b = nullptr;
+    DRIL_TRY(dril_buffer_create(c, T, N, 1, DRIL_ACT_DISCRETE, 1, &b));
+    size_t tn = (size_t)T * N;
+    std::vector<uint8_t> flags(tn);
+    for (size_t i = 0; i < tn; ++i) flags[i] = (terminated[i] ? 1 : 0) | (truncated[i] ? 2 : 0);
+    int32_t st = DRIL_OK;
+    do {
+        if ((st = dril_buffer_upload(b, DRIL_BUF_REWARDS, rewards, tn * 4))) break;
+        if ((st = dril_buffer_upload(b, DRIL_BUF_VALUES, values, tn * 4))) break;
+        if ((st = dril_buffer_upload(b, DRIL_BUF_FLAGS, flags.data(), tn))) break;
+        if ((st = dril_buffer_upload(b, DRIL_BUF_BOOT, boot, tn * 4))) break;
+        if ((st = dril_buffer_upload(b, DRIL_BUF_LAST_VALUES, last_values, (size_t)N * 4))) break;
+        if ((st = dril_gae(b, gamma, lambda))) break;
+        if ((st = dril_buffer_download(b, DRIL_BUF_ADVANTAGES, advantages, tn * 4))) break;
+        if ((st = dril_buffer_download(b, DRIL_BUF_RETURNS, returns, tn * 4))) break;
+    } while (0);
+    dril_buffer_destroy(b);
+    return st;
+}
+
+// ---------------------------------------------------------------------------------------
+// update
+// ---------------------------------------------------------------------------------------
+static UpdateHyper to_hyper(const dril_ppo_hyper* h) {
+    UpdateHyper u;
+    u.clip_range = h->clip_range; u.clip_range_vf = h->clip_range_vf; u.ent_coef = h->ent_coef; u.vf_coef = h->vf_coef;
+    u.max_grad_norm = h->max_grad_norm; u.target_kl = h->target_kl; u.normalize_advantage = h->normalize_advantage;
+    u.lr = h->learning_rate; u.beta1 = h->adam_beta1; u.beta2 = h->adam_beta2; u.adam_eps = h->adam_eps;
+    return u;
+}
+static FeistelKey make_feistel(long long n_total, uint64_t epoch_counter, int rank, uint64_t seed) {
+    FeistelKey fk;
+    uint32_t k[4];
+    philox4x32((uint32_t)epoch_counter, (uint32_t)rank, 0u, DRIL_TAG_SHUFFLE, seed, k);
+    for (int i = 0; i < 4; ++i) fk.k[i] = k[i];
+    int bits = 0;
+    unsigned long long v = (unsigned long long)(n_total - 1);
+    while (v) { ++bits; v >>= 1; }
+    bits = std::max(bits, 2);
+    fk.half_bits = (bits + 1) / 2;
+    fk.half_mask = (1u << fk.half_bits) - 1u;
+    return fk;
+}
+
+struct LossLaunch { int M4; bool ws; size_t smem; int grid_cap; };
+static int32_t plan_loss(dril_policy* p, LossLaunch* out) {
+    const PolicyDesc& pd = p->pd;
+    int M4 = 64;
+    bool ws = true;
+    auto total = [&](int m4, bool w) { return loss_smem_layout(pd, m4, w).total; };
+    while (M4 > 8 && total(M4, true) > DRIL_SMEM_MAX && total(M4, false) > DRIL_SMEM_MAX) M4 -= 4;
+    if (total(M4, true) > DRIL_SMEM_MAX) ws = false;
+    if (ws && M4 < 32 && total(32, false) <= DRIL_SMEM_MAX) {
+        ws = false; M4 = 32;
+        while (M4 < 64 && total(M4 + 4, false) <= DRIL_SMEM_MAX) M4 += 4;
+    }
+    if (total(M4, ws) > DRIL_SMEM_MAX) { dril_set_error("network too wide for the loss kernel's shared memory"); return DRIL_ERR_UNSUPPORTED; }
+    out->M4 = M4; out->ws = ws; out->smem = total(M4, ws);
+    int per_sm = 0;
+    DRIL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppo_loss_grad_kernel, DRIL_THREADS, out->smem));
+    per_sm = std::max(1, std::min(per_sm, 2));
+    out->grid_cap = std::min(per_sm * p->ctx->sm_count, p->gpart_ctas);
+    return DRIL_OK;
+}
+
+// one minibatch: loss/grad kernel -> reduce -> (allreduce) -> clip + Adam
+static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch& mb, const double* mbstats_dev,
+                              const UpdateHyper& hp, const LossLaunch& ll, bool apply, int apply_stats) {
+    dril_ctx* c = p->ctx;
+    const PolicyDesc& pd = p->pd;
+    LossArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pd = pd; a.buf = bd; a.pack = p->pack; a.flat = p->flat; a.mbstats = mbstats_dev; a.gpart = p->gpart;
+    a.stop_flag = p->stop_flag; a.mb = mb; a.hp = hp; a.M4 = ll.M4; a.weights_smem = ll.ws;
+    long long tiles = (mb.count + ll.M4 - 1) / ll.M4;
+    int grid = (int)std::max<long long>(1, std::min<long long>(tiles, ll.grid_cap));
+    {
+        Span sp(c, DRIL_K_LOSS_GRAD);
+        ppo_loss_grad_kernel<<<grid, DRIL_THREADS, ll.smem, c->stream>>>(a);
+        DRIL_CUDA(cudaGetLastError());
+    }
+    {
+        Span sp(c, DRIL_K_GRAD_REDUCE);
+        int n = pd.n_params + 6;
+        grad_reduce_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(p->gpart, grid, pd.gpack, p->flat2g, pd.n_params,
+                                                                  pd.pack_fwd + pd.act_n, p->g, p->stop_flag);
+        DRIL_CUDA(cudaGetLastError());
+    }
+    DRIL_TRY(allreduce_sum(c, p->g, (size_t)pd.n_params + 6, false));
+    if (apply) {
+        AdamArgs aa;
+        aa.g = p->g; aa.flat = p->flat; aa.m = p->m; aa.v = p->v; aa.pack = p->pack; aa.flat2pack = p->flat2pack;
+        aa.flat2packT = p->flat2packT; aa.step = p->step; aa.iter_acc = p->iter_acc; aa.stop_flag = p->stop_flag;
+        aa.global_count = mb.global_count; aa.hp = hp; aa.n_params = pd.n_params; aa.apply_stats = apply_stats;
+        Span sp(c, DRIL_K_ADAM);
+        adam_finalize_kernel<<<1, 1024, 0, c->stream>>>(aa);
+        DRIL_CUDA(cudaGetLastError());
+    }
+    return DRIL_OK;
+}
+
+static int32_t ensure_mbstats(dril_policy* p, int n_mb, int blocks_per_mb) {
+    if (p->mbstats_cap >= n_mb) return DRIL_OK;
+    if (p->mbstats) cudaFree(p->mbstats);
+    if (p->adv_partial) cudaFree(p->adv_partial);
+    p->mbstats = nullptr; p->adv_partial = nullptr; p->mbstats_cap = 0;
+    DRIL_TRY(dmalloc(&p->mbstats, (size_t)n_mb * 2));
+    DRIL_TRY(dmalloc(&p->adv_partial, (size_t)n_mb * 64 * 2));
+    p->mbstats_cap = n_mb;
+    return DRIL_OK;
+}
+
+static int32_t update_async(dril_policy* p, dril_buffer* b, const dril_ppo_hyper* h, int epochs, int64_t batch_size,
+                            uint64_t shuffle_seed, uint64_t epoch_counter) {
+    dril_ctx* c = p->ctx;
+    const long long n_total = b->d.T * b->d.N;
+    DRIL_REQUIRE(batch_size >= 1, "batch_size must be positive");
+    DRIL_REQUIRE(epochs >= 0, "epochs must be non-negative");
+    const int n_mb = (int)((n_total + batch_size - 1) / batch_size);
+    const UpdateHyper hp = to_hyper(h);
+    LossLaunch ll;
+    DRIL_TRY(plan_loss(p, &ll));
+    const int bpm = (int)std::max<long long>(1, std::min<long long>(64, (std::min<long long>(batch_size, n_total) + 2047) / 2048));
+    DRIL_TRY(ensure_mbstats(p, n_mb, bpm));
+    DRIL_CUDA(cudaMemsetAsync(p->iter_acc, 0, ITER_ACC_N * 8, c->stream));
+    DRIL_CUDA(cudaMemsetAsync(p->stop_flag, 0, 4, c->stream));
+    for (int epoch = 0; epoch < epochs; ++epoch) {
+        FeistelKey fk = make_feistel(n_total, epoch_counter + epoch, c->rank, shuffle_seed);
+        if (hp.normalize_advantage) {
+            {
+                Span sp(c, DRIL_K_ADV_STATS);
+                adv_stats_kernel<<<dim3(bpm, n_mb), 256, 0, c->stream>>>(b->d.advantages, n_total, batch_size, fk, 0, p->adv_partial);
+                DRIL_CUDA(cudaGetLastError());
+            }
+            {
+                Span sp(c, DRIL_K_ADV_STATS);
+                adv_stats_finalize_kernel<<<(n_mb * 2 + 127) / 128, 128, 0, c->stream>>>(p->adv_partial, bpm, n_mb, p->mbstats);
+                DRIL_CUDA(cudaGetLastError());
+            }
+            DRIL_TRY(allreduce_sum(c, p->mbstats, (size_t)n_mb * 2, true));
+        }
+        for (int i = 0; i < n_mb; ++i) {
+            Minibatch mb;
+            mb.n_total = n_total; mb.start = (long long)i * batch_size;
+            mb.count = std::min<long long>(batch_size, n_total - mb.start);
+            mb.global_count = (double)mb.count * c->nranks;
+            mb.fk = fk; mb.identity = 0;
+            DRIL_TRY(minibatch_step(p, b->d, mb, p->mbstats + 2 * i, hp, ll, true, 1));
+        }
+    }
+    return DRIL_OK;
+}
+
+static int32_t ev_async(dril_policy* p, dril_buffer* b) {
+    dril_ctx* c = p->ctx;
+    DRIL_CUDA(cudaMemsetAsync(p->ev_acc, 0, 32, c->stream));
+    Span sp(c, DRIL_K_EXPLAINED_VAR);
+    long long n = b->d.T * b->d.N;
+    int grid = (int)std::min<long long>((n + 255) / 256, (long long)c->sm_count * 8);
+    explained_variance_kernel<<<grid, 256, 0, c->stream>>>(b->d.values, b->d.returns, n, p->ev_acc);
+    DRIL_CUDA(cudaGetLastError());
+    return DRIL_OK;
+}
+static int32_t ev_finish(dril_policy* p, long long n_local, float* out) {
+    dril_ctx* c = p->ctx;
+    DRIL_TRY(allreduce_sum(c, p->ev_acc, 4, true));
+    double acc[4];
+    DRIL_CUDA(cudaMemcpyAsync(acc, p->ev_acc, 32, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    double n = (double)n_local * c->nranks;
+    double var_d = (acc[1] - acc[0] * acc[0] / n) / (n - 1.0);
+    double var_r = (acc[3] - acc[2] * acc[2] / n) / (n - 1.0);
+    *out = (float)(1.0 - var_d / var_r);
+    return DRIL_OK;
+}
+extern "C" int32_t dril_explained_variance(dril_buffer* b, float* out) {
+    DRIL_REQUIRE(b && out, "NULL argument");
+    dril_ctx* c = b->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    double* acc = nullptr;
+    DRIL_TRY(dmalloc(&acc, 4));
+    DRIL_CUDA(cudaMemsetAsync(acc, 0, 32, c->stream));
+    long long n = b->d.T * b->d.N;
+    {
+        Span sp(c, DRIL_K_EXPLAINED_VAR);
+        int grid = (int)std::min<long long>((n + 255) / 256, (long long)c->sm_count * 8);
+        explained_variance_kernel<<<grid, 256, 0, c->stream>>>(b->d.values, b->d.returns, n, acc);
+    }
+    double h[4];
+    DRIL_CUDA(cudaMemcpyAsync(h, acc, 32, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(acc);
+    double dn = (double)n;
+    *out = (float)(1.0 - ((h[1] - h[0] * h[0] / dn) / (dn - 1.0)) / ((h[3] - h[2] * h[2] / dn) / (dn - 1.0)));
+    return DRIL_OK;
+}
+
+static int32_t collect_iter_stats(dril_policy* p, dril_iter_stats* s, bool with_rollout) {
+    dril_ctx* c = p->ctx;
+    double acc[ITER_ACC_N];
+    int stop = 0;
+    DRIL_CUDA(cudaMemcpyAsync(acc, p->iter_acc, ITER_ACC_N * 8, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaMemcpyAsync(&stop, p->stop_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+    double rs[2] = {0, 0};
+    unsigned long long eps = 0;
+    if (with_rollout && p->last_env) {
+        DRIL_CUDA(cudaMemcpyAsync(rs, p->last_env->d.roll_sums, 16, cudaMemcpyDeviceToHost, c->stream));
+        DRIL_CUDA(cudaMemcpyAsync(&eps, p->last_env->d.roll_eps, 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    memset(s, 0, sizeof(*s));
+    double n = acc[9];
+    // means over the iteration's applied minibatches; empty -> NaN like mean(Float32[]) (ppo.jl:257-263)
+    s->policy_loss = (float)(acc[0] / n); s->value_loss = (float)(acc[1] / n); s->entropy_loss = (float)(acc[2] / n);
+    s->clip_fraction = (float)(acc[3] / n); s->approx_kl_div = (float)(acc[4] / n); s->entropy = (float)(acc[5] / n);
+    s->ratio = (float)(acc[6] / n); s->loss = (float)(acc[7] / n);
+    s->grad_norm = (float)(acc[8] / acc[10]);
+    s->n_minibatch_steps = (int32_t)n;
+    s->kl_stopped = stop;
+    s->learning_rate = p->last_lr;
+    s->episodes = (int64_t)eps; s->episode_return_sum = rs[0]; s->episode_length_sum = rs[1];
+    return DRIL_OK;
+}
+
+extern "C" int32_t dril_ppo_update(dril_policy* p, dril_buffer* b, const dril_ppo_hyper* h, int32_t epochs,
+                                   int64_t batch_size, uint64_t shuffle_seed, uint64_t epoch_counter, dril_iter_stats* stats_out) {
+    DRIL_REQUIRE(p && b && h, "NULL argument");
+    DRIL_REQUIRE(p->ctx == b->ctx, "policy and buffer must share a ctx");
+    dril_ctx* c = p->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    p->last_lr = h->learning_rate;
+    DRIL_CUDA(cudaEventRecord(p->ev[1], c->stream));
+    DRIL_TRY(update_async(p, b, h, epochs, batch_size, shuffle_seed, epoch_counter));
+    DRIL_CUDA(cudaEventRecord(p->ev[2], c->stream));
+    DRIL_TRY(ev_async(p, b));
+    dril_iter_stats s;
+    dril_env* keep = p->last_env;
+    p->last_env = nullptr;
+    DRIL_TRY(collect_iter_stats(p, &s, false));
+    p->last_env = keep;
+    DRIL_TRY(ev_finish(p, b->d.T * b->d.N, &s.explained_variance));
+    float ms = 0.f;
+    DRIL_CUDA(cudaEventElapsedTime(&ms, p->ev[1], p->ev[2]));
+    s.update_ms = ms;
+    if (stats_out) *stats_out = s;
+    return DRIL_OK;
+}
+
+extern "C" int32_t dril_ppo_iteration_async(dril_env* e, dril_policy* p, dril_buffer* b, const dril_ppo_hyper* h,
+                                            int32_t epochs, int64_t batch_size, uint64_t shuffle_seed, uint64_t epoch_counter) {
+    DRIL_TRY(check_compat(e, p, b));
+    DRIL_REQUIRE(h, "hyper is NULL");
+    dril_ctx* c = e->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    p->last_env = e; p->last_buf = b; p->last_lr = h->learning_rate;
+    DRIL_CUDA(cudaEventRecord(p->ev[0], c->stream));
+    DRIL_TRY(rollout_async(e, p, b, nullptr));
+    DRIL_TRY(gae_async(c, b->d, h->gamma, h->gae_lambda));
+    DRIL_TRY(launch_monitor_finalize(e, b));
+    DRIL_CUDA(cudaEventRecord(p->ev[1], c->stream));
+    DRIL_TRY(ev_async(p, b));   // explained variance uses the rollout's values/returns (ppo.jl:256)
+    DRIL_TRY(update_async(p, b, h, epochs, batch_size, shuffle_seed, epoch_counter));
+    DRIL_CUDA(cudaEventRecord(p->ev[2], c->stream));
+    return DRIL_OK;
+}
+extern "C" int32_t dril_iteration_result(dril_policy* p, dril_iter_stats* stats_out) {
+    DRIL_REQUIRE(p && stats_out, "NULL argument");
+    DRIL_REQUIRE(p->last_buf, "no iteration in flight");
+    dril_ctx* c = p->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    dril_iter_stats s;
+    DRIL_TRY(collect_iter_stats(p, &s, true));
+    DRIL_TRY(ev_finish(p, p->last_buf->d.T * p->last_buf->d.N, &s.explained_variance));
+    float ms = 0.f;
+    DRIL_CUDA(cudaEventElapsedTime(&ms, p->ev[0], p->ev[1])); s.rollout_ms = ms;
+    DRIL_CUDA(cudaEventElapsedTime(&ms, p->ev[1], p->ev[2])); s.update_ms = ms;
+    if (p->last_env) p->last_env->total_episodes += s.episodes;
+    *stats_out = s;
+    return DRIL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// parity entries on host minibatches
+// ---------------------------------------------------------------------------------------
+extern "C" int32_t dril_ppo_loss_grad(dril_policy* p, const float* obs, const void* actions, const float* advantages,
+                                      const float* returns, const float* old_logprobs, const float* old_values, int64_t B,
+                                      const dril_ppo_hyper* h, float* loss, float* stats7, float* grads) {
+    DRIL_REQUIRE(p && obs && actions && advantages && returns && old_logprobs && old_values && h, "NULL argument");
+    DRIL_REQUIRE(B >= 1, "empty minibatch");
+    dril_ctx* c = p->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    const PolicyDesc& pd = p->pd;
+    dril_buffer* b = nullptr;
+    DRIL_TRY(dril_buffer_create(c, 1, B, pd.obs_dim, pd.act_kind, pd.act_kind == DRIL_ACT_DISCRETE ? 1 : pd.act_n, &b));
+    int32_t st = DRIL_OK;
+    do {
+        if ((st = dril_buffer_upload(b, DRIL_BUF_OBS, obs, (size_t)B * pd.obs_dim * 4))) break;
+        if ((st = stage_actions(c, pd.act_kind, pd.act_n, actions, B, b->d.actions))) break;
+        if ((st = dril_buffer_upload(b, DRIL_BUF_ADVANTAGES, advantages, B * 4))) break;
+        if ((st = dril_buffer_upload(b, DRIL_BUF_RETURNS, returns, B * 4))) break;
+        if ((st = dril_buffer_upload(b, DRIL_BUF_LOGPROBS, old_logprobs, B * 4))) break;
+        if ((st = dril_buffer_upload(b, DRIL_BUF_VALUES, old_values, B * 4))) break;
+        const UpdateHyper hp = to_hyper(h);
+        LossLaunch ll;
+        if ((st = plan_loss(p, &ll))) break;
+        if ((st = ensure_mbstats(p, 1, 64))) break;
+        cudaMemsetAsync(p->stop_flag, 0, 4, c->stream);
+        FeistelKey fk = make_feistel(B, 0, 0, 0);
+        int bpm = (int)std::max<int64_t>(1, std::min<int64_t>(64, (B + 2047) / 2048));
+        adv_stats_kernel<<<dim3(bpm, 1), 256, 0, c->stream>>>(b->d.advantages, B, B, fk, 1, p->adv_partial);
+        adv_stats_finalize_kernel<<<1, 128, 0, c->stream>>>(p->adv_partial, bpm, 1, p->mbstats);
+        c->launches += 2;
+        Minibatch mb;
+        mb.n_total = B; mb.start = 0; mb.count = B; mb.global_count = (double)B; mb.fk = fk; mb.identity = 1;
+        if ((st = minibatch_step(p, b->d, mb, p->mbstats, hp, ll, false, 0))) break;
+        std::vector<float> g((size_t)pd.n_params + 6);
+        cudaMemcpyAsync(g.data(), p->g, g.size() * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { dril_set_error("CUDA failure in dril_ppo_loss_grad: %s", cudaGetErrorString(cudaGetLastError())); st = DRIL_ERR_CUDA; break; }
+        const float* s6 = g.data() + pd.n_params;
+        float invB = (float)(1.0 / (double)B);
+        float p_loss = s6[0] * invB, v_loss = s6[1] * invB, ent = s6[2] * invB;
+        if (stats7) {
+            stats7[0] = p_loss; stats7[1] = v_loss; stats7[2] = -ent; stats7[3] = s6[3] * invB; stats7[4] = s6[4] * invB;
+            stats7[5] = ent; stats7[6] = s6[5] * invB;
+        }
+        if (loss) *loss = p_loss + h->ent_coef * (-ent) + h->vf_coef * v_loss;
+        if (grads) memcpy(grads, g.data(), (size_t)pd.n_params * 4);
+    } while (0);
+    dril_buffer_destroy(b);
+    return st;
+}
+
+extern "C" int32_t dril_optimizer_step(dril_policy* p, const float* grads, int64_t n, const dril_ppo_hyper* h, float* grad_norm) {
+    DRIL_REQUIRE(p && grads && h, "NULL argument");
+    DRIL_REQUIRE(n == p->pd.n_params, "expected %d gradients, got %lld", p->pd.n_params, (long long)n);
+    dril_ctx* c = p->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    DRIL_CUDA(cudaMemcpyAsync(p->g, grads, n * 4, cudaMemcpyHostToDevice, c->stream));
+    DRIL_CUDA(cudaMemsetAsync(p->stop_flag, 0, 4, c->stream));
+    AdamArgs aa;
+    aa.g = p->g; aa.flat = p->flat; aa.m = p->m; aa.v = p->v; aa.pack = p->pack; aa.flat2pack = p->flat2pack;
+    aa.flat2packT = p->flat2packT; aa.step = p->step; aa.iter_acc = p->iter_acc; aa.stop_flag = p->stop_flag;
+    aa.global_count = 1.0; aa.hp = to_hyper(h); aa.n_params = p->pd.n_params; aa.apply_stats = 0;
+    {
+        Span sp(c, DRIL_K_ADAM);
+        adam_finalize_kernel<<<1, 1024, 0, c->stream>>>(aa);
+        DRIL_CUDA(cudaGetLastError());
+    }
+    double acc8 = 0;
+    DRIL_CUDA(cudaMemcpyAsync(&acc8, p->iter_acc + 8, 8, cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    if (grad_norm) *grad_norm = (float)acc8;
+    return DRIL_OK;
+}

@@ -1,0 +1,587 @@
+// Fused rollout engine: observe -> normalise -> actor/critic forward -> sample -> to_env ->
+// env step -> monitor / normaliser statistics -> auto-reset, for n_steps, written straight
+// into the device-resident rollout buffer.  One persistent kernel per rollout.
+//
+// Replaces the n_steps loop of collect_trajectories (buffers/trajectory.jl:33-76) together
+// with NormalizeWrapperEnv.observe/act! (environment_wrappers/normalizeWrapperEnv.jl:123-165),
+// MonitorWrapperEnv.act! (monitorWrapperEnv.jl:44-60), MultiThreadedParallelEnv.act!
+// (multithreadedParallelEnv.jl:47-74), the layer call (layers/layer_forward.jl:3-39) and the
+// batch-of-1 bootstrap predict_values calls (trajectory.jl:57-70).
+//
+// Work decomposition: a CTA owns tiles of M consecutive envs.  Without a training
+// NormalizeWrapperEnv the envs are independent for the whole rollout, so the grid is one
+// tile per CTA and there is no inter-CTA communication.  With running statistics every step
+// needs the batch moments over ALL envs before rewards / the next observation can be
+// normalised: the kernel is then launched cooperatively and uses one grid barrier per step
+// (the reward-return moments of step t and the observation moments of observe t+1 share it).
+#pragma once
+#include <cooperative_groups.h>
+
+#include "env.cuh"
+#include "mlp.cuh"
+
+namespace cg = cooperative_groups;
+
+enum {
+    RO_HAS_POLICY = 1,        // run the actor-critic (fused rollout); off: compat act!/observe
+    RO_INITIAL_OBSERVE = 2,   // the observe() before the loop (trajectory.jl:32) updates obs stats
+    RO_FOLD_NEXT_OBSERVE = 4, // the observe() after each act! (trajectory.jl:45) is folded into the step
+    RO_WEIGHTS_SMEM = 8,
+    RO_GRID_SYNC = 16,        // training normaliser: cooperative launch + grid barrier per step
+    RO_WRITE_OBS_OUT = 32     // compat observe: write normalised obs to obs_out
+};
+
+struct RolloutArgs {
+    EnvDev env;
+    BufDev buf;
+    PolicyDesc pd;
+    const float* pack;       // packed parameters (global)
+    const float* flat;       // flat parameters (log_std)
+    const void* forced;      // forced actions [T][N] int32 | [T][N][A] float, or null
+    float* obs_out;          // compat observe output [N][D]
+    unsigned long long pseed;
+    unsigned int step0;
+    int T, M4, n_tiles, flags;
+};
+
+struct RolloutSmem {
+    int ld, raw_rows;
+    size_t w, raw, x, acta, actc, envact, stat, part, total;  // float offsets (part: bytes offset for doubles)
+};
+
+__host__ __device__ inline RolloutSmem rollout_smem_layout(const PolicyDesc& pd, int obs_dim, int act_dim, int M4,
+                                                           bool weights_smem, bool has_policy) {
+    RolloutSmem s;
+    s.ld = M4 + 4;
+    int Dp = (obs_dim + 3) & ~3;
+    s.raw_rows = Dp + 4;
+    size_t o = 0;
+    s.w = o; o += (weights_smem && has_policy) ? (size_t)pd.pack_fwd : 0;
+    s.raw = o; o += (size_t)s.raw_rows * s.ld;
+    s.x = o; o += (size_t)Dp * s.ld;
+    s.acta = o; o += has_policy ? (size_t)2 * pd.max_np * s.ld : 0;
+    s.actc = o; o += has_policy ? (size_t)2 * pd.max_np * s.ld : 0;
+    int adp = act_dim < 1 ? 1 : act_dim;
+    s.envact = o; o += (size_t)adp * s.ld;
+    s.stat = o; o += (size_t)4 * Dp + 8;
+    o = (o + 3) & ~(size_t)3;
+    s.part = o * sizeof(float);                       // doubles: [2*D+2] accumulators + 64 scratch + 4 counts
+    s.total = s.part + (size_t)(2 * obs_dim + 2 + 64 + 4) * sizeof(double);
+    return s;
+}
+
+// Chan/Welford merge exactly as RunningMeanStd.update_from_moments! (normalizeWrapperEnv.jl:28-50), fp32.
+__device__ __forceinline__ void rms_merge(float& mean, float& var, long long count, float bm, float bv, long long bc) {
+    if (count == 0) {
+        mean = bm; var = bv;
+    } else {
+        float delta = __fsub_rn(bm, mean);
+        long long total = count + bc;
+        float fc = (float)count, fb = (float)bc, ft = (float)total;
+        float new_mean = __fadd_rn(mean, __fdiv_rn(__fmul_rn(delta, fb), ft));
+        float m_a = __fmul_rn(var, fc);
+        float m_b = __fmul_rn(bv, fb);
+        float m2 = __fadd_rn(__fadd_rn(m_a, m_b),
+                             __fdiv_rn(__fmul_rn(__fmul_rn(__fmul_rn(delta, delta), fc), fb), ft));
+        mean = new_mean;
+        var = __fdiv_rn(m2, ft);
+    }
+}
+
+__device__ __forceinline__ float normalize_obs_val(float x, float mean, float var, float eps, float clip) {
+    float v = __fdiv_rn(__fsub_rn(x, mean), __fsqrt_rn(__fadd_rn(var, eps)));
+    return fminf(fmaxf(v, -clip), clip);
+}
+
+// column sums (double) of rows [0,rows) of sRaw over the valid samples of this tile, accumulated
+// into acc[2*c], acc[2*c+1] (sum, sum of squares) by a fixed warp per column => deterministic.
+__device__ __forceinline__ void tile_column_sums(const float* sRaw, int ld, int row0, int rows, int col0, int nvalid,
+                                                 double* acc) {
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int r = warp; r < rows; r += nw) {
+        double s = 0.0, q = 0.0;
+        for (int e = lane; e < nvalid; e += 32) {
+            double v = (double)sRaw[(size_t)(row0 + r) * ld + e];
+            s += v; q += v * v;
+        }
+        s = warp_sum(s); q = warp_sum(q);
+        if (lane == 0) { acc[2 * (col0 + r)] += s; acc[2 * (col0 + r) + 1] += q; }
+    }
+}
+
+__global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_constant__ RolloutArgs a) {
+    extern __shared__ float4 smem4[];
+    float* smem = reinterpret_cast<float*>(smem4);
+    const EnvDev& env = a.env;
+    const BufDev& buf = a.buf;
+    const PolicyDesc& pd = a.pd;
+    const bool has_policy = a.flags & RO_HAS_POLICY;
+    const bool grid_sync = a.flags & RO_GRID_SYNC;
+    const int D = env.obs_dim, Dp = (D + 3) & ~3;
+    const int M4 = a.M4;
+    const long long N = env.n_envs;
+    const RolloutSmem L = rollout_smem_layout(pd, D, env.act_dim, M4, a.flags & RO_WEIGHTS_SMEM, has_policy);
+    const int ld = L.ld;
+    float* sW = smem + L.w;
+    float* sRaw = smem + L.raw;
+    float* sX = smem + L.x;
+    float* sActA = smem + L.acta;
+    float* sActC = smem + L.actc;
+    float* sEnvAct = smem + L.envact;
+    float* sMean = smem + L.stat;        // [Dp]
+    float* sVar = sMean + Dp;            // [Dp]
+    float* sNewMean = sVar + Dp;         // [Dp]
+    float* sNewVar = sNewMean + Dp;      // [Dp]
+    float* sRet = sNewVar + Dp;          // [0] ret_mean [1] ret_var
+    double* sAcc = reinterpret_cast<double*>(reinterpret_cast<char*>(smem) + L.part);  // [2*D+2]
+    double* sScratch = sAcc + 2 * D + 2;                                                // [64]
+    long long* sCnt = reinterpret_cast<long long*>(sScratch + 64);                      // obs_count, ret_count
+    const int tid = threadIdx.x;
+    const int ncol = D + 1;  // obs columns + the discounted-return column
+    const bool upd_obs = env.normalize && env.training && env.norm_obs;
+    const bool upd_ret = env.normalize && env.training && env.norm_reward;
+
+    const float* Wbase = a.pack;
+    if (has_policy && (a.flags & RO_WEIGHTS_SMEM)) {
+        const float4* src = reinterpret_cast<const float4*>(a.pack);
+        float4* dst = reinterpret_cast<float4*>(sW);
+        for (int i = tid; i < pd.pack_fwd / 4; i += blockDim.x) dst[i] = src[i];
+        Wbase = sW;
+    }
+    for (int d = tid; d < Dp; d += blockDim.x) {
+        sMean[d] = (env.normalize && d < D) ? env.obs_mean[d] : 0.f;
+        sVar[d] = (env.normalize && d < D) ? env.obs_var[d] : 1.f;
+    }
+    if (tid == 0) {
+        sRet[0] = env.normalize ? env.ret_stats[0] : 0.f;
+        sRet[1] = env.normalize ? env.ret_stats[1] : 1.f;
+        sCnt[0] = env.normalize ? env.counts[0] : 0;
+        sCnt[1] = env.normalize ? env.counts[1] : 0;
+    }
+    for (int i = tid; i < 2 * ncol; i += blockDim.x) sAcc[i] = 0.0;
+    __syncthreads();
+
+    int parity = 0;
+    // merge this step's batch moments (all CTAs compute the same values in the same order)
+    auto reduce_and_merge = [&](bool do_obs, bool do_ret) {
+        double* mine = env.partials + ((size_t)parity * gridDim.x + blockIdx.x) * (2 * ncol);
+        for (int i = tid; i < 2 * ncol; i += blockDim.x) { mine[i] = sAcc[i]; }
+        __threadfence();
+        cg::this_grid().sync();
+        const double* all = env.partials + (size_t)parity * gridDim.x * (2 * ncol);
+        int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+        for (int c = warp; c < 2 * ncol; c += nw) {
+            double s = 0.0;
+            for (int b = lane; b < (int)gridDim.x; b += 32) s += all[(size_t)b * (2 * ncol) + c];
+            s = warp_sum(s);
+            if (lane == 0) sAcc[c] = s;
+        }
+        __syncthreads();
+        double dn = (double)N;
+        if (do_obs) {
+            for (int d = tid; d < D; d += blockDim.x) {
+                double bm = sAcc[2 * d] / dn;
+                double bv = sAcc[2 * d + 1] / dn - bm * bm;
+                if (bv < 0.0) bv = 0.0;
+                float m = sMean[d], v = sVar[d];
+                rms_merge(m, v, sCnt[0], (float)bm, (float)bv, N);
+                sNewMean[d] = m; sNewVar[d] = v;
+            }
+        }
+        if (do_ret && tid == 0) {
+            double bm = sAcc[2 * D] / dn;
+            double bv = sAcc[2 * D + 1] / dn - bm * bm;
+            if (bv < 0.0) bv = 0.0;
+            float m = sRet[0], v = sRet[1];
+            rms_merge(m, v, sCnt[1], (float)bm, (float)bv, N);
+            sRet[0] = m; sRet[1] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (do_obs) sCnt[0] += N;
+            if (do_ret) sCnt[1] += N;
+        }
+        for (int i = tid; i < 2 * ncol; i += blockDim.x) sAcc[i] = 0.0;
+        parity ^= 1;
+        __syncthreads();
+    };
+    auto commit_obs_stats = [&]() {
+        for (int d = tid; d < D; d += blockDim.x) { sMean[d] = sNewMean[d]; sVar[d] = sNewVar[d]; }
+        __syncthreads();
+    };
+
+    // raw observation of every env of a tile -> sRaw rows [0,D) (feature-major); zero padding.
+    auto tile_raw_obs = [&](long long n0, int nvalid) {
+        if (env.kind == DRIL_ENV_SYNTHETIC) {
+            int nb = Dp >> 2;
+            for (int i = tid; i < nb * M4; i += blockDim.x) {
+                int b = i / M4, e = i - b * M4;
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+                if (e < nvalid) synthetic_obs_block((uint32_t)(env.gid_offset + n0 + e), env.life[n0 + e], b, env.seed, o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sRaw[(size_t)(4 * b + j) * ld + e] = (4 * b + j < D) ? o[j] : 0.f;
+            }
+        } else {
+            if (tid < M4) {
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+                if (tid < nvalid) {
+                    float st[ENV_MAX_STATE] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int k = 0; k < ENV_MAX_STATE; ++k) if (k < env.state_dim) st[k] = env.state[(size_t)k * N + n0 + tid];
+                    env_raw_obs(env.kind, st, o);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j < Dp) sRaw[(size_t)j * ld + tid] = o[j];
+            }
+        }
+        __syncthreads();
+    };
+    // normalise sRaw -> sX with (mean,var); optionally also record old_obs
+    auto tile_normalize = [&](const float* mean, const float* var, int nvalid) {
+        for (int i = tid; i < Dp * M4; i += blockDim.x) {
+            int d = i / M4, e = i - d * M4;
+            float x = sRaw[(size_t)d * ld + e];
+            if (env.normalize && env.norm_obs && d < D && e < nvalid)
+                x = normalize_obs_val(x, mean[d], var[d], env.eps, env.clip_obs);
+            sX[(size_t)d * ld + e] = x;
+        }
+        __syncthreads();
+    };
+
+    // ---------------- the observe() before the loop -----------------------------------------
+    if ((a.flags & RO_INITIAL_OBSERVE) && upd_obs) {
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            long long n0 = (long long)tile * M4;
+            int nvalid = (int)min((long long)M4, N - n0);
+            tile_raw_obs(n0, nvalid);
+            tile_column_sums(sRaw, ld, 0, D, 0, nvalid, sAcc);
+            __syncthreads();
+        }
+        reduce_and_merge(true, false);
+        commit_obs_stats();
+    }
+    if (a.flags & RO_WRITE_OBS_OUT) {  // compat observe(): normalised obs out, raw obs cached
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            long long n0 = (long long)tile * M4;
+            int nvalid = (int)min((long long)M4, N - n0);
+            tile_raw_obs(n0, nvalid);
+            tile_normalize(sMean, sVar, nvalid);
+            for (int i = tid; i < nvalid * D; i += blockDim.x) {
+                int e = i / D, d = i - e * D;
+                a.obs_out[(size_t)n0 * D + i] = sX[(size_t)d * ld + e];
+                if (env.old_obs) env.old_obs[(size_t)n0 * D + i] = sRaw[(size_t)d * ld + e];
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---------------- n_steps ---------------------------------------------------------------
+    for (int t = 0; t < a.T; ++t) {
+        const size_t row = (size_t)t * N;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            long long n0 = (long long)tile * M4;
+            int nvalid = (int)min((long long)M4, N - n0);
+            const bool mine = tid < nvalid;
+            const long long n = n0 + tid;
+            int fin = 0;
+            if (has_policy) {
+                // observe: raw -> normalised -> buffer
+                tile_raw_obs(n0, nvalid);
+                tile_normalize(sMean, sVar, nvalid);
+                for (int i = tid; i < nvalid * D; i += blockDim.x) {
+                    int e = i / D, d = i - e * D;
+                    buf.obs[(row + n0) * D + i] = sX[(size_t)d * ld + e];
+                }
+                // actor + critic forward
+                fin = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, 3);
+            }
+            // sample / replay action, log-prob, value; hand the env-space action to the step
+            int a_disc = 0;
+            if (mine) {
+                const uint32_t gid = (uint32_t)(env.gid_offset + n);
+                if (has_policy) {
+                    const float* z = sActA + (size_t)fin * pd.max_np * ld + tid;
+                    float value = sActC[(size_t)fin * pd.max_np * ld + tid];
+                    float logp;
+                    if (pd.act_kind == DRIL_ACT_DISCRETE) {
+                        int mode = 0, forced_v = 0;
+                        double u = 0.0;
+                        if (a.forced) { mode = 2; forced_v = reinterpret_cast<const int*>(a.forced)[row + n]; }
+                        else {
+                            uint32_t x[4];
+                            philox4x32(gid, a.step0 + (uint32_t)t, 0u, DRIL_TAG_SAMPLE, a.pseed, x);
+                            u = u01_f64(x[0], x[1]);
+                        }
+                        HeadOut h = categorical_head(z, ld, pd.act_n, pd.act_start, mode, u, forced_v, false);
+                        logp = h.logp;
+                        a_disc = h.action_idx;
+                        reinterpret_cast<int*>(buf.actions)[row + n] = a_disc;
+                    } else {
+                        const int A = pd.act_n;
+                        float ls_sum = 0.f, dss = 0.f;
+                        for (int j = 0; j < A; ++j) {
+                            float mean = z[(size_t)j * ld];
+                            float ls = a.flat[pd.log_std_off + j];
+                            float act;
+                            if (a.forced) act = reinterpret_cast<const float*>(a.forced)[(row + n) * A + j];
+                            else act = __fadd_rn(mean, __fmul_rn(expf(ls), sample_normal(gid, a.step0 + (uint32_t)t, j, a.pseed)));
+                            float diff = act - mean;
+                            dss += diff * diff * expf(-2.0f * ls);
+                            ls_sum += ls;
+                            reinterpret_cast<float*>(buf.actions)[(row + n) * A + j] = act;   // raw, unclamped (trajectory.jl:48)
+                            sEnvAct[(size_t)j * ld + tid] = fminf(fmaxf(act, pd.act_low[j]), pd.act_high[j]);  // ClampAdapter
+                        }
+                        logp = -0.5f * (2.0f * ls_sum + dss + (float)A * DRIL_LOG2PI);
+                    }
+                    buf.values[row + n] = value;
+                    buf.logprobs[row + n] = logp;
+                } else {  // compat act!: actions are given in env space
+                    if (env.act_dim == 0) a_disc = reinterpret_cast<const int*>(a.forced)[row + n];
+                    else for (int j = 0; j < env.act_dim; ++j)
+                        sEnvAct[(size_t)j * ld + tid] = reinterpret_cast<const float*>(a.forced)[(row + n) * env.act_dim + j];
+                }
+            }
+            // env step + monitor + auto-reset (thread per env)
+            if (mine) {
+                const uint32_t gid = (uint32_t)(env.gid_offset + n);
+                float st[ENV_MAX_STATE] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < ENV_MAX_STATE; ++k) if (k < env.state_dim) st[k] = env.state[(size_t)k * N + n];
+                int steps = env.steps[n];
+                bool term = false;
+                float r;
+                uint32_t life = 0;
+                if (env.kind == DRIL_ENV_CARTPOLE) r = cartpole_step(st, a_disc - env.act_start, &term);
+                else if (env.kind == DRIL_ENV_PENDULUM) r = pendulum_step(st, sEnvAct[tid]);
+                else { life = env.life[n]; r = synthetic_step(gid, life, env.seed, &term); life += 1; env.life[n] = life; }
+                steps += 1;
+                const bool trunc = steps >= env.max_steps;
+                const bool done = term || trunc;
+                buf.flags[row + n] = (unsigned char)((term ? 1 : 0) | (trunc ? 2 : 0));
+                buf.rewards[row + n] = r;                       // raw for now; normalised after the barrier
+                if (env.old_rewards) env.old_rewards[n] = r;
+                if (env.monitor) {                              // monitorWrapperEnv.jl:44-60 (raw rewards)
+                    float er = __fadd_rn(env.ep_ret[n], r);
+                    int el = env.ep_len[n] + 1;
+                    if (done) {
+                        buf.episode_r[row + n] = er;
+                        buf.episode_l[row + n] = el;
+                        atomicAdd(&buf.done_count[t], 1);
+                        atomicAdd(&env.roll_sums[0], (double)er);
+                        atomicAdd(&env.roll_sums[1], (double)el);
+                        atomicAdd(env.roll_eps, 1ull);
+                        er = 0.f; el = 0;
+                    }
+                    env.ep_ret[n] = er; env.ep_len[n] = el;
+                }
+                if (trunc) {                                    // terminal_observation iff truncated
+                    if (env.kind == DRIL_ENV_SYNTHETIC) {
+                        for (int b = 0; b < (Dp >> 2); ++b) {
+                            float o[4];
+                            synthetic_obs_block(gid, life, b, env.seed, o);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) if (4 * b + j < D) env.tobs[(size_t)n * D + 4 * b + j] = o[j];
+                        }
+                    } else {
+                        float o[4];
+                        env_raw_obs(env.kind, st, o);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (j < D) env.tobs[(size_t)n * D + j] = o[j];
+                    }
+                }
+                if (done) {                                     // reset!(env_i)
+                    uint32_t ep = env.episode[n];
+                    env_reset_state(env.kind, gid, ep, env.seed, st);
+                    env.episode[n] = ep + 1;
+                    steps = 0;
+                }
+#pragma unroll
+                for (int k = 0; k < ENV_MAX_STATE; ++k) if (k < env.state_dim) env.state[(size_t)k * N + n] = st[k];
+                env.steps[n] = steps;
+                if (upd_ret) {                                  // update_reward_stats! (normalizeWrapperEnv.jl:167-171)
+                    float ret = __fadd_rn(__fmul_rn(env.ret[n], env.ngamma), r);
+                    sRaw[(size_t)Dp * ld + tid] = ret;
+                    env.ret[n] = done ? 0.f : ret;              // zeroed after the statistics saw it (:153-156)
+                } else if (env.normalize && done) {
+                    env.ret[n] = 0.f;
+                }
+            }
+            __syncthreads();
+            if (grid_sync) {
+                if (upd_ret) tile_column_sums(sRaw, ld, Dp, 1, D, nvalid, sAcc);
+                if (upd_obs && (a.flags & RO_FOLD_NEXT_OBSERVE)) {
+                    __syncthreads();
+                    tile_raw_obs(n0, nvalid);                   // post-reset observation = next observe()
+                    tile_column_sums(sRaw, ld, 0, D, 0, nvalid, sAcc);
+                }
+                __syncthreads();
+            }
+        }
+        if (grid_sync) reduce_and_merge(upd_obs && (a.flags & RO_FOLD_NEXT_OBSERVE), upd_ret);
+
+        // after the barrier: reward normalisation, truncation bootstrap values
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            long long n0 = (long long)tile * M4;
+            int nvalid = (int)min((long long)M4, N - n0);
+            const bool mine = tid < nvalid;
+            const long long n = n0 + tid;
+            int trunc = 0;
+            if (mine) {
+                trunc = (buf.flags[row + n] >> 1) & 1;
+                if (env.normalize && env.norm_reward) {         // normalize_rewards! (:188-197)
+                    float r = buf.rewards[row + n];
+                    r = __fdiv_rn(r, __fsqrt_rn(__fadd_rn(sRet[1], env.eps)));
+                    buf.rewards[row + n] = fminf(fmaxf(r, -env.clip_reward), env.clip_reward);
+                }
+            }
+            int any_trunc = __syncthreads_or(trunc);
+            if (any_trunc) {
+                // terminal observations are normalised with the statistics BEFORE the next observe's update
+                for (int i = tid; i < Dp * M4; i += blockDim.x) {
+                    int d = i / M4, e = i - d * M4;
+                    float x = 0.f;
+                    if (d < D && e < nvalid && ((buf.flags[row + n0 + e] >> 1) & 1)) {
+                        x = env.tobs[(size_t)(n0 + e) * D + d];
+                        if (env.normalize && env.norm_obs) {
+                            x = normalize_obs_val(x, sMean[d], sVar[d], env.eps, env.clip_obs);
+                            if (!has_policy) env.tobs[(size_t)(n0 + e) * D + d] = x;   // compat: infos["terminal_observation"]
+                        }
+                    }
+                    sX[(size_t)d * ld + e] = x;
+                }
+                __syncthreads();
+                if (has_policy) {                               // V(terminal_obs), trajectory.jl:57-61
+                    int f = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, 2);
+                    if (mine && trunc) buf.boot[row + n] = sActC[(size_t)f * pd.max_np * ld + tid];
+                    __syncthreads();
+                }
+            }
+        }
+        if (grid_sync && upd_obs && (a.flags & RO_FOLD_NEXT_OBSERVE)) commit_obs_stats();
+    }
+
+    // ---------------- V(new_obs) after the final step (trajectory.jl:65-70) ----------------
+    if (has_policy && a.T > 0) {
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            long long n0 = (long long)tile * M4;
+            int nvalid = (int)min((long long)M4, N - n0);
+            tile_raw_obs(n0, nvalid);
+            tile_normalize(sMean, sVar, nvalid);
+            int f = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, 2);
+            if (tid < nvalid) buf.last_values[n0 + tid] = sActC[(size_t)f * pd.max_np * ld + tid];
+            __syncthreads();
+        }
+    }
+    if (env.normalize && blockIdx.x == 0) {
+        for (int d = tid; d < D; d += blockDim.x) { env.obs_mean[d] = sMean[d]; env.obs_var[d] = sVar[d]; }
+        if (tid == 0) { env.ret_stats[0] = sRet[0]; env.ret_stats[1] = sRet[1]; env.counts[0] = sCnt[0]; env.counts[1] = sCnt[1]; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Stand-alone layer application on an arbitrary batch (compat / evaluation path):
+//   mode 0: sample (layer call, layer_forward.jl:3-39)    mode 1: deterministic (mode.(ds))
+//   mode 2: evaluate_actions (layer_methods.jl:28-55)     mode 3: predict_values (:57-61)
+// ---------------------------------------------------------------------------------------
+struct ApplyArgs {
+    PolicyDesc pd;
+    const float* pack;
+    const float* flat;
+    const float* obs;        // [B][D]
+    const void* actions_in;  // mode 2
+    const long long* gids;   // optional sample-stream ids
+    void* actions_out;       // int32 [B] | float [B][A]
+    float *values, *logprobs, *entropy;
+    long long B;
+    unsigned long long pseed;
+    unsigned int step;
+    int mode, M4, weights_smem;
+};
+
+__global__ void __launch_bounds__(DRIL_THREADS) policy_apply_kernel(const __grid_constant__ ApplyArgs a) {
+    extern __shared__ float4 smem4[];
+    float* smem = reinterpret_cast<float*>(smem4);
+    const PolicyDesc& pd = a.pd;
+    const int D = pd.obs_dim, Dp = pd.obs_dim_p, M4 = a.M4, ld = M4 + 4;
+    float* sW = smem;
+    float* sX = smem + (a.weights_smem ? pd.pack_fwd : 0);
+    float* sActA = sX + (size_t)Dp * ld;
+    float* sActC = sActA + (size_t)2 * pd.max_np * ld;
+    const int tid = threadIdx.x;
+    const float* Wbase = a.pack;
+    if (a.weights_smem) {
+        const float4* src = reinterpret_cast<const float4*>(a.pack);
+        float4* dst = reinterpret_cast<float4*>(sW);
+        for (int i = tid; i < pd.pack_fwd / 4; i += blockDim.x) dst[i] = src[i];
+        Wbase = sW;
+    }
+    const long long n_tiles = (a.B + M4 - 1) / M4;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        long long n0 = tile * M4;
+        int nvalid = (int)min((long long)M4, a.B - n0);
+        __syncthreads();
+        for (int i = tid; i < Dp * M4; i += blockDim.x) {
+            int e = i / Dp, d = i - e * Dp;
+            sX[(size_t)d * ld + e] = (e < nvalid && d < D) ? a.obs[(size_t)(n0 + e) * D + d] : 0.f;
+        }
+        __syncthreads();
+        int fin = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, a.mode == 3 ? 2 : 3);
+        if (tid < nvalid) {
+            long long n = n0 + tid;
+            float value = sActC[(size_t)fin * pd.max_np * ld + tid];
+            if (a.values) a.values[n] = value;
+            if (a.mode != 3) {
+                const float* z = sActA + (size_t)fin * pd.max_np * ld + tid;
+                uint32_t gid = (uint32_t)(a.gids ? a.gids[n] : n);
+                float logp, ent;
+                if (pd.act_kind == DRIL_ACT_DISCRETE) {
+                    int mode = a.mode == 0 ? 0 : (a.mode == 1 ? 1 : 2);
+                    double u = 0.0;
+                    int forced_v = 0;
+                    if (mode == 0) {
+                        uint32_t x[4];
+                        philox4x32(gid, a.step, 0u, DRIL_TAG_SAMPLE, a.pseed, x);
+                        u = u01_f64(x[0], x[1]);
+                    } else if (mode == 2) forced_v = reinterpret_cast<const int*>(a.actions_in)[n];
+                    HeadOut h = categorical_head(z, ld, pd.act_n, pd.act_start, mode, u, forced_v, a.entropy != nullptr);
+                    logp = h.logp; ent = h.entropy;
+                    if (a.actions_out) reinterpret_cast<int*>(a.actions_out)[n] = h.action_idx;
+                } else {
+                    const int A = pd.act_n;
+                    float ls_sum = 0.f, dss = 0.f;
+                    for (int j = 0; j < A; ++j) {
+                        float mean = z[(size_t)j * ld];
+                        float ls = a.flat[pd.log_std_off + j];
+                        float act;
+                        if (a.mode == 2) act = reinterpret_cast<const float*>(a.actions_in)[n * A + j];
+                        else if (a.mode == 1) act = mean;
+                        else act = __fadd_rn(mean, __fmul_rn(expf(ls), sample_normal(gid, a.step, j, a.pseed)));
+                        float diff = act - mean;
+                        dss += diff * diff * expf(-2.0f * ls);
+                        ls_sum += ls;
+                        if (a.actions_out) reinterpret_cast<float*>(a.actions_out)[n * A + j] = act;
+                    }
+                    logp = -0.5f * (2.0f * ls_sum + dss + (float)A * DRIL_LOG2PI);
+                    ent = 0.5f * (float)A * (1.0f + DRIL_LOG2PI) + ls_sum;
+                }
+                if (a.logprobs) a.logprobs[n] = logp;
+                if (a.entropy) a.entropy[n] = ent;
+            }
+        }
+    }
+}
+
+// env reset (reset!(env)): new episode for every env, monitor/normaliser accumulators zeroed.
+__global__ void env_reset_kernel(EnvDev env) {
+    long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= env.n_envs) return;
+    float st[ENV_MAX_STATE] = {0.f, 0.f, 0.f, 0.f};
+    uint32_t ep = env.episode[n];
+    env_reset_state(env.kind, (uint32_t)(env.gid_offset + n), ep, env.seed, st);
+    env.episode[n] = ep + 1;
+#pragma unroll
+    for (int k = 0; k < ENV_MAX_STATE; ++k) if (k < env.state_dim) env.state[(size_t)k * env.n_envs + n] = st[k];
+    env.steps[n] = 0;
+    if (env.monitor) { env.ep_ret[n] = 0.f; env.ep_len[n] = 0; }
+    if (env.normalize) env.ret[n] = 0.f;
+}

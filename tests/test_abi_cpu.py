@@ -1,0 +1,64 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/dril_b200.h declares, and fails loudly (no CPU fallback) without a CUDA device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "dril_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(dril_[a-z0-9_]+)\s*\(", hdr)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__
+    __graft_entry__.build()
+    import dril_b200
+    return dril_b200.load(require_device=False)
+
+
+def test_header_symbols_exported(lib):
+    syms = _declared_symbols()
+    assert len(syms) >= 50
+    for s in syms:
+        assert hasattr(lib, s), f"libdril_b200.so does not export {s}"
+
+
+def test_binding_covers_header():
+    import dril_b200
+    from dril_b200 import _lib
+    declared = set(_declared_symbols())
+    bound = set(_lib.PROTOTYPES) | set(_lib.SPECIAL_RESTYPE)
+    assert declared == bound, declared ^ bound
+
+
+def test_struct_layouts_match_header():
+    from dril_b200 import _lib
+    assert ctypes.sizeof(_lib.NormCfg) == 28
+    assert ctypes.sizeof(_lib.PPOHyper) == 52
+    assert ctypes.sizeof(_lib.IterStats) == 88
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    import dril_b200
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(dril_b200.DrilError):
+        dril_b200.Context()
+    assert b"no CPU fallback" in lib.dril_last_error()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "dril.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

@@ -1,0 +1,84 @@
+"""(d) end-to-end: PPO on the batched CartPole reaches a return of 500 (north_star), and the
+reference's learning bar in spirit (test/test_ppo_integration.jl:1-40)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def D():
+    import __graft_entry__
+    __graft_entry__.build()
+    import dril_b200
+    return dril_b200
+
+
+def test_cartpole_reaches_500(D):
+    n, T = 4096, 128
+    env = D.CudaBatchedEnv("cartpole", n, seed=0, monitor_window=100)
+    layer = D.ActorCriticLayer(env.observation_space(), env.action_space(), hidden_dims=[64, 64])
+    alg = D.PPO(n_steps=T, batch_size=T * n // 4, epochs=4, learning_rate=1e-3, ent_coef=0.0)
+    logger = D.DictLogger()
+    agent = D.Agent(layer, alg, rng=np.random.default_rng(0), logger=logger)
+    best = 0.0
+    for it in range(60):
+        out = D.train(agent, env, alg, n * T)
+        assert out is not None and np.isfinite(out[0]["losses"]).all()
+        best = max(best, env.monitor_stats()["ep_len_mean"])
+        if best >= 499.5:
+            break
+    assert best >= 499.5, best
+    # deterministic evaluation through the compat path (evaluation.jl:54-143) also holds the pole
+    eval_env = D.CudaBatchedEnv("cartpole", 16, max_steps=500, seed=123, monitor_window=100)
+    res = D.evaluate_agent(agent, eval_env, n_eval_episodes=16, deterministic=True)
+    assert res["mean_reward"] >= 475, res
+    pol = D.extract_policy(agent)
+    a = pol(np.zeros(4, np.float32))
+    assert a in (1, 2)
+    assert "train/loss" in logger.scalars and "env/ep_rew_mean" in logger.scalars
+
+
+def test_pendulum_normalized_improves(D):
+    n, T = 1024, 128
+    env = D.CudaBatchedEnv("pendulum", n, seed=0, monitor_window=100, normalize=D.NormalizeConfig())
+    layer = D.ActorCriticLayer(env.observation_space(), env.action_space(), hidden_dims=[64, 64])
+    alg = D.PPO(n_steps=T, batch_size=T * n // 8, epochs=6, learning_rate=1e-3, gamma=0.95)
+    agent = D.Agent(layer, alg, rng=np.random.default_rng(0))
+    D.train(agent, env, alg, n * T * 2)
+    first = env.monitor_stats()["ep_rew_mean"]
+    D.train(agent, env, alg, n * T * 40)
+    last = env.monitor_stats()["ep_rew_mean"]
+    assert last > first + 200, (first, last)
+
+
+def test_callbacks_and_save_load(D, tmp_path):
+    """test/test_callbacks.jl:24-38,70-99 and test/test_ppo_integration.jl:42-83."""
+    seen = {}
+
+    class CB(D.AbstractCallback):
+        def on_training_start(self, loc):
+            seen["keys"] = set(loc)
+            return True
+
+        def on_rollout_end(self, loc):
+            seen["i"] = loc["i"]
+            return loc["i"] < 2
+
+    env = D.CudaBatchedEnv("cartpole", 8, seed=0, monitor_window=100, normalize=D.NormalizeConfig())
+    layer = D.ActorCriticLayer(env.observation_space(), env.action_space(), hidden_dims=[16, 16])
+    alg = D.PPO(n_steps=64, batch_size=64, epochs=2)
+    agent = D.Agent(layer, alg, rng=np.random.default_rng(0))
+    out = D.train(agent, env, alg, 8 * 64 * 5, callbacks=[CB()])
+    assert out is None and seen["i"] == 2 and D.steps_taken(agent) == 2 * 8 * 64
+    need = {"agent", "env", "alg", "iterations", "total_steps", "max_steps", "n_steps", "n_envs", "roll_buffer",
+            "total_fps", "callbacks"}
+    assert need <= seen["keys"], need - seen["keys"]
+    path = D.save_policy_params_and_state(agent, str(tmp_path / "agent"))
+    p0 = agent.sync_from_device().copy()
+    agent2 = D.Agent(layer, alg, rng=np.random.default_rng(5))
+    D.load_policy_params_and_state(agent2, path)
+    np.testing.assert_array_equal(agent2.train_state.parameters, p0)
+    obs = np.random.default_rng(0).normal(size=(5, 4)).astype(np.float32)
+    np.testing.assert_array_equal(D.predict_actions(agent, obs, deterministic=True),
+                                  D.predict_actions(agent2, obs, deterministic=True))
