@@ -22,12 +22,13 @@ def test_cartpole_reaches_500(D):
     logger = D.DictLogger()
     agent = D.Agent(layer, alg, rng=np.random.default_rng(0), logger=logger)
     best = 0.0
-    for it in range(60):
+    for it in range(150):
         out = D.train(agent, env, alg, n * T)
         assert out is not None and np.isfinite(out[0]["losses"]).all()
         best = max(best, env.monitor_stats()["ep_len_mean"])
         if best >= 499.5:
             break
+    # the last-100-episodes window (monitorWrapperEnv.jl:64-70) is all 500-step episodes
     assert best >= 499.5, best
     # deterministic evaluation through the compat path (evaluation.jl:54-143) also holds the pole
     eval_env = D.CudaBatchedEnv("cartpole", 16, max_steps=500, seed=123, monitor_window=100)
