@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -13,6 +14,7 @@
 #include "update.cuh"
 
 #define DRIL_SMEM_MAX 232448  // 227 KB opt-in per CTA on sm_100
+#define DRIL_GPLANES 8        // gradient partial planes per CTA (sample-range splits of the dW tiles)
 
 // ---------------------------------------------------------------------------------------
 // errors
@@ -128,6 +130,11 @@ struct dril_policy {
     PolicyDesc pd;
     float *flat = nullptr, *pack = nullptr, *m = nullptr, *v = nullptr, *g = nullptr, *gpart = nullptr;
     int *flat2pack = nullptr, *flat2packT = nullptr, *flat2g = nullptr;
+    unsigned char* f2planes = nullptr;   // partial planes holding contributions to each parameter's gradient
+    double* sq_part = nullptr;
+    unsigned int* ticket = nullptr;
+    int loss_M4 = 0, loss_splits = 1;
+    bool loss_ws = true;
     long long* step = nullptr;
     double *iter_acc = nullptr, *ev_acc = nullptr, *mbstats = nullptr, *adv_partial = nullptr;
     int* stop_flag = nullptr;
@@ -216,9 +223,12 @@ extern "C" int32_t dril_ctx_create(int32_t device, uint64_t seed, dril_ctx** out
     c->seed = seed;
     c->sm_count = prop.multiProcessorCount;
     DRIL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    DRIL_CUDA(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
-    DRIL_CUDA(cudaFuncSetAttribute(policy_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
-    DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
+    DRIL_CUDA(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
+    DRIL_CUDA(cudaFuncSetAttribute(rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
+    DRIL_CUDA(cudaFuncSetAttribute(policy_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
+    DRIL_CUDA(cudaFuncSetAttribute(policy_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
+    DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
+    DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
     *out = c;
     return DRIL_OK;
 }
@@ -420,6 +430,8 @@ extern "C" int32_t dril_buffer_upload(dril_buffer* b, int32_t field, const void*
 // policy
 // ---------------------------------------------------------------------------------------
 static inline int pad4(int x) { return (x + 3) & ~3; }
+struct LossLaunch { int M4; bool ws; size_t smem; int grid_cap; int splits; };
+static int32_t plan_loss(dril_policy* p, LossLaunch* out);
 
 extern "C" int32_t dril_policy_create(dril_ctx* c, int32_t obs_dim, int32_t n_hidden, const int32_t* hidden,
                                       int32_t act_kind, int32_t act_n, int32_t act_start, const float* act_low,
@@ -492,8 +504,8 @@ extern "C" int32_t dril_policy_create(dril_ctx* c, int32_t obs_dim, int32_t n_hi
     DRIL_TRY(dmalloc(&p->flat2pack, np)); DRIL_TRY(dmalloc(&p->flat2packT, np)); DRIL_TRY(dmalloc(&p->flat2g, np));
     DRIL_TRY(dmalloc(&p->step, 1)); DRIL_TRY(dmalloc(&p->iter_acc, ITER_ACC_N)); DRIL_TRY(dmalloc(&p->ev_acc, 4));
     DRIL_TRY(dmalloc(&p->stop_flag, 1));
-    p->gpart_ctas = c->sm_count * 2;
-    DRIL_TRY(dmalloc(&p->gpart, (size_t)p->gpart_ctas * pd.gpack));
+    p->gpart_ctas = c->sm_count * 2;   // CTAs per partial plane
+    DRIL_TRY(dmalloc(&p->gpart, (size_t)DRIL_GPLANES * p->gpart_ctas * pd.gpack));
     DRIL_CUDA(cudaMemcpy(p->flat2pack, f2p.data(), np * 4, cudaMemcpyHostToDevice));
     DRIL_CUDA(cudaMemcpy(p->flat2packT, f2t.data(), np * 4, cudaMemcpyHostToDevice));
     DRIL_CUDA(cudaMemcpy(p->flat2g, f2g.data(), np * 4, cudaMemcpyHostToDevice));
@@ -501,8 +513,27 @@ extern "C" int32_t dril_policy_create(dril_ctx* c, int32_t obs_dim, int32_t n_hi
     DRIL_CUDA(cudaMemset(p->g, 0, (np + 8) * 4)); DRIL_CUDA(cudaMemset(p->pack, 0, (size_t)pd.pack_total * 4));
     DRIL_CUDA(cudaMemset(p->step, 0, 8)); DRIL_CUDA(cudaMemset(p->iter_acc, 0, ITER_ACC_N * 8));
     DRIL_CUDA(cudaMemset(p->ev_acc, 0, 32)); DRIL_CUDA(cudaMemset(p->stop_flag, 0, 4));
-    DRIL_CUDA(cudaMemset(p->gpart, 0, (size_t)p->gpart_ctas * pd.gpack * 4));
+    DRIL_CUDA(cudaMemset(p->gpart, 0, (size_t)DRIL_GPLANES * p->gpart_ctas * pd.gpack * 4));
     for (int i = 0; i < 3; ++i) DRIL_CUDA(cudaEventCreate(&p->ev[i]));
+    {   // gradient partial planes per parameter (must mirror the tile choice in ppo_loss_grad_kernel)
+        LossLaunch ll;
+        DRIL_TRY(plan_loss(p, &ll));
+        p->loss_M4 = ll.M4; p->loss_ws = ll.ws; p->loss_splits = ll.splits;
+        std::vector<unsigned char> planes(np, 1);
+        for (int net = 0; net < 2; ++net)
+            for (int l = 0; l < pd.n_layers; ++l) {
+                const LayerDesc& L = pd.L[net][l];
+                const bool t8 = (ll.M4 % 16) == 0 && (L.Kp % 8) == 0 && (L.Np % 8) == 0;
+                for (int i = 0; i < L.K * L.N; ++i) planes[L.w_off + i] = (unsigned char)(t8 ? 2 : ll.splits);
+            }
+        DRIL_TRY(dmalloc(&p->f2planes, np));
+        DRIL_CUDA(cudaMemcpy(p->f2planes, planes.data(), np, cudaMemcpyHostToDevice));
+        DRIL_TRY(dmalloc(&p->sq_part, 8192));
+        DRIL_TRY(dmalloc(&p->ticket, 1));
+        DRIL_CUDA(cudaMemset(p->ticket, 0, 4));
+        double ones[2] = {1.0, 1.0};
+        DRIL_CUDA(cudaMemcpy(p->iter_acc + 12, ones, 16, cudaMemcpyHostToDevice));
+    }
     *out = p;
     return DRIL_OK;
 }
@@ -511,7 +542,8 @@ extern "C" int32_t dril_policy_destroy(dril_policy* p) {
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     void* ps[] = {p->flat, p->pack, p->m, p->v, p->g, p->gpart, p->flat2pack, p->flat2packT, p->flat2g, p->step,
-                  p->iter_acc, p->ev_acc, p->mbstats, p->adv_partial, p->stop_flag, p->scratch};
+                  p->iter_acc, p->ev_acc, p->mbstats, p->adv_partial, p->stop_flag, p->scratch, p->f2planes, p->sq_part,
+                  p->ticket};
     for (void* q : ps) if (q) cudaFree(q);
     for (int i = 0; i < 3; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
     delete p;
@@ -566,6 +598,8 @@ extern "C" int32_t dril_policy_set_opt_state(dril_policy* p, const float* m, con
     DRIL_CUDA(cudaMemcpyAsync(p->m, m, n * 4, cudaMemcpyHostToDevice, p->ctx->stream));
     DRIL_CUDA(cudaMemcpyAsync(p->v, v, n * 4, cudaMemcpyHostToDevice, p->ctx->stream));
     DRIL_CUDA(cudaMemcpyAsync(p->step, &s, 8, cudaMemcpyHostToDevice, p->ctx->stream));
+    double pw[2] = {pow(0.9, (double)step), pow(0.999, (double)step)};   // Optimisers.Adam default betas (ppo.jl:64-66)
+    DRIL_CUDA(cudaMemcpyAsync(p->iter_acc + 12, pw, 16, cudaMemcpyHostToDevice, p->ctx->stream));
     DRIL_CUDA(cudaStreamSynchronize(p->ctx->stream));
     return DRIL_OK;
 }
@@ -595,7 +629,8 @@ static int32_t launch_apply(dril_policy* p, ApplyArgs& a) {
     long long tiles = (a.B + M4 - 1) / M4;
     int grid = (int)std::min<long long>(tiles, (long long)c->sm_count * 4);
     Span sp(c, DRIL_K_POLICY);
-    policy_apply_kernel<<<grid, DRIL_THREADS, bytes(M4, ws), c->stream>>>(a);
+    if (ws) policy_apply_kernel<true><<<grid, DRIL_THREADS, bytes(M4, ws), c->stream>>>(a);
+    else policy_apply_kernel<false><<<grid, DRIL_THREADS, bytes(M4, ws), c->stream>>>(a);
     DRIL_CUDA(cudaGetLastError());
     return DRIL_OK;
 }
@@ -796,8 +831,13 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
     const bool upd = d.normalize && d.training && (d.norm_obs || d.norm_reward);
     if (upd) flags |= RO_GRID_SYNC;
     const long long N = d.n_envs;
-    // tile width: fill the SMs, at most 64 envs per tile, shrink until shared memory fits
-    int M4 = (int)std::min<long long>(64, ((N + c->sm_count - 1) / c->sm_count + 3) & ~3ll);
+    // tile width: the per-step critical path (state load -> forward -> sample -> dynamics) is latency
+    // bound, so small batches are cut into ~4 CTAs per SM that overlap each other's phases; at most
+    // 64 envs per tile, shrink until shared memory fits
+    static const int env_ctas = getenv("DRIL_ROLLOUT_CTAS_PER_SM") ? atoi(getenv("DRIL_ROLLOUT_CTAS_PER_SM")) : 4;
+    static const int env_threads = getenv("DRIL_ROLLOUT_THREADS") ? atoi(getenv("DRIL_ROLLOUT_THREADS")) : 0;
+    const long long want_ctas = (long long)c->sm_count * std::max(env_ctas, 1);
+    int M4 = (int)std::min<long long>(64, ((N + want_ctas - 1) / want_ctas + 3) & ~3ll);
     M4 = std::max(M4, 4);
     bool ws = has_policy;
     auto total = [&](int m4, bool w) { return rollout_smem_layout(a.pd, d.obs_dim, d.act_dim, m4, w, has_policy).total; };
@@ -811,16 +851,29 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
     a.n_tiles = (int)((N + M4 - 1) / M4);
     size_t smem = total(M4, ws);
     int grid = a.n_tiles;
+    // block size: enough threads for the 4x4 thread-tiles of the widest layer of both nets
+    int threads = DRIL_THREADS;
+    if (has_policy) {
+        int tiles = 2 * (a.pd.max_np >> 2) * (M4 >> 2);
+        threads = std::min(DRIL_THREADS, std::max(128, (tiles + 31) & ~31));
+    } else {
+        threads = std::min(DRIL_THREADS, std::max(64, (M4 + 31) & ~31));
+    }
+    if (env_threads >= 32 && env_threads <= DRIL_THREADS) threads = env_threads & ~31;
+    threads = std::max(threads, (M4 + 31) & ~31);
     Span sp(c, has_policy ? DRIL_K_ROLLOUT : DRIL_K_ENV);
     if (flags & RO_GRID_SYNC) {
         int per_sm = 0;
-        DRIL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kernel, DRIL_THREADS, smem));
+        if (ws) DRIL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kernel<true>, threads, smem));
+        else DRIL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kernel<false>, threads, smem));
         DRIL_REQUIRE(per_sm >= 1, "rollout kernel does not fit on an SM");
         grid = std::min(grid, std::min(per_sm * c->sm_count, e->max_blocks));
         void* args[] = {(void*)&a};
-        DRIL_CUDA(cudaLaunchCooperativeKernel((void*)rollout_kernel, dim3(grid), dim3(DRIL_THREADS), args, smem, c->stream));
+        void* fn = ws ? (void*)rollout_kernel<true> : (void*)rollout_kernel<false>;
+        DRIL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, c->stream));
     } else {
-        rollout_kernel<<<grid, DRIL_THREADS, smem, c->stream>>>(a);
+        if (ws) rollout_kernel<true><<<grid, threads, smem, c->stream>>>(a);
+        else rollout_kernel<false><<<grid, threads, smem, c->stream>>>(a);
         DRIL_CUDA(cudaGetLastError());
     }
     return DRIL_OK;
@@ -1077,22 +1130,26 @@ static FeistelKey make_feistel(long long n_total, uint64_t epoch_counter, int ra
     return fk;
 }
 
-struct LossLaunch { int M4; bool ws; size_t smem; int grid_cap; };
 static int32_t plan_loss(dril_policy* p, LossLaunch* out) {
     const PolicyDesc& pd = p->pd;
-    int M4 = 64;
+    // widest tile (<= 128 samples, multiple of 16 so the 8x8 paths apply) that fits; weights in
+    // shared memory when there is room for at least a 32-sample tile next to them
+    int M4 = 128;
     bool ws = true;
     auto total = [&](int m4, bool w) { return loss_smem_layout(pd, m4, w).total; };
-    while (M4 > 8 && total(M4, true) > DRIL_SMEM_MAX && total(M4, false) > DRIL_SMEM_MAX) M4 -= 4;
-    if (total(M4, true) > DRIL_SMEM_MAX) ws = false;
-    if (ws && M4 < 32 && total(32, false) <= DRIL_SMEM_MAX) {
-        ws = false; M4 = 32;
-        while (M4 < 64 && total(M4 + 4, false) <= DRIL_SMEM_MAX) M4 += 4;
+    while (M4 > 16 && total(M4, true) > DRIL_SMEM_MAX) M4 -= 16;
+    if (total(M4, true) > DRIL_SMEM_MAX || M4 < 32) {
+        ws = false; M4 = 128;
+        while (M4 > 16 && total(M4, false) > DRIL_SMEM_MAX) M4 -= 16;
     }
     if (total(M4, ws) > DRIL_SMEM_MAX) { dril_set_error("network too wide for the loss kernel's shared memory"); return DRIL_ERR_UNSUPPORTED; }
     out->M4 = M4; out->ws = ws; out->smem = total(M4, ws);
+    int splits = 1;
+    while (splits < DRIL_GPLANES && (M4 / (splits * 2)) % 4 == 0 && M4 / (splits * 2) >= 4) splits *= 2;
+    out->splits = splits;
     int per_sm = 0;
-    DRIL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppo_loss_grad_kernel, DRIL_THREADS, out->smem));
+    if (ws) DRIL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppo_loss_grad_kernel<true>, DRIL_THREADS, out->smem));
+    else DRIL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppo_loss_grad_kernel<false>, DRIL_THREADS, out->smem));
     per_sm = std::max(1, std::min(per_sm, 2));
     out->grid_cap = std::min(per_sm * p->ctx->sm_count, p->gpart_ctas);
     return DRIL_OK;
@@ -1107,26 +1164,38 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
     memset(&a, 0, sizeof(a));
     a.pd = pd; a.buf = bd; a.pack = p->pack; a.flat = p->flat; a.mbstats = mbstats_dev; a.gpart = p->gpart;
     a.stop_flag = p->stop_flag; a.mb = mb; a.hp = hp; a.M4 = ll.M4; a.weights_smem = ll.ws;
+    a.half_stride = p->gpart_ctas; a.small_splits = ll.splits;
     long long tiles = (mb.count + ll.M4 - 1) / ll.M4;
     int grid = (int)std::max<long long>(1, std::min<long long>(tiles, ll.grid_cap));
     {
         Span sp(c, DRIL_K_LOSS_GRAD);
-        ppo_loss_grad_kernel<<<grid, DRIL_THREADS, ll.smem, c->stream>>>(a);
+        if (ll.ws) ppo_loss_grad_kernel<true><<<grid, DRIL_THREADS, ll.smem, c->stream>>>(a);
+        else ppo_loss_grad_kernel<false><<<grid, DRIL_THREADS, ll.smem, c->stream>>>(a);
         DRIL_CUDA(cudaGetLastError());
+    }
+    AdamArgs aa;
+    aa.g = p->g; aa.flat = p->flat; aa.m = p->m; aa.v = p->v; aa.pack = p->pack; aa.flat2pack = p->flat2pack;
+    aa.flat2packT = p->flat2packT; aa.step = p->step; aa.iter_acc = p->iter_acc; aa.stop_flag = p->stop_flag;
+    aa.global_count = mb.global_count; aa.hp = hp; aa.n_params = pd.n_params; aa.apply_stats = apply_stats;
+    const int n = pd.n_params + 6;
+    const int rgrid = (n + 255) / 256;
+    const int fgrid = (n + RA_PARAMS_PER_BLOCK - 1) / RA_PARAMS_PER_BLOCK;
+    if (apply && c->nranks == 1 && fgrid <= 8192) {
+        // single GPU: reduction over CTAs / planes, norm, clip, Adam in one kernel
+        Span sp(c, DRIL_K_ADAM);
+        reduce_adam_kernel<<<fgrid, 1024, 0, c->stream>>>(p->gpart, grid, p->gpart_ctas, pd.gpack, p->flat2g, p->f2planes,
+                                                        pd.pack_fwd + pd.act_n, p->sq_part, p->ticket, aa);
+        DRIL_CUDA(cudaGetLastError());
+        return DRIL_OK;
     }
     {
         Span sp(c, DRIL_K_GRAD_REDUCE);
-        int n = pd.n_params + 6;
-        grad_reduce_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(p->gpart, grid, pd.gpack, p->flat2g, pd.n_params,
-                                                                  pd.pack_fwd + pd.act_n, p->g, p->stop_flag);
+        grad_reduce_kernel<<<rgrid, 256, 0, c->stream>>>(p->gpart, grid, p->gpart_ctas, pd.gpack, p->flat2g, p->f2planes,
+                                                        pd.n_params, pd.pack_fwd + pd.act_n, p->g, p->stop_flag);
         DRIL_CUDA(cudaGetLastError());
     }
     DRIL_TRY(allreduce_sum(c, p->g, (size_t)pd.n_params + 6, false));
     if (apply) {
-        AdamArgs aa;
-        aa.g = p->g; aa.flat = p->flat; aa.m = p->m; aa.v = p->v; aa.pack = p->pack; aa.flat2pack = p->flat2pack;
-        aa.flat2packT = p->flat2packT; aa.step = p->step; aa.iter_acc = p->iter_acc; aa.stop_flag = p->stop_flag;
-        aa.global_count = mb.global_count; aa.hp = hp; aa.n_params = pd.n_params; aa.apply_stats = apply_stats;
         Span sp(c, DRIL_K_ADAM);
         adam_finalize_kernel<<<1, 1024, 0, c->stream>>>(aa);
         DRIL_CUDA(cudaGetLastError());
@@ -1157,7 +1226,7 @@ static int32_t update_async(dril_policy* p, dril_buffer* b, const dril_ppo_hyper
     DRIL_TRY(plan_loss(p, &ll));
     const int bpm = (int)std::max<long long>(1, std::min<long long>(64, (std::min<long long>(batch_size, n_total) + 2047) / 2048));
     DRIL_TRY(ensure_mbstats(p, n_mb, bpm));
-    DRIL_CUDA(cudaMemsetAsync(p->iter_acc, 0, ITER_ACC_N * 8, c->stream));
+    DRIL_CUDA(cudaMemsetAsync(p->iter_acc, 0, 12 * 8, c->stream));   // [12],[13] carry beta^t across iterations
     DRIL_CUDA(cudaMemsetAsync(p->stop_flag, 0, 4, c->stream));
     for (int epoch = 0; epoch < epochs; ++epoch) {
         FeistelKey fk = make_feistel(n_total, epoch_counter + epoch, c->rank, shuffle_seed);

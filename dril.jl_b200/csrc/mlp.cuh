@@ -23,9 +23,9 @@ __device__ __forceinline__ void dense_tile_fwd(const float* __restrict__ W, cons
     const float* wp = W + n0;
     const float* ap = A + m0;
 #pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-        float4 w = *reinterpret_cast<const float4*>(wp + (size_t)k * Np);
-        float4 a = *reinterpret_cast<const float4*>(ap + (size_t)k * ld);
+    for (int k = 0; k < K; ++k, wp += Np, ap += ld) {
+        float4 w = *reinterpret_cast<const float4*>(wp);
+        float4 a = *reinterpret_cast<const float4*>(ap);
         acc[0][0] = fmaf(w.x, a.x, acc[0][0]); acc[0][1] = fmaf(w.x, a.y, acc[0][1]);
         acc[0][2] = fmaf(w.x, a.z, acc[0][2]); acc[0][3] = fmaf(w.x, a.w, acc[0][3]);
         acc[1][0] = fmaf(w.y, a.x, acc[1][0]); acc[1][1] = fmaf(w.y, a.y, acc[1][1]);
@@ -43,6 +43,82 @@ __device__ __forceinline__ void dense_tile_fwd(const float* __restrict__ W, cons
         o.x = acc[i][0] + bb[i]; o.y = acc[i][1] + bb[i]; o.z = acc[i][2] + bb[i]; o.w = acc[i][3] + bb[i];
         if (apply_tanh) { o.x = fast_tanh(o.x); o.y = fast_tanh(o.y); o.z = fast_tanh(o.z); o.w = fast_tanh(o.w); }
         *reinterpret_cast<float4*>(C + (size_t)(n0 + i) * ld + m0) = o;
+    }
+}
+
+// 8x8 register tile: rows n in {4nt..4nt+3} U {nh+4nt..}, cols m in {4mt..4mt+3} U {mh+4mt..}.
+// 64 FMA per 4 LDS.128 (1 B of shared-memory traffic per FMA: the LDS pipe moves 128 B/clk/SM, the
+// FMA pipes 128 FMA/clk/SM, so anything smaller than 8x8 is LDS-bound — profiles/r01).
+// Lane mapping (mt fastest) makes the A loads 8 consecutive float4 per quarter-warp and the W
+// loads a broadcast: conflict-free.
+__device__ __forceinline__ void dense_tile_fwd8(const float* __restrict__ W, const float* __restrict__ bias,
+                                                int K, int Np, const float* __restrict__ A, float* __restrict__ C,
+                                                int ld, int nt, int mt, int nh, int mh, bool apply_tanh) {
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const float* w0p = W + 4 * nt;
+    const float* w1p = W + nh + 4 * nt;
+    const float* a0p = A + 4 * mt;
+    const float* a1p = A + mh + 4 * mt;
+#pragma unroll 2
+    for (int k = 0; k < K; ++k, w0p += Np, w1p += Np, a0p += ld, a1p += ld) {
+        float4 w0 = *reinterpret_cast<const float4*>(w0p);
+        float4 w1 = *reinterpret_cast<const float4*>(w1p);
+        float4 a0 = *reinterpret_cast<const float4*>(a0p);
+        float4 a1 = *reinterpret_cast<const float4*>(a1p);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(w[i], a[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int n = (i < 4) ? 4 * nt + i : nh + 4 * nt + (i - 4);
+        const float b = bias[n];
+        float4 o0, o1;
+        o0.x = acc[i][0] + b; o0.y = acc[i][1] + b; o0.z = acc[i][2] + b; o0.w = acc[i][3] + b;
+        o1.x = acc[i][4] + b; o1.y = acc[i][5] + b; o1.z = acc[i][6] + b; o1.w = acc[i][7] + b;
+        if (apply_tanh) {
+            o0.x = fast_tanh(o0.x); o0.y = fast_tanh(o0.y); o0.z = fast_tanh(o0.z); o0.w = fast_tanh(o0.w);
+            o1.x = fast_tanh(o1.x); o1.y = fast_tanh(o1.y); o1.z = fast_tanh(o1.z); o1.w = fast_tanh(o1.w);
+        }
+        *reinterpret_cast<float4*>(C + (size_t)n * ld + 4 * mt) = o0;
+        *reinterpret_cast<float4*>(C + (size_t)n * ld + mh + 4 * mt) = o1;
+    }
+}
+
+// layer forward with 8x8 tiles where the shapes allow it (Np, M4 multiples of 8 and enough tiles to
+// occupy the block), 4x4 tiles otherwise.
+__device__ __forceinline__ void dense_layer_auto(const PolicyDesc& pd, const float* __restrict__ Wbase, int layer,
+                                                 const float* in_a, const float* in_c, float* out_a, float* out_c,
+                                                 int M4, int ld, int net_mask) {
+    const LayerDesc& La = pd.L[0][layer];
+    const LayerDesc& Lc = pd.L[1][layer];
+    const bool act = layer < pd.n_layers - 1;
+    const bool m8 = (M4 & 7) == 0;
+    const int mt4 = M4 >> 2, mt8 = M4 >> 3;
+    const bool a8 = (net_mask & 1) && m8 && (La.Np & 7) == 0 && La.K >= 8;
+    const bool c8 = (net_mask & 2) && m8 && (Lc.Np & 7) == 0 && Lc.K >= 8;
+    const int ta = (net_mask & 1) ? (a8 ? (La.Np >> 3) * mt8 : (La.Np >> 2) * mt4) : 0;
+    const int tc = (net_mask & 2) ? (c8 ? (Lc.Np >> 3) * mt8 : (Lc.Np >> 2) * mt4) : 0;
+    for (int t = threadIdx.x; t < ta + tc; t += blockDim.x) {
+        const bool crit = t >= ta;
+        const int u = crit ? t - ta : t;
+        const LayerDesc& Ld = crit ? Lc : La;
+        const float* in = crit ? in_c : in_a;
+        float* out = crit ? out_c : out_a;
+        if (crit ? c8 : a8) {
+            const int nt = u / mt8, m = u - nt * mt8;
+            dense_tile_fwd8(Wbase + Ld.pw_off, Wbase + Ld.pb_off, Ld.K, Ld.Np, in, out, ld, nt, m, Ld.Np >> 1, M4 >> 1, act);
+        } else {
+            const int nt = u / mt4, m = u - nt * mt4;
+            dense_tile_fwd(Wbase + Ld.pw_off, Wbase + Ld.pb_off, Ld.K, Ld.Np, in, out, ld, nt << 2, m << 2, act);
+        }
     }
 }
 

@@ -109,6 +109,7 @@ __device__ __forceinline__ void tile_column_sums(const float* sRaw, int ld, int 
     }
 }
 
+template <bool WS>
 __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_constant__ RolloutArgs a) {
     extern __shared__ float4 smem4[];
     float* smem = reinterpret_cast<float*>(smem4);
@@ -120,9 +121,8 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
     const int D = env.obs_dim, Dp = (D + 3) & ~3;
     const int M4 = a.M4;
     const long long N = env.n_envs;
-    const RolloutSmem L = rollout_smem_layout(pd, D, env.act_dim, M4, a.flags & RO_WEIGHTS_SMEM, has_policy);
+    const RolloutSmem L = rollout_smem_layout(pd, D, env.act_dim, M4, WS, has_policy);
     const int ld = L.ld;
-    float* sW = smem + L.w;
     float* sRaw = smem + L.raw;
     float* sX = smem + L.x;
     float* sActA = smem + L.acta;
@@ -141,12 +141,12 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
     const bool upd_obs = env.normalize && env.training && env.norm_obs;
     const bool upd_ret = env.normalize && env.training && env.norm_reward;
 
-    const float* Wbase = a.pack;
-    if (has_policy && (a.flags & RO_WEIGHTS_SMEM)) {
+    // WS: weights staged in shared memory (L.w == 0; address space known at compile time -> LDS)
+    const float* __restrict__ Wbase = WS ? smem : a.pack;
+    if (WS) {
         const float4* src = reinterpret_cast<const float4*>(a.pack);
-        float4* dst = reinterpret_cast<float4*>(sW);
+        float4* dst = reinterpret_cast<float4*>(smem);
         for (int i = tid; i < pd.pack_fwd / 4; i += blockDim.x) dst[i] = src[i];
-        Wbase = sW;
     }
     for (int d = tid; d < Dp; d += blockDim.x) {
         sMean[d] = (env.normalize && d < D) ? env.obs_mean[d] : 0.f;
@@ -498,22 +498,21 @@ struct ApplyArgs {
     int mode, M4, weights_smem;
 };
 
+template <bool WS>
 __global__ void __launch_bounds__(DRIL_THREADS) policy_apply_kernel(const __grid_constant__ ApplyArgs a) {
     extern __shared__ float4 smem4[];
     float* smem = reinterpret_cast<float*>(smem4);
     const PolicyDesc& pd = a.pd;
     const int D = pd.obs_dim, Dp = pd.obs_dim_p, M4 = a.M4, ld = M4 + 4;
-    float* sW = smem;
-    float* sX = smem + (a.weights_smem ? pd.pack_fwd : 0);
+    float* sX = smem + (WS ? pd.pack_fwd : 0);
     float* sActA = sX + (size_t)Dp * ld;
     float* sActC = sActA + (size_t)2 * pd.max_np * ld;
     const int tid = threadIdx.x;
-    const float* Wbase = a.pack;
-    if (a.weights_smem) {
+    const float* __restrict__ Wbase = WS ? smem : a.pack;
+    if (WS) {
         const float4* src = reinterpret_cast<const float4*>(a.pack);
-        float4* dst = reinterpret_cast<float4*>(sW);
+        float4* dst = reinterpret_cast<float4*>(smem);
         for (int i = tid; i < pd.pack_fwd / 4; i += blockDim.x) dst[i] = src[i];
-        Wbase = sW;
     }
     const long long n_tiles = (a.B + M4 - 1) / M4;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {

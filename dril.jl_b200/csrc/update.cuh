@@ -57,9 +57,15 @@ __global__ void adv_stats_finalize_kernel(const double* __restrict__ partial, in
 }
 
 // ---- fused loss forward + backward ------------------------------------------------------
+// Shared-memory plan per tile of M4 samples (feature-major rows of ld = M4+4 floats):
+//   X [obs_dim_p] | per net: H_0 .. H_{L-1} (layer outputs; the deltas dZ_l overwrite H_l in place)
+//   | per net: dOut [Np_last] | per-sample rows: adv, ret, old_logp, old_val, actions (+ log_std terms)
+// Phases per tile: gather | L forward layers | loss head | for l = L-1..0: {dW_l, db_l} then
+// {dZ_{l-1} = (dZ_l W_l^T) .* (1 - H_{l-1}^2) in place}.  dW partial sums go to this CTA's packed
+// gradient partial in global memory (L2-resident read-modify-write by the owning thread).
 struct LossSmem {
     int ld;
-    size_t w, x, h[2][DRIL_MAX_LAYERS], g[2], samp, total_floats, dbl_bytes_off, total;
+    size_t w, x, h[2][DRIL_MAX_LAYERS], dout[2], samp, dbl_bytes_off, total;
 };
 
 __host__ __device__ inline LossSmem loss_smem_layout(const PolicyDesc& pd, int M4, bool weights_smem) {
@@ -70,11 +76,10 @@ __host__ __device__ inline LossSmem loss_smem_layout(const PolicyDesc& pd, int M
     s.x = o; o += (size_t)pd.obs_dim_p * s.ld;
     for (int net = 0; net < 2; ++net)
         for (int l = 0; l < pd.n_layers; ++l) { s.h[net][l] = o; o += (size_t)pd.L[net][l].Np * s.ld; }
-    for (int net = 0; net < 2; ++net) { s.g[net] = o; o += (size_t)2 * pd.max_np * s.ld; }
+    for (int net = 0; net < 2; ++net) { s.dout[net] = o; o += (size_t)pd.L[net][pd.n_layers - 1].Np * s.ld; }
     int arows = pd.act_kind == DRIL_ACT_CONTINUOUS ? 2 * pd.act_n : 1;   // actions (+ log_std grad contributions)
     s.samp = o; o += (size_t)(4 + arows) * s.ld;   // adv, ret, old_logp, old_val, actions...
     o = (o + 3) & ~(size_t)3;
-    s.total_floats = o;
     s.dbl_bytes_off = o * sizeof(float);
     s.total = s.dbl_bytes_off + 40 * sizeof(double);
     return s;
@@ -86,17 +91,19 @@ struct LossArgs {
     const float* pack;     // packed W + bias + Wt
     const float* flat;     // log_std
     const double* mbstats; // [2] sum / sum of squares of advantages over the global minibatch
-    float* gpart;          // [gridDim.x][pd.gpack] per-CTA packed gradient partials (+ log_std + stats)
+    float* gpart;          // [2 halves][half_stride][pd.gpack] per-CTA packed gradient partials (+ log_std + stats)
     const int* stop_flag;  // target_kl stop already fired: do nothing
     Minibatch mb;
     UpdateHyper hp;
-    int M4, weights_smem;
+    int M4, weights_smem, half_stride;   // half_stride: CTAs per partial plane
+    int small_splits;                    // sample-range splits of the 4x4 dW tiles (planes 0..small_splits-1)
 };
 
 // dW[k][n] (+)= sum_m Ain[k][m] * dZ[n][m] for the 4 interleaved rows k = kt + kstride*i and the
 // 4 columns n0..n0+3; accumulated into this CTA's packed partial.
-__device__ __forceinline__ void dense_tile_dw(const float* __restrict__ Ain, const float* __restrict__ dZ, int M4, int ld,
-                                              int kt, int kstride, int n0, float* __restrict__ gW, int Np, bool first) {
+__device__ __forceinline__ void dense_tile_dw(const float* __restrict__ Ain, const float* __restrict__ dZ, int m_begin,
+                                              int m_end, int ld, int kt, int kstride, int n0, float* __restrict__ gW,
+                                              int Np, bool first) {
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -105,7 +112,7 @@ __device__ __forceinline__ void dense_tile_dw(const float* __restrict__ Ain, con
     const float* hp0 = Ain + (size_t)kt * ld;
     const float* dp0 = dZ + (size_t)n0 * ld;
 #pragma unroll 2
-    for (int m = 0; m < M4; m += 4) {
+    for (int m = m_begin; m < m_end; m += 4) {
         float4 h[4], d[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) h[i] = *reinterpret_cast<const float4*>(hp0 + (size_t)i * kstride * ld + m);
@@ -130,9 +137,51 @@ __device__ __forceinline__ void dense_tile_dw(const float* __restrict__ Ain, con
     }
 }
 
-// dZprev[k0..k0+3][m0..m0+3] = (sum_n Wt[n][k0..] * dZ[n][m0..]) * (1 - H[k][m]^2)
+// 8x8 version over the sample range [m_begin, m_end): rows k = kt + 8*i (i<8, consecutive lanes ->
+// consecutive rows, 4 banks apart: conflict-free), columns n = 8*nt + j.
+__device__ __forceinline__ void dense_tile_dw8(const float* __restrict__ Ain, const float* __restrict__ dZ, int m_begin,
+                                               int m_end, int ld, int kt, int kstride, int n0, float* __restrict__ gW,
+                                               int Np, bool first) {
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const float* hp0 = Ain + (size_t)kt * ld;
+    const float* dp0 = dZ + (size_t)n0 * ld;
+    for (int m = m_begin; m < m_end; m += 4) {
+        float4 h[8], d[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = *reinterpret_cast<const float4*>(hp0 + (size_t)i * kstride * ld + m);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = *reinterpret_cast<const float4*>(dp0 + (size_t)j * ld + m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[i][j] = fmaf(h[i].x, d[j].x, acc[i][j]);
+                acc[i][j] = fmaf(h[i].y, d[j].y, acc[i][j]);
+                acc[i][j] = fmaf(h[i].z, d[j].z, acc[i][j]);
+                acc[i][j] = fmaf(h[i].w, d[j].w, acc[i][j]);
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float4* g = reinterpret_cast<float4*>(gW + (size_t)(kt + i * kstride) * Np + n0);
+        float4 v0 = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        float4 v1 = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+        if (!first) {
+            float4 o0 = g[0], o1 = g[1];
+            v0.x += o0.x; v0.y += o0.y; v0.z += o0.z; v0.w += o0.w;
+            v1.x += o1.x; v1.y += o1.y; v1.z += o1.z; v1.w += o1.w;
+        }
+        g[0] = v0; g[1] = v1;
+    }
+}
+
+// H[k0..k0+3][m0..m0+3] <- (sum_n Wt[n][k0..] * dZ[n][m0..]) * (1 - H[k][m]^2)      (in place)
 __device__ __forceinline__ void dense_tile_dh(const float* __restrict__ Wt, int Nred, int Kp, const float* __restrict__ dZ,
-                                              const float* __restrict__ H, float* __restrict__ dZprev, int ld, int k0, int m0) {
+                                              float* __restrict__ H, int ld, int k0, int m0) {
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -141,9 +190,9 @@ __device__ __forceinline__ void dense_tile_dh(const float* __restrict__ Wt, int 
     const float* wp = Wt + k0;
     const float* dp = dZ + m0;
 #pragma unroll 4
-    for (int n = 0; n < Nred; ++n) {
-        float4 w = *reinterpret_cast<const float4*>(wp + (size_t)n * Kp);
-        float4 d = *reinterpret_cast<const float4*>(dp + (size_t)n * ld);
+    for (int n = 0; n < Nred; ++n, wp += Kp, dp += ld) {
+        float4 w = *reinterpret_cast<const float4*>(wp);
+        float4 d = *reinterpret_cast<const float4*>(dp);
         acc[0][0] = fmaf(w.x, d.x, acc[0][0]); acc[0][1] = fmaf(w.x, d.y, acc[0][1]);
         acc[0][2] = fmaf(w.x, d.z, acc[0][2]); acc[0][3] = fmaf(w.x, d.w, acc[0][3]);
         acc[1][0] = fmaf(w.y, d.x, acc[1][0]); acc[1][1] = fmaf(w.y, d.y, acc[1][1]);
@@ -155,21 +204,61 @@ __device__ __forceinline__ void dense_tile_dh(const float* __restrict__ Wt, int 
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float4 h = *reinterpret_cast<const float4*>(H + (size_t)(k0 + i) * ld + m0);
-        float4 o;
+        float4* hp = reinterpret_cast<float4*>(H + (size_t)(k0 + i) * ld + m0);
+        float4 h = *hp, o;
         o.x = acc[i][0] * (1.0f - h.x * h.x); o.y = acc[i][1] * (1.0f - h.y * h.y);
         o.z = acc[i][2] * (1.0f - h.z * h.z); o.w = acc[i][3] * (1.0f - h.w * h.w);
-        *reinterpret_cast<float4*>(dZprev + (size_t)(k0 + i) * ld + m0) = o;
+        *hp = o;
     }
 }
 
+// 8x8 version: rows k in {4kt..} U {kh+4kt..}, cols m in {4mt..} U {mh+4mt..}
+__device__ __forceinline__ void dense_tile_dh8(const float* __restrict__ Wt, int Nred, int Kp, const float* __restrict__ dZ,
+                                               float* __restrict__ H, int ld, int kt, int mt, int kh, int mh) {
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const float* w0p = Wt + 4 * kt;
+    const float* w1p = Wt + kh + 4 * kt;
+    const float* d0p = dZ + 4 * mt;
+    const float* d1p = dZ + mh + 4 * mt;
+#pragma unroll 2
+    for (int n = 0; n < Nred; ++n, w0p += Kp, w1p += Kp, d0p += ld, d1p += ld) {
+        float4 w0 = *reinterpret_cast<const float4*>(w0p);
+        float4 w1 = *reinterpret_cast<const float4*>(w1p);
+        float4 d0 = *reinterpret_cast<const float4*>(d0p);
+        float4 d1 = *reinterpret_cast<const float4*>(d1p);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(w[i], d[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k = (i < 4) ? 4 * kt + i : kh + 4 * kt + (i - 4);
+        float4* hp0 = reinterpret_cast<float4*>(H + (size_t)k * ld + 4 * mt);
+        float4* hp1 = reinterpret_cast<float4*>(H + (size_t)k * ld + mh + 4 * mt);
+        float4 h0 = *hp0, h1 = *hp1, o0, o1;
+        o0.x = acc[i][0] * (1.0f - h0.x * h0.x); o0.y = acc[i][1] * (1.0f - h0.y * h0.y);
+        o0.z = acc[i][2] * (1.0f - h0.z * h0.z); o0.w = acc[i][3] * (1.0f - h0.w * h0.w);
+        o1.x = acc[i][4] * (1.0f - h1.x * h1.x); o1.y = acc[i][5] * (1.0f - h1.y * h1.y);
+        o1.z = acc[i][6] * (1.0f - h1.z * h1.z); o1.w = acc[i][7] * (1.0f - h1.w * h1.w);
+        *hp0 = o0; *hp1 = o1;
+    }
+}
+
+template <bool WS>
 __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __grid_constant__ LossArgs a) {
     extern __shared__ float4 smem4[];
     float* smem = reinterpret_cast<float*>(smem4);
     const PolicyDesc& pd = a.pd;
     const BufDev& buf = a.buf;
     const int M4 = a.M4, D = pd.obs_dim, Dp = pd.obs_dim_p, NL = pd.n_layers;
-    const LossSmem S = loss_smem_layout(pd, M4, a.weights_smem);
+    const LossSmem S = loss_smem_layout(pd, M4, WS);
     const int ld = S.ld;
     const int tid = threadIdx.x;
     float* sX = smem + S.x;
@@ -179,16 +268,18 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
     float* sOldV = sOldLp + ld;
     float* sActn = sOldV + ld;                       // discrete: 1 row (int bits); continuous: act_n rows + act_n rows of log_std contributions
     double* sDbl = reinterpret_cast<double*>(reinterpret_cast<char*>(smem) + S.dbl_bytes_off);
-    float* gp = a.gpart + (size_t)blockIdx.x * pd.gpack;
+    float* gp = a.gpart + (size_t)blockIdx.x * pd.gpack;                       // half 0 partial of this CTA
+    float* gp1 = a.gpart + ((size_t)a.half_stride + blockIdx.x) * pd.gpack;    // half 1 (8x8 dW only)
 
     if (*a.stop_flag) return;
 
-    const float* Wbase = a.pack;
-    if (a.weights_smem) {
+    // WS: weights staged in shared memory (address space known at compile time -> LDS);
+    // otherwise streamed from global/L2 through L1
+    const float* __restrict__ Wbase = WS ? smem : a.pack;   // S.w == 0
+    if (WS) {
         const float4* src = reinterpret_cast<const float4*>(a.pack);
-        float4* dst = reinterpret_cast<float4*>(smem + S.w);
+        float4* dst = reinterpret_cast<float4*>(smem);
         for (int i = tid; i < pd.pack_total / 4; i += blockDim.x) dst[i] = src[i];
-        Wbase = smem + S.w;
     }
     // advantage normalisation constants of this (global) minibatch
     float adv_mean = 0.f, adv_den = 1.f;
@@ -204,6 +295,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
     double st_p = 0, st_v = 0, st_e = 0, st_clip = 0, st_kl = 0, st_ratio = 0;   // per-thread stat sums
     double ls_acc = 0;                                                          // thread j < act_n: log_std gradient
     const long long n_tiles = (a.mb.count + M4 - 1) / M4;
+    const bool m8 = (M4 & 7) == 0;
     bool first = true;
     __syncthreads();
 
@@ -211,8 +303,8 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
         const long long p0 = a.mb.start + tile * M4;
         const int nvalid = (int)min((long long)M4, a.mb.start + a.mb.count - p0);
         // ---- gather the tile through the Feistel bijection --------------------------------
-        long long sidx = -1;
         if (tid < M4) {
+            long long sidx = -1;
             if (tid < nvalid) sidx = a.mb.identity ? (p0 + tid) : feistel_permute(p0 + tid, a.mb.n_total, a.mb.fk);
             float adv = 0.f, ret = 0.f, olp = 0.f, ov = 0.f;
             if (sidx >= 0) {
@@ -233,12 +325,12 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
         for (int l = 0; l < NL; ++l) {
             const float* ia = l == 0 ? sX : smem + S.h[0][l - 1];
             const float* ic = l == 0 ? sX : smem + S.h[1][l - 1];
-            dense_layer(pd, Wbase, l, ia, ic, smem + S.h[0][l], smem + S.h[1][l], M4, ld, 3);
+            dense_layer_auto(pd, Wbase, l, ia, ic, smem + S.h[0][l], smem + S.h[1][l], M4, ld, 3);
             __syncthreads();
         }
         // ---- loss head: dL/dlogits (or dL/dmean), dL/dvalue ---------------------------------
-        float* gA = smem + S.g[0] + (size_t)((NL - 1) & 1) * pd.max_np * ld;
-        float* gC = smem + S.g[1] + (size_t)((NL - 1) & 1) * pd.max_np * ld;
+        float* gA = smem + S.dout[0];
+        float* gC = smem + S.dout[1];
         if (tid < M4) {
             const bool valid = tid < nvalid;
             const float* z = smem + S.h[0][NL - 1] + tid;
@@ -330,60 +422,87 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
         }
         // ---- backward -----------------------------------------------------------------------
         for (int l = NL - 1; l >= 0; --l) {
-            const int mt = M4 >> 2;
-            int counts[5];   // dW actor, dW critic, dH actor, dH critic, db (both nets)
             const LayerDesc& La = pd.L[0][l];
             const LayerDesc& Lc = pd.L[1][l];
-            counts[0] = (La.Kp >> 2) * (La.Np >> 2);
-            counts[1] = (Lc.Kp >> 2) * (Lc.Np >> 2);
-            counts[2] = l > 0 ? (La.Kp >> 2) * mt : 0;
-            counts[3] = l > 0 ? (Lc.Kp >> 2) * mt : 0;
-            counts[4] = La.N + Lc.N;
-            const int total = counts[0] + counts[1] + counts[2] + counts[3] + counts[4];
-            for (int t = tid; t < total; t += blockDim.x) {
-                int u = t;
-                if (u < counts[0] + counts[1]) {
-                    const int net = u >= counts[0];
-                    if (net) u -= counts[0];
-                    const LayerDesc& Ld = net ? Lc : La;
-                    const int kq = Ld.Kp >> 2;
-                    const int nt = u / kq, kt = u - nt * kq;
-                    const float* Ain = l == 0 ? sX : smem + S.h[net][l - 1];
-                    const float* dZ = smem + S.g[net] + (size_t)(l & 1) * pd.max_np * ld;
-                    dense_tile_dw(Ain, dZ, M4, ld, kt, kq, nt << 2, gp + Ld.pw_off, Ld.Np, first);
-                    continue;
-                }
-                u -= counts[0] + counts[1];
-                if (u < counts[2] + counts[3]) {
-                    const int net = u >= counts[2];
-                    if (net) u -= counts[2];
-                    const LayerDesc& Ld = net ? Lc : La;
-                    const int kq_t = u / mt, m = u - kq_t * mt;
-                    const float* dZ = smem + S.g[net] + (size_t)(l & 1) * pd.max_np * ld;
-                    float* dZprev = smem + S.g[net] + (size_t)((l - 1) & 1) * pd.max_np * ld;
-                    dense_tile_dh(Wbase + Ld.pwt_off, Ld.N, Ld.Kp, dZ, smem + S.h[net][l - 1], dZprev, ld, kq_t << 2, m << 2);
-                    continue;
-                }
-                u -= counts[2] + counts[3];
-                {
-                    const int net = u >= La.N;
-                    if (net) u -= La.N;
-                    const LayerDesc& Ld = net ? Lc : La;
-                    const float* dZ = smem + S.g[net] + (size_t)(l & 1) * pd.max_np * ld + (size_t)u * ld;
-                    float s = 0.f;
-                    for (int m = 0; m < M4; ++m) s += dZ[m];
-                    float* g = gp + Ld.pb_off + u;
-                    *g = first ? s : *g + s;
+            const float* dZa = l == NL - 1 ? gA : smem + S.h[0][l];
+            const float* dZc = l == NL - 1 ? gC : smem + S.h[1][l];
+            // phase 1: dW_l, db_l (reads the layer input and dZ_l)
+            {
+                const bool a8 = m8 && (M4 & 15) == 0 && (La.Kp & 7) == 0 && (La.Np & 7) == 0;
+                const bool c8 = m8 && (M4 & 15) == 0 && (Lc.Kp & 7) == 0 && (Lc.Np & 7) == 0;
+                const int nsplit = a.small_splits;
+                const int ca = a8 ? (La.Kp >> 3) * (La.Np >> 3) * 2 : (La.Kp >> 2) * (La.Np >> 2) * nsplit;
+                const int cc = c8 ? (Lc.Kp >> 3) * (Lc.Np >> 3) * 2 : (Lc.Kp >> 2) * (Lc.Np >> 2) * nsplit;
+                const int cb = La.N + Lc.N;
+                for (int t = tid; t < ca + cc + cb; t += blockDim.x) {
+                    if (t < ca + cc) {
+                        const bool crit = t >= ca;
+                        int u = crit ? t - ca : t;
+                        const LayerDesc& Ld = crit ? Lc : La;
+                        const float* Ain = l == 0 ? sX : smem + S.h[crit][l - 1];
+                        const float* dZ = crit ? dZc : dZa;
+                        if (crit ? c8 : a8) {
+                            const int kq = Ld.Kp >> 3, per_half = kq * (Ld.Np >> 3);
+                            const int half = u / per_half;
+                            u -= half * per_half;
+                            const int nt = u / kq, kt = u - nt * kq;
+                            const int mh = M4 >> 1;
+                            dense_tile_dw8(Ain, dZ, half * mh, half * mh + mh, ld, kt, kq, nt << 3,
+                                           (half ? gp1 : gp) + Ld.pw_off, Ld.Np, first);
+                        } else {
+                            // small layer: the sample range is split so that all threads get a tile; split s
+                            // accumulates into partial plane s of this CTA
+                            const int kq = Ld.Kp >> 2, per_split = kq * (Ld.Np >> 2);
+                            const int sp = u / per_split;
+                            u -= sp * per_split;
+                            const int nt = u / kq, kt = u - nt * kq;
+                            const int ms = M4 / nsplit;
+                            float* gq = a.gpart + ((size_t)sp * a.half_stride + blockIdx.x) * pd.gpack;
+                            dense_tile_dw(Ain, dZ, sp * ms, sp * ms + ms, ld, kt, kq, nt << 2, gq + Ld.pw_off, Ld.Np, first);
+                        }
+                    } else {
+                        int u = t - ca - cc;
+                        const bool crit = u >= La.N;
+                        if (crit) u -= La.N;
+                        const LayerDesc& Ld = crit ? Lc : La;
+                        const float* dZ = (crit ? dZc : dZa) + (size_t)u * ld;
+                        float s = 0.f;
+                        for (int m = 0; m < M4; m += 4) {
+                            float4 d = *reinterpret_cast<const float4*>(dZ + m);
+                            s += (d.x + d.y) + (d.z + d.w);
+                        }
+                        float* g = gp + Ld.pb_off + u;
+                        *g = first ? s : *g + s;
+                    }
                 }
             }
             __syncthreads();
+            // phase 2: dZ_{l-1} = (dZ_l W_l^T) .* (1 - H_{l-1}^2), in place over H_{l-1}
+            if (l > 0) {
+                const bool a8 = m8 && (La.Kp & 7) == 0 && La.N >= 8;
+                const bool c8 = m8 && (Lc.Kp & 7) == 0 && Lc.N >= 8;
+                const int mt4 = M4 >> 2, mt8 = M4 >> 3;
+                const int ca = a8 ? (La.Kp >> 3) * mt8 : (La.Kp >> 2) * mt4;
+                const int cc = c8 ? (Lc.Kp >> 3) * mt8 : (Lc.Kp >> 2) * mt4;
+                for (int t = tid; t < ca + cc; t += blockDim.x) {
+                    const bool crit = t >= ca;
+                    const int u = crit ? t - ca : t;
+                    const LayerDesc& Ld = crit ? Lc : La;
+                    const float* dZ = crit ? dZc : dZa;
+                    float* H = smem + S.h[crit][l - 1];
+                    if (crit ? c8 : a8) {
+                        const int kt = u / mt8, m = u - kt * mt8;
+                        dense_tile_dh8(Wbase + Ld.pwt_off, Ld.N, Ld.Kp, dZ, H, ld, kt, m, Ld.Kp >> 1, M4 >> 1);
+                    } else {
+                        const int kt = u / mt4, m = u - kt * mt4;
+                        dense_tile_dh(Wbase + Ld.pwt_off, Ld.N, Ld.Kp, dZ, H, ld, kt << 2, m << 2);
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
     // ---- per-CTA tail: log_std gradient + statistic sums --------------------------------------
-    if (n_tiles <= blockIdx.x) {
-        // this CTA had no tile: its partial must still read as zero
-        for (int i = tid; i < pd.pack_fwd; i += blockDim.x) gp[i] = 0.f;
-    }
     if (pd.act_kind == DRIL_ACT_CONTINUOUS && tid < pd.act_n) gp[pd.pack_fwd + tid] = (float)ls_acc;
     double sums[6] = {st_p, st_v, st_e, st_clip, st_kl, st_ratio};
 #pragma unroll
@@ -393,24 +512,37 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
     }
 }
 
-// g_flat[p] = sum over CTAs of the packed partials; stats6 likewise (fixed order => deterministic)
-__global__ void __launch_bounds__(256) grad_reduce_kernel(const float* __restrict__ gpart, int n_cta, int gpack,
-                                                          const int* __restrict__ flat2g, int n_params,
+// g_flat[p] = sum over the partial planes / CTAs of the packed partials (fixed order => deterministic)
+__device__ __forceinline__ float reduce_partials(const float* __restrict__ gpart, int n_cta, int half_stride, int gpack,
+                                                 int idx, int planes) {
+    float s = 0.f;
+    for (int pl = 0; pl < planes; ++pl) {
+        const float* base = gpart + (size_t)pl * half_stride * gpack + idx;
+        float sp = 0.f;
+#pragma unroll 4
+        for (int c = 0; c < n_cta; ++c) sp += base[(size_t)c * gpack];
+        s += sp;
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(256) grad_reduce_kernel(const float* __restrict__ gpart, int n_cta, int half_stride,
+                                                          int gpack, const int* __restrict__ flat2g,
+                                                          const unsigned char* __restrict__ f2planes, int n_params,
                                                           int stats_off, float* __restrict__ g_flat /* [n_params + 8] */,
                                                           const int* stop_flag) {
     if (*stop_flag) return;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_params + 6) return;
     int idx = p < n_params ? flat2g[p] : stats_off + (p - n_params);
-    float s = 0.f;
-    for (int c = 0; c < n_cta; ++c) s += gpart[(size_t)c * gpack + idx];
-    g_flat[p] = s;
+    int planes = p < n_params ? f2planes[p] : 1;
+    g_flat[p] = reduce_partials(gpart, n_cta, half_stride, gpack, idx, planes);
 }
 
 // iteration accumulators (device): [0..6] sums over applied minibatches of policy_loss, value_loss,
 // entropy_loss, clip_fraction, approx_kl, entropy, ratio; [7] loss; [8] grad_norm sum; [9] applied
-// count; [10] grad_norm count
-#define ITER_ACC_N 12
+// count; [10] grad_norm count; [12],[13] running beta1^t, beta2^t
+#define ITER_ACC_N 16
 
 struct AdamArgs {
     float* g;            // [n_params + 6]: gradient then the six stat sums (already summed over ranks)
@@ -429,63 +561,143 @@ struct AdamArgs {
     int apply_stats;     // 0 for the dril_optimizer_step parity entry (no stat bookkeeping)
 };
 
-// single CTA: global grad norm -> clip -> KL stop -> Adam -> refresh packed layouts
-__global__ void __launch_bounds__(1024) adam_finalize_kernel(AdamArgs a) {
-    __shared__ double scratch[32];
-    __shared__ float s_scale;
-    __shared__ int s_stop;
+// One CTA: (given sum of squares q) clip scale -> KL stop -> statistics -> Adam -> refresh packed layouts.
+// The twelve accumulator updates run on twelve threads (independent global round trips).
+__device__ __forceinline__ void adam_apply(const AdamArgs& a, double q, float* s_f, int* s_i) {
     const int tid = threadIdx.x;
-    if (*a.stop_flag) return;
-    double q = 0;
-    for (int p = tid; p < a.n_params; p += blockDim.x) { double g = a.g[p]; q += g * g; }
-    q = block_sum(q, scratch);
-    if (tid == 0) {
-        float norm = (float)sqrt(q);
-        float scale = 1.f;
-        if (a.hp.max_grad_norm >= 0.f && norm > a.hp.max_grad_norm) scale = a.hp.max_grad_norm / norm;   // no epsilon (optimization_utils.jl:99-107)
-        s_scale = scale;
-        int stop = 0;
+    const float norm = (float)sqrt(q);
+    const float* st = a.g + a.n_params;
+    const float invB = (float)(1.0 / a.global_count);
+    const float kl = st[4] * invB;
+    const int stop = (a.apply_stats && a.hp.target_kl >= 0.f && kl > 1.5f * a.hp.target_kl) ? 1 : 0;   // ppo.jl:235-238: BEFORE applying
+    if (tid < 16) {
         if (a.apply_stats) {
-            const float* st = a.g + a.n_params;
-            float invB = (float)(1.0 / a.global_count);
-            float p_loss = st[0] * invB, v_loss = st[1] * invB, ent = st[2] * invB;
-            float clipf = st[3] * invB, kl = st[4] * invB, ratio = st[5] * invB;
-            a.iter_acc[8] += (double)norm;                 // grad_norms gets the PRE-clip norm, before the KL check (ppo.jl:216-223)
-            a.iter_acc[10] += 1.0;
-            if (a.hp.target_kl >= 0.f && kl > 1.5f * a.hp.target_kl) stop = 1;   // ppo.jl:235-238: stop BEFORE applying
-            if (!stop) {
-                float ent_loss = -ent;
-                float loss = p_loss + a.hp.ent_coef * ent_loss + a.hp.vf_coef * v_loss;
-                a.iter_acc[0] += p_loss; a.iter_acc[1] += v_loss; a.iter_acc[2] += ent_loss;
-                a.iter_acc[3] += clipf; a.iter_acc[4] += kl; a.iter_acc[5] += ent; a.iter_acc[6] += ratio;
-                a.iter_acc[7] += loss; a.iter_acc[9] += 1.0;
-            } else {
-                *a.stop_flag = 1;
+            const float p_loss = st[0] * invB, v_loss = st[1] * invB, ent = st[2] * invB;
+            const float ent_loss = -ent;
+            double add = 0.0;
+            bool on_apply = true;
+            switch (tid) {
+                case 0: add = p_loss; break;
+                case 1: add = v_loss; break;
+                case 2: add = ent_loss; break;
+                case 3: add = st[3] * invB; break;
+                case 4: add = kl; break;
+                case 5: add = ent; break;
+                case 6: add = st[5] * invB; break;
+                case 7: add = p_loss + a.hp.ent_coef * ent_loss + a.hp.vf_coef * v_loss; break;
+                case 8: add = norm; on_apply = false; break;     // grad_norms gets the PRE-clip norm before the KL check (ppo.jl:216-223)
+                case 9: add = 1.0; break;
+                case 10: add = 1.0; on_apply = false; break;
+                default: add = 0.0; on_apply = false; break;
             }
-        } else {
+            if (tid <= 10 && (!on_apply || !stop)) a.iter_acc[tid] += add;
+        } else if (tid == 8) {
             a.iter_acc[8] = (double)norm;
         }
-        s_stop = stop;
-        if (!stop) *a.step += 1;
+        if (!stop && (tid == 12 || tid == 13)) {
+            double b = tid == 12 ? (double)a.hp.beta1 : (double)a.hp.beta2;
+            double pw = a.iter_acc[tid] * b;
+            a.iter_acc[tid] = pw;
+            s_f[tid - 12] = (float)(1.0 - pw);
+        }
+        if (tid == 14) {
+            if (stop) *a.stop_flag = 1; else *a.step += 1;
+            *s_i = stop;
+        }
     }
     __syncthreads();
-    if (s_stop) return;
-    const long long t = *a.step;
-    const float c1 = (float)(1.0 - pow((double)a.hp.beta1, (double)t));
-    const float c2 = (float)(1.0 - pow((double)a.hp.beta2, (double)t));
-    const float scale = s_scale, b1 = a.hp.beta1, b2 = a.hp.beta2;
+    if (stop) return;
+    float scale = 1.f;
+    if (a.hp.max_grad_norm >= 0.f && norm > a.hp.max_grad_norm) scale = a.hp.max_grad_norm / norm;   // no epsilon (optimization_utils.jl:99-107)
+    const float c1 = s_f[0], c2 = s_f[1];
+    const float b1 = a.hp.beta1, b2 = a.hp.beta2;
+    const float* __restrict__ gsrc = a.g;
+    float* __restrict__ pm = a.m;
+    float* __restrict__ pv = a.v;
+    float* __restrict__ pw = a.flat;
+    float* __restrict__ pk = a.pack;
+    const int* __restrict__ f2p = a.flat2pack;
+    const int* __restrict__ f2t = a.flat2packT;
+#pragma unroll 4
     for (int p = tid; p < a.n_params; p += blockDim.x) {
-        float g = __fmul_rn(a.g[p], scale);
-        float m = __fadd_rn(__fmul_rn(b1, a.m[p]), __fmul_rn(__fsub_rn(1.0f, b1), g));
-        float v = __fadd_rn(__fmul_rn(b2, a.v[p]), __fmul_rn(__fmul_rn(__fsub_rn(1.0f, b2), g), g));
+        float g = __fmul_rn(gsrc[p], scale);
+        float m = __fadd_rn(__fmul_rn(b1, pm[p]), __fmul_rn(__fsub_rn(1.0f, b1), g));
+        float v = __fadd_rn(__fmul_rn(b2, pv[p]), __fmul_rn(__fmul_rn(__fsub_rn(1.0f, b2), g), g));
         float upd = __fmul_rn(__fdiv_rn(__fdiv_rn(m, c1), __fadd_rn(__fsqrt_rn(__fdiv_rn(v, c2)), a.hp.adam_eps)), a.hp.lr);
-        float w = __fsub_rn(a.flat[p], upd);
-        a.m[p] = m; a.v[p] = v; a.flat[p] = w;
-        int ip = a.flat2pack[p];
-        if (ip >= 0) a.pack[ip] = w;
-        int it = a.flat2packT[p];
-        if (it >= 0) a.pack[it] = w;
+        float w = __fsub_rn(pw[p], upd);
+        int ip = f2p[p];
+        int it = f2t[p];
+        pm[p] = m; pv[p] = v; pw[p] = w;
+        if (ip >= 0) pk[ip] = w;
+        if (it >= 0) pk[it] = w;
     }
+}
+
+// stand-alone (multi-GPU path after the NCCL allreduce, and the dril_optimizer_step parity entry)
+__global__ void __launch_bounds__(1024) adam_finalize_kernel(AdamArgs a) {
+    __shared__ double scratch[32];
+    __shared__ float s_f[2];
+    __shared__ int s_i;
+    if (*a.stop_flag) return;
+    double q = 0;
+    for (int p = threadIdx.x; p < a.n_params; p += blockDim.x) { double g = a.g[p]; q += g * g; }
+    q = block_sum(q, scratch);
+    adam_apply(a, q, s_f, &s_i);
+}
+
+// single-GPU path: partial reduction over CTAs/planes by many CTAs, then the last CTA to finish
+// (ticket) computes the global norm from the per-CTA sums of squares and applies clip + Adam.
+// Block = 32 parameters x 32 CTA-groups: lanes read 32 consecutive packed entries (coalesced), the 32
+// warps split the (plane, CTA) list 32 ways; partial sums meet in shared memory in a fixed order.
+#define RA_PARAMS_PER_BLOCK 32
+#define RA_GROUPS 32
+__global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restrict__ gpart, int n_cta, int half_stride,
+                                                          int gpack, const int* __restrict__ flat2g,
+                                                          const unsigned char* __restrict__ f2planes, int stats_off,
+                                                          double* __restrict__ sq_part, unsigned int* __restrict__ ticket,
+                                                          AdamArgs a) {
+    __shared__ double scratch[32];
+    __shared__ float s_red[RA_GROUPS][RA_PARAMS_PER_BLOCK + 1];
+    __shared__ float s_f[2];
+    __shared__ int s_i;
+    __shared__ unsigned int s_ticket;
+    if (*a.stop_flag) return;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int p = blockIdx.x * RA_PARAMS_PER_BLOCK + lane;
+    float part = 0.f;
+    if (p < a.n_params + 6) {
+        const int idx = p < a.n_params ? flat2g[p] : stats_off + (p - a.n_params);
+        const int planes = p < a.n_params ? f2planes[p] : 1;
+        const int total = planes * n_cta;
+        for (int i = grp; i < total; i += RA_GROUPS) {
+            const int pl = i / n_cta, c = i - pl * n_cta;
+            part += gpart[((size_t)pl * half_stride + c) * gpack + idx];
+        }
+    }
+    s_red[grp][lane] = part;
+    __syncthreads();
+    double sq = 0.0;
+    if (grp == 0 && p < a.n_params + 6) {
+        float g = 0.f;
+#pragma unroll
+        for (int j = 0; j < RA_GROUPS; ++j) g += s_red[j][lane];
+        a.g[p] = g;
+        if (p < a.n_params) sq = (double)g * (double)g;
+        __threadfence();                  // publish this thread's slice before the ticket
+    }
+    sq = block_sum(sq, scratch);
+    if (threadIdx.x == 0) {
+        sq_part[blockIdx.x] = sq;
+        __threadfence();
+        s_ticket = atomicAdd(ticket, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    if (threadIdx.x == 0) *ticket = 0u;
+    double q = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) q += sq_part[b];     // fixed order; every thread computes the same value
+    adam_apply(a, q, s_f, &s_i);
 }
 
 // (re)build the packed layouts from the flat vector (after set_params)
