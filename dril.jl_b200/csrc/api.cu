@@ -225,6 +225,8 @@ extern "C" int32_t dril_ctx_create(int32_t device, uint64_t seed, dril_ctx** out
     DRIL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     DRIL_CUDA(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
     DRIL_CUDA(cudaFuncSetAttribute(rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
+    DRIL_CUDA(cudaFuncSetAttribute(rollout_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
+    DRIL_CUDA(cudaFuncSetAttribute(rollout_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
     DRIL_CUDA(cudaFuncSetAttribute(policy_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
     DRIL_CUDA(cudaFuncSetAttribute(policy_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
     DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
@@ -831,6 +833,40 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
     const bool upd = d.normalize && d.training && (d.norm_obs || d.norm_reward);
     if (upd) flags |= RO_GRID_SYNC;
     const long long N = d.n_envs;
+    static const int env_nofast = getenv("DRIL_ROLLOUT_NO_FAST") ? atoi(getenv("DRIL_ROLLOUT_NO_FAST")) : 0;
+    if (has_policy && !upd && !env_nofast && d.kind != DRIL_ENV_SYNTHETIC && a.pd.act_n <= RF_MAX_OUT - 1 && T > 0 &&
+        (a.pd.act_kind == DRIL_ACT_DISCRETE || a.pd.act_n == 1)) {
+        // fast path: state in registers, one tile per CTA, K-split output layers
+        static const int f_ctas = getenv("DRIL_FAST_CTAS_PER_SM") ? atoi(getenv("DRIL_FAST_CTAS_PER_SM")) : 2;
+        const long long want = (long long)c->sm_count * std::max(f_ctas, 1);
+        int M4 = (int)std::min<long long>(64, ((N + want - 1) / want + 3) & ~3ll);
+        M4 = std::max(M4, 8);
+        if (M4 > 32) M4 = 64; else if (M4 > 16) M4 = 32; else if (M4 > 8) M4 = 16; else M4 = 8;   // threads % M4 == 0
+        int tiles = 2 * (a.pd.max_np >> 2) * (M4 >> 2);
+        // many envs per SM: the rollout is throughput bound -> 64-env tiles, 8x8 register tiles
+        // (1 B of shared-memory traffic per FMA instead of 2), several CTAs per SM
+        static const int f_t8 = getenv("DRIL_FAST_TILES8") ? atoi(getenv("DRIL_FAST_TILES8")) : -1;
+        const bool t8 = f_t8 >= 0 ? (f_t8 != 0 && M4 >= 16) : (M4 == 64 && N >= 96ll * c->sm_count);
+        if (t8) { flags |= RO_TILES_8X8; tiles = 2 * (a.pd.max_np >> 3) * (M4 >> 3); }
+        int threads = std::min(DRIL_THREADS, std::max(128, (tiles + 31) & ~31));
+        const int tq = std::max(32, M4);
+        threads = std::min(DRIL_THREADS, (threads + tq - 1) / tq * tq);
+        static const int f_threads = getenv("DRIL_FAST_THREADS") ? atoi(getenv("DRIL_FAST_THREADS")) : 0;
+        if (f_threads >= tq && f_threads <= DRIL_THREADS && f_threads % tq == 0) threads = f_threads;
+        bool ws = true;
+        auto tot = [&](int m4, int th, bool w) { return rollout_fast_smem_layout(a.pd, m4, th, w).total; };
+        if (tot(M4, threads, true) > DRIL_SMEM_MAX) ws = false;
+        while (M4 > 8 && tot(M4, threads, ws) > DRIL_SMEM_MAX) M4 >>= 1;
+        if (tot(M4, threads, ws) <= DRIL_SMEM_MAX) {
+            a.M4 = M4; a.flags = flags | (ws ? RO_WEIGHTS_SMEM : 0);
+            a.n_tiles = (int)((N + M4 - 1) / M4);
+            Span sp(c, DRIL_K_ROLLOUT);
+            if (ws) rollout_fast_kernel<true><<<a.n_tiles, threads, tot(M4, threads, ws), c->stream>>>(a);
+            else rollout_fast_kernel<false><<<a.n_tiles, threads, tot(M4, threads, ws), c->stream>>>(a);
+            DRIL_CUDA(cudaGetLastError());
+            return DRIL_OK;
+        }
+    }
     // tile width: the per-step critical path (state load -> forward -> sample -> dynamics) is latency
     // bound, so small batches are cut into ~4 CTAs per SM that overlap each other's phases; at most
     // 64 envs per tile, shrink until shared memory fits

@@ -28,7 +28,8 @@ enum {
     RO_FOLD_NEXT_OBSERVE = 4, // the observe() after each act! (trajectory.jl:45) is folded into the step
     RO_WEIGHTS_SMEM = 8,
     RO_GRID_SYNC = 16,        // training normaliser: cooperative launch + grid barrier per step
-    RO_WRITE_OBS_OUT = 32     // compat observe: write normalised obs to obs_out
+    RO_WRITE_OBS_OUT = 32,    // compat observe: write normalised obs to obs_out
+    RO_TILES_8X8 = 64         // throughput mode (many envs per SM): 8x8 register tiles in the hidden layers
 };
 
 struct RolloutArgs {
@@ -475,6 +476,307 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
     if (env.normalize && blockIdx.x == 0) {
         for (int d = tid; d < D; d += blockDim.x) { env.obs_mean[d] = sMean[d]; env.obs_var[d] = sVar[d]; }
         if (tid == 0) { env.ret_stats[0] = sRet[0]; env.ret_stats[1] = sRet[1]; env.counts[0] = sCnt[0]; env.counts[1] = sCnt[1]; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Fast path of the fused rollout (the common case): CartPole / Pendulum, no running-statistics
+// update (no NormalizeWrapperEnv, or one in eval mode), one tile of envs per CTA.
+//   * env state, step counters and monitor accumulators stay in registers for all n_steps
+//     (no global round trip on the per-step critical path);
+//   * the output layers (hidden -> n_actions | act_dim, hidden -> 1) are K-split over all threads
+//     and reduced through shared memory, and the env-owning thread goes straight from the reduced
+//     logits to sampling and the dynamics step: 2 + n_hidden barriers per step;
+//   * per-step results are written straight into the time-major buffer (coalesced rows).
+// Semantics identical to rollout_kernel (same reference citations).
+// ---------------------------------------------------------------------------------------
+#define RF_MAX_OUT 9   // actor outputs (<= 8) + value
+
+struct RolloutFastSmem {
+    int ld, slices;
+    size_t w, x, acta, actc, part, stat, total;   // float offsets; total in bytes
+};
+
+__host__ __device__ inline RolloutFastSmem rollout_fast_smem_layout(const PolicyDesc& pd, int M4, int threads, bool weights_smem) {
+    RolloutFastSmem s;
+    s.ld = M4 + 4;
+    s.slices = threads / M4;
+    size_t o = 0;
+    s.w = o; o += weights_smem ? (size_t)pd.pack_fwd : 0;
+    s.x = o; o += (size_t)pd.obs_dim_p * s.ld;
+    s.acta = o; o += (size_t)2 * pd.max_np * s.ld;
+    s.actc = o; o += (size_t)2 * pd.max_np * s.ld;
+    s.part = o; o += (size_t)s.slices * RF_MAX_OUT * s.ld;
+    s.stat = o; o += (size_t)2 * pd.obs_dim_p + 4;
+    s.total = ((o + 3) & ~(size_t)3) * sizeof(float);
+    return s;
+}
+
+template <bool WS>
+__global__ void __launch_bounds__(DRIL_THREADS) rollout_fast_kernel(const __grid_constant__ RolloutArgs a) {
+    extern __shared__ float4 smem4[];
+    float* smem = reinterpret_cast<float*>(smem4);
+    const EnvDev& env = a.env;
+    const BufDev& buf = a.buf;
+    const PolicyDesc& pd = a.pd;
+    const int D = env.obs_dim, Dp = pd.obs_dim_p, M4 = a.M4, NL = pd.n_layers;
+    const long long N = env.n_envs;
+    const RolloutFastSmem L = rollout_fast_smem_layout(pd, M4, blockDim.x, WS);
+    const int ld = L.ld, S = L.slices;
+    float* sX = smem + L.x;
+    float* sActA = smem + L.acta;
+    float* sActC = smem + L.actc;
+    float* sPart = smem + L.part;
+    float* sMean = smem + L.stat;
+    float* sVar = sMean + Dp;
+    const int tid = threadIdx.x;
+    const float* __restrict__ Wbase = WS ? smem : a.pack;
+    if (WS) {
+        const float4* src = reinterpret_cast<const float4*>(a.pack);
+        float4* dst = reinterpret_cast<float4*>(smem);
+        for (int i = tid; i < pd.pack_fwd / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    for (int d = tid; d < Dp; d += blockDim.x) {
+        sMean[d] = (env.normalize && d < D) ? env.obs_mean[d] : 0.f;
+        sVar[d] = (env.normalize && d < D) ? env.obs_var[d] : 1.f;
+    }
+    const bool norm_obs = env.normalize && env.norm_obs;
+    const float ret_scale_var = env.normalize ? env.ret_stats[1] : 1.f;
+
+    const long long n0 = (long long)blockIdx.x * M4;
+    const int nvalid = (int)min((long long)M4, N - n0);
+    const bool mine = tid < nvalid;
+    const long long n = n0 + tid;
+    const uint32_t gid = (uint32_t)(env.gid_offset + n);
+    // per-env state in registers
+    float st[ENV_MAX_STATE] = {0.f, 0.f, 0.f, 0.f};
+    int steps = 0, ep_len = 0;
+    float ep_ret = 0.f;
+    uint32_t episode = 0;
+    if (mine) {
+#pragma unroll
+        for (int k = 0; k < ENV_MAX_STATE; ++k) if (k < env.state_dim) st[k] = env.state[(size_t)k * N + n];
+        steps = env.steps[n];
+        episode = env.episode[n];
+        if (env.monitor) { ep_ret = env.ep_ret[n]; ep_len = env.ep_len[n]; }
+    }
+    // output-layer split: thread (e = tid % M4, ks = tid / M4) covers k in [ks*Kc, ks*Kc + Kc)
+    const LayerDesc& Lao = pd.L[0][NL - 1];
+    const LayerDesc& Lco = pd.L[1][NL - 1];
+    const int Kout = Lao.K;
+    const int Kc = (Kout + S - 1) / S;
+    const int oe = tid % M4, oks = tid / M4;
+    const int A = pd.act_n;
+    __syncthreads();
+
+    // write the (normalised) observation of the register state into sX and optionally the buffer
+    auto stage_obs = [&](float* obs_row /* nullable global [D] */) {
+        if (tid < M4) {
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+            if (mine) {
+                env_raw_obs(env.kind, st, o);
+                if (norm_obs) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (j < D) o[j] = normalize_obs_val(o[j], sMean[j], sVar[j], env.eps, env.clip_obs);
+                }
+                if (obs_row) {
+                    if (D == 4) *reinterpret_cast<float4*>(obs_row) = make_float4(o[0], o[1], o[2], o[3]);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (j < D) obs_row[j] = o[j];
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < Dp) sX[(size_t)j * ld + tid] = o[j];
+        }
+        __syncthreads();
+    };
+    // hidden layers (all but the output layer) of the selected nets; returns the buffer parity of the
+    // last hidden activation (or -1 if the network has no hidden layer: the input is sX)
+    auto hidden_forward = [&](int net_mask) -> int {
+        const size_t bufsz = (size_t)pd.max_np * ld;
+        for (int l = 0; l < NL - 1; ++l) {
+            const float* ia = l == 0 ? sX : sActA + ((l - 1) & 1) * bufsz;
+            const float* ic = l == 0 ? sX : sActC + ((l - 1) & 1) * bufsz;
+            if (a.flags & RO_TILES_8X8)
+                dense_layer_auto(pd, Wbase, l, ia, ic, sActA + (l & 1) * bufsz, sActC + (l & 1) * bufsz, M4, ld, net_mask);
+            else
+                dense_layer(pd, Wbase, l, ia, ic, sActA + (l & 1) * bufsz, sActC + (l & 1) * bufsz, M4, ld, net_mask);
+            __syncthreads();
+        }
+        return NL >= 2 ? ((NL - 2) & 1) : -1;
+    };
+    // K-split partial sums of the output layers -> sPart[(ks*RF_MAX_OUT + j)*ld + e]; j < A actor, j == A critic
+    auto output_partials = [&](int par, int net_mask) {
+        const size_t bufsz = (size_t)pd.max_np * ld;
+        const float* ha = par < 0 ? sX : sActA + par * bufsz;
+        const float* hc = par < 0 ? sX : sActC + par * bufsz;
+        if (oks < S) {
+            float acc[RF_MAX_OUT];
+#pragma unroll
+            for (int j = 0; j < RF_MAX_OUT; ++j) acc[j] = 0.f;
+            const int k0 = oks * Kc, k1 = min(Kout, k0 + Kc);
+            const float* wa = Wbase + Lao.pw_off;
+            const float* wc = Wbase + Lco.pw_off;
+            for (int k = k0; k < k1; ++k) {
+                if (net_mask & 1) {
+                    const float h = ha[(size_t)k * ld + oe];
+#pragma unroll
+                    for (int j = 0; j < RF_MAX_OUT - 1; ++j) if (j < A) acc[j] = fmaf(h, wa[k * Lao.Np + j], acc[j]);
+                }
+                if (net_mask & 2) acc[RF_MAX_OUT - 1] = fmaf(hc[(size_t)k * ld + oe], wc[k * Lco.Np], acc[RF_MAX_OUT - 1]);
+            }
+#pragma unroll
+            for (int j = 0; j < RF_MAX_OUT - 1; ++j) if (j < A) sPart[((size_t)oks * RF_MAX_OUT + j) * ld + oe] = acc[j];
+            sPart[((size_t)oks * RF_MAX_OUT + RF_MAX_OUT - 1) * ld + oe] = acc[RF_MAX_OUT - 1];
+        }
+        __syncthreads();
+    };
+    auto reduce_out = [&](int j, int which /*0 actor j, 1 critic*/) -> float {
+        const int jj = which ? RF_MAX_OUT - 1 : j;
+        float s = 0.f;
+        for (int ks = 0; ks < S; ++ks) s += sPart[((size_t)ks * RF_MAX_OUT + jj) * ld + tid];
+        return s + (which ? Wbase[Lco.pb_off] : Wbase[Lao.pb_off + j]);
+    };
+
+    for (int t = 0; t < a.T; ++t) {
+        const size_t row = (size_t)t * N;
+        stage_obs(mine ? buf.obs + (row + n) * D : nullptr);
+        const int par = hidden_forward(3);
+        output_partials(par, 3);
+        int trunc_i = 0;
+        float tobs[4] = {0.f, 0.f, 0.f, 0.f};
+        if (mine) {
+            const float value = reduce_out(0, 1);
+            float z[RF_MAX_OUT - 1];
+#pragma unroll
+            for (int j = 0; j < RF_MAX_OUT - 1; ++j) z[j] = j < A ? reduce_out(j, 0) : -INFINITY;
+            float logp;
+            int a_disc = 0;
+            float a_cont = 0.f;
+            if (pd.act_kind == DRIL_ACT_DISCRETE) {
+                float m = z[0];
+#pragma unroll
+                for (int j = 1; j < RF_MAX_OUT - 1; ++j) if (j < A) m = fmaxf(m, z[j]);
+                float ex[RF_MAX_OUT - 1];
+                float ssum = 0.f;
+#pragma unroll
+                for (int j = 0; j < RF_MAX_OUT - 1; ++j) { ex[j] = j < A ? expf(z[j] - m) : 0.f; if (j < A) ssum += ex[j]; }
+                int idx = A - 1;
+                if (a.forced) {
+                    idx = reinterpret_cast<const int*>(a.forced)[row + n] - pd.act_start;
+                    idx = idx < 0 ? 0 : (idx >= A ? A - 1 : idx);
+                } else {
+                    uint32_t x[4];
+                    philox4x32(gid, a.step0 + (uint32_t)t, 0u, DRIL_TAG_SAMPLE, a.pseed, x);
+                    const double u = u01_f64(x[0], x[1]);
+                    float cum = 0.f;
+                    bool found = false;
+#pragma unroll
+                    for (int j = 0; j < RF_MAX_OUT - 1; ++j) {
+                        if (j < A) {
+                            cum += ex[j] / ssum;                 // fp32 cumsum vs Float64 u (categorical.jl:45-47)
+                            if (!found && (double)cum >= u) { idx = j; found = true; }
+                        }
+                    }
+                }
+                float pe = ex[0];
+#pragma unroll
+                for (int j = 1; j < RF_MAX_OUT - 1; ++j) if (j == idx) pe = ex[j];
+                logp = logf(pe / ssum);
+                a_disc = idx + pd.act_start;
+                reinterpret_cast<int*>(buf.actions)[row + n] = a_disc;
+            } else {
+                float ls_sum = 0.f, dss = 0.f;
+#pragma unroll
+                for (int j = 0; j < RF_MAX_OUT - 1; ++j) {
+                    if (j < A) {
+                        const float mean = z[j];
+                        const float ls = a.flat[pd.log_std_off + j];
+                        float act;
+                        if (a.forced) act = reinterpret_cast<const float*>(a.forced)[(row + n) * A + j];
+                        else act = __fadd_rn(mean, __fmul_rn(expf(ls), sample_normal(gid, a.step0 + (uint32_t)t, j, a.pseed)));
+                        const float diff = act - mean;
+                        dss += diff * diff * expf(-2.0f * ls);
+                        ls_sum += ls;
+                        reinterpret_cast<float*>(buf.actions)[(row + n) * A + j] = act;          // raw, unclamped (trajectory.jl:48)
+                        if (j == 0) a_cont = fminf(fmaxf(act, pd.act_low[0]), pd.act_high[0]);    // ClampAdapter
+                    }
+                }
+                logp = -0.5f * (2.0f * ls_sum + dss + (float)A * DRIL_LOG2PI);
+            }
+            buf.values[row + n] = value;
+            buf.logprobs[row + n] = logp;
+            // env step + monitor + auto-reset
+            bool term = false;
+            float r;
+            if (env.kind == DRIL_ENV_CARTPOLE) r = cartpole_step(st, a_disc - env.act_start, &term);
+            else r = pendulum_step(st, a_cont);
+            steps += 1;
+            const bool trunc = steps >= env.max_steps;
+            const bool done = term || trunc;
+            buf.flags[row + n] = (unsigned char)((term ? 1 : 0) | (trunc ? 2 : 0));
+            float rn = r;
+            if (env.normalize && env.norm_reward) {              // eval-mode normaliser: frozen statistics
+                rn = __fdiv_rn(r, __fsqrt_rn(__fadd_rn(ret_scale_var, env.eps)));
+                rn = fminf(fmaxf(rn, -env.clip_reward), env.clip_reward);
+            }
+            buf.rewards[row + n] = rn;
+            if (env.monitor) {
+                ep_ret = __fadd_rn(ep_ret, r);
+                ep_len += 1;
+                if (done) {
+                    buf.episode_r[row + n] = ep_ret;
+                    buf.episode_l[row + n] = ep_len;
+                    atomicAdd(&buf.done_count[t], 1);
+                    atomicAdd(&env.roll_sums[0], (double)ep_ret);
+                    atomicAdd(&env.roll_sums[1], (double)ep_len);
+                    atomicAdd(env.roll_eps, 1ull);
+                    ep_ret = 0.f; ep_len = 0;
+                }
+            }
+            if (trunc) {
+                trunc_i = 1;
+                env_raw_obs(env.kind, st, tobs);
+                if (norm_obs) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (j < D) tobs[j] = normalize_obs_val(tobs[j], sMean[j], sVar[j], env.eps, env.clip_obs);
+                }
+            }
+            if (done) {
+                env_reset_state(env.kind, gid, episode, env.seed, st);
+                episode += 1;
+                steps = 0;
+                if (env.normalize) env.ret[n] = 0.f;             // normalizeWrapperEnv.jl:153-156
+            }
+        }
+        // V(terminal_obs) for truncated envs (trajectory.jl:57-61): rare, CTA-uniform branch
+        if (__syncthreads_or(trunc_i)) {
+            if (tid < M4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j < Dp) sX[(size_t)j * ld + tid] = trunc_i ? tobs[j] : 0.f;
+            }
+            __syncthreads();
+            const int p2 = hidden_forward(2);
+            output_partials(p2, 2);
+            if (mine && trunc_i) buf.boot[row + n] = reduce_out(0, 1);
+            __syncthreads();
+        }
+    }
+    // V(new_obs) after the final step (trajectory.jl:65-70)
+    if (a.T > 0) {
+        stage_obs(nullptr);
+        const int p2 = hidden_forward(2);
+        output_partials(p2, 2);
+        if (mine) buf.last_values[n] = reduce_out(0, 1);
+    }
+    if (mine) {
+#pragma unroll
+        for (int k = 0; k < ENV_MAX_STATE; ++k) if (k < env.state_dim) env.state[(size_t)k * N + n] = st[k];
+        env.steps[n] = steps;
+        env.episode[n] = episode;
+        if (env.monitor) { env.ep_ret[n] = ep_ret; env.ep_len[n] = ep_len; }
     }
 }
 
