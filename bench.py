@@ -93,6 +93,7 @@ def dist_setup(n_gpus):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout (one JSON line only)
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -198,6 +199,9 @@ def run_ours(args):
     L.check(lib.dril_iteration_result(agent.device.h, C.byref(st)))
 
     if rank != 0:
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     pk = peaks()
     D_obs = env.obs_dim
@@ -253,7 +257,10 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.workload)
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -312,7 +319,7 @@ def run_reference(args):
             "config": {"workload": w["name"], "epochs": EPOCHS, "minibatches_per_epoch": N_MINIBATCHES},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():

@@ -1214,22 +1214,16 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
     aa.flat2packT = p->flat2packT; aa.step = p->step; aa.iter_acc = p->iter_acc; aa.stop_flag = p->stop_flag;
     aa.global_count = mb.global_count; aa.hp = hp; aa.n_params = pd.n_params; aa.apply_stats = apply_stats;
     const int n = pd.n_params + 6;
-    const int rgrid = (n + 255) / 256;
     const int fgrid = (n + RA_PARAMS_PER_BLOCK - 1) / RA_PARAMS_PER_BLOCK;
-    if (apply && c->nranks == 1 && fgrid <= 8192) {
-        // single GPU: reduction over CTAs / planes, norm, clip, Adam in one kernel
-        Span sp(c, DRIL_K_ADAM);
-        reduce_adam_kernel<<<fgrid, 1024, 0, c->stream>>>(p->gpart, grid, p->gpart_ctas, pd.gpack, p->flat2g, p->f2planes,
-                                                        pd.pack_fwd + pd.act_n, p->sq_part, p->ticket, aa);
-        DRIL_CUDA(cudaGetLastError());
-        return DRIL_OK;
-    }
+    const bool fused = apply && c->nranks == 1;
     {
-        Span sp(c, DRIL_K_GRAD_REDUCE);
-        grad_reduce_kernel<<<rgrid, 256, 0, c->stream>>>(p->gpart, grid, p->gpart_ctas, pd.gpack, p->flat2g, p->f2planes,
-                                                        pd.n_params, pd.pack_fwd + pd.act_n, p->g, p->stop_flag);
+        // reduction over CTAs / planes (+ norm, clip, Adam in the same kernel on a single GPU)
+        Span sp(c, fused ? DRIL_K_ADAM : DRIL_K_GRAD_REDUCE);
+        reduce_adam_kernel<<<fgrid, 1024, 0, c->stream>>>(p->gpart, grid, p->gpart_ctas, pd.gpack, p->flat2g, p->f2planes,
+                                                         pd.pack_fwd + pd.act_n, p->sq_part, p->ticket, aa, fused ? 1 : 0);
         DRIL_CUDA(cudaGetLastError());
     }
+    if (fused) return DRIL_OK;
     DRIL_TRY(allreduce_sum(c, p->g, (size_t)pd.n_params + 6, false));
     if (apply) {
         Span sp(c, DRIL_K_ADAM);

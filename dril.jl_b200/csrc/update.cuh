@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
                                                           int gpack, const int* __restrict__ flat2g,
                                                           const unsigned char* __restrict__ f2planes, int stats_off,
                                                           double* __restrict__ sq_part, unsigned int* __restrict__ ticket,
-                                                          AdamArgs a) {
+                                                          AdamArgs a, int do_adam) {
     __shared__ double scratch[32];
     __shared__ float s_red[RA_GROUPS][RA_PARAMS_PER_BLOCK + 1];
     __shared__ float s_f[2];
@@ -685,6 +685,7 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
         if (p < a.n_params) sq = (double)g * (double)g;
         __threadfence();                  // publish this thread's slice before the ticket
     }
+    if (!do_adam) return;                 // multi-GPU: NCCL allreduce of g, then adam_finalize_kernel
     sq = block_sum(sq, scratch);
     if (threadIdx.x == 0) {
         sq_part[blockIdx.x] = sq;

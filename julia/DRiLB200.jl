@@ -1,0 +1,296 @@
+# DRiLB200.jl — Julia host shim over libdril_b200.so (include/dril_b200.h).
+#
+# UNVERIFIED IN THIS REPO: the build image has no Julia toolchain (SURVEY.md §8c), so this file is
+# the binding a DRiL.jl maintainer would add, kept thin and mechanical: every method is one or two
+# `ccall`s.  The same ABI is exercised end-to-end from Python (dril.jl_b200/_lib.py, tests/).
+#
+# What it provides (dispatch contract of the reference, paths relative to DRiL.jl):
+#   CudaBatchedEnv <: AbstractParallelEnv      src/interfaces/environments.jl:39-157
+#   train!(agent, env::CudaBatchedEnv, alg::PPO, max_steps; callbacks)   src/algorithms/ppo.jl:100-325
+#   collect_rollout!(buf::DeviceRolloutBuffer, agent, alg, env::CudaBatchedEnv)  src/buffers/rollout_buffer.jl:46-90
+# Agent.train_state.parameters stays the source of truth: parameters are flattened in
+# ComponentVector order on the way in and copied back after train! so extract_policy,
+# predict_actions and save_policy_params_and_state keep working unchanged.
+module DRiLB200
+
+using DRiL
+using DRiL: AbstractParallelEnv, AbstractCallback, Agent, PPO, Box, Discrete
+using ComponentArrays: ComponentVector, getaxes
+using Random
+
+const LIB = get(ENV, "DRIL_B200_LIB", joinpath(@__DIR__, "..", "dril.jl_b200", "libdril_b200.so"))
+
+struct DrilError <: Exception
+    msg::String
+end
+last_error() = unsafe_string(ccall((:dril_last_error, LIB), Cstring, ()))
+check(status::Int32) = status == 0 ? nothing : throw(DrilError(last_error()))
+
+# ---- mirrors of the C structs ------------------------------------------------------------------
+struct NormCfg
+    training::Int32; norm_obs::Int32; norm_reward::Int32
+    clip_obs::Float32; clip_reward::Float32; gamma::Float32; epsilon::Float32
+end
+struct PPOHyper
+    gamma::Float32; gae_lambda::Float32; clip_range::Float32; clip_range_vf::Float32
+    ent_coef::Float32; vf_coef::Float32; max_grad_norm::Float32; target_kl::Float32
+    normalize_advantage::Int32; learning_rate::Float32
+    adam_beta1::Float32; adam_beta2::Float32; adam_eps::Float32
+end
+struct IterStats
+    entropy_loss::Float32; policy_loss::Float32; value_loss::Float32; approx_kl_div::Float32
+    clip_fraction::Float32; loss::Float32; explained_variance::Float32; grad_norm::Float32
+    learning_rate::Float32; entropy::Float32; ratio::Float32; rollout_ms::Float32; update_ms::Float32
+    n_minibatch_steps::Int32; kl_stopped::Int32; episodes::Int64
+    episode_return_sum::Float64; episode_length_sum::Float64
+end
+neg(x) = isnothing(x) ? -1.0f0 : Float32(x)
+PPOHyper(alg::PPO) = PPOHyper(alg.gamma, alg.gae_lambda, alg.clip_range, neg(alg.clip_range_vf), alg.ent_coef,
+    alg.vf_coef, neg(alg.max_grad_norm), neg(alg.target_kl), Int32(alg.normalize_advantage), alg.learning_rate,
+    0.9f0, 0.999f0, 1.0f-5)   # Optimisers.Adam(eta, (0.9, 0.999), 1e-5): src/algorithms/ppo.jl:64-66
+
+# ---- context -----------------------------------------------------------------------------------
+mutable struct Context
+    h::Ptr{Cvoid}
+    function Context(device::Integer = 0; seed::Integer = 0)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:dril_ctx_create, LIB), Int32, (Int32, UInt64, Ref{Ptr{Cvoid}}), device, seed, out))
+        ctx = new(out[])
+        finalizer(c -> ccall((:dril_ctx_destroy, LIB), Int32, (Ptr{Cvoid},), c.h), ctx)
+    end
+end
+const DEFAULT_CTX = Ref{Union{Nothing, Context}}(nothing)
+default_ctx() = (isnothing(DEFAULT_CTX[]) && (DEFAULT_CTX[] = Context()); DEFAULT_CTX[])
+
+# ---- batched env -------------------------------------------------------------------------------
+const ENV_KINDS = Dict(:cartpole => 0, :pendulum => 1, :synthetic => 2)
+
+"""
+    CudaBatchedEnv(kind, n_envs; max_steps, act_start, monitor_window, normalize)
+
+Device-resident replacement of `NormalizeWrapperEnv(MonitorWrapperEnv(MultiThreadedParallelEnv(envs)))`
+for `kind in (:cartpole, :pendulum, :synthetic)`.
+"""
+mutable struct CudaBatchedEnv <: AbstractParallelEnv
+    ctx::Context
+    h::Ptr{Cvoid}
+    kind::Symbol
+    n_envs::Int
+    obs_space::Box{Float32}
+    act_space::Union{Box{Float32}, Discrete{Int}}
+    monitor_window::Int
+    normalize::Union{Nothing, NormCfg}
+    terminated::Vector{Bool}
+    truncated::Vector{Bool}
+end
+
+function CudaBatchedEnv(kind::Symbol, n_envs::Integer; ctx = default_ctx(), max_steps = 0, obs_dim = 0, act_start = 1,
+        monitor_window = 0, normalize::Union{Nothing, NormCfg} = nothing, gid_offset = 0)
+    obs_space, act_space = if kind == :cartpole
+        hi = Float32[4.8, Inf32, 0.41887903, Inf32]
+        Box(-hi, hi), Discrete(2, act_start)
+    elseif kind == :pendulum
+        Box(Float32[-1, -1, -8], Float32[1, 1, 8]), Box(Float32[-2], Float32[2])
+    else
+        Box(-ones(Float32, obs_dim), ones(Float32, obs_dim)), Discrete(2, act_start)
+    end
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    normptr = isnothing(normalize) ? C_NULL : Ref(normalize)
+    GC.@preserve normptr check(ccall((:dril_env_create, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Int64, Int32, Int32, Int32, Int64, Ptr{NormCfg}, Int32, Ref{Ptr{Cvoid}}),
+        ctx.h, ENV_KINDS[kind], n_envs, max_steps, size(obs_space)[1], act_start, gid_offset,
+        isnothing(normalize) ? C_NULL : Base.unsafe_convert(Ptr{NormCfg}, normptr), monitor_window, out))
+    env = CudaBatchedEnv(ctx, out[], kind, n_envs, obs_space, act_space, monitor_window, normalize,
+        falses(n_envs), falses(n_envs))
+    finalizer(e -> ccall((:dril_env_destroy, LIB), Int32, (Ptr{Cvoid},), e.h), env)
+end
+
+DRiL.number_of_envs(env::CudaBatchedEnv) = env.n_envs
+DRiL.observation_space(env::CudaBatchedEnv) = env.obs_space
+DRiL.action_space(env::CudaBatchedEnv) = env.act_space
+DRiL.terminated(env::CudaBatchedEnv) = copy(env.terminated)
+DRiL.truncated(env::CudaBatchedEnv) = copy(env.truncated)
+DRiL.get_info(env::CudaBatchedEnv) = [Dict{String, Any}() for _ in 1:env.n_envs]
+DRiL.is_monitored(env::CudaBatchedEnv) = env.monitor_window > 0
+Random.seed!(env::CudaBatchedEnv, seed::Integer) =
+    (check(ccall((:dril_env_seed, LIB), Int32, (Ptr{Cvoid}, UInt64), env.h, seed)); env)
+
+function DRiL.reset!(env::CudaBatchedEnv)
+    check(ccall((:dril_env_reset, LIB), Int32, (Ptr{Cvoid},), env.h))
+    fill!(env.terminated, false); fill!(env.truncated, false)
+    return nothing
+end
+
+function DRiL.observe(env::CudaBatchedEnv)
+    D = size(env.obs_space)[1]
+    obs = Matrix{Float32}(undef, D, env.n_envs)          # C layout [n][D] == Julia (D, n) column-major
+    check(ccall((:dril_env_observe, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}), env.h, obs))
+    return [obs[:, i] for i in 1:env.n_envs]
+end
+
+function DRiL.act!(env::CudaBatchedEnv, actions::AbstractVector)
+    n, D = env.n_envs, size(env.obs_space)[1]
+    acts = env.act_space isa Discrete ? Int64.(actions) : reduce(hcat, [Float32.(vec(a)) for a in actions])
+    rewards = Vector{Float32}(undef, n); term = Vector{UInt8}(undef, n); trunc = Vector{UInt8}(undef, n)
+    tobs = Matrix{Float32}(undef, D, n); epr = Vector{Float32}(undef, n); epl = Vector{Int64}(undef, n)
+    check(ccall((:dril_env_step, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float32}, Ptr{UInt8}, Ptr{UInt8}, Ptr{Float32}, Ptr{Float32}, Ptr{Int64}),
+        env.h, acts, rewards, term, trunc, tobs, epr, epl))
+    env.terminated .= term .!= 0; env.truncated .= trunc .!= 0
+    infos = Vector{Dict{String, Any}}(undef, n)
+    for i in 1:n
+        d = Dict{String, Any}()
+        env.truncated[i] && (d["terminal_observation"] = tobs[:, i])
+        if env.monitor_window > 0 && (env.terminated[i] || env.truncated[i])
+            d["episode"] = Dict("r" => epr[i], "l" => Int(epl[i]))
+        end
+        infos[i] = d
+    end
+    return rewards, copy(env.terminated), copy(env.truncated), infos
+end
+
+function DRiL.log_stats(env::CudaBatchedEnv, logger::DRiL.AbstractTrainingLogger)
+    env.monitor_window > 0 || return nothing
+    r = Ref{Float32}(0); l = Ref{Float32}(0); nw = Ref{Int64}(0); tot = Ref{Int64}(0)
+    check(ccall((:dril_env_monitor_stats, LIB), Int32, (Ptr{Cvoid}, Ref{Float32}, Ref{Float32}, Ref{Int64}, Ref{Int64}),
+        env.h, r, l, nw, tot))
+    if nw[] > 0
+        DRiL.log_scalar!(logger, "env/ep_rew_mean", r[])
+        DRiL.log_scalar!(logger, "env/ep_len_mean", l[])
+    end
+    return nothing
+end
+
+# ---- device policy (one per Agent, cached in agent.aux-like side table) -------------------------
+mutable struct DevicePolicy
+    h::Ptr{Cvoid}
+    n_params::Int
+end
+const POLICIES = IdDict{Any, DevicePolicy}()
+
+function device_policy(agent::Agent, ctx::Context)
+    get!(POLICIES, agent) do
+        layer = agent.layer
+        as = DRiL.action_space(layer)
+        hidden = Int32[size(l.weight, 1) for l in values(agent.train_state.parameters.critic_head)][1:end-1]
+        obs_dim = prod(size(DRiL.observation_space(layer)))
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        if as isa Discrete
+            check(ccall((:dril_policy_create, LIB), Int32,
+                (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Int32, Int32, Int32, Ptr{Float32}, Ptr{Float32}, Ref{Ptr{Cvoid}}),
+                ctx.h, obs_dim, length(hidden), hidden, 0, as.n, as.start, C_NULL, C_NULL, out))
+        else
+            lo, hi = Float32.(vec(as.low)), Float32.(vec(as.high))
+            check(ccall((:dril_policy_create, LIB), Int32,
+                (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Int32, Int32, Int32, Ptr{Float32}, Ptr{Float32}, Ref{Ptr{Cvoid}}),
+                ctx.h, obs_dim, length(hidden), hidden, 1, length(lo), 0, lo, hi, out))
+        end
+        n = Ref{Int64}(0)
+        check(ccall((:dril_policy_num_params, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), out[], n))
+        DevicePolicy(out[], n[])
+    end
+end
+
+"Flatten Lux parameters in ComponentVector order (== layers/layer_lux.jl:4-52 NamedTuple order)."
+flat_params(agent::Agent) = Vector{Float32}(ComponentVector(agent.train_state.parameters))
+function push_params!(p::DevicePolicy, agent::Agent)
+    flat = flat_params(agent)
+    @assert length(flat) == p.n_params
+    check(ccall((:dril_policy_set_params, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int64), p.h, flat, length(flat)))
+end
+function pull_params!(agent::Agent, p::DevicePolicy)
+    flat = Vector{Float32}(undef, p.n_params)
+    check(ccall((:dril_policy_get_params, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int64), p.h, flat, length(flat)))
+    ax = getaxes(ComponentVector(agent.train_state.parameters))
+    ps = NamedTuple(ComponentVector(flat, ax))
+    agent.train_state = DRiL.Accessors.@set agent.train_state.parameters = ps
+    return agent
+end
+
+# ---- rollout buffer ------------------------------------------------------------------------------
+mutable struct DeviceRolloutBuffer
+    h::Ptr{Cvoid}
+    n_steps::Int
+    n_envs::Int
+end
+function DeviceRolloutBuffer(ctx::Context, env::CudaBatchedEnv, n_steps::Integer)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    as = env.act_space
+    check(ccall((:dril_buffer_create, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int32, Int32, Int32, Ref{Ptr{Cvoid}}),
+        ctx.h, n_steps, env.n_envs, size(env.obs_space)[1], as isa Discrete ? 0 : 1, as isa Discrete ? 1 : prod(size(as)), out))
+    b = DeviceRolloutBuffer(out[], n_steps, env.n_envs)
+    finalizer(x -> ccall((:dril_buffer_destroy, LIB), Int32, (Ptr{Cvoid},), x.h), b)
+end
+Base.length(b::DeviceRolloutBuffer) = b.n_steps * b.n_envs
+
+"collect_rollout!(buffer, agent, alg, env) -> (fps, success)  (src/buffers/rollout_buffer.jl:46-90)"
+function DRiL.collect_rollout!(buf::DeviceRolloutBuffer, agent::Agent, alg::PPO, env::CudaBatchedEnv; callbacks = nothing)
+    p = device_policy(agent, env.ctx)
+    push_params!(p, agent)
+    fps = Ref{Float32}(0)
+    check(ccall((:dril_rollout_collect, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Float32}),
+        env.h, p.h, buf.h, C_NULL, fps))
+    check(ccall((:dril_gae, LIB), Int32, (Ptr{Cvoid}, Float32, Float32), buf.h, alg.gamma, alg.gae_lambda))
+    return fps[], true
+end
+
+"""
+    train!(agent, env::CudaBatchedEnv, alg::PPO, max_steps; callbacks) -> (learn_stats, to)
+
+Same contract as src/algorithms/ppo.jl:100-325: returns the 10-field `learn_stats` NamedTuple and a
+TimerOutput; callbacks get a `Dict{Symbol,Any}` with the keys pinned by test/test_callbacks.jl:24-38;
+a callback returning `false` aborts and `train!` returns `nothing`; `add_step!` once per rollout.
+"""
+function DRiL.train!(agent::Agent, env::CudaBatchedEnv, alg::PPO{T}, max_steps::Int;
+        ad_type = nothing, callbacks::Union{Vector{<:AbstractCallback}, Nothing} = nothing) where {T}
+    to = DRiL.TimerOutput()
+    n_steps, n_envs = alg.n_steps, env.n_envs
+    roll_buffer = DeviceRolloutBuffer(env.ctx, env, n_steps)
+    iterations = max_steps ÷ (n_steps * n_envs)
+    total_steps = iterations * n_steps * n_envs
+    p = device_policy(agent, env.ctx)
+    push_params!(p, agent)
+    keys10 = (:entropy_losses, :policy_losses, :value_losses, :approx_kl_divs, :clip_fractions, :losses,
+        :explained_variances, :fps, :grad_norms, :learning_rates)
+    stats = Dict(k => Float32[] for k in keys10)
+    total_fps = stats[:fps]
+    shuffle_seed = rand(agent.rng, UInt64)
+    epoch_counter = UInt64(0)
+    hook(f, loc) = isnothing(callbacks) || all(c -> f(c, loc), callbacks)
+    hook(DRiL.on_training_start, Base.@locals) || return nothing
+    for i in 1:iterations
+        learning_rate = alg.learning_rate
+        hook(DRiL.on_rollout_start, Base.@locals) || return nothing
+        hyper = Ref(PPOHyper(alg))
+        check(ccall((:dril_ppo_iteration_async, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{PPOHyper}, Int32, Int64, UInt64, UInt64),
+            env.h, p.h, roll_buffer.h, hyper, alg.epochs, alg.batch_size, shuffle_seed, epoch_counter))
+        epoch_counter += alg.epochs
+        st = Ref{IterStats}()
+        check(ccall((:dril_iteration_result, LIB), Int32, (Ptr{Cvoid}, Ref{IterStats}), p.h, st))
+        s = st[]
+        fps = Float32(n_steps * n_envs / (s.rollout_ms * 1.0f-3))
+        push!(total_fps, fps)
+        DRiL.add_step!(agent, n_steps * n_envs)
+        DRiL.increment_step!(agent.logger, n_steps * n_envs)
+        DRiL.log_scalar!(agent.logger, "env/fps", fps)
+        DRiL.log_stats(env, agent.logger)
+        hook(DRiL.on_rollout_end, Base.@locals) || return nothing
+        push!(stats[:learning_rates], learning_rate); push!(stats[:explained_variances], s.explained_variance)
+        push!(stats[:entropy_losses], s.entropy_loss); push!(stats[:policy_losses], s.policy_loss)
+        push!(stats[:value_losses], s.value_loss); push!(stats[:approx_kl_divs], s.approx_kl_div)
+        push!(stats[:clip_fractions], s.clip_fraction); push!(stats[:losses], s.loss); push!(stats[:grad_norms], s.grad_norm)
+        for (k, v) in ("train/entropy_loss" => s.entropy_loss, "train/explained_variance" => s.explained_variance,
+            "train/policy_loss" => s.policy_loss, "train/value_loss" => s.value_loss, "train/approx_kl_div" => s.approx_kl_div,
+            "train/clip_fraction" => s.clip_fraction, "train/loss" => s.loss, "train/grad_norm" => s.grad_norm,
+            "train/learning_rate" => learning_rate)
+            DRiL.log_scalar!(agent.logger, k, v)
+        end
+    end
+    pull_params!(agent, p)
+    learn_stats = NamedTuple{keys10}(Tuple(stats[k] for k in keys10))
+    hook(DRiL.on_training_end, Base.@locals) || return nothing
+    return learn_stats, to
+end
+
+end # module
