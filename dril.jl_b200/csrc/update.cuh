@@ -656,8 +656,8 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
                                                           const unsigned char* __restrict__ f2planes, int stats_off,
                                                           double* __restrict__ sq_part, unsigned int* __restrict__ ticket,
                                                           AdamArgs a, int do_adam) {
-    __shared__ double scratch[32];
     __shared__ float s_red[RA_GROUPS][RA_PARAMS_PER_BLOCK + 1];
+    __shared__ double scratch[32];
     __shared__ float s_f[2];
     __shared__ int s_i;
     __shared__ unsigned int s_ticket;
@@ -668,36 +668,51 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
     if (p < a.n_params + 6) {
         const int idx = p < a.n_params ? flat2g[p] : stats_off + (p - a.n_params);
         const int planes = p < a.n_params ? f2planes[p] : 1;
-        const int total = planes * n_cta;
-        for (int i = grp; i < total; i += RA_GROUPS) {
-            const int pl = i / n_cta, c = i - pl * n_cta;
-            part += gpart[((size_t)pl * half_stride + c) * gpack + idx];
+        for (int pl = 0; pl < planes; ++pl) {
+            const float* base = gpart + (size_t)pl * half_stride * gpack + idx;
+            // up to 8 independent loads in flight per thread (n_cta <= 8 * RA_GROUPS)
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = grp + j * RA_GROUPS;
+                v[j] = c < n_cta ? base[(size_t)c * gpack] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) part += v[j];
+            for (int c = grp + 8 * RA_GROUPS; c < n_cta; c += RA_GROUPS) part += base[(size_t)c * gpack];
         }
     }
     s_red[grp][lane] = part;
     __syncthreads();
-    double sq = 0.0;
-    if (grp == 0 && p < a.n_params + 6) {
-        float g = 0.f;
+    if (grp == 0) {
+        double sq = 0.0;
+        if (p < a.n_params + 6) {
+            float g = 0.f;
 #pragma unroll
-        for (int j = 0; j < RA_GROUPS; ++j) g += s_red[j][lane];
-        a.g[p] = g;
-        if (p < a.n_params) sq = (double)g * (double)g;
-        __threadfence();                  // publish this thread's slice before the ticket
+            for (int j = 0; j < RA_GROUPS; ++j) g += s_red[j][lane];
+            a.g[p] = g;
+            if (p < a.n_params) sq = (double)g * (double)g;
+            __threadfence();              // publish this thread's slice before the ticket
+        }
+        if (do_adam) {
+            sq = warp_sum(sq);
+            if (lane == 0) {
+                sq_part[blockIdx.x] = sq;
+                __threadfence();
+                s_ticket = atomicAdd(ticket, 1u);
+            }
+        }
     }
     if (!do_adam) return;                 // multi-GPU: NCCL allreduce of g, then adam_finalize_kernel
-    sq = block_sum(sq, scratch);
-    if (threadIdx.x == 0) {
-        sq_part[blockIdx.x] = sq;
-        __threadfence();
-        s_ticket = atomicAdd(ticket, 1u);
-    }
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
     __threadfence();
     if (threadIdx.x == 0) *ticket = 0u;
+    // global sum of squares: one load per thread + fixed-order block reduction (a per-thread serial
+    // loop over gridDim.x L2 round trips was the critical path of this kernel)
     double q = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) q += sq_part[b];     // fixed order; every thread computes the same value
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) q += sq_part[b];
+    q = block_sum(q, scratch);
     adam_apply(a, q, s_f, &s_i);
 }
 
