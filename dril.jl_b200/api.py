@@ -318,8 +318,19 @@ def train(agent, env, alg, max_steps, callbacks=None, sync_every_iteration=True)
     to = {"setup": 0.0, "training_loop": 0.0, "collect_rollout_ms": 0.0, "update_ms": 0.0}
     t_setup = time.time()
     n_steps, n_envs = alg.n_steps, env.number_of_envs()
-    roll_buffer = RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, n_steps, n_envs,
-                                ctx=agent.ctx)
+    # the device buffer is kept on the agent between calls (the reference allocates per train! call;
+    # device allocation is the expensive part here) and is fully overwritten by every rollout
+    key = (n_steps, n_envs, repr(env.observation_space()), repr(env.action_space()))
+    cache = agent.__dict__.setdefault("_roll_buffers", {})
+    roll_buffer = cache.get(key)
+    if roll_buffer is None or roll_buffer.h is None:
+        for old in cache.values():
+            old.close()
+        cache.clear()
+        roll_buffer = RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, n_steps, n_envs,
+                                    ctx=agent.ctx)
+        cache[key] = roll_buffer
+    roll_buffer.gamma, roll_buffer.gae_lambda = float(alg.gamma), float(alg.gae_lambda)
     iterations = max_steps // (n_steps * n_envs)
     total_steps = iterations * n_steps * n_envs
     learn = {k: [] for k in LEARN_STATS_KEYS}
@@ -378,7 +389,6 @@ def train(agent, env, alg, max_steps, callbacks=None, sync_every_iteration=True)
     learn_stats = {k: np.asarray(v, dtype=np.float32) for k, v in learn.items()}
     if not _hook(callbacks, "on_training_end", dict(locals())):
         return None
-    roll_buffer.close()
     return learn_stats, to
 
 

@@ -109,6 +109,7 @@ struct dril_ctx {
 
 struct dril_buffer {
     dril_ctx* ctx;
+    void* slab = nullptr;
     BufDev d;
     int act_elems;  // per-sample action elements
 };
@@ -354,21 +355,25 @@ extern "C" int32_t dril_buffer_create(dril_ctx* c, int64_t T, int64_t N, int32_t
     b->d.act_dim = act_kind == DRIL_ACT_DISCRETE ? 1 : act_dim;
     b->act_elems = b->d.act_dim;
     size_t tn = (size_t)T * N;
-    DRIL_TRY(dmalloc(&b->d.obs, tn * obs_dim));
-    DRIL_CUDA(cudaMalloc(&b->d.actions, tn * b->act_elems * 4));
-    DRIL_TRY(dmalloc(&b->d.rewards, tn)); DRIL_TRY(dmalloc(&b->d.values, tn)); DRIL_TRY(dmalloc(&b->d.logprobs, tn));
-    DRIL_TRY(dmalloc(&b->d.advantages, tn)); DRIL_TRY(dmalloc(&b->d.returns, tn)); DRIL_TRY(dmalloc(&b->d.boot, tn));
-    DRIL_TRY(dmalloc(&b->d.last_values, (size_t)N)); DRIL_TRY(dmalloc(&b->d.episode_r, tn));
-    DRIL_TRY(dmalloc(&b->d.episode_l, tn)); DRIL_TRY(dmalloc(&b->d.flags, tn)); DRIL_TRY(dmalloc(&b->d.done_count, (size_t)T));
+    // one slab (one cudaMalloc + one memset) carved into the fields, each 256-byte aligned
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0, o_obs = off; off += al(tn * obs_dim * 4);
+    size_t o_act = off; off += al(tn * b->act_elems * 4);
+    size_t o_f[7];
+    for (int i = 0; i < 7; ++i) { o_f[i] = off; off += al(tn * 4); }
+    size_t o_last = off; off += al((size_t)N * 4);
+    size_t o_epl = off; off += al(tn * 4);
+    size_t o_flags = off; off += al(tn);
+    size_t o_dc = off; off += al((size_t)T * 4);
+    DRIL_CUDA(cudaMalloc(&b->slab, off));
+    char* base = (char*)b->slab;
+    b->d.obs = (float*)(base + o_obs); b->d.actions = base + o_act;
+    b->d.rewards = (float*)(base + o_f[0]); b->d.values = (float*)(base + o_f[1]); b->d.logprobs = (float*)(base + o_f[2]);
+    b->d.advantages = (float*)(base + o_f[3]); b->d.returns = (float*)(base + o_f[4]); b->d.boot = (float*)(base + o_f[5]);
+    b->d.episode_r = (float*)(base + o_f[6]); b->d.last_values = (float*)(base + o_last); b->d.episode_l = (int*)(base + o_epl);
+    b->d.flags = (unsigned char*)(base + o_flags); b->d.done_count = (int*)(base + o_dc);
     // reset!(rollout_buffer) zero-fills (rollout_buffer.jl:35-44)
-    DRIL_CUDA(cudaMemsetAsync(b->d.obs, 0, tn * obs_dim * 4, c->stream));
-    DRIL_CUDA(cudaMemsetAsync(b->d.actions, 0, tn * b->act_elems * 4, c->stream));
-    float* fz[] = {b->d.rewards, b->d.values, b->d.logprobs, b->d.advantages, b->d.returns, b->d.boot, b->d.episode_r};
-    for (float* p : fz) DRIL_CUDA(cudaMemsetAsync(p, 0, tn * 4, c->stream));
-    DRIL_CUDA(cudaMemsetAsync(b->d.last_values, 0, (size_t)N * 4, c->stream));
-    DRIL_CUDA(cudaMemsetAsync(b->d.episode_l, 0, tn * 4, c->stream));
-    DRIL_CUDA(cudaMemsetAsync(b->d.flags, 0, tn, c->stream));
-    DRIL_CUDA(cudaMemsetAsync(b->d.done_count, 0, (size_t)T * 4, c->stream));
+    DRIL_CUDA(cudaMemsetAsync(b->slab, 0, off, c->stream));
     DRIL_CUDA(cudaStreamSynchronize(c->stream));
     *out = b;
     return DRIL_OK;
@@ -377,9 +382,7 @@ extern "C" int32_t dril_buffer_destroy(dril_buffer* b) {
     if (!b) return DRIL_OK;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    void* ps[] = {b->d.obs, b->d.actions, b->d.rewards, b->d.values, b->d.logprobs, b->d.advantages, b->d.returns,
-                  b->d.boot, b->d.last_values, b->d.episode_r, b->d.episode_l, b->d.flags, b->d.done_count};
-    for (void* p : ps) cudaFree(p);
+    cudaFree(b->slab);
     delete b;
     return DRIL_OK;
 }

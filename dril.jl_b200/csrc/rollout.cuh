@@ -619,13 +619,24 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_fast_kernel(const __grid
             const int k0 = oks * Kc, k1 = min(Kout, k0 + Kc);
             const float* wa = Wbase + Lao.pw_off;
             const float* wc = Wbase + Lco.pw_off;
-            for (int k = k0; k < k1; ++k) {
-                if (net_mask & 1) {
-                    const float h = ha[(size_t)k * ld + oe];
-#pragma unroll
-                    for (int j = 0; j < RF_MAX_OUT - 1; ++j) if (j < A) acc[j] = fmaf(h, wa[k * Lao.Np + j], acc[j]);
+            if (A <= 2) {          // the common case (CartPole: 2 actions, Pendulum: 1 mean): no predicated-off work
+                for (int k = k0; k < k1; ++k) {
+                    if (net_mask & 1) {
+                        const float h = ha[(size_t)k * ld + oe];
+                        acc[0] = fmaf(h, wa[k * Lao.Np], acc[0]);
+                        acc[1] = fmaf(h, wa[k * Lao.Np + 1], acc[1]);     // padded column (zero weights) when A == 1
+                    }
+                    if (net_mask & 2) acc[RF_MAX_OUT - 1] = fmaf(hc[(size_t)k * ld + oe], wc[k * Lco.Np], acc[RF_MAX_OUT - 1]);
                 }
-                if (net_mask & 2) acc[RF_MAX_OUT - 1] = fmaf(hc[(size_t)k * ld + oe], wc[k * Lco.Np], acc[RF_MAX_OUT - 1]);
+            } else {
+                for (int k = k0; k < k1; ++k) {
+                    if (net_mask & 1) {
+                        const float h = ha[(size_t)k * ld + oe];
+#pragma unroll
+                        for (int j = 0; j < RF_MAX_OUT - 1; ++j) if (j < A) acc[j] = fmaf(h, wa[k * Lao.Np + j], acc[j]);
+                    }
+                    if (net_mask & 2) acc[RF_MAX_OUT - 1] = fmaf(hc[(size_t)k * ld + oe], wc[k * Lco.Np], acc[RF_MAX_OUT - 1]);
+                }
             }
 #pragma unroll
             for (int j = 0; j < RF_MAX_OUT - 1; ++j) if (j < A) sPart[((size_t)oks * RF_MAX_OUT + j) * ld + oe] = acc[j];

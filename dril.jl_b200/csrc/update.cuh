@@ -99,6 +99,13 @@ struct LossArgs {
     int small_splits;                    // sample-range splits of the 4x4 dW tiles (planes 0..small_splits-1)
 };
 
+// fire-and-forget vector reduction into this CTA's own gradient partial (no load on the critical path;
+// the partial is private to the CTA, so there is no contention and the order of the adds per address is
+// the program order of one thread => deterministic)
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // dW[k][n] (+)= sum_m Ain[k][m] * dZ[n][m] for the 4 interleaved rows k = kt + kstride*i and the
 // 4 columns n0..n0+3; accumulated into this CTA's packed partial.
 __device__ __forceinline__ void dense_tile_dw(const float* __restrict__ Ain, const float* __restrict__ dZ, int m_begin,
@@ -132,8 +139,7 @@ __device__ __forceinline__ void dense_tile_dw(const float* __restrict__ Ain, con
     for (int i = 0; i < 4; ++i) {
         float4* g = reinterpret_cast<float4*>(gW + (size_t)(kt + i * kstride) * Np + n0);
         float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        if (!first) { float4 o = *g; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-        *g = v;
+        if (first) *g = v; else red_add_v4(reinterpret_cast<float*>(g), v);
     }
 }
 
@@ -170,12 +176,8 @@ __device__ __forceinline__ void dense_tile_dw8(const float* __restrict__ Ain, co
         float4* g = reinterpret_cast<float4*>(gW + (size_t)(kt + i * kstride) * Np + n0);
         float4 v0 = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         float4 v1 = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-        if (!first) {
-            float4 o0 = g[0], o1 = g[1];
-            v0.x += o0.x; v0.y += o0.y; v0.z += o0.z; v0.w += o0.w;
-            v1.x += o1.x; v1.y += o1.y; v1.z += o1.z; v1.w += o1.w;
-        }
-        g[0] = v0; g[1] = v1;
+        if (first) { g[0] = v0; g[1] = v1; }
+        else { red_add_v4(reinterpret_cast<float*>(g), v0); red_add_v4(reinterpret_cast<float*>(g + 1), v1); }
     }
 }
 
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
                             s += (d.x + d.y) + (d.z + d.w);
                         }
                         float* g = gp + Ld.pb_off + u;
-                        *g = first ? s : *g + s;
+                        if (first) *g = s; else atomicAdd(g, s);
                     }
                 }
             }

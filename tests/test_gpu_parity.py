@@ -278,6 +278,39 @@ def test_fused_rollout_replay(D, kind, n, T, ms, monitor, norm):
         buf.close()
 
 
+@pytest.mark.parametrize("obs_dim,n,T,norm", [(10, 300, 20, False), (64, 130, 12, True), (5, 2000, 8, False)])
+def test_fused_rollout_synthetic_env(D, obs_dim, n, T, norm):
+    """Rollout-sweep env through the general (cooperative) rollout kernel, replayed actions."""
+    ms = 7
+    env = D.CudaBatchedEnv("synthetic", n, obs_dim=obs_dim, max_steps=ms, seed=4, monitor_window=100,
+                           normalize=D.NormalizeConfig() if norm else None)
+    oenv = OE.MonitorWrapper(OE.ParallelEnv(OE.SyntheticBatch(n, obs_dim, seed=4, max_steps=ms)))
+    if norm:
+        oenv = OE.NormalizeWrapper(oenv, obs_dim)
+    spec = OP.PolicySpec(obs_dim, [32, 32], "discrete", 2, act_start=1)
+    rng = np.random.default_rng(2)
+    flat = (OP.init_params(spec, seed=1) + rng.normal(size=spec.n_params()).astype(f32) * 0.05).astype(f32)
+    forced = rng.integers(1, 3, (T, n))
+    layer = D.ActorCriticLayer(env.observation_space(), env.action_space(), hidden_dims=[32, 32])
+    alg = D.PPO(n_steps=T)
+    agent = D.Agent(layer, alg, rng=np.random.default_rng(0))
+    agent.set_parameters(flat)
+    buf = D.RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, T, n)
+    D.collect_rollout(buf, agent, alg, env, forced_actions=forced)
+    ob = OO.collect_rollout_timemajor(oenv, spec, flat, T, forced_actions=forced)
+    te, tr = _flags(buf)
+    np.testing.assert_array_equal(te, ob["term"])
+    np.testing.assert_array_equal(tr, ob["trunc"])
+    tol = dict(rtol=3e-5, atol=3e-5)
+    np.testing.assert_allclose(buf.download("obs"), ob["obs"], **tol)
+    np.testing.assert_allclose(buf.download("rewards"), ob["rewards"], **tol)
+    np.testing.assert_allclose(buf.download("values"), ob["values"], **tol)
+    np.testing.assert_allclose(np.where(tr, buf.download("boot"), 0), ob["boot"], **tol)
+    np.testing.assert_allclose(buf.download("last_values"), ob["last_values"], **tol)
+    assert tr.any() and te.any() if n >= 300 else tr.any()
+    buf.close()
+
+
 def test_fused_rollout_sampling_consistency(D):
     """Sampling mode: stored logprobs/values equal evaluate_actions on the stored (obs, actions)
     (test/test_buffers.jl:3-27,166-214) and actions follow the Philox stream."""
