@@ -140,6 +140,17 @@ def run_ours(args):
     batch = n_steps * n_envs // N_MINIBATCHES                      # per-rank minibatch; global = batch * world
     alg = D.PPO(n_steps=n_steps, batch_size=batch, epochs=EPOCHS)
     agent = D.Agent(layer, alg, rng=np.random.default_rng(0), ctx=ctx)   # same init on every rank
+    comm = "single GPU"
+    if world > 1:
+        comm = "NCCL allreduce of the flat gradient per minibatch"
+        if os.environ.get("DRIL_NO_P2P", "0") != "1":
+            def all_gather(b):
+                out = [None] * world
+                dist.all_gather_object(out, b)
+                return out
+            ctx.comm_p2p_setup(all_gather, agent.device.n_params + 8)
+            comm = ("one-shot NVLink peer-memory allreduce of the flat gradient fused into the reduce/Adam kernels "
+                    "(NCCL only for the per-update advantage moments)")
     buf = D.RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, n_steps, n_envs, ctx=ctx)
     import ctypes as C
     from dril_b200 import _lib as L
@@ -261,7 +272,7 @@ def run_ours(args):
         "config": {"workload": w["name"], "epochs": EPOCHS, "minibatches_per_epoch": N_MINIBATCHES, "batch_size_per_gpu": batch,
                    "env_steps_per_step_per_gpu": steps_per_iter, "adam_steps_per_step": EPOCHS * N_MINIBATCHES,
                    "l2": "flushed: 256 MB memset on the stream before every timed step (inside the timed region)",
-                   "parallelism": f"dp{world} over envs, NCCL allreduce of the flat gradient per minibatch" if world > 1 else "single GPU"},
+                   "parallelism": f"dp{world} over envs, {comm}" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "dril_b200.train (train!): host parameters in, per-iteration learn_stats + final parameters out, wall clock"},
         "gpu_launches": int(launches),

@@ -56,6 +56,8 @@ PROTOTYPES = {
     "dril_comm_unique_id": [P],
     "dril_comm_init": [P, c_i32, c_i32, P],
     "dril_comm_destroy": [P],
+    "dril_comm_p2p_export": [P, c_i64, P],
+    "dril_comm_p2p_import": [P, P],
     "dril_env_create": [P, c_i32, c_i64, c_i32, c_i32, c_i32, c_i64, C.POINTER(NormCfg), c_i32, C.POINTER(P)],
     "dril_env_destroy": [P],
     "dril_env_seed": [P, c_u64],

@@ -72,6 +72,16 @@ class Context:
         L.check(self.lib.dril_comm_init(self.h, rank, nranks, buf))
         self.rank, self.nranks = rank, nranks
 
+    def comm_p2p_setup(self, all_gather, n_slots):
+        """Peer-memory gradient allreduce: export this rank's region, exchange the IPC handles with
+        `all_gather(bytes) -> list[bytes]` (rank order), import the peers' regions."""
+        buf = (C.c_uint8 * 64)()
+        L.check(self.lib.dril_comm_p2p_export(self.h, int(n_slots), buf))
+        handles = all_gather(bytes(buf))
+        assert len(handles) == self.nranks
+        blob = (C.c_uint8 * (64 * self.nranks)).from_buffer_copy(b"".join(handles))
+        L.check(self.lib.dril_comm_p2p_import(self.h, blob))
+
     @staticmethod
     def comm_unique_id():
         lib = L.load()

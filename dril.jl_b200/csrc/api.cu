@@ -103,6 +103,11 @@ struct dril_ctx {
     nccl_comm comm = nullptr;
     int rank = 0, nranks = 1;
     cudaEvent_t user_ev[16] = {nullptr};
+    // peer-memory allreduce (CUDA IPC)
+    void* p2p_region = nullptr;
+    void* p2p_peer_base[DRIL_MAX_RANKS] = {nullptr};
+    P2PDev p2p;
+    bool p2p_enabled = false;
     void* l2_scratch = nullptr;
     size_t l2_bytes = 0;
 };
@@ -329,7 +334,53 @@ extern "C" int32_t dril_comm_init(dril_ctx* c, int32_t rank, int32_t nranks, con
 extern "C" int32_t dril_comm_destroy(dril_ctx* c) {
     DRIL_REQUIRE(c, "ctx is NULL");
     if (c->comm) { cudaStreamSynchronize(c->stream); g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
+    if (c->p2p_enabled) {
+        for (int r = 0; r < c->nranks; ++r) if (r != c->rank && c->p2p_peer_base[r]) cudaIpcCloseMemHandle(c->p2p_peer_base[r]);
+        c->p2p_enabled = false;
+    }
     c->rank = 0; c->nranks = 1;
+    return DRIL_OK;
+}
+#define P2P_HDR_BYTES 256   // [0] flag (u64), [8] seq (u64), [16] err (int)
+extern "C" int32_t dril_comm_p2p_export(dril_ctx* c, int64_t n_slots, uint8_t handle_out[64]) {
+    DRIL_REQUIRE(c && handle_out && n_slots >= 1, "bad p2p arguments");
+    DRIL_REQUIRE(c->nranks >= 1 && c->nranks <= DRIL_MAX_RANKS, "p2p allreduce supports up to %d ranks", DRIL_MAX_RANKS);
+    DRIL_CUDA(cudaSetDevice(c->device));
+    if (c->p2p_region) { cudaFree(c->p2p_region); c->p2p_region = nullptr; c->p2p_enabled = false; }
+    size_t slots = ((size_t)n_slots + 63) & ~(size_t)63;
+    size_t bytes = P2P_HDR_BYTES + 2 * slots * sizeof(float);
+    DRIL_CUDA(cudaMalloc(&c->p2p_region, bytes));
+    DRIL_CUDA(cudaMemset(c->p2p_region, 0, bytes));
+    memset(&c->p2p, 0, sizeof(c->p2p));
+    c->p2p.n_slots = (int)slots;
+    cudaIpcMemHandle_t h;
+    DRIL_CUDA(cudaIpcGetMemHandle(&h, c->p2p_region));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle_out, &h, 64);
+    return DRIL_OK;
+}
+extern "C" int32_t dril_comm_p2p_import(dril_ctx* c, const uint8_t* handles) {
+    DRIL_REQUIRE(c && handles && c->p2p_region, "dril_comm_p2p_export must be called first");
+    DRIL_CUDA(cudaSetDevice(c->device));
+    char* local = (char*)c->p2p_region;
+    for (int r = 0; r < c->nranks; ++r) {
+        void* base = nullptr;
+        if (r == c->rank) base = c->p2p_region;
+        else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + 64 * r, 64);
+            DRIL_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        }
+        c->p2p_peer_base[r] = base;
+        c->p2p.peer_flag[r] = (const volatile unsigned long long*)base;
+        c->p2p.peer_gbuf[r] = (const float*)((char*)base + P2P_HDR_BYTES);
+    }
+    c->p2p.local_flag = (volatile unsigned long long*)local;
+    c->p2p.local_seq = (unsigned long long*)(local + 8);
+    c->p2p.err = (int*)(local + 16);
+    c->p2p.local_gbuf = (float*)(local + P2P_HDR_BYTES);
+    c->p2p.nranks = c->nranks; c->p2p.rank = c->rank;
+    c->p2p_enabled = true;
     return DRIL_OK;
 }
 static int32_t allreduce_sum(dril_ctx* c, void* buf, size_t count, bool is_double) {
@@ -1219,14 +1270,26 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
     const int n = pd.n_params + 6;
     const int fgrid = (n + RA_PARAMS_PER_BLOCK - 1) / RA_PARAMS_PER_BLOCK;
     const bool fused = apply && c->nranks == 1;
+    const bool p2p = apply && c->nranks > 1 && c->p2p_enabled && n <= c->p2p.n_slots;
     {
-        // reduction over CTAs / planes (+ norm, clip, Adam in the same kernel on a single GPU)
+        // reduction over CTAs / planes (+ norm, clip, Adam in the same kernel on a single GPU; + publication
+        // of this rank's gradient to its peers on the peer-memory path)
         Span sp(c, fused ? DRIL_K_ADAM : DRIL_K_GRAD_REDUCE);
         reduce_adam_kernel<<<fgrid, 1024, 0, c->stream>>>(p->gpart, grid, p->gpart_ctas, pd.gpack, p->flat2g, p->f2planes,
-                                                         pd.pack_fwd + pd.act_n, p->sq_part, p->ticket, aa, fused ? 1 : 0);
+                                                         pd.pack_fwd + pd.act_n, p->sq_part, p->ticket, aa,
+                                                         fused ? 1 : (p2p ? 2 : 0), p2p ? c->p2p.local_gbuf : nullptr,
+                                                         p2p ? c->p2p.n_slots : 0, p2p ? c->p2p.local_seq : nullptr,
+                                                         p2p ? c->p2p.local_flag : nullptr);
         DRIL_CUDA(cudaGetLastError());
     }
     if (fused) return DRIL_OK;
+    if (p2p) {
+        // cross-rank sum over NVLink peer memory + norm, clip, Adam
+        Span sp(c, DRIL_K_ALLREDUCE);
+        p2p_sum_adam_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->p2p, p->sq_part, p->ticket, aa);
+        DRIL_CUDA(cudaGetLastError());
+        return DRIL_OK;
+    }
     DRIL_TRY(allreduce_sum(c, p->g, (size_t)pd.n_params + 6, false));
     if (apply) {
         Span sp(c, DRIL_K_ADAM);
@@ -1258,31 +1321,37 @@ static int32_t update_async(dril_policy* p, dril_buffer* b, const dril_ppo_hyper
     LossLaunch ll;
     DRIL_TRY(plan_loss(p, &ll));
     const int bpm = (int)std::max<long long>(1, std::min<long long>(64, (std::min<long long>(batch_size, n_total) + 2047) / 2048));
-    DRIL_TRY(ensure_mbstats(p, n_mb, bpm));
     DRIL_CUDA(cudaMemsetAsync(p->iter_acc, 0, 12 * 8, c->stream));   // [12],[13] carry beta^t across iterations
     DRIL_CUDA(cudaMemsetAsync(p->stop_flag, 0, 4, c->stream));
-    for (int epoch = 0; epoch < epochs; ++epoch) {
-        FeistelKey fk = make_feistel(n_total, epoch_counter + epoch, c->rank, shuffle_seed);
+    // minibatch advantage moments of up to DRIL_MAX_EPOCHS_BATCHED epochs per launch / allreduce
+    for (int e0 = 0; e0 < epochs; e0 += DRIL_MAX_EPOCHS_BATCHED) {
+        const int ne = std::min(DRIL_MAX_EPOCHS_BATCHED, epochs - e0);
+        DRIL_TRY(ensure_mbstats(p, n_mb * ne, bpm));
+        FeistelKeys fks;
+        for (int e = 0; e < ne; ++e) fks.k[e] = make_feistel(n_total, epoch_counter + e0 + e, c->rank, shuffle_seed);
+        for (int e = ne; e < DRIL_MAX_EPOCHS_BATCHED; ++e) fks.k[e] = fks.k[0];
         if (hp.normalize_advantage) {
             {
                 Span sp(c, DRIL_K_ADV_STATS);
-                adv_stats_kernel<<<dim3(bpm, n_mb), 256, 0, c->stream>>>(b->d.advantages, n_total, batch_size, fk, 0, p->adv_partial);
+                adv_stats_kernel<<<dim3(bpm, n_mb, ne), 256, 0, c->stream>>>(b->d.advantages, n_total, batch_size, fks, 0, p->adv_partial);
                 DRIL_CUDA(cudaGetLastError());
             }
             {
                 Span sp(c, DRIL_K_ADV_STATS);
-                adv_stats_finalize_kernel<<<(n_mb * 2 + 127) / 128, 128, 0, c->stream>>>(p->adv_partial, bpm, n_mb, p->mbstats);
+                adv_stats_finalize_kernel<<<(n_mb * ne * 2 + 127) / 128, 128, 0, c->stream>>>(p->adv_partial, bpm, n_mb * ne, p->mbstats);
                 DRIL_CUDA(cudaGetLastError());
             }
-            DRIL_TRY(allreduce_sum(c, p->mbstats, (size_t)n_mb * 2, true));
+            DRIL_TRY(allreduce_sum(c, p->mbstats, (size_t)n_mb * ne * 2, true));
         }
-        for (int i = 0; i < n_mb; ++i) {
-            Minibatch mb;
-            mb.n_total = n_total; mb.start = (long long)i * batch_size;
-            mb.count = std::min<long long>(batch_size, n_total - mb.start);
-            mb.global_count = (double)mb.count * c->nranks;
-            mb.fk = fk; mb.identity = 0;
-            DRIL_TRY(minibatch_step(p, b->d, mb, p->mbstats + 2 * i, hp, ll, true, 1));
+        for (int e = 0; e < ne; ++e) {
+            for (int i = 0; i < n_mb; ++i) {
+                Minibatch mb;
+                mb.n_total = n_total; mb.start = (long long)i * batch_size;
+                mb.count = std::min<long long>(batch_size, n_total - mb.start);
+                mb.global_count = (double)mb.count * c->nranks;
+                mb.fk = fks.k[e]; mb.identity = 0;
+                DRIL_TRY(minibatch_step(p, b->d, mb, p->mbstats + 2 * ((size_t)e * n_mb + i), hp, ll, true, 1));
+            }
         }
     }
     return DRIL_OK;
@@ -1344,7 +1413,10 @@ static int32_t collect_iter_stats(dril_policy* p, dril_iter_stats* s, bool with_
         DRIL_CUDA(cudaMemcpyAsync(rs, p->last_env->d.roll_sums, 16, cudaMemcpyDeviceToHost, c->stream));
         DRIL_CUDA(cudaMemcpyAsync(&eps, p->last_env->d.roll_eps, 8, cudaMemcpyDeviceToHost, c->stream));
     }
+    int p2p_err = 0;
+    if (c->p2p_enabled) DRIL_CUDA(cudaMemcpyAsync(&p2p_err, c->p2p.err, 4, cudaMemcpyDeviceToHost, c->stream));
     DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    if (p2p_err) { dril_set_error("peer-memory allreduce timed out waiting for a peer rank"); return DRIL_ERR_NCCL; }
     memset(s, 0, sizeof(*s));
     double n = acc[9];
     // means over the iteration's applied minibatches; empty -> NaN like mean(Float32[]) (ppo.jl:257-263)
@@ -1444,7 +1516,9 @@ extern "C" int32_t dril_ppo_loss_grad(dril_policy* p, const float* obs, const vo
         cudaMemsetAsync(p->stop_flag, 0, 4, c->stream);
         FeistelKey fk = make_feistel(B, 0, 0, 0);
         int bpm = (int)std::max<int64_t>(1, std::min<int64_t>(64, (B + 2047) / 2048));
-        adv_stats_kernel<<<dim3(bpm, 1), 256, 0, c->stream>>>(b->d.advantages, B, B, fk, 1, p->adv_partial);
+        FeistelKeys fks;
+        for (int e = 0; e < DRIL_MAX_EPOCHS_BATCHED; ++e) fks.k[e] = fk;
+        adv_stats_kernel<<<dim3(bpm, 1, 1), 256, 0, c->stream>>>(b->d.advantages, B, B, fks, 1, p->adv_partial);
         adv_stats_finalize_kernel<<<1, 128, 0, c->stream>>>(p->adv_partial, bpm, 1, p->mbstats);
         c->launches += 2;
         Minibatch mb;

@@ -27,10 +27,16 @@ struct Minibatch {
 
 // ---- minibatch advantage moments (normalize!, ppo.jl:350-356) ---------------------------
 // grid (blocks_per_mb, n_minibatches); partial[(mb*gridDim.x + blk)*2 + {0,1}] = sum, sum of squares
+#define DRIL_MAX_EPOCHS_BATCHED 16
+struct FeistelKeys { FeistelKey k[DRIL_MAX_EPOCHS_BATCHED]; };
+// grid (blocks_per_mb, n_minibatches, epochs): the moments of every minibatch of every epoch of an update in
+// one launch (advantages and permutations are fixed during the update) => one allreduce per update
 __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict__ adv, long long n_total,
-                                                        long long batch_size, FeistelKey fk, int identity,
-                                                        double* __restrict__ partial) {
+                                                        long long batch_size, const __grid_constant__ FeistelKeys fks,
+                                                        int identity, double* __restrict__ partial) {
     __shared__ double scratch[32];
+    const FeistelKey& fk = fks.k[blockIdx.z];
+    partial += (size_t)blockIdx.z * gridDim.y * gridDim.x * 2;
     long long start = (long long)blockIdx.y * batch_size;
     long long end = min(start + batch_size, n_total);
     double s = 0, q = 0;
@@ -657,7 +663,8 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
                                                           int gpack, const int* __restrict__ flat2g,
                                                           const unsigned char* __restrict__ f2planes, int stats_off,
                                                           double* __restrict__ sq_part, unsigned int* __restrict__ ticket,
-                                                          AdamArgs a, int do_adam) {
+                                                          AdamArgs a, int do_adam, float* p2p_gbuf, int p2p_slots,
+                                                          unsigned long long* p2p_seq, volatile unsigned long long* p2p_flag) {
     __shared__ float s_red[RA_GROUPS][RA_PARAMS_PER_BLOCK + 1];
     __shared__ double scratch[32];
     __shared__ float s_f[2];
@@ -692,9 +699,15 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
             float g = 0.f;
 #pragma unroll
             for (int j = 0; j < RA_GROUPS; ++j) g += s_red[j][lane];
-            a.g[p] = g;
-            if (p < a.n_params) sq = (double)g * (double)g;
-            __threadfence();              // publish this thread's slice before the ticket
+            if (do_adam == 2) {
+                // P2P path: this rank's contribution goes to the peer-visible buffer of the NEXT sequence number
+                p2p_gbuf[(size_t)((*p2p_seq + 1ull) & 1ull) * p2p_slots + p] = g;
+                __threadfence_system();
+            } else {
+                a.g[p] = g;
+                if (p < a.n_params) sq = (double)g * (double)g;
+                __threadfence();          // publish this thread's slice before the ticket
+            }
         }
         if (do_adam) {
             sq = warp_sum(sq);
@@ -705,13 +718,97 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
             }
         }
     }
-    if (!do_adam) return;                 // multi-GPU: NCCL allreduce of g, then adam_finalize_kernel
+    if (!do_adam) return;                 // multi-GPU without peer access: NCCL allreduce of g, then adam_finalize_kernel
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
+    if (do_adam == 2) {                   // last CTA: everything of this rank is written -> publish the sequence number
+        if (threadIdx.x == 0) {
+            *ticket = 0u;
+            __threadfence_system();
+            const unsigned long long sq_ = *p2p_seq + 1ull;
+            *p2p_seq = sq_;
+            __threadfence_system();
+            *p2p_flag = sq_;
+            __threadfence_system();
+        }
+        return;
+    }
     __threadfence();
     if (threadIdx.x == 0) *ticket = 0u;
     // global sum of squares: one load per thread + fixed-order block reduction (a per-thread serial
     // loop over gridDim.x L2 round trips was the critical path of this kernel)
+    double q = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) q += sq_part[b];
+    q = block_sum(q, scratch);
+    adam_apply(a, q, s_f, &s_i);
+}
+
+// ---------------------------------------------------------------------------------------
+// Multi-GPU: one-shot gradient allreduce over NVLink peer memory, fused into the reduce / Adam kernels
+// (replaces reduce -> ncclAllReduce -> Adam for the 36.6 KB latency-bound message).
+// Every rank owns a region {gbuf[2][n_slots], seq, flag} mapped into all peers with CUDA IPC.
+//   kernel R (reduce_adam_kernel, do_adam = 2): partial planes -> LOCAL gbuf[(seq+1)&1]; the last CTA
+//            (ticket) bumps seq and publishes flag = seq with a system-scope fence.
+//   kernel X (p2p_sum_adam_kernel): waits until every peer's flag >= seq, sums the peers' gbuf in rank
+//            order (identical on all ranks => bit-identical parameters without broadcast), per-CTA
+//            sums of squares, ticket, last CTA: clip + KL stop + Adam.
+// Double buffering is enough: a rank can only start step s+2 after every peer published s+1, i.e. after
+// every peer finished reading step s.  Spins are bounded; a timeout raises err (checked on the host).
+// ---------------------------------------------------------------------------------------
+#define DRIL_MAX_RANKS 16
+struct P2PDev {
+    float* local_gbuf;                         // [2][n_slots]
+    unsigned long long* local_seq;             // device-side step sequence of this rank
+    volatile unsigned long long* local_flag;   // published sequence (read by peers)
+    const float* peer_gbuf[DRIL_MAX_RANKS];
+    const volatile unsigned long long* peer_flag[DRIL_MAX_RANKS];
+    int* err;
+    int n_slots, nranks, rank;
+};
+
+__global__ void __launch_bounds__(256) p2p_sum_adam_kernel(P2PDev pp, double* __restrict__ sq_part,
+                                                           unsigned int* __restrict__ ticket, AdamArgs a) {
+    __shared__ double scratch[32];
+    __shared__ float s_f[2];
+    __shared__ int s_i;
+    __shared__ unsigned int s_ticket;
+    if (*a.stop_flag) return;
+    const unsigned long long seq = *pp.local_seq;
+    if (threadIdx.x < pp.nranks) {
+        const volatile unsigned long long* f = pp.peer_flag[threadIdx.x];
+        long long spins = 0;
+        while (*f < seq) {
+            __nanosleep(64);
+            if (++spins > (1ll << 24)) { atomicExch(pp.err, 1); break; }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = a.n_params + 6;
+    double sq = 0.0;
+    if (p < n) {
+        const size_t off = (size_t)(seq & 1ull) * pp.n_slots + p;
+        float v[DRIL_MAX_RANKS];
+#pragma unroll
+        for (int r = 0; r < DRIL_MAX_RANKS; ++r) v[r] = r < pp.nranks ? __ldcv(pp.peer_gbuf[r] + off) : 0.f;
+        float g = 0.f;
+#pragma unroll
+        for (int r = 0; r < DRIL_MAX_RANKS; ++r) g += v[r];
+        a.g[p] = g;
+        if (p < a.n_params) sq = (double)g * (double)g;
+        __threadfence();
+    }
+    sq = block_sum(sq, scratch);
+    if (threadIdx.x == 0) {
+        sq_part[blockIdx.x] = sq;
+        __threadfence();
+        s_ticket = atomicAdd(ticket, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    if (threadIdx.x == 0) *ticket = 0u;
     double q = 0.0;
     for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) q += sq_part[b];
     q = block_sum(q, scratch);

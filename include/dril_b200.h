@@ -139,6 +139,12 @@ int32_t dril_ctx_flush_l2(dril_ctx* ctx);
 int32_t dril_comm_unique_id(uint8_t id_out[128]);
 int32_t dril_comm_init(dril_ctx* ctx, int32_t rank, int32_t nranks, const uint8_t id[128]);
 int32_t dril_comm_destroy(dril_ctx* ctx);
+/* Optional one-shot NVLink allreduce fused into the reduce/Adam kernels (peer memory through CUDA IPC):
+ * every rank exports a region of n_slots floats x 2 buffers, the host exchanges the 64-byte handles (any
+ * transport: torch.distributed, MPI.jl, a file) and every rank imports all of them in rank order.
+ * Without this the gradient allreduce goes through NCCL. Requires dril_comm_init first. */
+int32_t dril_comm_p2p_export(dril_ctx* ctx, int64_t n_slots, uint8_t handle_out[64]);
+int32_t dril_comm_p2p_import(dril_ctx* ctx, const uint8_t* handles /* [nranks][64] */);
 
 /* ---- batched env: replaces MultiThreadedParallelEnv (environment_wrappers/
  *      multithreadedParallelEnv.jl:1-92) wrapped in MonitorWrapperEnv (monitorWrapperEnv.jl)
