@@ -1286,7 +1286,7 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
     if (p2p) {
         // cross-rank sum over NVLink peer memory + norm, clip, Adam
         Span sp(c, DRIL_K_ALLREDUCE);
-        p2p_sum_adam_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->p2p, p->sq_part, p->ticket, aa);
+        p2p_sum_adam_kernel<<<(n + 1023) / 1024, 1024, 0, c->stream>>>(c->p2p, p->sq_part, p->ticket, aa);
         DRIL_CUDA(cudaGetLastError());
         return DRIL_OK;
     }

@@ -702,7 +702,7 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
             if (do_adam == 2) {
                 // P2P path: this rank's contribution goes to the peer-visible buffer of the NEXT sequence number
                 p2p_gbuf[(size_t)((*p2p_seq + 1ull) & 1ull) * p2p_slots + p] = g;
-                __threadfence_system();
+                __threadfence();          // gpu scope; the last CTA's system-scope fence below is cumulative over these
             } else {
                 a.g[p] = g;
                 if (p < a.n_params) sq = (double)g * (double)g;
@@ -766,7 +766,7 @@ struct P2PDev {
     int n_slots, nranks, rank;
 };
 
-__global__ void __launch_bounds__(256) p2p_sum_adam_kernel(P2PDev pp, double* __restrict__ sq_part,
+__global__ void __launch_bounds__(1024) p2p_sum_adam_kernel(P2PDev pp, double* __restrict__ sq_part,
                                                            unsigned int* __restrict__ ticket, AdamArgs a) {
     __shared__ double scratch[32];
     __shared__ float s_f[2];
