@@ -5,7 +5,7 @@ host-side mirror of the reference interface; importing it without the built libr
 it without a CUDA device raises (no CPU fallback)."""
 from ._lib import DrilError, IterStats, NormCfg, PPOHyper, load  # noqa: F401
 from .spaces import Box, Discrete  # noqa: F401
-from .core import (Context, CudaBatchedEnv, DevicePolicy, NormalizeConfig, RolloutBuffer, gae_raw)  # noqa: F401
+from .core import (Context, CudaBatchedEnv, DevicePolicy, NormalizeConfig, RolloutBuffer, gae_raw, set_option)  # noqa: F401
 from .api import (AbstractCallback, AbstractTrainingLogger, ActorCriticLayer, Agent, BroadcastedParallelEnv,  # noqa: F401
                   ContinuousActorCriticLayer, DictLogger, DiscreteActorCriticLayer, MonitorWrapperEnv,
                   MultiThreadedParallelEnv, NeuralPolicy, NormalizeWrapperEnv, NormWrapperPolicy, NoTrainingLogger, PPO,

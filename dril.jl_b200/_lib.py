@@ -42,6 +42,7 @@ class IterStats(C.Structure):
 # every symbol declared in include/dril_b200.h: name -> argtypes (restype is int32 unless noted)
 PROTOTYPES = {
     "dril_device_count": [C.POINTER(c_i32)],
+    "dril_set_option": [C.c_char_p, c_i32],
     "dril_ctx_create": [c_i32, c_u64, C.POINTER(P)],
     "dril_ctx_destroy": [P],
     "dril_ctx_synchronize": [P],

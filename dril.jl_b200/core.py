@@ -90,6 +90,12 @@ class Context:
         return bytes(buf)
 
 
+def set_option(key, value):
+    """Process-wide tuning switch of the library (dril_set_option), e.g. set_option("tc", 1)."""
+    lib = L.load(require_device=False)
+    L.check(lib.dril_set_option(key.encode(), int(value)))
+
+
 class NormalizeConfig:
     """kwargs of NormalizeWrapperEnv (environment_wrappers/normalizeWrapperEnv.jl:71-80)."""
 

@@ -12,6 +12,7 @@
 #include "gae.cuh"
 #include "rollout.cuh"
 #include "update.cuh"
+#include "update_tc.cuh"
 
 #define DRIL_SMEM_MAX 232448  // 227 KB opt-in per CTA on sm_100
 #define DRIL_GPLANES 8        // gradient partial planes per CTA (sample-range splits of the dW tiles)
@@ -28,6 +29,27 @@ void dril_set_error(const char* fmt, ...) {
 }
 extern "C" const char* dril_last_error(void) { return g_err; }
 extern "C" int32_t dril_version(void) { return 100; }
+// ---------------------------------------------------------------------------------------
+// options
+// ---------------------------------------------------------------------------------------
+static int g_opt_tc = getenv("DRIL_TC") ? atoi(getenv("DRIL_TC")) : 0;
+extern "C" int32_t dril_set_option(const char* key, int32_t value) {
+    DRIL_REQUIRE(key, "key is NULL");
+    if (!strcmp(key, "tc")) { g_opt_tc = value; return DRIL_OK; }
+    dril_set_error("unknown option '%s'", key);
+    return DRIL_ERR_INVALID;
+}
+// the tensor-core loss/grad kernel covers the reference's default layer: hidden_dims = [64, 64], obs_dim <= 4,
+// Discrete(n <= 2)
+static bool tc_eligible(const PolicyDesc& pd) {
+    if (pd.n_layers != 3 || pd.obs_dim > 4 || pd.act_kind != DRIL_ACT_DISCRETE || pd.act_n > 2) return false;
+    for (int net = 0; net < 2; ++net) {
+        if (pd.L[net][0].N != 64 || pd.L[net][1].K != 64 || pd.L[net][1].N != 64 || pd.L[net][2].K != 64) return false;
+        if (pd.L[net][2].Np != 4) return false;
+    }
+    return true;
+}
+
 extern "C" int32_t dril_device_count(int32_t* count) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -137,6 +159,7 @@ struct dril_policy {
     float *flat = nullptr, *pack = nullptr, *m = nullptr, *v = nullptr, *g = nullptr, *gpart = nullptr;
     int *flat2pack = nullptr, *flat2packT = nullptr, *flat2g = nullptr;
     unsigned char* f2planes = nullptr;   // partial planes holding contributions to each parameter's gradient
+    unsigned char* f2planes_one = nullptr;   // all ones (tensor-core path: one partial plane per CTA)
     double* sq_part = nullptr;
     unsigned int* ticket = nullptr;
     int loss_M4 = 0, loss_splits = 1;
@@ -237,6 +260,7 @@ extern "C" int32_t dril_ctx_create(int32_t device, uint64_t seed, dril_ctx** out
     DRIL_CUDA(cudaFuncSetAttribute(policy_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
     DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
     DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
+    DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     *out = c;
     return DRIL_OK;
 }
@@ -584,6 +608,9 @@ extern "C" int32_t dril_policy_create(dril_ctx* c, int32_t obs_dim, int32_t n_hi
             }
         DRIL_TRY(dmalloc(&p->f2planes, np));
         DRIL_CUDA(cudaMemcpy(p->f2planes, planes.data(), np, cudaMemcpyHostToDevice));
+        std::vector<unsigned char> one_plane(np, 1);
+        DRIL_TRY(dmalloc(&p->f2planes_one, np));
+        DRIL_CUDA(cudaMemcpy(p->f2planes_one, one_plane.data(), np, cudaMemcpyHostToDevice));
         DRIL_TRY(dmalloc(&p->sq_part, 8192));
         DRIL_TRY(dmalloc(&p->ticket, 1));
         DRIL_CUDA(cudaMemset(p->ticket, 0, 4));
@@ -598,7 +625,7 @@ extern "C" int32_t dril_policy_destroy(dril_policy* p) {
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     void* ps[] = {p->flat, p->pack, p->m, p->v, p->g, p->gpart, p->flat2pack, p->flat2packT, p->flat2g, p->step,
-                  p->iter_acc, p->ev_acc, p->mbstats, p->adv_partial, p->stop_flag, p->scratch, p->f2planes, p->sq_part,
+                  p->iter_acc, p->ev_acc, p->mbstats, p->adv_partial, p->stop_flag, p->scratch, p->f2planes, p->f2planes_one, p->sq_part,
                   p->ticket};
     for (void* q : ps) if (q) cudaFree(q);
     for (int i = 0; i < 3; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
@@ -1255,14 +1282,17 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
     a.pd = pd; a.buf = bd; a.pack = p->pack; a.flat = p->flat; a.mbstats = mbstats_dev; a.gpart = p->gpart;
     a.stop_flag = p->stop_flag; a.mb = mb; a.hp = hp; a.M4 = ll.M4; a.weights_smem = ll.ws;
     a.half_stride = p->gpart_ctas; a.small_splits = ll.splits;
-    long long tiles = (mb.count + ll.M4 - 1) / ll.M4;
-    int grid = (int)std::max<long long>(1, std::min<long long>(tiles, ll.grid_cap));
+    const bool tc = g_opt_tc && tc_eligible(pd);
+    long long tiles = (mb.count + (tc ? TC_M : ll.M4) - 1) / (tc ? TC_M : ll.M4);
+    int grid = (int)std::max<long long>(1, std::min<long long>(tiles, tc ? std::min(c->sm_count, p->gpart_ctas) : ll.grid_cap));
     {
         Span sp(c, DRIL_K_LOSS_GRAD);
-        if (ll.ws) ppo_loss_grad_kernel<true><<<grid, DRIL_THREADS, ll.smem, c->stream>>>(a);
+        if (tc) ppo_loss_grad_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, c->stream>>>(a);
+        else if (ll.ws) ppo_loss_grad_kernel<true><<<grid, DRIL_THREADS, ll.smem, c->stream>>>(a);
         else ppo_loss_grad_kernel<false><<<grid, DRIL_THREADS, ll.smem, c->stream>>>(a);
         DRIL_CUDA(cudaGetLastError());
     }
+    const unsigned char* planes_dev = tc ? p->f2planes_one : p->f2planes;
     AdamArgs aa;
     aa.g = p->g; aa.flat = p->flat; aa.m = p->m; aa.v = p->v; aa.pack = p->pack; aa.flat2pack = p->flat2pack;
     aa.flat2packT = p->flat2packT; aa.step = p->step; aa.iter_acc = p->iter_acc; aa.stop_flag = p->stop_flag;
@@ -1275,7 +1305,7 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
         // reduction over CTAs / planes (+ norm, clip, Adam in the same kernel on a single GPU; + publication
         // of this rank's gradient to its peers on the peer-memory path)
         Span sp(c, fused ? DRIL_K_ADAM : DRIL_K_GRAD_REDUCE);
-        reduce_adam_kernel<<<fgrid, 1024, 0, c->stream>>>(p->gpart, grid, p->gpart_ctas, pd.gpack, p->flat2g, p->f2planes,
+        reduce_adam_kernel<<<fgrid, 1024, 0, c->stream>>>(p->gpart, grid, p->gpart_ctas, pd.gpack, p->flat2g, planes_dev,
                                                          pd.pack_fwd + pd.act_n, p->sq_part, p->ticket, aa,
                                                          fused ? 1 : (p2p ? 2 : 0), p2p ? c->p2p.local_gbuf : nullptr,
                                                          p2p ? c->p2p.n_slots : 0, p2p ? c->p2p.local_seq : nullptr,

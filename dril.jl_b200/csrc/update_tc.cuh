@@ -1,0 +1,485 @@
+// Tensor-core variant of the fused PPO loss forward/backward (ppo_loss_grad_kernel) for the reference's default
+// network shape: two tanh MLPs with hidden_dims = [64, 64] (layers/layer_constructors.jl:3-11,53-57), obs_dim <= 4,
+// Discrete(n <= 2) actions — i.e. the CartPole configurations of BASELINE.json.
+//
+// The three 64x64 GEMMs per net that hold 94 % of the FLOPs run on tcgen05.mma.kind::tf32 with the 3xTF32 split
+// (hi*hi + lo*hi + hi*lo, hi = x with 13 mantissa bits cleared, lo = x - hi; 2e-6 relative error measured in
+// tools/tc_probe.cu, so north_star check (c) at 1e-4 holds), accumulators in TMEM:
+//   G1  H1pre[m][n] = sum_k H0[m][k] W1[k][n]   A = H0 in TMEM (TS mode), B = W1^T K-major no-swizzle smem image
+//   G2  dH0[m][k]   = sum_n dZ1[m][n] W1[k][n]   A = dZ1 in TMEM,          B = W1   K-major no-swizzle smem image
+//   G3  dW1[k][n]   = sum_m H0[m][k] dZ1[m][n]   A, B MN-major SWIZZLE_128B_BASE32B smem images, M = 64; the
+//                                                 accumulator stays in TMEM across all tiles of the pass
+// Everything else is thread-per-sample CUDA-core code (thread m <-> TMEM lane m <-> sample m of the 128-sample
+// tile): layer 0 (K = obs_dim), the output layers, the loss head, the deltas, and the thin-layer gradients
+// (dW0, db0, db1, dW2, db2) which are reduced across the 32 samples of a warp with a shuffle transpose-reduce
+// and kept in registers across tiles.  Descriptor recipes are the ones verified on hardware by tools/tc_probe*.cu
+// (profiles/r01_tcgen05_probe.txt).  One pass over the minibatch per net (actor, then critic).
+#pragma once
+#include "update.cuh"
+
+#define TC_M 128
+#define TC_THREADS 128
+#define TC_COL_D1 0
+#define TC_COL_D2 64
+#define TC_COL_AHI 128
+#define TC_COL_ALO 192
+#define TC_COL_ZHI 256
+#define TC_COL_ZLO 320
+#define TC_COL_D3 384
+#define TC_TMEM_COLS 512
+#define TC_OFF_W1C_HI 0
+#define TC_OFF_W1C_LO 16384
+#define TC_OFF_WT1C_HI 32768
+#define TC_OFF_WT1C_LO 49152
+#define TC_OFF_H0_HI 65536
+#define TC_OFF_H0_LO 98304
+#define TC_OFF_Z1_HI 131072
+#define TC_OFF_Z1_LO 163840
+#define TC_OFF_SMALL 196608
+#define TC_SMALL_FLOATS 4096
+#define TC_RED_STRIDE 640   // per-warp reduction scratch: 384 + 64*NOUT + NOUT floats, NOUT <= 2
+#define TC_SMEM_BYTES (TC_OFF_SMALL + TC_SMALL_FLOATS * 4 + 1024)
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t tc_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout_type) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+           (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+__device__ __forceinline__ uint32_t tc_idesc(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_ss(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
+                 "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d),
+                 "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(tc_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float* r) {
+    uint32_t u[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __uint_as_float(u[j]);
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const float* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(__float_as_uint(r[0])),
+                 "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])), "r"(__float_as_uint(r[3])), "r"(__float_as_uint(r[4])),
+                 "r"(__float_as_uint(r[5])), "r"(__float_as_uint(r[6])), "r"(__float_as_uint(r[7])) : "memory");
+}
+__device__ __forceinline__ float tc_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// [R][C] matrix in the no-swizzle K-major core layout: cores of 8 rows x 4 columns (16-byte rows), cores ordered [r/8][c/4]
+__device__ __forceinline__ int tc_core_index(int r, int c, int C) { return ((r >> 3) * (C >> 2) + (c >> 2)) * 32 + (r & 7) * 4 + (c & 3); }
+
+// warp transpose-reduce: every lane contributes v[0..N); afterwards lane l holds in v[0..N/32) the warp sums of the
+// original indices l*(N/32) + i
+template <int N, int OFF>
+struct TcTR {
+    static __device__ __forceinline__ void run(float* v, int lane) {
+        const bool up = lane & OFF;
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            const float send = up ? v[i] : v[i + N / 2];
+            const float keep = up ? v[i + N / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        TcTR<N / 2, OFF / 2>::run(v, lane);
+    }
+};
+template <int N>
+struct TcTR<N, 0> {
+    static __device__ __forceinline__ void run(float*, int) {}
+};
+
+// one pass (one net) over all tiles of this CTA
+template <int NOUT, bool ACTOR>
+__device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, uint32_t sm_base, uint32_t tb, uint64_t* bar1,
+                                        uint64_t* bar2, uint32_t& bar_it, float adv_mean, float adv_den, float invB, double* stats,
+                                        float* gp) {
+    const PolicyDesc& pd = a.pd;
+    const BufDev& buf = a.buf;
+    const int net = ACTOR ? 0 : 1;
+    const LayerDesc& L0 = pd.L[net][0];
+    const LayerDesc& L1 = pd.L[net][1];
+    const LayerDesc& L2 = pd.L[net][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = pd.obs_dim;
+    float* sW1c_hi = reinterpret_cast<float*>(sm + TC_OFF_W1C_HI);
+    float* sW1c_lo = reinterpret_cast<float*>(sm + TC_OFF_W1C_LO);
+    float* sWt1c_hi = reinterpret_cast<float*>(sm + TC_OFF_WT1C_HI);
+    float* sWt1c_lo = reinterpret_cast<float*>(sm + TC_OFF_WT1C_LO);
+    float* sSmall = reinterpret_cast<float*>(sm + TC_OFF_SMALL);
+    float* sW0 = sSmall;            // [4][64]
+    float* sb0 = sW0 + 256;         // [64]
+    float* sb1 = sb0 + 64;          // [64]
+    float* sW2 = sb1 + 64;          // [64][4]
+    float* sb2 = sW2 + 256;         // [4]
+    float* sRed = sb2 + 8;          // cross-warp reduction scratch [4 warps][...]
+    // ---- stage this net's weights ------------------------------------------------------------
+    __syncthreads();
+    for (int i = tid; i < 64 * 64; i += TC_THREADS) {
+        const int k = i >> 6, n = i & 63;
+        const float w = a.pack[L1.pw_off + i];
+        const float hi = tc_hi(w), lo = w - hi;
+        sW1c_hi[tc_core_index(k, n, 64)] = hi; sW1c_lo[tc_core_index(k, n, 64)] = lo;
+        sWt1c_hi[tc_core_index(n, k, 64)] = hi; sWt1c_lo[tc_core_index(n, k, 64)] = lo;
+    }
+    for (int i = tid; i < 256; i += TC_THREADS) {
+        sW0[i] = a.pack[L0.pw_off + i];
+        sW2[i] = a.pack[L2.pw_off + i];
+    }
+    if (tid < 64) { sb0[tid] = a.pack[L0.pb_off + tid]; sb1[tid] = a.pack[L1.pb_off + tid]; }
+    if (tid < 4) sb2[tid] = a.pack[L2.pb_off + tid];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    // persistent (per lane, summed over this warp's samples and over tiles) thin-layer gradient accumulators
+    float accW0[4][2], accb0[2], accb1[2], accW2[NOUT][2], accb2[NOUT];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) { accW0[d][0] = 0.f; accW0[d][1] = 0.f; }
+    accb0[0] = accb0[1] = accb1[0] = accb1[1] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) { accW2[j][0] = 0.f; accW2[j][1] = 0.f; accb2[j] = 0.f; }
+
+    const uint32_t lane_base = tb + ((uint32_t)(warp * 32) << 16);
+    const uint32_t idesc_k = tc_idesc(128, 64, 0, 0);
+    const uint32_t idesc_mn = tc_idesc(64, 64, 1, 1);
+    const long long n_tiles = (a.mb.count + TC_M - 1) / TC_M;
+    bool first_tile = true;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first_tile = false) {
+        const uint32_t phase = bar_it & 1u;
+        ++bar_it;
+        // ---- gather (thread = sample) -----------------------------------------------------------
+        const long long pos = a.mb.start + tile * TC_M + tid;
+        const bool valid = pos < a.mb.start + a.mb.count;
+        long long sidx = 0;
+        if (valid) sidx = a.mb.identity ? pos : feistel_permute(pos, a.mb.n_total, a.mb.fk);
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
+        float adv = 0.f, ret = 0.f, olp = 0.f, ov = 0.f;
+        int aidx = 0;
+        if (valid) {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) if (d < D) x[d] = buf.obs[sidx * D + d];
+            if (ACTOR) {
+                adv = buf.advantages[sidx];
+                if (a.hp.normalize_advantage) adv = (adv - adv_mean) / adv_den;
+                olp = buf.logprobs[sidx];
+                aidx = reinterpret_cast<const int*>(buf.actions)[sidx] - pd.act_start;
+                aidx = aidx < 0 ? 0 : (aidx >= NOUT ? NOUT - 1 : aidx);
+            } else {
+                ret = buf.returns[sidx];
+                ov = buf.values[sidx];
+            }
+        }
+        // ---- layer 0 on CUDA cores, H0 -> TMEM (A operand of G1) + MN-major images (A operand of G3) -------------
+        {
+            const uint32_t r = tid & 3;
+            unsigned char* img_hi = sm + TC_OFF_H0_HI + ((tid >> 2) * 2) * 512 + r * 128;
+            unsigned char* img_lo = sm + TC_OFF_H0_LO + ((tid >> 2) * 2) * 512 + r * 128;
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 8) {
+                float h[8], hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) h[j] = sb0[c0 + j];
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(sW0 + d * 64 + c0);
+                    const float4 w1 = *reinterpret_cast<const float4*>(sW0 + d * 64 + c0 + 4);
+                    h[0] = fmaf(x[d], w0.x, h[0]); h[1] = fmaf(x[d], w0.y, h[1]); h[2] = fmaf(x[d], w0.z, h[2]); h[3] = fmaf(x[d], w0.w, h[3]);
+                    h[4] = fmaf(x[d], w1.x, h[4]); h[5] = fmaf(x[d], w1.y, h[5]); h[6] = fmaf(x[d], w1.z, h[6]); h[7] = fmaf(x[d], w1.w, h[7]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { h[j] = fast_tanh(h[j]); hi[j] = tc_hi(h[j]); lo[j] = h[j] - hi[j]; }
+                tc_st8(lane_base + TC_COL_AHI + c0, hi);
+                tc_st8(lane_base + TC_COL_ALO + c0, lo);
+                const int b = c0 >> 5, c = (c0 & 31) >> 3;
+                const uint32_t off = b * 512 + ((c ^ r) * 32);
+                *reinterpret_cast<float4*>(img_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(img_hi + off + 16) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                *reinterpret_cast<float4*>(img_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<float4*>(img_lo + off + 16) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        // ---- G1 -------------------------------------------------------------------------------------------
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int ps = 0; ps < 3; ++ps) {
+                const uint32_t acol = tb + (ps == 1 ? TC_COL_ALO : TC_COL_AHI);
+                const uint32_t bimg = sm_base + (ps == 2 ? TC_OFF_WT1C_LO : TC_OFF_WT1C_HI);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    tc_mma_ts(tb + TC_COL_D1, acol + kk * 8, tc_desc(bimg + kk * 256, 128, 2048, 0), idesc_k, (ps | kk) ? 1u : 0u);
+            }
+            tc_commit(bar1);
+        }
+        tc_wait(bar1, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- H1 = tanh(D1 + b1), output layer, loss head -------------------------------------------------
+        float h1[64];
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 8) {
+            float t[8];
+            tc_ld8(lane_base + TC_COL_D1 + c0, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h1[c0 + j] = fast_tanh(t[j] + sb1[c0 + j]);
+        }
+        float out[NOUT];
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j) out[j] = sb2[j];
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            const float4 w = *reinterpret_cast<const float4*>(sW2 + k * 4);
+            out[0] = fmaf(h1[k], w.x, out[0]);
+            if (NOUT > 1) out[NOUT > 1 ? 1 : 0] = fmaf(h1[k], w.y, out[NOUT > 1 ? 1 : 0]);
+        }
+        float dout[NOUT];
+        if (ACTOR) {
+            float m = out[0];
+#pragma unroll
+            for (int j = 1; j < NOUT; ++j) m = fmaxf(m, out[j]);
+            float ex[NOUT], s = 0.f;
+#pragma unroll
+            for (int j = 0; j < NOUT; ++j) { ex[j] = expf(out[j] - m); s += ex[j]; }
+            float pj[NOUT], lpj[NOUT], hsum = 0.f, p_a = 0.f;
+#pragma unroll
+            for (int j = 0; j < NOUT; ++j) {
+                pj[j] = ex[j] / s; lpj[j] = logf(pj[j]); hsum += pj[j] * lpj[j];
+                if (j == aidx) p_a = pj[j];
+            }
+            const float ent = -hsum;
+            const float logp = logf(p_a);
+            const float log_ratio = logp - olp;
+            const float ratio = expf(log_ratio);
+            const float rc = fminf(fmaxf(ratio, 1.0f - a.hp.clip_range), 1.0f + a.hp.clip_range);
+            const float s1 = ratio * adv, s2 = rc * adv;
+            const float g_logp = (!valid || s2 < s1) ? 0.f : -invB * adv * ratio;
+            const float g_ent = valid ? -a.hp.ent_coef * invB : 0.f;
+#pragma unroll
+            for (int j = 0; j < NOUT; ++j) dout[j] = g_logp * ((j == aidx ? 1.0f : 0.0f) - pj[j]) + g_ent * (-pj[j] * (lpj[j] + ent));
+            if (valid) {
+                stats[0] += (double)(-fminf(s1, s2));
+                stats[2] += (double)ent;
+                stats[3] += (ratio != rc) ? 1.0 : 0.0;
+                stats[4] += (double)(expf(log_ratio) - 1.0f - log_ratio);
+                stats[5] += (double)ratio;
+            }
+        } else {
+            const float v_raw = out[0];
+            float v = v_raw;
+            bool v_pass = true;
+            if (a.hp.clip_range_vf >= 0.f) {
+                const float dlt = v_raw - ov;
+                v_pass = dlt >= -a.hp.clip_range_vf && dlt <= a.hp.clip_range_vf;
+                v = ov + fminf(fmaxf(dlt, -a.hp.clip_range_vf), a.hp.clip_range_vf);
+            }
+            const float verr = v - ret;
+            dout[0] = (valid && v_pass) ? a.hp.vf_coef * 2.0f * verr * invB : 0.f;
+            if (valid) stats[1] += (double)(verr * verr);
+        }
+        // ---- thin-layer gradients of the output layer: dW2[k][j] = sum_m h1[m][k] dout[m][j], db2 ----------------
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j) {
+            float t[64];
+#pragma unroll
+            for (int k = 0; k < 64; ++k) t[k] = h1[k] * dout[j];
+            TcTR<64, 16>::run(t, lane);
+            accW2[j][0] += t[0]; accW2[j][1] += t[1];
+            accb2[j] += warp_sum(dout[j]);
+        }
+        // ---- dZ1 = (dout W2^T) .* (1 - H1^2) in place over h1; db1; dZ1 -> TMEM + MN-major images ----------------
+#pragma unroll
+        for (int n = 0; n < 64; ++n) {
+            const float4 w = *reinterpret_cast<const float4*>(sW2 + n * 4);
+            float s = dout[0] * w.x;
+            if (NOUT > 1) s = fmaf(dout[NOUT > 1 ? 1 : 0], w.y, s);
+            h1[n] = s * (1.0f - h1[n] * h1[n]);
+        }
+        {
+            float t[64];
+#pragma unroll
+            for (int n = 0; n < 64; ++n) t[n] = h1[n];
+            TcTR<64, 16>::run(t, lane);
+            accb1[0] += t[0]; accb1[1] += t[1];
+        }
+        {
+            const uint32_t r = tid & 3;
+            unsigned char* img_hi = sm + TC_OFF_Z1_HI + ((tid >> 2) * 2) * 512 + r * 128;
+            unsigned char* img_lo = sm + TC_OFF_Z1_LO + ((tid >> 2) * 2) * 512 + r * 128;
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 8) {
+                float hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { hi[j] = tc_hi(h1[c0 + j]); lo[j] = h1[c0 + j] - hi[j]; }
+                tc_st8(lane_base + TC_COL_ZHI + c0, hi);
+                tc_st8(lane_base + TC_COL_ZLO + c0, lo);
+                const int b = c0 >> 5, c = (c0 & 31) >> 3;
+                const uint32_t off = b * 512 + ((c ^ r) * 32);
+                *reinterpret_cast<float4*>(img_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(img_hi + off + 16) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                *reinterpret_cast<float4*>(img_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<float4*>(img_lo + off + 16) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        // ---- G2 (dH0) and G3 (dW1, accumulated in TMEM over the whole pass) -------------------------------------------
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int ps = 0; ps < 3; ++ps) {
+                const uint32_t acol = tb + (ps == 1 ? TC_COL_ZLO : TC_COL_ZHI);
+                const uint32_t bimg = sm_base + (ps == 2 ? TC_OFF_W1C_LO : TC_OFF_W1C_HI);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    tc_mma_ts(tb + TC_COL_D2, acol + kk * 8, tc_desc(bimg + kk * 256, 128, 2048, 0), idesc_k, (ps | kk) ? 1u : 0u);
+            }
+#pragma unroll
+            for (int ps = 0; ps < 3; ++ps) {
+                const uint32_t aimg = sm_base + (ps == 1 ? TC_OFF_H0_LO : TC_OFF_H0_HI);
+                const uint32_t bimg = sm_base + (ps == 2 ? TC_OFF_Z1_LO : TC_OFF_Z1_HI);
+#pragma unroll 4
+                for (int kk = 0; kk < 16; ++kk)
+                    tc_mma_ss(tb + TC_COL_D3, tc_desc(aimg + kk * 2048, 512, 1024, 1), tc_desc(bimg + kk * 2048, 512, 1024, 1), idesc_mn,
+                              (first_tile && ps == 0 && kk == 0) ? 0u : 1u);
+            }
+            tc_commit(bar2);
+        }
+        tc_wait(bar2, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- dZ0 = D2 .* (1 - H0^2); dW0[d][n] = sum_m x[m][d] dZ0[m][n]; db0 ---------------------------------------------
+        {
+            float dz0[64];
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 8) {
+                float t[8], hh[8], hl[8];
+                tc_ld8(lane_base + TC_COL_D2 + c0, t);
+                tc_ld8(lane_base + TC_COL_AHI + c0, hh);
+                tc_ld8(lane_base + TC_COL_ALO + c0, hl);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float h0 = hh[j] + hl[j]; dz0[c0 + j] = t[j] * (1.0f - h0 * h0); }
+            }
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                float t[64];
+#pragma unroll
+                for (int n = 0; n < 64; ++n) t[n] = x[d] * dz0[n];
+                TcTR<64, 16>::run(t, lane);
+                accW0[d][0] += t[0]; accW0[d][1] += t[1];
+            }
+            TcTR<64, 16>::run(dz0, lane);
+            accb0[0] += dz0[0]; accb0[1] += dz0[1];
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    // ---- end of pass: dW1 from TMEM (M = 64: row k <-> lane 32*(k/16) + k%16), thin layers through shared memory -----
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        const int k = warp * 16 + lane;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 8) {
+            float t[8];
+            tc_ld8(lane_base + TC_COL_D3 + c0, t);      // all 32 lanes take part in the load; lanes >= 16 hold nothing
+            if (lane < 16) {
+                float* g = gp + L1.pw_off + k * 64 + c0;
+                *reinterpret_cast<float4*>(g) = make_float4(t[0], t[1], t[2], t[3]);
+                *reinterpret_cast<float4*>(g + 4) = make_float4(t[4], t[5], t[6], t[7]);
+            }
+        }
+    }
+    // per-warp partial sums -> sRed[warp][...] -> fixed-order sum over the 4 warps
+    {
+        float* r = sRed + warp * TC_RED_STRIDE;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) { r[d * 64 + 2 * lane] = accW0[d][0]; r[d * 64 + 2 * lane + 1] = accW0[d][1]; }
+        r[256 + 2 * lane] = accb0[0]; r[256 + 2 * lane + 1] = accb0[1];
+        r[320 + 2 * lane] = accb1[0]; r[320 + 2 * lane + 1] = accb1[1];
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j) { r[384 + j * 64 + 2 * lane] = accW2[j][0]; r[384 + j * 64 + 2 * lane + 1] = accW2[j][1]; }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < NOUT; ++j) r[384 + NOUT * 64 + j] = accb2[j];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 384 + NOUT * 64 + NOUT; i += TC_THREADS) {
+        const float s = (sRed[i] + sRed[TC_RED_STRIDE + i]) + (sRed[2 * TC_RED_STRIDE + i] + sRed[3 * TC_RED_STRIDE + i]);
+        if (i < 256) gp[L0.pw_off + i] = s;                               // W0 packed [4][64]
+        else if (i < 320) gp[L0.pb_off + (i - 256)] = s;
+        else if (i < 384) gp[L1.pb_off + (i - 320)] = s;
+        else if (i < 384 + NOUT * 64) { const int j = (i - 384) >> 6, k = (i - 384) & 63; gp[L2.pw_off + k * 4 + j] = s; }
+        else gp[L2.pb_off + (i - 384 - NOUT * 64)] = s;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) ppo_loss_grad_tc_kernel(const __grid_constant__ LossArgs a) {
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ double scratch[32];
+    if (*a.stop_flag) return;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t raw = tc_smem_u32(tc_smem_raw);
+    const uint32_t sm_base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = tc_smem_raw + (sm_base - raw);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_s)), "r"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = tmem_base_s;
+
+    float adv_mean = 0.f, adv_den = 1.f;
+    if (a.hp.normalize_advantage) {
+        const double n = a.mb.global_count;
+        const double mean = a.mbstats[0] / n;
+        double var = (a.mbstats[1] - n * mean * mean) / (n - 1.0);
+        if (var < 0.0) var = 0.0;
+        adv_mean = (float)mean;
+        adv_den = (float)sqrt(var) + 1e-8f;
+    }
+    const float invB = (float)(1.0 / a.mb.global_count);
+    double stats[6] = {0, 0, 0, 0, 0, 0};
+    float* gp = a.gpart + (size_t)blockIdx.x * a.pd.gpack;
+    uint32_t bar_it = 0;
+    if (a.pd.act_n == 1) tc_pass<1, true>(a, sm, sm_base, tb, &bars[0], &bars[1], bar_it, adv_mean, adv_den, invB, stats, gp);
+    else tc_pass<2, true>(a, sm, sm_base, tb, &bars[0], &bars[1], bar_it, adv_mean, adv_den, invB, stats, gp);
+    tc_pass<1, false>(a, sm, sm_base, tb, &bars[0], &bars[1], bar_it, adv_mean, adv_den, invB, stats, gp);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double s = block_sum(stats[i], scratch);
+        if (tid == 0) gp[a.pd.pack_fwd + a.pd.act_n + i] = (float)s;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(TC_TMEM_COLS));
+}

@@ -117,6 +117,9 @@ const char* dril_last_error(void);
 int32_t dril_version(void);
 /* 0 if a CUDA device is usable, else an error (used by hosts to fail loudly, never to fall back) */
 int32_t dril_device_count(int32_t* count);
+/* process-wide tuning switches, e.g. ("tc", 1): tensor-core (tcgen05, 3xTF32) variant of the fused loss/grad
+ * kernel for hidden_dims = [64, 64] networks. Unknown keys are an error. */
+int32_t dril_set_option(const char* key, int32_t value);
 
 /* ---- context ---------------------------------------------------------------------------- */
 int32_t dril_ctx_create(int32_t device, uint64_t seed, dril_ctx** out);
