@@ -32,7 +32,7 @@ extern "C" int32_t dril_version(void) { return 100; }
 // ---------------------------------------------------------------------------------------
 // options
 // ---------------------------------------------------------------------------------------
-static int g_opt_tc = getenv("DRIL_TC") ? atoi(getenv("DRIL_TC")) : 0;
+static int g_opt_tc = getenv("DRIL_TC") ? atoi(getenv("DRIL_TC")) : 1;
 extern "C" int32_t dril_set_option(const char* key, int32_t value) {
     DRIL_REQUIRE(key, "key is NULL");
     if (!strcmp(key, "tc")) { g_opt_tc = value; return DRIL_OK; }

@@ -18,7 +18,7 @@
 #include "update.cuh"
 
 #define TC_M 128
-#define TC_THREADS 128
+#define TC_THREADS 256
 #define TC_COL_D1 0
 #define TC_COL_D2 64
 #define TC_COL_AHI 128
@@ -37,7 +37,7 @@
 #define TC_OFF_Z1_LO 163840
 #define TC_OFF_SMALL 196608
 #define TC_SMALL_FLOATS 4096
-#define TC_RED_STRIDE 640   // per-warp reduction scratch: 384 + 64*NOUT + NOUT floats, NOUT <= 2
+#define TC_RED_STRIDE 288   // per-warp reduction scratch: 192 + 32*NOUT + NOUT floats, NOUT <= 2
 #define TC_SMEM_BYTES (TC_OFF_SMALL + TC_SMALL_FLOATS * 4 + 1024)
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,7 +104,24 @@ struct TcTR<N, 0> {
     static __device__ __forceinline__ void run(float*, int) {}
 };
 
-// one pass (one net) over all tiles of this CTA
+// 32 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* r) {
+    uint32_t u[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+        "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]),
+          "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]),
+          "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]),
+          "=r"(u[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(u[j]);
+}
+
+// one pass (one net) over all tiles of this CTA.  256 threads: thread (m = tid & 127, half = tid >> 7) owns sample m
+// (TMEM lane m; warps w and w+4 share lane quadrant w) and the 32 hidden features [32*half, 32*half + 32).
 template <int NOUT, bool ACTOR>
 __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, uint32_t sm_base, uint32_t tb, uint64_t* bar1,
                                         uint64_t* bar2, uint32_t& bar_it, float adv_mean, float adv_den, float invB, double* stats,
@@ -116,6 +133,7 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     const LayerDesc& L1 = pd.L[net][1];
     const LayerDesc& L2 = pd.L[net][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = tid & 127, half = tid >> 7, f0 = half * 32;
     const int D = pd.obs_dim;
     float* sW1c_hi = reinterpret_cast<float*>(sm + TC_OFF_W1C_HI);
     float* sW1c_lo = reinterpret_cast<float*>(sm + TC_OFF_W1C_LO);
@@ -127,7 +145,8 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     float* sb1 = sb0 + 64;          // [64]
     float* sW2 = sb1 + 64;          // [64][4]
     float* sb2 = sW2 + 256;         // [4]
-    float* sRed = sb2 + 8;          // cross-warp reduction scratch [4 warps][...]
+    float* sOutP = sb2 + 8;         // [2 halves][NOUT<=2][128] partial output-layer dot products
+    float* sRed = sOutP + 512;      // cross-warp reduction scratch [8 warps][TC_RED_STRIDE]
     // ---- stage this net's weights ------------------------------------------------------------
     __syncthreads();
     for (int i = tid; i < 64 * 64; i += TC_THREADS) {
@@ -146,24 +165,26 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
-    // persistent (per lane, summed over this warp's samples and over tiles) thin-layer gradient accumulators
-    float accW0[4][2], accb0[2], accb1[2], accW2[NOUT][2], accb2[NOUT];
+    // persistent thin-layer gradient accumulators: lane l of this warp holds feature n = f0 + l, summed over the
+    // warp's 32 samples and over tiles
+    float accW0[4], accb0 = 0.f, accb1 = 0.f, accW2[NOUT], accb2[NOUT];
 #pragma unroll
-    for (int d = 0; d < 4; ++d) { accW0[d][0] = 0.f; accW0[d][1] = 0.f; }
-    accb0[0] = accb0[1] = accb1[0] = accb1[1] = 0.f;
+    for (int d = 0; d < 4; ++d) accW0[d] = 0.f;
 #pragma unroll
-    for (int j = 0; j < NOUT; ++j) { accW2[j][0] = 0.f; accW2[j][1] = 0.f; accb2[j] = 0.f; }
+    for (int j = 0; j < NOUT; ++j) { accW2[j] = 0.f; accb2[j] = 0.f; }
 
-    const uint32_t lane_base = tb + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_base = tb + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t idesc_k = tc_idesc(128, 64, 0, 0);
     const uint32_t idesc_mn = tc_idesc(64, 64, 1, 1);
     const long long n_tiles = (a.mb.count + TC_M - 1) / TC_M;
+    const uint32_t r4 = m & 3;
+    const uint32_t img_row = ((m >> 2) * 2 + half) * 512 + r4 * 128;     // this thread's 128-byte row of an MN-major image
     bool first_tile = true;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first_tile = false) {
         const uint32_t phase = bar_it & 1u;
         ++bar_it;
-        // ---- gather (thread = sample) -----------------------------------------------------------
-        const long long pos = a.mb.start + tile * TC_M + tid;
+        // ---- gather (both threads of a sample read the same scalars) -------------------------------------
+        const long long pos = a.mb.start + tile * TC_M + m;
         const bool valid = pos < a.mb.start + a.mb.count;
         long long sidx = 0;
         if (valid) sidx = a.mb.identity ? pos : feistel_permute(pos, a.mb.n_total, a.mb.fk);
@@ -185,33 +206,27 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
             }
         }
         // ---- layer 0 on CUDA cores, H0 -> TMEM (A operand of G1) + MN-major images (A operand of G3) -------------
-        {
-            const uint32_t r = tid & 3;
-            unsigned char* img_hi = sm + TC_OFF_H0_HI + ((tid >> 2) * 2) * 512 + r * 128;
-            unsigned char* img_lo = sm + TC_OFF_H0_LO + ((tid >> 2) * 2) * 512 + r * 128;
 #pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 8) {
-                float h[8], hi[8], lo[8];
+        for (int c0 = 0; c0 < 32; c0 += 8) {
+            float h[8], hi[8], lo[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) h[j] = sb0[c0 + j];
+            for (int j = 0; j < 8; ++j) h[j] = sb0[f0 + c0 + j];
 #pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(sW0 + d * 64 + c0);
-                    const float4 w1 = *reinterpret_cast<const float4*>(sW0 + d * 64 + c0 + 4);
-                    h[0] = fmaf(x[d], w0.x, h[0]); h[1] = fmaf(x[d], w0.y, h[1]); h[2] = fmaf(x[d], w0.z, h[2]); h[3] = fmaf(x[d], w0.w, h[3]);
-                    h[4] = fmaf(x[d], w1.x, h[4]); h[5] = fmaf(x[d], w1.y, h[5]); h[6] = fmaf(x[d], w1.z, h[6]); h[7] = fmaf(x[d], w1.w, h[7]);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { h[j] = fast_tanh(h[j]); hi[j] = tc_hi(h[j]); lo[j] = h[j] - hi[j]; }
-                tc_st8(lane_base + TC_COL_AHI + c0, hi);
-                tc_st8(lane_base + TC_COL_ALO + c0, lo);
-                const int b = c0 >> 5, c = (c0 & 31) >> 3;
-                const uint32_t off = b * 512 + ((c ^ r) * 32);
-                *reinterpret_cast<float4*>(img_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(img_hi + off + 16) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-                *reinterpret_cast<float4*>(img_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                *reinterpret_cast<float4*>(img_lo + off + 16) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+            for (int d = 0; d < 4; ++d) {
+                const float4 w0 = *reinterpret_cast<const float4*>(sW0 + d * 64 + f0 + c0);
+                const float4 w1 = *reinterpret_cast<const float4*>(sW0 + d * 64 + f0 + c0 + 4);
+                h[0] = fmaf(x[d], w0.x, h[0]); h[1] = fmaf(x[d], w0.y, h[1]); h[2] = fmaf(x[d], w0.z, h[2]); h[3] = fmaf(x[d], w0.w, h[3]);
+                h[4] = fmaf(x[d], w1.x, h[4]); h[5] = fmaf(x[d], w1.y, h[5]); h[6] = fmaf(x[d], w1.z, h[6]); h[7] = fmaf(x[d], w1.w, h[7]);
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { h[j] = fast_tanh(h[j]); hi[j] = tc_hi(h[j]); lo[j] = h[j] - hi[j]; }
+            tc_st8(lane_base + TC_COL_AHI + f0 + c0, hi);
+            tc_st8(lane_base + TC_COL_ALO + f0 + c0, lo);
+            const uint32_t off = img_row + (((c0 >> 3) ^ r4) * 32);
+            *reinterpret_cast<float4*>(sm + TC_OFF_H0_HI + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(sm + TC_OFF_H0_HI + off + 16) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<float4*>(sm + TC_OFF_H0_LO + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<float4*>(sm + TC_OFF_H0_LO + off + 16) = make_float4(lo[4], lo[5], lo[6], lo[7]);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -232,32 +247,36 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
         }
         tc_wait(bar1, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- H1 = tanh(D1 + b1), output layer, loss head -------------------------------------------------
-        float h1[64];
+        // ---- H1 = tanh(D1 + b1) (own 32 features), output layer (partials exchanged through smem), loss head ----------
+        float h1[32];
+        tc_ld32(lane_base + TC_COL_D1 + f0, h1);
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 8) {
-            float t[8];
-            tc_ld8(lane_base + TC_COL_D1 + c0, t);
+        for (int j = 0; j < 32; ++j) h1[j] = fast_tanh(h1[j] + sb1[f0 + j]);
+        {
+            float po[NOUT];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) h1[c0 + j] = fast_tanh(t[j] + sb1[c0 + j]);
+            for (int j = 0; j < NOUT; ++j) po[j] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const float4 w = *reinterpret_cast<const float4*>(sW2 + (f0 + k) * 4);
+                po[0] = fmaf(h1[k], w.x, po[0]);
+                if (NOUT > 1) po[NOUT > 1 ? 1 : 0] = fmaf(h1[k], w.y, po[NOUT > 1 ? 1 : 0]);
+            }
+#pragma unroll
+            for (int j = 0; j < NOUT; ++j) sOutP[(half * 2 + j) * 128 + m] = po[j];
         }
+        __syncthreads();
         float out[NOUT];
 #pragma unroll
-        for (int j = 0; j < NOUT; ++j) out[j] = sb2[j];
-#pragma unroll
-        for (int k = 0; k < 64; ++k) {
-            const float4 w = *reinterpret_cast<const float4*>(sW2 + k * 4);
-            out[0] = fmaf(h1[k], w.x, out[0]);
-            if (NOUT > 1) out[NOUT > 1 ? 1 : 0] = fmaf(h1[k], w.y, out[NOUT > 1 ? 1 : 0]);
-        }
+        for (int j = 0; j < NOUT; ++j) out[j] = sb2[j] + (sOutP[j * 128 + m] + sOutP[(2 + j) * 128 + m]);
         float dout[NOUT];
         if (ACTOR) {
-            float m = out[0];
+            float mx = out[0];
 #pragma unroll
-            for (int j = 1; j < NOUT; ++j) m = fmaxf(m, out[j]);
+            for (int j = 1; j < NOUT; ++j) mx = fmaxf(mx, out[j]);
             float ex[NOUT], s = 0.f;
 #pragma unroll
-            for (int j = 0; j < NOUT; ++j) { ex[j] = expf(out[j] - m); s += ex[j]; }
+            for (int j = 0; j < NOUT; ++j) { ex[j] = expf(out[j] - mx); s += ex[j]; }
             float pj[NOUT], lpj[NOUT], hsum = 0.f, p_a = 0.f;
 #pragma unroll
             for (int j = 0; j < NOUT; ++j) {
@@ -274,7 +293,7 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
             const float g_ent = valid ? -a.hp.ent_coef * invB : 0.f;
 #pragma unroll
             for (int j = 0; j < NOUT; ++j) dout[j] = g_logp * ((j == aidx ? 1.0f : 0.0f) - pj[j]) + g_ent * (-pj[j] * (lpj[j] + ent));
-            if (valid) {
+            if (valid && half == 0) {
                 stats[0] += (double)(-fminf(s1, s2));
                 stats[2] += (double)ent;
                 stats[3] += (ratio != rc) ? 1.0 : 0.0;
@@ -292,51 +311,45 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
             }
             const float verr = v - ret;
             dout[0] = (valid && v_pass) ? a.hp.vf_coef * 2.0f * verr * invB : 0.f;
-            if (valid) stats[1] += (double)(verr * verr);
+            if (valid && half == 0) stats[1] += (double)(verr * verr);
         }
         // ---- thin-layer gradients of the output layer: dW2[k][j] = sum_m h1[m][k] dout[m][j], db2 ----------------
 #pragma unroll
         for (int j = 0; j < NOUT; ++j) {
-            float t[64];
+            float t[32];
 #pragma unroll
-            for (int k = 0; k < 64; ++k) t[k] = h1[k] * dout[j];
-            TcTR<64, 16>::run(t, lane);
-            accW2[j][0] += t[0]; accW2[j][1] += t[1];
-            accb2[j] += warp_sum(dout[j]);
+            for (int k = 0; k < 32; ++k) t[k] = h1[k] * dout[j];
+            TcTR<32, 16>::run(t, lane);
+            accW2[j] += t[0];
+            if (half == 0) accb2[j] += warp_sum(dout[j]);
         }
         // ---- dZ1 = (dout W2^T) .* (1 - H1^2) in place over h1; db1; dZ1 -> TMEM + MN-major images ----------------
 #pragma unroll
-        for (int n = 0; n < 64; ++n) {
-            const float4 w = *reinterpret_cast<const float4*>(sW2 + n * 4);
+        for (int n = 0; n < 32; ++n) {
+            const float4 w = *reinterpret_cast<const float4*>(sW2 + (f0 + n) * 4);
             float s = dout[0] * w.x;
             if (NOUT > 1) s = fmaf(dout[NOUT > 1 ? 1 : 0], w.y, s);
             h1[n] = s * (1.0f - h1[n] * h1[n]);
         }
         {
-            float t[64];
+            float t[32];
 #pragma unroll
-            for (int n = 0; n < 64; ++n) t[n] = h1[n];
-            TcTR<64, 16>::run(t, lane);
-            accb1[0] += t[0]; accb1[1] += t[1];
+            for (int n = 0; n < 32; ++n) t[n] = h1[n];
+            TcTR<32, 16>::run(t, lane);
+            accb1 += t[0];
         }
-        {
-            const uint32_t r = tid & 3;
-            unsigned char* img_hi = sm + TC_OFF_Z1_HI + ((tid >> 2) * 2) * 512 + r * 128;
-            unsigned char* img_lo = sm + TC_OFF_Z1_LO + ((tid >> 2) * 2) * 512 + r * 128;
 #pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 8) {
-                float hi[8], lo[8];
+        for (int c0 = 0; c0 < 32; c0 += 8) {
+            float hi[8], lo[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { hi[j] = tc_hi(h1[c0 + j]); lo[j] = h1[c0 + j] - hi[j]; }
-                tc_st8(lane_base + TC_COL_ZHI + c0, hi);
-                tc_st8(lane_base + TC_COL_ZLO + c0, lo);
-                const int b = c0 >> 5, c = (c0 & 31) >> 3;
-                const uint32_t off = b * 512 + ((c ^ r) * 32);
-                *reinterpret_cast<float4*>(img_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(img_hi + off + 16) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-                *reinterpret_cast<float4*>(img_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                *reinterpret_cast<float4*>(img_lo + off + 16) = make_float4(lo[4], lo[5], lo[6], lo[7]);
-            }
+            for (int j = 0; j < 8; ++j) { hi[j] = tc_hi(h1[c0 + j]); lo[j] = h1[c0 + j] - hi[j]; }
+            tc_st8(lane_base + TC_COL_ZHI + f0 + c0, hi);
+            tc_st8(lane_base + TC_COL_ZLO + f0 + c0, lo);
+            const uint32_t off = img_row + (((c0 >> 3) ^ r4) * 32);
+            *reinterpret_cast<float4*>(sm + TC_OFF_Z1_HI + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(sm + TC_OFF_Z1_HI + off + 16) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<float4*>(sm + TC_OFF_Z1_LO + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<float4*>(sm + TC_OFF_Z1_LO + off + 16) = make_float4(lo[4], lo[5], lo[6], lo[7]);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -366,28 +379,26 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
         }
         tc_wait(bar2, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- dZ0 = D2 .* (1 - H0^2); dW0[d][n] = sum_m x[m][d] dZ0[m][n]; db0 ---------------------------------------------
+        // ---- dZ0 = D2 .* (1 - H0^2) (own 32 features); dW0[d][n] = sum_m x[m][d] dZ0[m][n]; db0 ------------------------------
         {
-            float dz0[64];
+            float dz0[32], hh[32];
+            tc_ld32(lane_base + TC_COL_D2 + f0, dz0);
+            tc_ld32(lane_base + TC_COL_AHI + f0, hh);
+            {
+                float hl[32];
+                tc_ld32(lane_base + TC_COL_ALO + f0, hl);
 #pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 8) {
-                float t[8], hh[8], hl[8];
-                tc_ld8(lane_base + TC_COL_D2 + c0, t);
-                tc_ld8(lane_base + TC_COL_AHI + c0, hh);
-                tc_ld8(lane_base + TC_COL_ALO + c0, hl);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { const float h0 = hh[j] + hl[j]; dz0[c0 + j] = t[j] * (1.0f - h0 * h0); }
+                for (int j = 0; j < 32; ++j) { const float h0 = hh[j] + hl[j]; dz0[j] *= (1.0f - h0 * h0); }
             }
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
-                float t[64];
 #pragma unroll
-                for (int n = 0; n < 64; ++n) t[n] = x[d] * dz0[n];
-                TcTR<64, 16>::run(t, lane);
-                accW0[d][0] += t[0]; accW0[d][1] += t[1];
+                for (int n = 0; n < 32; ++n) hh[n] = x[d] * dz0[n];
+                TcTR<32, 16>::run(hh, lane);
+                accW0[d] += hh[0];
             }
-            TcTR<64, 16>::run(dz0, lane);
-            accb0[0] += dz0[0]; accb0[1] += dz0[1];
+            TcTR<32, 16>::run(dz0, lane);
+            accb0 += dz0[0];
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -395,40 +406,49 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     {
-        const int k = warp * 16 + lane;
+        const int k = (warp & 3) * 16 + lane;
+        float t[32];
+        tc_ld32(lane_base + TC_COL_D3 + f0, t);         // all 32 lanes take part in the load; lanes >= 16 hold nothing
+        if (lane < 16) {
+            float* g = gp + L1.pw_off + k * 64 + f0;
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 8) {
-            float t[8];
-            tc_ld8(lane_base + TC_COL_D3 + c0, t);      // all 32 lanes take part in the load; lanes >= 16 hold nothing
-            if (lane < 16) {
-                float* g = gp + L1.pw_off + k * 64 + c0;
-                *reinterpret_cast<float4*>(g) = make_float4(t[0], t[1], t[2], t[3]);
-                *reinterpret_cast<float4*>(g + 4) = make_float4(t[4], t[5], t[6], t[7]);
-            }
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(g + j) = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
         }
     }
-    // per-warp partial sums -> sRed[warp][...] -> fixed-order sum over the 4 warps
+    // per-warp partial sums -> sRed[warp][...] -> fixed-order sum over the 4 warps that share a feature half
     {
         float* r = sRed + warp * TC_RED_STRIDE;
 #pragma unroll
-        for (int d = 0; d < 4; ++d) { r[d * 64 + 2 * lane] = accW0[d][0]; r[d * 64 + 2 * lane + 1] = accW0[d][1]; }
-        r[256 + 2 * lane] = accb0[0]; r[256 + 2 * lane + 1] = accb0[1];
-        r[320 + 2 * lane] = accb1[0]; r[320 + 2 * lane + 1] = accb1[1];
+        for (int d = 0; d < 4; ++d) r[d * 32 + lane] = accW0[d];
+        r[128 + lane] = accb0;
+        r[160 + lane] = accb1;
 #pragma unroll
-        for (int j = 0; j < NOUT; ++j) { r[384 + j * 64 + 2 * lane] = accW2[j][0]; r[384 + j * 64 + 2 * lane + 1] = accW2[j][1]; }
+        for (int j = 0; j < NOUT; ++j) r[192 + j * 32 + lane] = accW2[j];
         if (lane == 0) {
 #pragma unroll
-            for (int j = 0; j < NOUT; ++j) r[384 + NOUT * 64 + j] = accb2[j];
+            for (int j = 0; j < NOUT; ++j) r[192 + NOUT * 32 + j] = accb2[j];
         }
     }
     __syncthreads();
-    for (int i = tid; i < 384 + NOUT * 64 + NOUT; i += TC_THREADS) {
-        const float s = (sRed[i] + sRed[TC_RED_STRIDE + i]) + (sRed[2 * TC_RED_STRIDE + i] + sRed[3 * TC_RED_STRIDE + i]);
-        if (i < 256) gp[L0.pw_off + i] = s;                               // W0 packed [4][64]
-        else if (i < 320) gp[L0.pb_off + (i - 256)] = s;
-        else if (i < 384) gp[L1.pb_off + (i - 320)] = s;
-        else if (i < 384 + NOUT * 64) { const int j = (i - 384) >> 6, k = (i - 384) & 63; gp[L2.pw_off + k * 4 + j] = s; }
-        else gp[L2.pb_off + (i - 384 - NOUT * 64)] = s;
+    {
+        // entries: h in {0,1}; per half 192 + 32*NOUT feature entries; b2 (half 0 only)
+        const int per_half = 192 + NOUT * 32;
+        for (int i = tid; i < 2 * per_half + NOUT; i += TC_THREADS) {
+            if (i < 2 * per_half) {
+                const int h = i / per_half, e = i - h * per_half;
+                const float* r = sRed + (h * 4) * TC_RED_STRIDE + e;
+                const float s = (r[0] + r[TC_RED_STRIDE]) + (r[2 * TC_RED_STRIDE] + r[3 * TC_RED_STRIDE]);
+                const int n = h * 32 + (e & 31);
+                if (e < 128) gp[L0.pw_off + (e >> 5) * 64 + n] = s;            // W0 packed [4][64]
+                else if (e < 160) gp[L0.pb_off + n] = s;
+                else if (e < 192) gp[L1.pb_off + n] = s;
+                else gp[L2.pw_off + n * 4 + ((e - 192) >> 5)] = s;             // W2 packed [64][4]
+            } else {
+                const int j = i - 2 * per_half;
+                const float* r = sRed + 192 + NOUT * 32 + j;
+                gp[L2.pb_off + j] = (r[0] + r[TC_RED_STRIDE]) + (r[2 * TC_RED_STRIDE] + r[3 * TC_RED_STRIDE]);
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
