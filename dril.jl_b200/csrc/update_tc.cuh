@@ -7,37 +7,44 @@
 // tools/tc_probe.cu, so north_star check (c) at 1e-4 holds), accumulators in TMEM:
 //   G1  H1pre[m][n] = sum_k H0[m][k] W1[k][n]   A = H0 in TMEM (TS mode), B = W1^T K-major no-swizzle smem image
 //   G2  dH0[m][k]   = sum_n dZ1[m][n] W1[k][n]   A = dZ1 in TMEM,          B = W1   K-major no-swizzle smem image
-//   G3  dW1[k][n]   = sum_m H0[m][k] dZ1[m][n]   A, B MN-major SWIZZLE_128B_BASE32B smem images, M = 64; the
-//                                                 accumulator stays in TMEM across all tiles of the pass
-// Everything else is thread-per-sample CUDA-core code (thread m <-> TMEM lane m <-> sample m of the 128-sample
-// tile): layer 0 (K = obs_dim), the output layers, the loss head, the deltas, and the thin-layer gradients
-// (dW0, db0, db1, dW2, db2) which are reduced across the 32 samples of a warp with a shuffle transpose-reduce
-// and kept in registers across tiles.  Descriptor recipes are the ones verified on hardware by tools/tc_probe*.cu
+//   G3  dW1[k][n]   = sum_m H0[m][k] dZ1[m][n]   A = [H0_hi | H0_lo] (M = 128) and B = dZ1_hi, dZ1_lo: MN-major
+//                                                 SWIZZLE_128B_BASE32B smem images; the accumulator stays in TMEM
+//                                                 across all tiles of the pass (rows 0..63 hi part, 64..127 lo part)
+// Everything else is CUDA-core code with two threads per sample (thread (m, half) <-> TMEM lane m, hidden features
+// [32 half, 32 half + 32)): layer 0 (K = obs_dim), the output layers, the loss head, the deltas, and the thin-layer
+// gradients (dW0, db0, db1, dW2, db2), reduced across the 32 samples of a warp with a shuffle transpose-reduce and
+// kept in registers across tiles.
+//
+// Two groups of 8 warps work on alternate 128-sample tiles of the CTA (ping-pong): while one group's MMAs run, the
+// other group is in a CUDA-core phase.  Each group owns 192 TMEM columns (D | A/Z hi | A/Z lo; the dZ1 operand
+// overwrites the H0 operand once G1 has consumed it, layer-0 activations are recomputed for the layer-0 delta) and
+// its own pair of mbarriers; the dW1 accumulator (64 columns) and the G3 shared-memory images are shared: a group
+// writes the images only after the other group's previous G3 has completed (its mbarrier phase), so image use
+// strictly alternates.  tcgen05 rates measured on B200 by tools/tc_probe3.cu: max(44, N/2) cycles per tf32
+// instruction at M = 128.  Descriptor recipes are the ones verified on hardware by tools/tc_probe*.cu
 // (profiles/r01_tcgen05_probe.txt).  One pass over the minibatch per net (actor, then critic).
 #pragma once
 #include "update.cuh"
 
 #define TC_M 128
-#define TC_THREADS 256
-#define TC_COL_D1 0
-#define TC_COL_D2 64
-#define TC_COL_AHI 128
-#define TC_COL_ALO 192
-#define TC_COL_ZHI 256
-#define TC_COL_ZLO 320
+#define TC_THREADS 512
+#define TC_GROUP_THREADS 256
+#define TC_COL_GROUP 192      // TMEM columns per group
+#define TC_COL_D 0            // G1 output, later G2 output
+#define TC_COL_HI 64          // H0 hi, later dZ1 hi
+#define TC_COL_LO 128
 #define TC_COL_D3 384
 #define TC_TMEM_COLS 512
 #define TC_OFF_W1C_HI 0
 #define TC_OFF_W1C_LO 16384
 #define TC_OFF_WT1C_HI 32768
 #define TC_OFF_WT1C_LO 49152
-#define TC_OFF_H0_HI 65536
-#define TC_OFF_H0_LO 98304
+#define TC_OFF_H0CAT 65536    // [m/4][hi f<32 | hi f>=32 | lo f<32 | lo f>=32][m%4][32 floats], 64 KB
 #define TC_OFF_Z1_HI 131072
 #define TC_OFF_Z1_LO 163840
 #define TC_OFF_SMALL 196608
-#define TC_SMALL_FLOATS 4096
-#define TC_RED_STRIDE 288   // per-warp reduction scratch: 192 + 32*NOUT + NOUT floats, NOUT <= 2
+#define TC_SMALL_FLOATS 2048
+#define TC_RED_STRIDE 288   // per-warp reduction scratch: 192 + 32*NOUT + NOUT floats, NOUT <= 2 (aliases the images)
 #define TC_SMEM_BYTES (TC_OFF_SMALL + TC_SMALL_FLOATS * 4 + 1024)
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,12 +127,26 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* r) {
     for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(u[j]);
 }
 
-// one pass (one net) over all tiles of this CTA.  256 threads: thread (m = tid & 127, half = tid >> 7) owns sample m
-// (TMEM lane m; warps w and w+4 share lane quadrant w) and the 32 hidden features [32*half, 32*half + 32).
+__device__ __forceinline__ void tc_ld8x2(uint32_t ta, uint32_t tb2, float* ra, float* rb) {
+    uint32_t u[8], v[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]) : "r"(ta));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(tb2));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ra[j] = __uint_as_float(u[j]); rb[j] = __uint_as_float(v[j]); }
+}
+__device__ __forceinline__ void tc_group_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
+
+// one pass (one net) over all tiles of this CTA.  512 threads = 2 groups x 256; within a group thread
+// (m = t & 127, half = t >> 7) owns sample m (TMEM lane m; warps w and w+4 share lane quadrant w) and the 32 hidden
+// features [32*half, 32*half + 32).  n_own / n_other: tiles of this pass handled by this / the other group;
+// base_own / base_other: mbarrier phases the groups completed in earlier passes.
 template <int NOUT, bool ACTOR>
-__device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, uint32_t sm_base, uint32_t tb, uint64_t* bar1,
-                                        uint64_t* bar2, uint32_t& bar_it, float adv_mean, float adv_den, float invB, double* stats,
-                                        float* gp) {
+__device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, uint32_t sm_base, uint32_t tb, uint64_t* bars,
+                                        int n_own, uint32_t base_own, uint32_t base_other, float adv_mean, float adv_den,
+                                        float invB, float* stats, float* gp) {
     const PolicyDesc& pd = a.pd;
     const BufDev& buf = a.buf;
     const int net = ACTOR ? 0 : 1;
@@ -133,7 +154,8 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     const LayerDesc& L1 = pd.L[net][1];
     const LayerDesc& L2 = pd.L[net][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m = tid & 127, half = tid >> 7, f0 = half * 32;
+    const int g = tid >> 8, t = tid & 255;
+    const int m = t & 127, half = t >> 7, f0 = half * 32;
     const int D = pd.obs_dim;
     float* sW1c_hi = reinterpret_cast<float*>(sm + TC_OFF_W1C_HI);
     float* sW1c_lo = reinterpret_cast<float*>(sm + TC_OFF_W1C_LO);
@@ -145,9 +167,15 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     float* sb1 = sb0 + 64;          // [64]
     float* sW2 = sb1 + 64;          // [64][4]
     float* sb2 = sW2 + 256;         // [4]
-    float* sOutP = sb2 + 8;         // [2 halves][NOUT<=2][128] partial output-layer dot products
-    float* sRed = sOutP + 512;      // cross-warp reduction scratch [8 warps][TC_RED_STRIDE]
-    // ---- stage this net's weights ------------------------------------------------------------
+    float* sOutP = sb2 + 8 + g * 512;   // per group: [2 halves][NOUT<=2][128] partial output-layer dot products
+    float* sRed = reinterpret_cast<float*>(sm + TC_OFF_H0CAT);   // end-of-pass reduction scratch [16 warps][TC_RED_STRIDE]
+    uint64_t* bar1 = bars + g * 2;
+    uint64_t* bar2 = bars + g * 2 + 1;
+    uint64_t* obar2 = bars + (g ^ 1) * 2 + 1;
+    const uint32_t gcol = tb + (uint32_t)g * TC_COL_GROUP;
+    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t my = gcol + lane_base;       // this thread's lane, this group's columns
+    // ---- stage this net's weights; clear the dW1 accumulator ---------------------------------------------------
     __syncthreads();
     for (int i = tid; i < 64 * 64; i += TC_THREADS) {
         const int k = i >> 6, n = i & 63;
@@ -162,38 +190,45 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     }
     if (tid < 64) { sb0[tid] = a.pack[L0.pb_off + tid]; sb1[tid] = a.pack[L1.pb_off + tid]; }
     if (tid < 4) sb2[tid] = a.pack[L2.pb_off + tid];
+    if (g == 0) {
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 8) tc_st8(tb + lane_base + TC_COL_D3 + f0 + c0, z);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // persistent thin-layer gradient accumulators: lane l of this warp holds feature n = f0 + l, summed over the
-    // warp's 32 samples and over tiles
-    float accW0[4], accb0 = 0.f, accb1 = 0.f, accW2[NOUT], accb2[NOUT];
-#pragma unroll
-    for (int d = 0; d < 4; ++d) accW0[d] = 0.f;
+    // warp's 32 samples and over this group's tiles
+    float accW0_0 = 0.f, accW0_1 = 0.f, accW0_2 = 0.f, accW0_3 = 0.f, accb0 = 0.f, accb1 = 0.f, accW2[NOUT], accb2[NOUT];
 #pragma unroll
     for (int j = 0; j < NOUT; ++j) { accW2[j] = 0.f; accb2[j] = 0.f; }
 
-    const uint32_t lane_base = tb + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t idesc_k = tc_idesc(128, 64, 0, 0);
-    const uint32_t idesc_mn = tc_idesc(64, 64, 1, 1);
-    const long long n_tiles = (a.mb.count + TC_M - 1) / TC_M;
+    const uint32_t idesc_mn = tc_idesc(128, 64, 1, 1);
     const uint32_t r4 = m & 3;
-    const uint32_t img_row = ((m >> 2) * 2 + half) * 512 + r4 * 128;     // this thread's 128-byte row of an MN-major image
-    bool first_tile = true;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first_tile = false) {
-        const uint32_t phase = bar_it & 1u;
-        ++bar_it;
+    const uint32_t img_h0 = ((m >> 2) * 4 + half) * 512 + r4 * 128;   // this thread's 128-byte row of the H0 image (hi block)
+    const uint32_t img_z1 = ((m >> 2) * 2 + half) * 512 + r4 * 128;   // ... of a dZ1 image
+    for (int it = 0; it < n_own; ++it) {
+        const long long tile = (long long)blockIdx.x + (long long)(2 * it + g) * gridDim.x;
+        const uint32_t phase = (base_own + (uint32_t)it) & 1u;
         // ---- gather (both threads of a sample read the same scalars) -------------------------------------
         const long long pos = a.mb.start + tile * TC_M + m;
         const bool valid = pos < a.mb.start + a.mb.count;
         long long sidx = 0;
         if (valid) sidx = a.mb.identity ? pos : feistel_permute(pos, a.mb.n_total, a.mb.fk);
-        float x[4] = {0.f, 0.f, 0.f, 0.f};
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
         float adv = 0.f, ret = 0.f, olp = 0.f, ov = 0.f;
         int aidx = 0;
         if (valid) {
-#pragma unroll
-            for (int d = 0; d < 4; ++d) if (d < D) x[d] = buf.obs[sidx * D + d];
+            const float* xo = buf.obs + sidx * D;
+            x0 = xo[0];
+            if (D > 1) x1 = xo[1];
+            if (D > 2) x2 = xo[2];
+            if (D > 3) x3 = xo[3];
             if (ACTOR) {
                 adv = buf.advantages[sidx];
                 if (a.hp.normalize_advantage) adv = (adv - adv_mean) / adv_den;
@@ -205,51 +240,49 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
                 ov = buf.values[sidx];
             }
         }
-        // ---- layer 0 on CUDA cores, H0 -> TMEM (A operand of G1) + MN-major images (A operand of G3) -------------
+        // ---- layer 0 on CUDA cores, H0 hi/lo -> TMEM (A operand of G1) ----------------------------------------------
 #pragma unroll
         for (int c0 = 0; c0 < 32; c0 += 8) {
             float h[8], hi[8], lo[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) h[j] = sb0[f0 + c0 + j];
+            {
+                const float4 ba = *reinterpret_cast<const float4*>(sb0 + f0 + c0);
+                const float4 bb = *reinterpret_cast<const float4*>(sb0 + f0 + c0 + 4);
+                h[0] = ba.x; h[1] = ba.y; h[2] = ba.z; h[3] = ba.w; h[4] = bb.x; h[5] = bb.y; h[6] = bb.z; h[7] = bb.w;
+            }
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
+                const float xd = d == 0 ? x0 : (d == 1 ? x1 : (d == 2 ? x2 : x3));
                 const float4 w0 = *reinterpret_cast<const float4*>(sW0 + d * 64 + f0 + c0);
                 const float4 w1 = *reinterpret_cast<const float4*>(sW0 + d * 64 + f0 + c0 + 4);
-                h[0] = fmaf(x[d], w0.x, h[0]); h[1] = fmaf(x[d], w0.y, h[1]); h[2] = fmaf(x[d], w0.z, h[2]); h[3] = fmaf(x[d], w0.w, h[3]);
-                h[4] = fmaf(x[d], w1.x, h[4]); h[5] = fmaf(x[d], w1.y, h[5]); h[6] = fmaf(x[d], w1.z, h[6]); h[7] = fmaf(x[d], w1.w, h[7]);
+                h[0] = fmaf(xd, w0.x, h[0]); h[1] = fmaf(xd, w0.y, h[1]); h[2] = fmaf(xd, w0.z, h[2]); h[3] = fmaf(xd, w0.w, h[3]);
+                h[4] = fmaf(xd, w1.x, h[4]); h[5] = fmaf(xd, w1.y, h[5]); h[6] = fmaf(xd, w1.z, h[6]); h[7] = fmaf(xd, w1.w, h[7]);
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) { h[j] = fast_tanh(h[j]); hi[j] = tc_hi(h[j]); lo[j] = h[j] - hi[j]; }
-            tc_st8(lane_base + TC_COL_AHI + f0 + c0, hi);
-            tc_st8(lane_base + TC_COL_ALO + f0 + c0, lo);
-            const uint32_t off = img_row + (((c0 >> 3) ^ r4) * 32);
-            *reinterpret_cast<float4*>(sm + TC_OFF_H0_HI + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(sm + TC_OFF_H0_HI + off + 16) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-            *reinterpret_cast<float4*>(sm + TC_OFF_H0_LO + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            *reinterpret_cast<float4*>(sm + TC_OFF_H0_LO + off + 16) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+            tc_st8(my + TC_COL_HI + f0 + c0, hi);
+            tc_st8(my + TC_COL_LO + f0 + c0, lo);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        tc_group_sync(g);
         // ---- G1 -------------------------------------------------------------------------------------------
-        if (tid == 0) {
+        if (t == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int ps = 0; ps < 3; ++ps) {
-                const uint32_t acol = tb + (ps == 1 ? TC_COL_ALO : TC_COL_AHI);
+                const uint32_t acol = gcol + (ps == 1 ? TC_COL_LO : TC_COL_HI);
                 const uint32_t bimg = sm_base + (ps == 2 ? TC_OFF_WT1C_LO : TC_OFF_WT1C_HI);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk)
-                    tc_mma_ts(tb + TC_COL_D1, acol + kk * 8, tc_desc(bimg + kk * 256, 128, 2048, 0), idesc_k, (ps | kk) ? 1u : 0u);
+                    tc_mma_ts(gcol + TC_COL_D, acol + kk * 8, tc_desc(bimg + kk * 256, 128, 2048, 0), idesc_k, (ps | kk) ? 1u : 0u);
             }
             tc_commit(bar1);
         }
         tc_wait(bar1, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- H1 = tanh(D1 + b1) (own 32 features), output layer (partials exchanged through smem), loss head ----------
+        // ---- H1 = tanh(D + b1) (own 32 features), output layer (partials exchanged through smem), loss head ----------
         float h1[32];
-        tc_ld32(lane_base + TC_COL_D1 + f0, h1);
+        tc_ld32(my + TC_COL_D + f0, h1);
 #pragma unroll
         for (int j = 0; j < 32; ++j) h1[j] = fast_tanh(h1[j] + sb1[f0 + j]);
         {
@@ -265,7 +298,7 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
 #pragma unroll
             for (int j = 0; j < NOUT; ++j) sOutP[(half * 2 + j) * 128 + m] = po[j];
         }
-        __syncthreads();
+        tc_group_sync(g);
         float out[NOUT];
 #pragma unroll
         for (int j = 0; j < NOUT; ++j) out[j] = sb2[j] + (sOutP[j * 128 + m] + sOutP[(2 + j) * 128 + m]);
@@ -294,11 +327,11 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
 #pragma unroll
             for (int j = 0; j < NOUT; ++j) dout[j] = g_logp * ((j == aidx ? 1.0f : 0.0f) - pj[j]) + g_ent * (-pj[j] * (lpj[j] + ent));
             if (valid && half == 0) {
-                stats[0] += (double)(-fminf(s1, s2));
-                stats[2] += (double)ent;
-                stats[3] += (ratio != rc) ? 1.0 : 0.0;
-                stats[4] += (double)(expf(log_ratio) - 1.0f - log_ratio);
-                stats[5] += (double)ratio;
+                stats[0] += -fminf(s1, s2);
+                stats[2] += ent;
+                stats[3] += (ratio != rc) ? 1.0f : 0.0f;
+                stats[4] += expf(log_ratio) - 1.0f - log_ratio;
+                stats[5] += ratio;
             }
         } else {
             const float v_raw = out[0];
@@ -311,19 +344,19 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
             }
             const float verr = v - ret;
             dout[0] = (valid && v_pass) ? a.hp.vf_coef * 2.0f * verr * invB : 0.f;
-            if (valid && half == 0) stats[1] += (double)(verr * verr);
+            if (valid && half == 0) stats[1] += verr * verr;
         }
         // ---- thin-layer gradients of the output layer: dW2[k][j] = sum_m h1[m][k] dout[m][j], db2 ----------------
 #pragma unroll
         for (int j = 0; j < NOUT; ++j) {
-            float t[32];
+            float tt[32];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) t[k] = h1[k] * dout[j];
-            TcTR<32, 16>::run(t, lane);
-            accW2[j] += t[0];
+            for (int k = 0; k < 32; ++k) tt[k] = h1[k] * dout[j];
+            TcTR<32, 16>::run(tt, lane);
+            accW2[j] += tt[0];
             if (half == 0) accb2[j] += warp_sum(dout[j]);
         }
-        // ---- dZ1 = (dout W2^T) .* (1 - H1^2) in place over h1; db1; dZ1 -> TMEM + MN-major images ----------------
+        // ---- dZ1 = (dout W2^T) .* (1 - H1^2) in place over h1; db1 -------------------------------------------------
 #pragma unroll
         for (int n = 0; n < 32; ++n) {
             const float4 w = *reinterpret_cast<const float4*>(sW2 + (f0 + n) * 4);
@@ -332,94 +365,129 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
             h1[n] = s * (1.0f - h1[n] * h1[n]);
         }
         {
-            float t[32];
+            float tt[32];
 #pragma unroll
-            for (int n = 0; n < 32; ++n) t[n] = h1[n];
-            TcTR<32, 16>::run(t, lane);
-            accb1 += t[0];
+            for (int n = 0; n < 32; ++n) tt[n] = h1[n];
+            TcTR<32, 16>::run(tt, lane);
+            accb1 += tt[0];
         }
+        // ---- take over the G3 images: the other group's previous G3 must have completed -----------------------------
+        {
+            const int k = g ? it : it - 1;
+            if (k >= 0) {
+                tc_wait(obar2, (base_other + (uint32_t)k) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+        }
+        // H0 hi/lo back from TMEM -> H0 image; dZ1 hi/lo -> TMEM (over H0) + dZ1 images
 #pragma unroll
         for (int c0 = 0; c0 < 32; c0 += 8) {
-            float hi[8], lo[8];
+            float ahi[8], alo[8], hi[8], lo[8];
+            tc_ld8x2(my + TC_COL_HI + f0 + c0, my + TC_COL_LO + f0 + c0, ahi, alo);
+            const uint32_t sw = (((c0 >> 3) ^ r4) * 32);
+            *reinterpret_cast<float4*>(sm + TC_OFF_H0CAT + img_h0 + sw) = make_float4(ahi[0], ahi[1], ahi[2], ahi[3]);
+            *reinterpret_cast<float4*>(sm + TC_OFF_H0CAT + img_h0 + sw + 16) = make_float4(ahi[4], ahi[5], ahi[6], ahi[7]);
+            *reinterpret_cast<float4*>(sm + TC_OFF_H0CAT + img_h0 + 1024 + sw) = make_float4(alo[0], alo[1], alo[2], alo[3]);
+            *reinterpret_cast<float4*>(sm + TC_OFF_H0CAT + img_h0 + 1024 + sw + 16) = make_float4(alo[4], alo[5], alo[6], alo[7]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { hi[j] = tc_hi(h1[c0 + j]); lo[j] = h1[c0 + j] - hi[j]; }
-            tc_st8(lane_base + TC_COL_ZHI + f0 + c0, hi);
-            tc_st8(lane_base + TC_COL_ZLO + f0 + c0, lo);
-            const uint32_t off = img_row + (((c0 >> 3) ^ r4) * 32);
-            *reinterpret_cast<float4*>(sm + TC_OFF_Z1_HI + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(sm + TC_OFF_Z1_HI + off + 16) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-            *reinterpret_cast<float4*>(sm + TC_OFF_Z1_LO + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            *reinterpret_cast<float4*>(sm + TC_OFF_Z1_LO + off + 16) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+            tc_st8(my + TC_COL_HI + f0 + c0, hi);
+            tc_st8(my + TC_COL_LO + f0 + c0, lo);
+            *reinterpret_cast<float4*>(sm + TC_OFF_Z1_HI + img_z1 + sw) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(sm + TC_OFF_Z1_HI + img_z1 + sw + 16) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<float4*>(sm + TC_OFF_Z1_LO + img_z1 + sw) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<float4*>(sm + TC_OFF_Z1_LO + img_z1 + sw + 16) = make_float4(lo[4], lo[5], lo[6], lo[7]);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        // ---- G2 (dH0) and G3 (dW1, accumulated in TMEM over the whole pass) -------------------------------------------
-        if (tid == 0) {
+        tc_group_sync(g);
+        // ---- G2 (dH0) and G3 (dW1, accumulated in TMEM over the whole pass by both groups) ----------------------------
+        if (t == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int ps = 0; ps < 3; ++ps) {
-                const uint32_t acol = tb + (ps == 1 ? TC_COL_ZLO : TC_COL_ZHI);
+                const uint32_t acol = gcol + (ps == 1 ? TC_COL_LO : TC_COL_HI);
                 const uint32_t bimg = sm_base + (ps == 2 ? TC_OFF_W1C_LO : TC_OFF_W1C_HI);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk)
-                    tc_mma_ts(tb + TC_COL_D2, acol + kk * 8, tc_desc(bimg + kk * 256, 128, 2048, 0), idesc_k, (ps | kk) ? 1u : 0u);
+                    tc_mma_ts(gcol + TC_COL_D, acol + kk * 8, tc_desc(bimg + kk * 256, 128, 2048, 0), idesc_k, (ps | kk) ? 1u : 0u);
             }
 #pragma unroll
-            for (int ps = 0; ps < 3; ++ps) {
-                const uint32_t aimg = sm_base + (ps == 1 ? TC_OFF_H0_LO : TC_OFF_H0_HI);
-                const uint32_t bimg = sm_base + (ps == 2 ? TC_OFF_Z1_LO : TC_OFF_Z1_HI);
+            for (int ps = 0; ps < 2; ++ps) {
+                const uint32_t bimg = sm_base + (ps ? TC_OFF_Z1_LO : TC_OFF_Z1_HI);
 #pragma unroll 4
                 for (int kk = 0; kk < 16; ++kk)
-                    tc_mma_ss(tb + TC_COL_D3, tc_desc(aimg + kk * 2048, 512, 1024, 1), tc_desc(bimg + kk * 2048, 512, 1024, 1), idesc_mn,
-                              (first_tile && ps == 0 && kk == 0) ? 0u : 1u);
+                    tc_mma_ss(tb + TC_COL_D3, tc_desc(sm_base + TC_OFF_H0CAT + kk * 4096, 512, 2048, 1),
+                              tc_desc(bimg + kk * 2048, 512, 1024, 1), idesc_mn, 1u);
             }
             tc_commit(bar2);
         }
         tc_wait(bar2, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- dZ0 = D2 .* (1 - H0^2) (own 32 features); dW0[d][n] = sum_m x[m][d] dZ0[m][n]; db0 ------------------------------
+        // ---- dZ0 = dH0 .* (1 - H0^2) with H0 recomputed (own 32 features); dW0[d][n] = sum_m x[m][d] dZ0[m][n]; db0 ----
         {
-            float dz0[32], hh[32];
-            tc_ld32(lane_base + TC_COL_D2 + f0, dz0);
-            tc_ld32(lane_base + TC_COL_AHI + f0, hh);
-            {
-                float hl[32];
-                tc_ld32(lane_base + TC_COL_ALO + f0, hl);
+            float dz0[32];
+            tc_ld32(my + TC_COL_D + f0, dz0);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { const float h0 = hh[j] + hl[j]; dz0[j] *= (1.0f - h0 * h0); }
+            for (int c0 = 0; c0 < 32; c0 += 8) {
+                float h[8];
+                {
+                    const float4 ba = *reinterpret_cast<const float4*>(sb0 + f0 + c0);
+                    const float4 bb = *reinterpret_cast<const float4*>(sb0 + f0 + c0 + 4);
+                    h[0] = ba.x; h[1] = ba.y; h[2] = ba.z; h[3] = ba.w; h[4] = bb.x; h[5] = bb.y; h[6] = bb.z; h[7] = bb.w;
+                }
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const float xd = d == 0 ? x0 : (d == 1 ? x1 : (d == 2 ? x2 : x3));
+                    const float4 w0 = *reinterpret_cast<const float4*>(sW0 + d * 64 + f0 + c0);
+                    const float4 w1 = *reinterpret_cast<const float4*>(sW0 + d * 64 + f0 + c0 + 4);
+                    h[0] = fmaf(xd, w0.x, h[0]); h[1] = fmaf(xd, w0.y, h[1]); h[2] = fmaf(xd, w0.z, h[2]); h[3] = fmaf(xd, w0.w, h[3]);
+                    h[4] = fmaf(xd, w1.x, h[4]); h[5] = fmaf(xd, w1.y, h[5]); h[6] = fmaf(xd, w1.z, h[6]); h[7] = fmaf(xd, w1.w, h[7]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    // same rounding as the forward value the tensor cores consumed: hi + lo == h exactly
+                    const float h0 = fast_tanh(h[j]);
+                    dz0[c0 + j] *= (1.0f - h0 * h0);
+                }
             }
+            float tt[32];
 #pragma unroll
-            for (int d = 0; d < 4; ++d) {
+            for (int n = 0; n < 32; ++n) tt[n] = x0 * dz0[n];
+            TcTR<32, 16>::run(tt, lane);
+            accW0_0 += tt[0];
 #pragma unroll
-                for (int n = 0; n < 32; ++n) hh[n] = x[d] * dz0[n];
-                TcTR<32, 16>::run(hh, lane);
-                accW0[d] += hh[0];
-            }
+            for (int n = 0; n < 32; ++n) tt[n] = x1 * dz0[n];
+            TcTR<32, 16>::run(tt, lane);
+            accW0_1 += tt[0];
+#pragma unroll
+            for (int n = 0; n < 32; ++n) tt[n] = x2 * dz0[n];
+            TcTR<32, 16>::run(tt, lane);
+            accW0_2 += tt[0];
+#pragma unroll
+            for (int n = 0; n < 32; ++n) tt[n] = x3 * dz0[n];
+            TcTR<32, 16>::run(tt, lane);
+            accW0_3 += tt[0];
             TcTR<32, 16>::run(dz0, lane);
             accb0 += dz0[0];
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    // ---- end of pass: dW1 from TMEM (M = 64: row k <-> lane 32*(k/16) + k%16), thin layers through shared memory -----
+    // ---- end of pass: dW1 from TMEM (M = 128: row i <-> lane i; rows 0..63 -> plane 0, rows 64..127 (lo part) -> plane 1) -----
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {
-        const int k = (warp & 3) * 16 + lane;
-        float t[32];
-        tc_ld32(lane_base + TC_COL_D3 + f0, t);         // all 32 lanes take part in the load; lanes >= 16 hold nothing
-        if (lane < 16) {
-            float* g = gp + L1.pw_off + k * 64 + f0;
+    if (g == 0) {
+        float tt[32];
+        tc_ld32(tb + lane_base + TC_COL_D3 + f0, tt);
+        float* gw = gp + (size_t)(m >> 6) * a.half_stride * pd.gpack + L1.pw_off + (m & 63) * 64 + f0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(g + j) = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
-        }
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(gw + j) = make_float4(tt[j], tt[j + 1], tt[j + 2], tt[j + 3]);
     }
-    // per-warp partial sums -> sRed[warp][...] -> fixed-order sum over the 4 warps that share a feature half
+    // per-warp partial sums -> sRed[warp][...] -> fixed-order sum over the 8 warps (4 per group) that share a feature half
     {
         float* r = sRed + warp * TC_RED_STRIDE;
-#pragma unroll
-        for (int d = 0; d < 4; ++d) r[d * 32 + lane] = accW0[d];
+        r[0 * 32 + lane] = accW0_0; r[1 * 32 + lane] = accW0_1; r[2 * 32 + lane] = accW0_2; r[3 * 32 + lane] = accW0_3;
         r[128 + lane] = accb0;
         r[160 + lane] = accb1;
 #pragma unroll
@@ -431,23 +499,21 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     }
     __syncthreads();
     {
-        // entries: h in {0,1}; per half 192 + 32*NOUT feature entries; b2 (half 0 only)
+        // entries: h in {0,1}; per half 192 + 32*NOUT feature entries; b2 (half 0 warps only)
         const int per_half = 192 + NOUT * 32;
         for (int i = tid; i < 2 * per_half + NOUT; i += TC_THREADS) {
-            if (i < 2 * per_half) {
-                const int h = i / per_half, e = i - h * per_half;
-                const float* r = sRed + (h * 4) * TC_RED_STRIDE + e;
-                const float s = (r[0] + r[TC_RED_STRIDE]) + (r[2 * TC_RED_STRIDE] + r[3 * TC_RED_STRIDE]);
-                const int n = h * 32 + (e & 31);
-                if (e < 128) gp[L0.pw_off + (e >> 5) * 64 + n] = s;            // W0 packed [4][64]
-                else if (e < 160) gp[L0.pb_off + n] = s;
-                else if (e < 192) gp[L1.pb_off + n] = s;
-                else gp[L2.pw_off + n * 4 + ((e - 192) >> 5)] = s;             // W2 packed [64][4]
-            } else {
-                const int j = i - 2 * per_half;
-                const float* r = sRed + 192 + NOUT * 32 + j;
-                gp[L2.pb_off + j] = (r[0] + r[TC_RED_STRIDE]) + (r[2 * TC_RED_STRIDE] + r[3 * TC_RED_STRIDE]);
-            }
+            const int h = i < 2 * per_half ? i / per_half : 0;
+            const int e = i < 2 * per_half ? i - h * per_half : 192 + NOUT * 32 + (i - 2 * per_half);
+            const float* r0 = sRed + (h * 4) * TC_RED_STRIDE + e;         // group 0 warps h*4 .. h*4+3
+            const float* r1 = r0 + 8 * TC_RED_STRIDE;                     // group 1
+            const float s = ((r0[0] + r0[TC_RED_STRIDE]) + (r0[2 * TC_RED_STRIDE] + r0[3 * TC_RED_STRIDE])) +
+                            ((r1[0] + r1[TC_RED_STRIDE]) + (r1[2 * TC_RED_STRIDE] + r1[3 * TC_RED_STRIDE]));
+            const int n = h * 32 + (e & 31);
+            if (i >= 2 * per_half) gp[L2.pb_off + (i - 2 * per_half)] = s;
+            else if (e < 128) gp[L0.pw_off + (e >> 5) * 64 + n] = s;           // W0 packed [4][64]
+            else if (e < 160) gp[L0.pb_off + n] = s;
+            else if (e < 192) gp[L1.pb_off + n] = s;
+            else gp[L2.pw_off + n * 4 + ((e - 192) >> 5)] = s;                 // W2 packed [64][4]
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -456,11 +522,11 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
 
 __global__ void __launch_bounds__(TC_THREADS, 1) ppo_loss_grad_tc_kernel(const __grid_constant__ LossArgs a) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ __align__(8) uint64_t bars[4];
     __shared__ uint32_t tmem_base_s;
     __shared__ double scratch[32];
     if (*a.stop_flag) return;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, g = tid >> 8;
     const uint32_t raw = tc_smem_u32(tc_smem_raw);
     const uint32_t sm_base = (raw + 1023u) & ~1023u;
     unsigned char* sm = tc_smem_raw + (sm_base - raw);
@@ -469,8 +535,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_loss_grad_tc_kernel(const _
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[1])));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[i])));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -488,15 +554,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_loss_grad_tc_kernel(const _
         adv_den = (float)sqrt(var) + 1e-8f;
     }
     const float invB = (float)(1.0 / a.mb.global_count);
-    double stats[6] = {0, 0, 0, 0, 0, 0};
+    float stats[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float* gp = a.gpart + (size_t)blockIdx.x * a.pd.gpack;
-    uint32_t bar_it = 0;
-    if (a.pd.act_n == 1) tc_pass<1, true>(a, sm, sm_base, tb, &bars[0], &bars[1], bar_it, adv_mean, adv_den, invB, stats, gp);
-    else tc_pass<2, true>(a, sm, sm_base, tb, &bars[0], &bars[1], bar_it, adv_mean, adv_den, invB, stats, gp);
-    tc_pass<1, false>(a, sm, sm_base, tb, &bars[0], &bars[1], bar_it, adv_mean, adv_den, invB, stats, gp);
+    // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0 .. nt-1; group g takes j = g, g+2, ...
+    const long long n_tiles = (a.mb.count + TC_M - 1) / TC_M;
+    const int nt = (long long)blockIdx.x < n_tiles ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const int n_own = g ? nt / 2 : (nt + 1) / 2;
+    const int n_other = nt - n_own;
+    if (a.pd.act_n == 1) tc_pass<1, true>(a, sm, sm_base, tb, bars, n_own, 0u, 0u, adv_mean, adv_den, invB, stats, gp);
+    else tc_pass<2, true>(a, sm, sm_base, tb, bars, n_own, 0u, 0u, adv_mean, adv_den, invB, stats, gp);
+    tc_pass<1, false>(a, sm, sm_base, tb, bars, n_own, (uint32_t)n_own, (uint32_t)n_other, adv_mean, adv_den, invB, stats, gp);
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-        const double s = block_sum(stats[i], scratch);
+        const double s = block_sum((double)stats[i], scratch);
         if (tid == 0) gp[a.pd.pack_fwd + a.pd.act_n + i] = (float)s;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
