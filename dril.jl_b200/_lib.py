@@ -33,7 +33,8 @@ class IterStats(C.Structure):
                 ("clip_fraction", c_f32), ("loss", c_f32), ("explained_variance", c_f32), ("grad_norm", c_f32),
                 ("learning_rate", c_f32), ("entropy", c_f32), ("ratio", c_f32), ("rollout_ms", c_f32),
                 ("update_ms", c_f32), ("n_minibatch_steps", c_i32), ("kl_stopped", c_i32), ("episodes", c_i64),
-                ("episode_return_sum", c_f64), ("episode_length_sum", c_f64)]
+                ("episode_return_sum", c_f64), ("episode_length_sum", c_f64),
+                ("ep_rew_mean", c_f32), ("ep_len_mean", c_f32), ("episodes_in_window", c_i64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -76,6 +77,7 @@ PROTOTYPES = {
     "dril_policy_create": [P, c_i32, c_i32, P, c_i32, c_i32, c_i32, P, P, C.POINTER(P)],
     "dril_policy_destroy": [P],
     "dril_policy_num_params": [P, C.POINTER(c_i64)],
+    "dril_policy_update_path": [P, C.POINTER(c_i32)],
     "dril_policy_set_params": [P, P, c_i64],
     "dril_policy_get_params": [P, P, c_i64],
     "dril_policy_get_opt_state": [P, P, P, c_i64, C.POINTER(c_i64)],

@@ -341,15 +341,27 @@ def train(agent, env, alg, max_steps, callbacks=None, sync_every_iteration=True)
     if not _hook(callbacks, "on_training_start", dict(locals())):
         return None
     t_loop = time.time()
-    pending = []
-    for i in range(1, iterations + 1):
-        learning_rate = alg.learning_rate                   # Optimisers.adjust! each iteration (ppo.jl:155-157)
-        hyper = alg.hyper()
-        if not _hook(callbacks, "on_rollout_start", dict(locals())):
-            return None
-        L.check(lib.dril_ppo_iteration_async(env.h, agent.device.h, roll_buffer.h, C.byref(hyper), alg.epochs,
+    # Without callbacks nothing on the host can influence the next iteration, so iteration i+1 is enqueued before
+    # the statistics of iteration i are read (the library keeps results in FIFO order): the device never waits for
+    # the host.  With callbacks every hook sees the device state of its own iteration, as in the reference.
+    pipelined = not callbacks
+
+    def enqueue():
+        L.check(lib.dril_ppo_iteration_async(env.h, agent.device.h, roll_buffer.h, C.byref(alg.hyper()), alg.epochs,
                                              alg.batch_size, agent.shuffle_seed, agent.epoch_counter))
         agent.epoch_counter += alg.epochs
+
+    for i in range(1, iterations + 1):
+        learning_rate = alg.learning_rate                   # Optimisers.adjust! each iteration (ppo.jl:155-157)
+        if not _hook(callbacks, "on_rollout_start", dict(locals())):
+            return None
+        if pipelined:
+            if i == 1:
+                enqueue()
+            if i < iterations:
+                enqueue()
+        else:
+            enqueue()
         st = L.IterStats()
         L.check(lib.dril_iteration_result(agent.device.h, C.byref(st)))
         fps = n_steps * n_envs / max(st.rollout_ms * 1e-3, 1e-12)
@@ -358,7 +370,9 @@ def train(agent, env, alg, max_steps, callbacks=None, sync_every_iteration=True)
         agent.stats.gradient_updates += st.n_minibatch_steps
         agent.logger.increment_step(n_steps * n_envs)
         agent.logger.log_scalar("env/fps", fps)
-        env.log_stats(agent.logger)
+        if st.episodes_in_window > 0:                       # log_stats(env, logger), monitorWrapperEnv.jl:64-70
+            agent.logger.log_scalar("env/ep_rew_mean", st.ep_rew_mean)
+            agent.logger.log_scalar("env/ep_len_mean", st.ep_len_mean)
         if not _hook(callbacks, "on_rollout_end", dict(locals())):
             return None
         learn["learning_rates"].append(learning_rate)

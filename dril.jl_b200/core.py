@@ -294,6 +294,12 @@ class DevicePolicy:
         L.check(ctx.lib.dril_policy_num_params(h, C.byref(n)))
         self.n_params = n.value
 
+    def update_path(self):
+        """'tensor' when the update runs the tcgen05 (3xTF32) loss/grad kernel for this policy, else 'fp32'."""
+        o = L.c_i32(0)
+        L.check(self.ctx.lib.dril_policy_update_path(self.h, C.byref(o)))
+        return "tensor" if o.value else "fp32"
+
     def set_params(self, flat):
         flat = L.f32(flat)
         L.check(self.ctx.lib.dril_policy_set_params(self.h, L.ptr(flat), flat.size))

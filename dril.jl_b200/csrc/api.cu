@@ -15,6 +15,7 @@
 #include "update_tc.cuh"
 
 #define DRIL_SMEM_MAX 232448  // 227 KB opt-in per CTA on sm_100
+#define DRIL_RESULT_SLOTS 4   // iterations that may be enqueued before their results are read
 #define DRIL_GPLANES 8        // gradient partial planes per CTA (sample-range splits of the dW tiles)
 
 // ---------------------------------------------------------------------------------------
@@ -173,6 +174,16 @@ struct dril_policy {
     uint32_t step_index = 0;
     // last iteration bookkeeping
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // iterations in flight (dril_ppo_iteration_async -> dril_iteration_result, FIFO)
+    struct Slot {
+        cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // rollout start, update start, update end, record on host
+        IterRecord* host = nullptr;                                    // pinned
+        dril_env* env = nullptr;
+        long long n_local = 0;
+        float lr = 0.f;
+    } slots[DRIL_RESULT_SLOTS];
+    IterRecord* rec_dev = nullptr;       // [DRIL_RESULT_SLOTS]
+    unsigned long long slot_head = 0, slot_tail = 0;
     dril_env* last_env = nullptr;
     dril_buffer* last_buf = nullptr;
     float last_lr = 0.f;
@@ -634,12 +645,23 @@ extern "C" int32_t dril_policy_destroy(dril_policy* p) {
                   p->ticket};
     for (void* q : ps) if (q) cudaFree(q);
     for (int i = 0; i < 3; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+    for (auto& sl : p->slots) {
+        for (int i = 0; i < 4; ++i) if (sl.ev[i]) cudaEventDestroy(sl.ev[i]);
+        if (sl.host) cudaFreeHost(sl.host);
+    }
+    if (p->rec_dev) cudaFree(p->rec_dev);
     delete p;
     return DRIL_OK;
 }
 extern "C" int32_t dril_policy_num_params(dril_policy* p, int64_t* n) {
     DRIL_REQUIRE(p && n, "NULL argument");
     *n = p->pd.n_params;
+    return DRIL_OK;
+}
+/* 1 when dril_ppo_update / dril_ppo_loss_grad run the tensor-core (tcgen05) loss/grad kernel for this policy, else 0 */
+extern "C" int32_t dril_policy_update_path(dril_policy* p, int32_t* out) {
+    DRIL_REQUIRE(p && out, "NULL argument");
+    *out = (g_opt_tc && tc_eligible(p->pd)) ? 1 : 0;
     return DRIL_OK;
 }
 static int32_t repack(dril_policy* p) {
@@ -1463,6 +1485,7 @@ static int32_t collect_iter_stats(dril_policy* p, dril_iter_stats* s, bool with_
     s->kl_stopped = stop;
     s->learning_rate = p->last_lr;
     s->episodes = (int64_t)eps; s->episode_return_sum = rs[0]; s->episode_length_sum = rs[1];
+    s->ep_rew_mean = NAN; s->ep_len_mean = NAN;      // the monitor window is reported by dril_iteration_result only
     return DRIL_OK;
 }
 
@@ -1496,29 +1519,77 @@ extern "C" int32_t dril_ppo_iteration_async(dril_env* e, dril_policy* p, dril_bu
     DRIL_REQUIRE(h, "hyper is NULL");
     dril_ctx* c = e->ctx;
     DRIL_CUDA(cudaSetDevice(c->device));
+    const int si = (int)(p->slot_tail % DRIL_RESULT_SLOTS);
+    dril_policy::Slot& sl = p->slots[si];
+    if (p->slot_tail - p->slot_head >= DRIL_RESULT_SLOTS) {
+        // results are optional: the oldest unread one is dropped (its record must have landed before the slot is reused)
+        DRIL_CUDA(cudaEventSynchronize(sl.ev[3]));
+        if (sl.env) sl.env->total_episodes += (int64_t)sl.host->roll_eps;
+        p->slot_head += 1;
+    }
+    if (!sl.host) {
+        DRIL_CUDA(cudaMallocHost(&sl.host, sizeof(IterRecord)));
+        for (int i = 0; i < 4; ++i) DRIL_CUDA(cudaEventCreate(&sl.ev[i]));
+    }
+    if (!p->rec_dev) DRIL_CUDA(cudaMalloc(&p->rec_dev, sizeof(IterRecord) * DRIL_RESULT_SLOTS));
+    sl.env = e; sl.n_local = b->d.T * b->d.N; sl.lr = h->learning_rate;
     p->last_env = e; p->last_buf = b; p->last_lr = h->learning_rate;
-    DRIL_CUDA(cudaEventRecord(p->ev[0], c->stream));
+    DRIL_CUDA(cudaEventRecord(sl.ev[0], c->stream));
     DRIL_TRY(rollout_async(e, p, b, nullptr));
     DRIL_TRY(gae_async(c, b->d, h->gamma, h->gae_lambda));
     DRIL_TRY(launch_monitor_finalize(e, b));
-    DRIL_CUDA(cudaEventRecord(p->ev[1], c->stream));
+    DRIL_CUDA(cudaEventRecord(sl.ev[1], c->stream));
     DRIL_TRY(ev_async(p, b));   // explained variance uses the rollout's values/returns (ppo.jl:256)
+    DRIL_TRY(allreduce_sum(c, p->ev_acc, 4, true));
     DRIL_TRY(update_async(p, b, h, epochs, batch_size, shuffle_seed, epoch_counter));
-    DRIL_CUDA(cudaEventRecord(p->ev[2], c->stream));
+    DRIL_CUDA(cudaEventRecord(sl.ev[2], c->stream));
+    {
+        IterRecordSrc src;
+        src.acc = p->iter_acc; src.ev = p->ev_acc; src.roll_sums = e->d.roll_sums; src.roll_eps = e->d.roll_eps;
+        src.stop = p->stop_flag; src.p2p_err = c->p2p_enabled ? c->p2p.err : nullptr; src.ring = e->ring;
+        src.has_ring = e->d.monitor ? 1 : 0;
+        Span sp(c, DRIL_K_MONITOR);
+        iter_record_kernel<<<1, 32, 0, c->stream>>>(src, p->rec_dev + si);
+        DRIL_CUDA(cudaGetLastError());
+    }
+    DRIL_CUDA(cudaMemcpyAsync(sl.host, p->rec_dev + si, sizeof(IterRecord), cudaMemcpyDeviceToHost, c->stream));
+    DRIL_CUDA(cudaEventRecord(sl.ev[3], c->stream));
+    p->slot_tail += 1;
     return DRIL_OK;
 }
 extern "C" int32_t dril_iteration_result(dril_policy* p, dril_iter_stats* stats_out) {
     DRIL_REQUIRE(p && stats_out, "NULL argument");
-    DRIL_REQUIRE(p->last_buf, "no iteration in flight");
+    DRIL_REQUIRE(p->slot_head < p->slot_tail, "no iteration in flight");
     dril_ctx* c = p->ctx;
     DRIL_CUDA(cudaSetDevice(c->device));
+    dril_policy::Slot& sl = p->slots[p->slot_head % DRIL_RESULT_SLOTS];
+    p->slot_head += 1;
+    DRIL_CUDA(cudaEventSynchronize(sl.ev[3]));
+    const IterRecord& r = *sl.host;
+    if (r.p2p_err) { dril_set_error("peer-memory allreduce timed out waiting for a peer rank"); return DRIL_ERR_NCCL; }
     dril_iter_stats s;
-    DRIL_TRY(collect_iter_stats(p, &s, true));
-    DRIL_TRY(ev_finish(p, p->last_buf->d.T * p->last_buf->d.N, &s.explained_variance));
+    memset(&s, 0, sizeof(s));
+    const double n = r.acc[9];
+    // means over the iteration's applied minibatches; empty -> NaN like mean(Float32[]) (ppo.jl:257-263)
+    s.policy_loss = (float)(r.acc[0] / n); s.value_loss = (float)(r.acc[1] / n); s.entropy_loss = (float)(r.acc[2] / n);
+    s.clip_fraction = (float)(r.acc[3] / n); s.approx_kl_div = (float)(r.acc[4] / n); s.entropy = (float)(r.acc[5] / n);
+    s.ratio = (float)(r.acc[6] / n); s.loss = (float)(r.acc[7] / n);
+    s.grad_norm = (float)(r.acc[8] / r.acc[10]);
+    s.n_minibatch_steps = (int32_t)n;
+    s.kl_stopped = r.stop;
+    s.learning_rate = sl.lr;
+    s.episodes = (int64_t)r.roll_eps; s.episode_return_sum = r.roll_sums[0]; s.episode_length_sum = r.roll_sums[1];
+    {
+        const double nn = (double)sl.n_local * c->nranks;
+        const double var_d = (r.ev[1] - r.ev[0] * r.ev[0] / nn) / (nn - 1.0);
+        const double var_r = (r.ev[3] - r.ev[2] * r.ev[2] / nn) / (nn - 1.0);
+        s.explained_variance = (float)(1.0 - var_d / var_r);
+    }
+    s.ep_rew_mean = r.ring_rew_mean; s.ep_len_mean = r.ring_len_mean; s.episodes_in_window = r.ring_count;
     float ms = 0.f;
-    DRIL_CUDA(cudaEventElapsedTime(&ms, p->ev[0], p->ev[1])); s.rollout_ms = ms;
-    DRIL_CUDA(cudaEventElapsedTime(&ms, p->ev[1], p->ev[2])); s.update_ms = ms;
-    if (p->last_env) p->last_env->total_episodes += s.episodes;
+    DRIL_CUDA(cudaEventElapsedTime(&ms, sl.ev[0], sl.ev[1])); s.rollout_ms = ms;
+    DRIL_CUDA(cudaEventElapsedTime(&ms, sl.ev[1], sl.ev[2])); s.update_ms = ms;
+    if (sl.env) sl.env->total_episodes += s.episodes;
     *stats_out = s;
     return DRIL_OK;
 }

@@ -130,3 +130,45 @@ __global__ void __launch_bounds__(1024) monitor_finalize_kernel(MonitorRing ring
     }
     if (tid == 0) *ring.head = s_head;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Everything dril_iteration_result reports, gathered into one record at the end of an iteration so that the host
+// needs a single pinned device->host copy per iteration and may enqueue the next iteration before reading it.
+// ---------------------------------------------------------------------------------------------------------
+struct IterRecord {
+    double acc[16];             // iter_acc (update.cuh ITER_ACC_N)
+    double ev[4];               // explained-variance moments (already summed over ranks)
+    double roll_sums[2];
+    unsigned long long roll_eps;
+    long long ring_count;       // min(pushes, window)
+    float ring_rew_mean, ring_len_mean;   // mean(::CircularBuffer{Float32}) order: sequential over the ring slots
+    int stop, p2p_err;
+};
+struct IterRecordSrc {
+    const double* acc; const double* ev; const double* roll_sums; const unsigned long long* roll_eps;
+    const int* stop; const int* p2p_err; MonitorRing ring; int has_ring;
+};
+__global__ void iter_record_kernel(IterRecordSrc s, IterRecord* out) {
+    const int t = threadIdx.x;
+    if (t < 16) out->acc[t] = s.acc[t];
+    if (t < 4) out->ev[t] = s.ev[t];
+    if (t < 2) out->roll_sums[t] = s.roll_sums ? s.roll_sums[t] : 0.0;
+    if (t == 0) {
+        out->roll_eps = s.roll_eps ? *s.roll_eps : 0ull;
+        out->stop = *s.stop;
+        out->p2p_err = s.p2p_err ? *s.p2p_err : 0;
+    }
+    if (t == 31) {
+        long long cnt = 0;
+        float sr = 0.f;
+        double sl = 0.0;
+        if (s.has_ring) {
+            const long long head = *s.ring.head;
+            cnt = head < s.ring.window ? head : s.ring.window;
+            for (long long i = 0; i < cnt; ++i) { sr += s.ring.ret[i]; sl += (double)s.ring.len[i]; }
+        }
+        out->ring_count = cnt;
+        out->ring_rew_mean = cnt ? sr / (float)cnt : nanf("");
+        out->ring_len_mean = cnt ? (float)(sl / (double)cnt) : nanf("");
+    }
+}

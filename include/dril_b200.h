@@ -87,6 +87,10 @@ typedef struct {
     int32_t kl_stopped;               /* 1 if the target_kl stop fired (ppo.jl:235-238) */
     int64_t episodes;                 /* episodes finished during this rollout */
     double episode_return_sum, episode_length_sum;
+    /* the monitor window after this rollout (mean over the last `stats_window` episodes, monitorWrapperEnv.jl:64-70);
+     * NaN / 0 when the env has no MonitorWrapperEnv or no episode has finished yet */
+    float ep_rew_mean, ep_len_mean;
+    int64_t episodes_in_window;
 } dril_iter_stats;
 
 /* rollout-buffer fields (buffers/buffer_types.jl:3-15); device layout is time-major
@@ -194,6 +198,10 @@ int32_t dril_policy_create(dril_ctx* ctx, int32_t obs_dim, int32_t n_hidden, con
                            const float* act_low, const float* act_high, dril_policy** out);
 int32_t dril_policy_destroy(dril_policy* p);
 int32_t dril_policy_num_params(dril_policy* p, int64_t* n);
+/* which loss/grad kernel the update uses for this policy: 1 = tensor cores (tcgen05, 3xTF32; hidden_dims = [64, 64],
+ * obs_dim <= 4, Discrete(n <= 2), option "tc" on), 0 = fp32 CUDA cores.  Both replace the same reference code
+ * (src/algorithms/ppo.jl:188-254 loss functor + Zygote pullback) and meet the same 1e-4 parity bound. */
+int32_t dril_policy_update_path(dril_policy* p, int32_t* out);
 /* flat fp32 vector in ComponentVector(ps) order: actor_head layers (weight (out,in) column-major,
  * bias), critic_head layers, log_std (layers/layer_lux.jl:4-52) */
 int32_t dril_policy_set_params(dril_policy* p, const float* flat, int64_t n);
@@ -247,7 +255,10 @@ int32_t dril_ppo_update(dril_policy* p, dril_buffer* buf, const dril_ppo_hyper* 
                         int64_t batch_size, uint64_t shuffle_seed, uint64_t epoch_counter,
                         dril_iter_stats* stats_out);
 /* one train! iteration (ppo.jl:154-297): rollout + GAE + update + explained variance.
- * The _async form only enqueues; dril_iteration_result waits and returns the statistics. */
+ * The _async form only enqueues; dril_iteration_result waits for the OLDEST enqueued iteration whose result has not
+ * been read yet and returns its statistics (one pinned device->host record per iteration).  Up to 4 iterations may
+ * be in flight, so a host loop can enqueue iteration i+1 before it reads iteration i and the device never idles;
+ * enqueueing a fifth drops the oldest unread result. */
 int32_t dril_ppo_iteration_async(dril_env* env, dril_policy* p, dril_buffer* buf, const dril_ppo_hyper* hyper,
                                  int32_t epochs, int64_t batch_size, uint64_t shuffle_seed,
                                  uint64_t epoch_counter);

@@ -43,6 +43,7 @@ struct IterStats
     learning_rate::Float32; entropy::Float32; ratio::Float32; rollout_ms::Float32; update_ms::Float32
     n_minibatch_steps::Int32; kl_stopped::Int32; episodes::Int64
     episode_return_sum::Float64; episode_length_sum::Float64
+    ep_rew_mean::Float32; ep_len_mean::Float32; episodes_in_window::Int64
 end
 neg(x) = isnothing(x) ? -1.0f0 : Float32(x)
 PPOHyper(alg::PPO) = PPOHyper(alg.gamma, alg.gae_lambda, alg.clip_range, neg(alg.clip_range_vf), alg.ent_coef,

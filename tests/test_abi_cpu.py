@@ -42,7 +42,7 @@ def test_struct_layouts_match_header():
     from dril_b200 import _lib
     assert ctypes.sizeof(_lib.NormCfg) == 28
     assert ctypes.sizeof(_lib.PPOHyper) == 52
-    assert ctypes.sizeof(_lib.IterStats) == 88
+    assert ctypes.sizeof(_lib.IterStats) == 104
 
 
 def test_no_cpu_fallback(lib):

@@ -83,3 +83,31 @@ def test_callbacks_and_save_load(D, tmp_path):
     obs = np.random.default_rng(0).normal(size=(5, 4)).astype(np.float32)
     np.testing.assert_array_equal(D.predict_actions(agent, obs, deterministic=True),
                                   D.predict_actions(agent2, obs, deterministic=True))
+
+
+def test_pipelined_train_matches_sequential(D):
+    """train! without callbacks enqueues iteration i+1 before reading iteration i; with a (no-op) callback it runs one
+    iteration at a time.  Both must produce the same parameters, statistics and monitor window bit for bit."""
+    class Noop(D.AbstractCallback):
+        pass
+
+    def run(callbacks):
+        n, T = 256, 32
+        env = D.CudaBatchedEnv("cartpole", n, seed=5, monitor_window=100)
+        layer = D.ActorCriticLayer(env.observation_space(), env.action_space(), hidden_dims=[64, 64])
+        alg = D.PPO(n_steps=T, batch_size=T * n // 2, epochs=2)
+        logger = D.DictLogger()
+        agent = D.Agent(layer, alg, rng=np.random.default_rng(3), logger=logger)
+        out = D.train(agent, env, alg, n * T * 7, callbacks=callbacks)
+        assert out is not None
+        return agent.train_state.parameters.copy(), out[0], env.monitor_stats(), logger.scalars
+
+    p_a, s_a, m_a, l_a = run(None)
+    p_b, s_b, m_b, l_b = run([Noop()])
+    np.testing.assert_array_equal(p_a, p_b)
+    for k in s_a:
+        if k != "fps":
+            np.testing.assert_array_equal(s_a[k], s_b[k], err_msg=k)
+    assert len(s_a["losses"]) == 7
+    assert m_a == m_b
+    assert [v for _, v in l_a["env/ep_rew_mean"]] == [v for _, v in l_b["env/ep_rew_mean"]]

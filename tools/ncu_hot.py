@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep: stall-reason totals and the hottest SASS instructions of the first kernel.
+usage: python tools/ncu_hot.py report.ncu-rep [top_n]"""
+import csv, subprocess, sys, io
+rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+h, v = rows[0], rows[2]
+want = ['gpu__time_duration.sum', 'sm__cycles_elapsed.max', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'sm__inst_executed_pipe_xu.sum', 'smsp__inst_executed_pipe_xu.sum',
+        'sm__warps_active.avg.per_cycle_active', 'launch__grid_size', 'launch__block_size']
+for a, b in zip(h, v):
+    if any(a.endswith(w) for w in want): print(f'{a} = {b}')
+src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(src)))
+h = rows[1]; data = rows[2:]
+isrc = h.index('Source'); isamp = h.index('# Samples'); iinst = h.index('Instructions Executed')
+stalls = [i for i, c in enumerate(h) if c.startswith('stall_') and 'Not Issued' not in c]
+tot = sum(int(r[isamp] or 0) for r in data)
+print('total samples', tot, 'SASS instructions', len(data))
+agg = {}
+for r in data:
+    for i in stalls: agg[h[i]] = agg.get(h[i], 0) + int(r[i] or 0)
+for k, val in sorted(agg.items(), key=lambda x: -x[1])[:10]: print(f'  {k:26s}{val:8d} {100 * val / max(tot, 1):5.1f}%')
+for r in sorted(data, key=lambda r: -int(r[isamp] or 0))[:topn]:
+    st = sorted([(int(r[i] or 0), h[i]) for i in stalls], reverse=True)[:2]
+    print(r[isamp].rjust(6), r[iinst].rjust(8), r[isrc][:70].ljust(70), st)
