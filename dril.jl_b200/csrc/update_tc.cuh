@@ -11,16 +11,17 @@
 //                                                 SWIZZLE_128B_BASE32B smem images; the accumulator stays in TMEM
 //                                                 across all tiles of the pass (rows 0..63 hi part, 64..127 lo part)
 // Everything else is CUDA-core code with two threads per sample (thread (m, half) <-> TMEM lane m, hidden features
-// [32 half, 32 half + 32)): layer 0 (K = obs_dim), the output layers, the loss head, the deltas, and the thin-layer
-// gradients (dW0, db0, db1, dW2, db2), reduced across the 32 samples of a warp with a shuffle transpose-reduce and
-// kept in registers across tiles.
+// [32 half, 32 half + 32)): layer 0 (K = obs_dim), the output layers, the loss head and the deltas.  The thin-layer
+// gradients (dW0, db0, db1, dW2) are sums over samples: the per-sample factors are staged in shared memory as
+// [sample][68] rows and thread (feature f, sample quarter) accumulates its 32 samples per tile in registers (no
+// shuffles); the partial sums are combined once at the end of the pass.
 //
-// Two groups of 8 warps work on alternate 128-sample tiles of the CTA (ping-pong): while one group's MMAs run, the
-// other group is in a CUDA-core phase.  Each group owns 192 TMEM columns (D | A/Z hi | A/Z lo; the dZ1 operand
-// overwrites the H0 operand once G1 has consumed it, layer-0 activations are recomputed for the layer-0 delta) and
-// its own pair of mbarriers; the dW1 accumulator (64 columns) and the G3 shared-memory images are shared: a group
-// writes the images only after the other group's previous G3 has completed (its mbarrier phase), so image use
-// strictly alternates.  tcgen05 rates measured on B200 by tools/tc_probe3.cu: max(44, N/2) cycles per tf32
+// Two groups of 8 warps work on alternate 128-sample tiles of the CTA (ping-pong): while one group's MMAs run or
+// it waits, the other group is in a CUDA-core phase.  Each group owns 192 TMEM columns (D | A/Z hi | A/Z lo; the dZ1
+// operand overwrites the H0 operand once G1 has consumed it) and its own mbarriers; the dW1 accumulator (64
+// columns) and the 128 KB image region are shared.  A group holds the image region from the staging of its
+// output-layer factors until its layer-0 gradient sums are done (staging -> images -> G2/G3 -> layer-0 delta, which
+// re-reads H0 from the image -> staging) and then releases it through an mbarrier, so use strictly alternates.  tcgen05 rates measured on B200 by tools/tc_probe3.cu: max(44, N/2) cycles per tf32
 // instruction at M = 128.  Descriptor recipes are the ones verified on hardware by tools/tc_probe*.cu
 // (profiles/r01_tcgen05_probe.txt).  One pass over the minibatch per net (actor, then critic).
 #pragma once
@@ -43,8 +44,8 @@
 #define TC_OFF_Z1_HI 131072
 #define TC_OFF_Z1_LO 163840
 #define TC_OFF_SMALL 196608
-#define TC_SMALL_FLOATS 2048
-#define TC_RED_STRIDE 288   // per-warp reduction scratch: 192 + 32*NOUT + NOUT floats, NOUT <= 2 (aliases the images)
+#define TC_SMALL_FLOATS 3328
+#define TC_STAGE_LD 68      // floats per sample row of a staging buffer (272 B: conflict-free 16-byte stores by 32 samples)
 #define TC_SMEM_BYTES (TC_OFF_SMALL + TC_SMALL_FLOATS * 4 + 1024)
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -141,8 +142,9 @@ __device__ __forceinline__ void tc_group_sync(int g) { asm volatile("bar.sync %0
 
 // one pass (one net) over all tiles of this CTA.  512 threads = 2 groups x 256; within a group thread
 // (m = t & 127, half = t >> 7) owns sample m (TMEM lane m; warps w and w+4 share lane quadrant w) and the 32 hidden
-// features [32*half, 32*half + 32).  n_own / n_other: tiles of this pass handled by this / the other group;
-// base_own / base_other: mbarrier phases the groups completed in earlier passes.
+// features [32*half, 32*half + 32); for the sums over samples the same thread is (f = t & 63, quarter = t >> 6).
+// n_own: tiles of this pass handled by this group; base_own / base_other: mbarrier phases the groups completed in
+// earlier passes.
 template <int NOUT, bool ACTOR>
 __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, uint32_t sm_base, uint32_t tb, uint64_t* bars,
                                         int n_own, uint32_t base_own, uint32_t base_other, float adv_mean, float adv_den,
@@ -153,9 +155,10 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     const LayerDesc& L0 = pd.L[net][0];
     const LayerDesc& L1 = pd.L[net][1];
     const LayerDesc& L2 = pd.L[net][2];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int g = tid >> 8, t = tid & 255;
     const int m = t & 127, half = t >> 7, f0 = half * 32;
+    const int rf = t & 63, rq = t >> 6;            // reducer role: feature, sample quarter
     const int D = pd.obs_dim;
     float* sW1c_hi = reinterpret_cast<float*>(sm + TC_OFF_W1C_HI);
     float* sW1c_lo = reinterpret_cast<float*>(sm + TC_OFF_W1C_LO);
@@ -167,11 +170,17 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     float* sb1 = sb0 + 64;          // [64]
     float* sW2 = sb1 + 64;          // [64][4]
     float* sb2 = sW2 + 256;         // [4]
-    float* sOutP = sb2 + 8 + g * 512;   // per group: [2 halves][NOUT<=2][128] partial output-layer dot products
-    float* sRed = reinterpret_cast<float*>(sm + TC_OFF_H0CAT);   // end-of-pass reduction scratch [16 warps][TC_RED_STRIDE]
-    uint64_t* bar1 = bars + g * 2;
-    uint64_t* bar2 = bars + g * 2 + 1;
-    uint64_t* obar2 = bars + (g ^ 1) * 2 + 1;
+    float* sGrp = sb2 + 8 + g * 1280;
+    float* sOutP = sGrp;            // per group: [2 halves][NOUT<=2][128] partial output-layer dot products
+    float* sDout = sGrp + 512;      // per group: [128][2] output-layer deltas
+    float* sX = sGrp + 768;         // per group: [128][4] observations
+    float* sStageA = reinterpret_cast<float*>(sm + TC_OFF_H0CAT);   // [128][68] staging (H1), before the images are written
+    float* sStageB = reinterpret_cast<float*>(sm + TC_OFF_Z1_HI);   // [128][68] staging (dZ1, later dZ0)
+    float* sRed = reinterpret_cast<float*>(sm + TC_OFF_H0CAT);      // end-of-pass scratch [8 slots][8 sums][64]
+    uint64_t* bar1 = bars + g * 3;
+    uint64_t* bar2 = bars + g * 3 + 1;
+    uint64_t* bfree = bars + g * 3 + 2;
+    uint64_t* obfree = bars + (g ^ 1) * 3 + 2;
     const uint32_t gcol = tb + (uint32_t)g * TC_COL_GROUP;
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t my = gcol + lane_base;       // this thread's lane, this group's columns
@@ -201,11 +210,12 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // persistent thin-layer gradient accumulators: lane l of this warp holds feature n = f0 + l, summed over the
-    // warp's 32 samples and over this group's tiles
-    float accW0_0 = 0.f, accW0_1 = 0.f, accW0_2 = 0.f, accW0_3 = 0.f, accb0 = 0.f, accb1 = 0.f, accW2[NOUT], accb2[NOUT];
+    // persistent thin-layer gradient accumulators of reducer (rf, rq): sums over the samples of quarter rq of this
+    // group's tiles
+    float accW0_0 = 0.f, accW0_1 = 0.f, accW0_2 = 0.f, accW0_3 = 0.f, accb0 = 0.f, accb1 = 0.f, accW2_0 = 0.f, accW2_1 = 0.f;
+    float accb2[NOUT];
 #pragma unroll
-    for (int j = 0; j < NOUT; ++j) { accW2[j] = 0.f; accb2[j] = 0.f; }
+    for (int j = 0; j < NOUT; ++j) accb2[j] = 0.f;
 
     const uint32_t idesc_k = tc_idesc(128, 64, 0, 0);
     const uint32_t idesc_mn = tc_idesc(128, 64, 1, 1);
@@ -240,6 +250,8 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
                 ov = buf.values[sidx];
             }
         }
+        // sX of the previous tile was last read before the group barrier that ended that tile
+        if (half == 0) *reinterpret_cast<float4*>(sX + m * 4) = make_float4(x0, x1, x2, x3);
         // ---- layer 0 on CUDA cores, H0 hi/lo -> TMEM (A operand of G1) ----------------------------------------------
 #pragma unroll
         for (int c0 = 0; c0 < 32; c0 += 8) {
@@ -284,7 +296,11 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
         float h1[32];
         tc_ld32(my + TC_COL_D + f0, h1);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) h1[j] = fast_tanh(h1[j] + sb1[f0 + j]);
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(sb1 + f0 + j);
+            h1[j] = fast_tanh(h1[j] + b.x); h1[j + 1] = fast_tanh(h1[j + 1] + b.y);
+            h1[j + 2] = fast_tanh(h1[j + 2] + b.z); h1[j + 3] = fast_tanh(h1[j + 3] + b.w);
+        }
         {
             float po[NOUT];
 #pragma unroll
@@ -346,17 +362,22 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
             dout[0] = (valid && v_pass) ? a.hp.vf_coef * 2.0f * verr * invB : 0.f;
             if (valid && half == 0) stats[1] += verr * verr;
         }
-        // ---- thin-layer gradients of the output layer: dW2[k][j] = sum_m h1[m][k] dout[m][j], db2 ----------------
+        if (half == 0) {
 #pragma unroll
-        for (int j = 0; j < NOUT; ++j) {
-            float tt[32];
-#pragma unroll
-            for (int k = 0; k < 32; ++k) tt[k] = h1[k] * dout[j];
-            TcTR<32, 16>::run(tt, lane);
-            accW2[j] += tt[0];
-            if (half == 0) accb2[j] += warp_sum(dout[j]);
+            for (int j = 0; j < NOUT; ++j) accb2[j] += warp_sum(dout[j]);
+            *reinterpret_cast<float2*>(sDout + m * 2) = make_float2(dout[0], NOUT > 1 ? dout[NOUT > 1 ? 1 : 0] : 0.f);
         }
-        // ---- dZ1 = (dout W2^T) .* (1 - H1^2) in place over h1; db1 -------------------------------------------------
+        // ---- take over the image region: the other group's previous tile must have released it ------------------------
+        {
+            const int k = g ? it : it - 1;
+            if (k >= 0) tc_wait(obfree, (base_other + (uint32_t)k) & 1u);
+        }
+        // ---- stage H1 and dZ1 = (dout W2^T) .* (1 - H1^2) (in place over h1) as [sample][68] rows -----------------------
+        {
+            float* ra = sStageA + m * TC_STAGE_LD + f0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(ra + j) = make_float4(h1[j], h1[j + 1], h1[j + 2], h1[j + 3]);
+        }
 #pragma unroll
         for (int n = 0; n < 32; ++n) {
             const float4 w = *reinterpret_cast<const float4*>(sW2 + (f0 + n) * 4);
@@ -365,21 +386,29 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
             h1[n] = s * (1.0f - h1[n] * h1[n]);
         }
         {
-            float tt[32];
+            float* rb = sStageB + m * TC_STAGE_LD + f0;
 #pragma unroll
-            for (int n = 0; n < 32; ++n) tt[n] = h1[n];
-            TcTR<32, 16>::run(tt, lane);
-            accb1 += tt[0];
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(rb + j) = make_float4(h1[j], h1[j + 1], h1[j + 2], h1[j + 3]);
         }
-        // ---- take over the G3 images: the other group's previous G3 must have completed -----------------------------
+        tc_group_sync(g);
+        // ---- dW2[f][j] += sum_m H1[m][f] dout[m][j], db1[f] += sum_m dZ1[m][f] over this reducer's 32 samples -----------
         {
-            const int k = g ? it : it - 1;
-            if (k >= 0) {
-                tc_wait(obar2, (base_other + (uint32_t)k) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const float* pa = sStageA + (rq * 32) * TC_STAGE_LD + rf;
+            const float* pb = sStageB + (rq * 32) * TC_STAGE_LD + rf;
+            const float* pd2 = sDout + (rq * 32) * 2;
+            float s0 = 0.f, s1 = 0.f, sb = 0.f;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                const float hv = pa[i * TC_STAGE_LD];
+                const float2 dd = *reinterpret_cast<const float2*>(pd2 + i * 2);
+                s0 = fmaf(hv, dd.x, s0);
+                if (NOUT > 1) s1 = fmaf(hv, dd.y, s1);
+                sb += pb[i * TC_STAGE_LD];
             }
+            accW2_0 += s0; accW2_1 += s1; accb1 += sb;
         }
-        // H0 hi/lo back from TMEM -> H0 image; dZ1 hi/lo -> TMEM (over H0) + dZ1 images
+        tc_group_sync(g);
+        // ---- H0 hi/lo back from TMEM -> H0 image; dZ1 hi/lo -> TMEM (over H0) + dZ1 images ---------------------------
 #pragma unroll
         for (int c0 = 0; c0 < 32; c0 += 8) {
             float ahi[8], alo[8], hi[8], lo[8];
@@ -425,54 +454,44 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
         }
         tc_wait(bar2, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- dZ0 = dH0 .* (1 - H0^2) with H0 recomputed (own 32 features); dW0[d][n] = sum_m x[m][d] dZ0[m][n]; db0 ----
+        // ---- dZ0 = dH0 .* (1 - H0^2), H0 = hi + lo re-read from this thread's own rows of the H0 image; staged over the
+        //      dZ1 images (G3 has consumed them) -------------------------------------------------------------------------
         {
             float dz0[32];
             tc_ld32(my + TC_COL_D + f0, dz0);
 #pragma unroll
             for (int c0 = 0; c0 < 32; c0 += 8) {
-                float h[8];
-                {
-                    const float4 ba = *reinterpret_cast<const float4*>(sb0 + f0 + c0);
-                    const float4 bb = *reinterpret_cast<const float4*>(sb0 + f0 + c0 + 4);
-                    h[0] = ba.x; h[1] = ba.y; h[2] = ba.z; h[3] = ba.w; h[4] = bb.x; h[5] = bb.y; h[6] = bb.z; h[7] = bb.w;
-                }
+                const uint32_t sw = (((c0 >> 3) ^ r4) * 32);
+                const float4 ha = *reinterpret_cast<const float4*>(sm + TC_OFF_H0CAT + img_h0 + sw);
+                const float4 hb = *reinterpret_cast<const float4*>(sm + TC_OFF_H0CAT + img_h0 + sw + 16);
+                const float4 la = *reinterpret_cast<const float4*>(sm + TC_OFF_H0CAT + img_h0 + 1024 + sw);
+                const float4 lb = *reinterpret_cast<const float4*>(sm + TC_OFF_H0CAT + img_h0 + 1024 + sw + 16);
+                const float h0[8] = {ha.x + la.x, ha.y + la.y, ha.z + la.z, ha.w + la.w, hb.x + lb.x, hb.y + lb.y, hb.z + lb.z, hb.w + lb.w};
 #pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    const float xd = d == 0 ? x0 : (d == 1 ? x1 : (d == 2 ? x2 : x3));
-                    const float4 w0 = *reinterpret_cast<const float4*>(sW0 + d * 64 + f0 + c0);
-                    const float4 w1 = *reinterpret_cast<const float4*>(sW0 + d * 64 + f0 + c0 + 4);
-                    h[0] = fmaf(xd, w0.x, h[0]); h[1] = fmaf(xd, w0.y, h[1]); h[2] = fmaf(xd, w0.z, h[2]); h[3] = fmaf(xd, w0.w, h[3]);
-                    h[4] = fmaf(xd, w1.x, h[4]); h[5] = fmaf(xd, w1.y, h[5]); h[6] = fmaf(xd, w1.z, h[6]); h[7] = fmaf(xd, w1.w, h[7]);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    // same rounding as the forward value the tensor cores consumed: hi + lo == h exactly
-                    const float h0 = fast_tanh(h[j]);
-                    dz0[c0 + j] *= (1.0f - h0 * h0);
-                }
+                for (int j = 0; j < 8; ++j) dz0[c0 + j] *= (1.0f - h0[j] * h0[j]);
             }
-            float tt[32];
+            float* rb = sStageB + m * TC_STAGE_LD + f0;
 #pragma unroll
-            for (int n = 0; n < 32; ++n) tt[n] = x0 * dz0[n];
-            TcTR<32, 16>::run(tt, lane);
-            accW0_0 += tt[0];
-#pragma unroll
-            for (int n = 0; n < 32; ++n) tt[n] = x1 * dz0[n];
-            TcTR<32, 16>::run(tt, lane);
-            accW0_1 += tt[0];
-#pragma unroll
-            for (int n = 0; n < 32; ++n) tt[n] = x2 * dz0[n];
-            TcTR<32, 16>::run(tt, lane);
-            accW0_2 += tt[0];
-#pragma unroll
-            for (int n = 0; n < 32; ++n) tt[n] = x3 * dz0[n];
-            TcTR<32, 16>::run(tt, lane);
-            accW0_3 += tt[0];
-            TcTR<32, 16>::run(dz0, lane);
-            accb0 += dz0[0];
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(rb + j) = make_float4(dz0[j], dz0[j + 1], dz0[j + 2], dz0[j + 3]);
+        }
+        tc_group_sync(g);
+        // ---- dW0[d][f] += sum_m x[m][d] dZ0[m][f], db0[f] += sum_m dZ0[m][f] over this reducer's 32 samples ----------------
+        {
+            const float* pb = sStageB + (rq * 32) * TC_STAGE_LD + rf;
+            const float* px = sX + (rq * 32) * 4;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, sb = 0.f;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                const float z = pb[i * TC_STAGE_LD];
+                const float4 xv = *reinterpret_cast<const float4*>(px + i * 4);
+                s0 = fmaf(xv.x, z, s0); s1 = fmaf(xv.y, z, s1); s2 = fmaf(xv.z, z, s2); s3 = fmaf(xv.w, z, s3);
+                sb += z;
+            }
+            accW0_0 += s0; accW0_1 += s1; accW0_2 += s2; accW0_3 += s3; accb0 += sb;
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        tc_group_sync(g);
+        if (t == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bfree)) : "memory");
     }
     // ---- end of pass: dW1 from TMEM (M = 128: row i <-> lane i; rows 0..63 -> plane 0, rows 64..127 (lo part) -> plane 1) -----
     __syncthreads();
@@ -484,36 +503,31 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
 #pragma unroll
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(gw + j) = make_float4(tt[j], tt[j + 1], tt[j + 2], tt[j + 3]);
     }
-    // per-warp partial sums -> sRed[warp][...] -> fixed-order sum over the 8 warps (4 per group) that share a feature half
+    // reducer partial sums -> sRed[slot = g*4 + rq][sum][f] -> fixed-order sum over the 8 slots
     {
-        float* r = sRed + warp * TC_RED_STRIDE;
-        r[0 * 32 + lane] = accW0_0; r[1 * 32 + lane] = accW0_1; r[2 * 32 + lane] = accW0_2; r[3 * 32 + lane] = accW0_3;
-        r[128 + lane] = accb0;
-        r[160 + lane] = accb1;
+        float* r = sRed + ((g * 4 + rq) * 8) * 64 + rf;
+        r[0 * 64] = accW0_0; r[1 * 64] = accW0_1; r[2 * 64] = accW0_2; r[3 * 64] = accW0_3;
+        r[4 * 64] = accb0; r[5 * 64] = accb1; r[6 * 64] = accW2_0; r[7 * 64] = accW2_1;
+        if ((tid & 31) == 0 && half == 0) {
 #pragma unroll
-        for (int j = 0; j < NOUT; ++j) r[192 + j * 32 + lane] = accW2[j];
-        if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < NOUT; ++j) r[192 + NOUT * 32 + j] = accb2[j];
+            for (int j = 0; j < NOUT; ++j) sRed[8 * 8 * 64 + warp * 2 + j] = accb2[j];
         }
     }
     __syncthreads();
-    {
-        // entries: h in {0,1}; per half 192 + 32*NOUT feature entries; b2 (half 0 warps only)
-        const int per_half = 192 + NOUT * 32;
-        for (int i = tid; i < 2 * per_half + NOUT; i += TC_THREADS) {
-            const int h = i < 2 * per_half ? i / per_half : 0;
-            const int e = i < 2 * per_half ? i - h * per_half : 192 + NOUT * 32 + (i - 2 * per_half);
-            const float* r0 = sRed + (h * 4) * TC_RED_STRIDE + e;         // group 0 warps h*4 .. h*4+3
-            const float* r1 = r0 + 8 * TC_RED_STRIDE;                     // group 1
-            const float s = ((r0[0] + r0[TC_RED_STRIDE]) + (r0[2 * TC_RED_STRIDE] + r0[3 * TC_RED_STRIDE])) +
-                            ((r1[0] + r1[TC_RED_STRIDE]) + (r1[2 * TC_RED_STRIDE] + r1[3 * TC_RED_STRIDE]));
-            const int n = h * 32 + (e & 31);
-            if (i >= 2 * per_half) gp[L2.pb_off + (i - 2 * per_half)] = s;
-            else if (e < 128) gp[L0.pw_off + (e >> 5) * 64 + n] = s;           // W0 packed [4][64]
-            else if (e < 160) gp[L0.pb_off + n] = s;
-            else if (e < 192) gp[L1.pb_off + n] = s;
-            else gp[L2.pw_off + n * 4 + ((e - 192) >> 5)] = s;                 // W2 packed [64][4]
+    for (int i = tid; i < (6 + NOUT) * 64 + NOUT; i += TC_THREADS) {
+        if (i < (6 + NOUT) * 64) {
+            const int q = i >> 6, f = i & 63;
+            float s = 0.f;
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl) s += sRed[(sl * 8 + q) * 64 + f];
+            if (q < 4) gp[L0.pw_off + q * 64 + f] = s;                    // W0 packed [4][64]
+            else if (q == 4) gp[L0.pb_off + f] = s;
+            else if (q == 5) gp[L1.pb_off + f] = s;
+            else gp[L2.pw_off + f * 4 + (q - 6)] = s;                     // W2 packed [64][4]
+        } else {
+            const int j = i - (6 + NOUT) * 64;
+            const float* r = sRed + 8 * 8 * 64 + j;                      // warps 0..3 and 8..11 hold half 0
+            gp[L2.pb_off + j] = ((r[0] + r[2]) + (r[4] + r[6])) + ((r[16] + r[18]) + (r[20] + r[22]));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -522,7 +536,7 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
 
 __global__ void __launch_bounds__(TC_THREADS, 1) ppo_loss_grad_tc_kernel(const __grid_constant__ LossArgs a) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-    __shared__ __align__(8) uint64_t bars[4];
+    __shared__ __align__(8) uint64_t bars[6];
     __shared__ uint32_t tmem_base_s;
     __shared__ double scratch[32];
     if (*a.stop_flag) return;
@@ -536,7 +550,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_loss_grad_tc_kernel(const _
     }
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[i])));
+        for (int i = 0; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[i])));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
