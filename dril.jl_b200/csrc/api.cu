@@ -1669,3 +1669,11 @@ extern "C" int32_t dril_optimizer_step(dril_policy* p, const float* grads, int64
     if (grad_norm) *grad_norm = (float)acc8;
     return DRIL_OK;
 }
+
+#ifdef TC_TRACE
+extern "C" int32_t dril_debug_tc_trace(long long* out) {
+    DRIL_CUDA(cudaDeviceSynchronize());
+    DRIL_CUDA(cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(long long) * 2 * 32 * 16));
+    return DRIL_OK;
+}
+#endif

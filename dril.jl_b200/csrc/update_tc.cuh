@@ -138,7 +138,58 @@ __device__ __forceinline__ void tc_ld8x2(uint32_t ta, uint32_t tb2, float* ra, f
 #pragma unroll
     for (int j = 0; j < 8; ++j) { ra[j] = __uint_as_float(u[j]); rb[j] = __uint_as_float(v[j]); }
 }
+// -DTC_TRACE: phase timestamps (clock64) of CTA 0, written by thread 0 of each group: [group][tile slot][point]
+#ifdef TC_TRACE
+__device__ long long g_tc_trace[2][32][16];
+#define TC_MARK(pt) do { if (t == 0 && blockIdx.x == 0) g_tc_trace[g][(ACTOR ? 0 : 16) + (it & 15)][pt] = clock64(); } while (0)
+#else
+#define TC_MARK(pt) do { } while (0)
+#endif
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_group_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
+
+// per-sample minibatch scalars of one tile row (both threads of a sample load the same values)
+struct TcSample {
+    float x0, x1, x2, x3;
+    float p, q;        // actor: advantage (raw), old log-prob; critic: return, old value
+    int aidx;
+    bool valid;
+};
+template <int NOUT, bool ACTOR>
+__device__ __forceinline__ TcSample tc_gather(const LossArgs& a, long long tile, int m) {
+    const BufDev& buf = a.buf;
+    const int D = a.pd.obs_dim;
+    TcSample s;
+    s.x0 = s.x1 = s.x2 = s.x3 = 0.f; s.p = 0.f; s.q = 0.f; s.aidx = 0;
+    const long long pos = a.mb.start + tile * TC_M + m;
+    s.valid = pos < a.mb.start + a.mb.count;
+    if (s.valid) {
+        const long long sidx = a.mb.identity ? pos : feistel_permute(pos, a.mb.n_total, a.mb.fk);
+        const float* xo = buf.obs + sidx * D;
+        if (D == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(xo);
+            s.x0 = v.x; s.x1 = v.y; s.x2 = v.z; s.x3 = v.w;
+        } else {
+            s.x0 = xo[0];
+            if (D > 1) s.x1 = xo[1];
+            if (D > 2) s.x2 = xo[2];
+        }
+        if (ACTOR) {
+            s.p = buf.advantages[sidx];
+            s.q = buf.logprobs[sidx];
+            int ai = reinterpret_cast<const int*>(buf.actions)[sidx] - a.pd.act_start;
+            s.aidx = ai < 0 ? 0 : (ai >= NOUT ? NOUT - 1 : ai);
+        } else {
+            s.p = buf.returns[sidx];
+            s.q = buf.values[sidx];
+        }
+    }
+    return s;
+}
 
 // one pass (one net) over all tiles of this CTA.  512 threads = 2 groups x 256; within a group thread
 // (m = t & 127, half = t >> 7) owns sample m (TMEM lane m; warps w and w+4 share lane quadrant w) and the 32 hidden
@@ -150,16 +201,16 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
                                         int n_own, uint32_t base_own, uint32_t base_other, float adv_mean, float adv_den,
                                         float invB, float* stats, float* gp) {
     const PolicyDesc& pd = a.pd;
-    const BufDev& buf = a.buf;
     const int net = ACTOR ? 0 : 1;
     const LayerDesc& L0 = pd.L[net][0];
     const LayerDesc& L1 = pd.L[net][1];
     const LayerDesc& L2 = pd.L[net][2];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int g = tid >> 8, t = tid & 255;
-    const int m = t & 127, half = t >> 7, f0 = half * 32;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler (uniform datapath, no waterfalls)
+    const int g = warp >> 3, t = tid & 255, lane = tid & 31;
+    const int m = t & 127, half = (warp >> 2) & 1, f0 = half * 32;
     const int rf = t & 63, rq = t >> 6;            // reducer role: feature, sample quarter
-    const int D = pd.obs_dim;
+    const bool issuer = (warp & 7) == 0;           // warp that issues this group's MMAs (one elected lane)
     float* sW1c_hi = reinterpret_cast<float*>(sm + TC_OFF_W1C_HI);
     float* sW1c_lo = reinterpret_cast<float*>(sm + TC_OFF_W1C_LO);
     float* sWt1c_hi = reinterpret_cast<float*>(sm + TC_OFF_WT1C_HI);
@@ -172,10 +223,8 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     float* sb2 = sW2 + 256;         // [4]
     float* sGrp = sb2 + 8 + g * 1280;
     float* sOutP = sGrp;            // per group: [2 halves][NOUT<=2][128] partial output-layer dot products
-    float* sDout = sGrp + 512;      // per group: [128][2] output-layer deltas
     float* sX = sGrp + 768;         // per group: [128][4] observations
-    float* sStageA = reinterpret_cast<float*>(sm + TC_OFF_H0CAT);   // [128][68] staging (H1), before the images are written
-    float* sStageB = reinterpret_cast<float*>(sm + TC_OFF_Z1_HI);   // [128][68] staging (dZ1, later dZ0)
+    float* sStageB = reinterpret_cast<float*>(sm + TC_OFF_Z1_HI);   // [128][68] staging of dZ0 once G3 has consumed the dZ1 images
     float* sRed = reinterpret_cast<float*>(sm + TC_OFF_H0CAT);      // end-of-pass scratch [8 slots][8 sums][64]
     uint64_t* bar1 = bars + g * 3;
     uint64_t* bar2 = bars + g * 3 + 1;
@@ -222,33 +271,24 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     const uint32_t r4 = m & 3;
     const uint32_t img_h0 = ((m >> 2) * 4 + half) * 512 + r4 * 128;   // this thread's 128-byte row of the H0 image (hi block)
     const uint32_t img_z1 = ((m >> 2) * 2 + half) * 512 + r4 * 128;   // ... of a dZ1 image
+    TcSample cur;
+    cur.valid = false; cur.x0 = cur.x1 = cur.x2 = cur.x3 = cur.p = cur.q = 0.f; cur.aidx = 0;
+    if (n_own > 0) cur = tc_gather<NOUT, ACTOR>(a, (long long)blockIdx.x + (long long)g * gridDim.x, m);
     for (int it = 0; it < n_own; ++it) {
-        const long long tile = (long long)blockIdx.x + (long long)(2 * it + g) * gridDim.x;
         const uint32_t phase = (base_own + (uint32_t)it) & 1u;
-        // ---- gather (both threads of a sample read the same scalars) -------------------------------------
-        const long long pos = a.mb.start + tile * TC_M + m;
-        const bool valid = pos < a.mb.start + a.mb.count;
-        long long sidx = 0;
-        if (valid) sidx = a.mb.identity ? pos : feistel_permute(pos, a.mb.n_total, a.mb.fk);
-        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+        TC_MARK(0);
+        // ---- this tile's samples were gathered during the previous tile's G2/G3 (or before the loop) ------------------
+        const bool valid = cur.valid;
+        const float x0 = cur.x0, x1 = cur.x1, x2 = cur.x2, x3 = cur.x3;
         float adv = 0.f, ret = 0.f, olp = 0.f, ov = 0.f;
-        int aidx = 0;
-        if (valid) {
-            const float* xo = buf.obs + sidx * D;
-            x0 = xo[0];
-            if (D > 1) x1 = xo[1];
-            if (D > 2) x2 = xo[2];
-            if (D > 3) x3 = xo[3];
-            if (ACTOR) {
-                adv = buf.advantages[sidx];
-                if (a.hp.normalize_advantage) adv = (adv - adv_mean) / adv_den;
-                olp = buf.logprobs[sidx];
-                aidx = reinterpret_cast<const int*>(buf.actions)[sidx] - pd.act_start;
-                aidx = aidx < 0 ? 0 : (aidx >= NOUT ? NOUT - 1 : aidx);
-            } else {
-                ret = buf.returns[sidx];
-                ov = buf.values[sidx];
-            }
+        const int aidx = cur.aidx;
+        if (ACTOR) {
+            adv = cur.p;
+            if (valid && a.hp.normalize_advantage) adv = (adv - adv_mean) / adv_den;
+            olp = cur.q;
+        } else {
+            ret = cur.p;
+            ov = cur.q;
         }
         // sX of the previous tile was last read before the group barrier that ended that tile
         if (half == 0) *reinterpret_cast<float4*>(sX + m * 4) = make_float4(x0, x1, x2, x3);
@@ -274,11 +314,12 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
             tc_st8(my + TC_COL_HI + f0 + c0, hi);
             tc_st8(my + TC_COL_LO + f0 + c0, lo);
         }
+        TC_MARK(1);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         tc_group_sync(g);
         // ---- G1 -------------------------------------------------------------------------------------------
-        if (t == 0) {
+        if (issuer && tc_elect_one()) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int ps = 0; ps < 3; ++ps) {
@@ -290,8 +331,10 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
             }
             tc_commit(bar1);
         }
+        TC_MARK(2);
         tc_wait(bar1, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        TC_MARK(3);
         // ---- H1 = tanh(D + b1) (own 32 features), output layer (partials exchanged through smem), loss head ----------
         float h1[32];
         tc_ld32(my + TC_COL_D + f0, h1);
@@ -365,18 +408,23 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
         if (half == 0) {
 #pragma unroll
             for (int j = 0; j < NOUT; ++j) accb2[j] += warp_sum(dout[j]);
-            *reinterpret_cast<float2*>(sDout + m * 2) = make_float2(dout[0], NOUT > 1 ? dout[NOUT > 1 ? 1 : 0] : 0.f);
         }
-        // ---- take over the image region: the other group's previous tile must have released it ------------------------
+        // ---- dW2[k][j] += sum_m H1[m][k] dout[m][j] and db1 += sum_m dZ1[m][.] over the warp's 32 samples (shuffle
+        //      transpose-reduce: lane l ends up with feature f0 + l); dZ1 = (dout W2^T) .* (1 - H1^2) in place over h1.
+        //      Done on registers so that it stays outside the image-region critical section. --------------------------------
+        TC_MARK(4);
         {
-            const int k = g ? it : it - 1;
-            if (k >= 0) tc_wait(obfree, (base_other + (uint32_t)k) & 1u);
-        }
-        // ---- stage H1 and dZ1 = (dout W2^T) .* (1 - H1^2) (in place over h1) as [sample][68] rows -----------------------
-        {
-            float* ra = sStageA + m * TC_STAGE_LD + f0;
+            float tt[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(ra + j) = make_float4(h1[j], h1[j + 1], h1[j + 2], h1[j + 3]);
+            for (int k = 0; k < 32; ++k) tt[k] = h1[k] * dout[0];
+            TcTR<32, 16>::run(tt, lane);
+            accW2_0 += tt[0];
+            if (NOUT > 1) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) tt[k] = h1[k] * dout[NOUT > 1 ? 1 : 0];
+                TcTR<32, 16>::run(tt, lane);
+                accW2_1 += tt[0];
+            }
         }
 #pragma unroll
         for (int n = 0; n < 32; ++n) {
@@ -386,28 +434,20 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
             h1[n] = s * (1.0f - h1[n] * h1[n]);
         }
         {
-            float* rb = sStageB + m * TC_STAGE_LD + f0;
+            float tt[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(rb + j) = make_float4(h1[j], h1[j + 1], h1[j + 2], h1[j + 3]);
+            for (int n = 0; n < 32; ++n) tt[n] = h1[n];
+            TcTR<32, 16>::run(tt, lane);
+            accb1 += tt[0];
         }
-        tc_group_sync(g);
-        // ---- dW2[f][j] += sum_m H1[m][f] dout[m][j], db1[f] += sum_m dZ1[m][f] over this reducer's 32 samples -----------
+        TC_MARK(5);
+        // ---- take over the image region: the other group's previous tile must have released it ------------------------
         {
-            const float* pa = sStageA + (rq * 32) * TC_STAGE_LD + rf;
-            const float* pb = sStageB + (rq * 32) * TC_STAGE_LD + rf;
-            const float* pd2 = sDout + (rq * 32) * 2;
-            float s0 = 0.f, s1 = 0.f, sb = 0.f;
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) {
-                const float hv = pa[i * TC_STAGE_LD];
-                const float2 dd = *reinterpret_cast<const float2*>(pd2 + i * 2);
-                s0 = fmaf(hv, dd.x, s0);
-                if (NOUT > 1) s1 = fmaf(hv, dd.y, s1);
-                sb += pb[i * TC_STAGE_LD];
-            }
-            accW2_0 += s0; accW2_1 += s1; accb1 += sb;
+            const int k = g ? it : it - 1;
+            if (k >= 0) tc_wait(obfree, (base_other + (uint32_t)k) & 1u);
         }
-        tc_group_sync(g);
+        TC_MARK(6);
+        TC_MARK(7);
         // ---- H0 hi/lo back from TMEM -> H0 image; dZ1 hi/lo -> TMEM (over H0) + dZ1 images ---------------------------
 #pragma unroll
         for (int c0 = 0; c0 < 32; c0 += 8) {
@@ -431,8 +471,9 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         tc_group_sync(g);
+        TC_MARK(8);
         // ---- G2 (dH0) and G3 (dW1, accumulated in TMEM over the whole pass by both groups) ----------------------------
-        if (t == 0) {
+        if (issuer && tc_elect_one()) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int ps = 0; ps < 3; ++ps) {
@@ -452,8 +493,10 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
             }
             tc_commit(bar2);
         }
+        TC_MARK(9);
         tc_wait(bar2, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        TC_MARK(10);
         // ---- dZ0 = dH0 .* (1 - H0^2), H0 = hi + lo re-read from this thread's own rows of the H0 image; staged over the
         //      dZ1 images (G3 has consumed them) -------------------------------------------------------------------------
         {
@@ -475,6 +518,7 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
             for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(rb + j) = make_float4(dz0[j], dz0[j + 1], dz0[j + 2], dz0[j + 3]);
         }
         tc_group_sync(g);
+        TC_MARK(11);
         // ---- dW0[d][f] += sum_m x[m][d] dZ0[m][f], db0[f] += sum_m dZ0[m][f] over this reducer's 32 samples ----------------
         {
             const float* pb = sStageB + (rq * 32) * TC_STAGE_LD + rf;
@@ -491,6 +535,7 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         tc_group_sync(g);
+        TC_MARK(12);
         if (t == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bfree)) : "memory");
     }
     // ---- end of pass: dW1 from TMEM (M = 128: row i <-> lane i; rows 0..63 -> plane 0, rows 64..127 (lo part) -> plane 1) -----
@@ -507,7 +552,10 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     {
         float* r = sRed + ((g * 4 + rq) * 8) * 64 + rf;
         r[0 * 64] = accW0_0; r[1 * 64] = accW0_1; r[2 * 64] = accW0_2; r[3 * 64] = accW0_3;
-        r[4 * 64] = accb0; r[5 * 64] = accb1; r[6 * 64] = accW2_0; r[7 * 64] = accW2_1;
+        r[4 * 64] = accb0;
+        // the shuffle-reduced sums live in (sample quadrant = warp & 3, feature = f0 + lane)
+        float* r2 = sRed + ((g * 4 + (warp & 3)) * 8) * 64 + f0 + lane;
+        r2[5 * 64] = accb1; r2[6 * 64] = accW2_0; r2[7 * 64] = accW2_1;
         if ((tid & 31) == 0 && half == 0) {
 #pragma unroll
             for (int j = 0; j < NOUT; ++j) sRed[8 * 8 * 64 + warp * 2 + j] = accb2[j];
@@ -540,7 +588,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_loss_grad_tc_kernel(const _
     __shared__ uint32_t tmem_base_s;
     __shared__ double scratch[32];
     if (*a.stop_flag) return;
-    const int tid = threadIdx.x, warp = tid >> 5, g = tid >> 8;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), g = warp >> 3;
     const uint32_t raw = tc_smem_u32(tc_smem_raw);
     const uint32_t sm_base = (raw + 1023u) & ~1023u;
     unsigned char* sm = tc_smem_raw + (sm_base - raw);
@@ -556,7 +604,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_loss_grad_tc_kernel(const _
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tb = tmem_base_s;
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base_s, 0);
 
     float adv_mean = 0.f, adv_den = 1.f;
     if (a.hp.normalize_advantage) {
