@@ -34,9 +34,11 @@ extern "C" int32_t dril_version(void) { return 100; }
 // options
 // ---------------------------------------------------------------------------------------
 static int g_opt_tc = getenv("DRIL_TC") ? atoi(getenv("DRIL_TC")) : 1;
+static int g_opt_tail = getenv("DRIL_TAIL") ? atoi(getenv("DRIL_TAIL")) : 1;   // fused reduce/clip/Adam tail of the TC kernel
 extern "C" int32_t dril_set_option(const char* key, int32_t value) {
     DRIL_REQUIRE(key, "key is NULL");
     if (!strcmp(key, "tc")) { g_opt_tc = value; return DRIL_OK; }
+    if (!strcmp(key, "fused_tail")) { g_opt_tail = value; return DRIL_OK; }
     dril_set_error("unknown option '%s'", key);
     return DRIL_ERR_INVALID;
 }
@@ -1312,13 +1314,6 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
     const bool tc = g_opt_tc && tc_eligible(pd);
     long long tiles = (mb.count + (tc ? TC_M : ll.M4) - 1) / (tc ? TC_M : ll.M4);
     int grid = (int)std::max<long long>(1, std::min<long long>(tiles, tc ? std::min(c->sm_count, p->gpart_ctas) : ll.grid_cap));
-    {
-        Span sp(c, DRIL_K_LOSS_GRAD);
-        if (tc) ppo_loss_grad_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, c->stream>>>(a);
-        else if (ll.ws) ppo_loss_grad_kernel<true><<<grid, DRIL_THREADS, ll.smem, c->stream>>>(a);
-        else ppo_loss_grad_kernel<false><<<grid, DRIL_THREADS, ll.smem, c->stream>>>(a);
-        DRIL_CUDA(cudaGetLastError());
-    }
     const unsigned char* planes_dev = tc ? p->f2planes_one : p->f2planes;
     AdamArgs aa;
     aa.g = p->g; aa.flat = p->flat; aa.m = p->m; aa.v = p->v; aa.pack = p->pack; aa.flat2pack = p->flat2pack;
@@ -1328,6 +1323,30 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
     const int fgrid = (n + RA_PARAMS_PER_BLOCK - 1) / RA_PARAMS_PER_BLOCK;
     const bool fused = apply && c->nranks == 1;
     const bool p2p = apply && c->nranks > 1 && c->p2p_enabled && n <= c->p2p.n_slots;
+    // tensor-core path: reduction (+ peer-memory exchange) + clip + Adam run as the tail of the loss/grad kernel
+    const bool tail = tc && g_opt_tail && (fused || p2p) && grid <= c->sm_count;
+    {
+        Span sp(c, DRIL_K_LOSS_GRAD);
+        if (tc) {
+            TailArgs tl;
+            memset(&tl, 0, sizeof(tl));
+            tl.mode = tail ? (fused ? 1 : 2) : 0;
+            tl.flat2g = p->flat2g; tl.f2planes = planes_dev; tl.stats_off = pd.pack_fwd + pd.act_n; tl.sq_part = p->sq_part;
+            tl.adam = aa;
+            if (p2p) tl.pp = c->p2p;
+            if (tail) {
+                void* args[] = {(void*)&a, (void*)&tl};
+                DRIL_CUDA(cudaLaunchCooperativeKernel((const void*)ppo_loss_grad_tc_kernel, dim3(grid), dim3(TC_THREADS), args,
+                                                      TC_SMEM_BYTES, c->stream));
+            } else {
+                ppo_loss_grad_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, c->stream>>>(a, tl);
+            }
+        }
+        else if (ll.ws) ppo_loss_grad_kernel<true><<<grid, DRIL_THREADS, ll.smem, c->stream>>>(a);
+        else ppo_loss_grad_kernel<false><<<grid, DRIL_THREADS, ll.smem, c->stream>>>(a);
+        DRIL_CUDA(cudaGetLastError());
+    }
+    if (tail) return DRIL_OK;
     {
         // reduction over CTAs / planes (+ norm, clip, Adam in the same kernel on a single GPU; + publication
         // of this rank's gradient to its peers on the peer-memory path)

@@ -569,76 +569,79 @@ struct AdamArgs {
     int apply_stats;     // 0 for the dril_optimizer_step parity entry (no stat bookkeeping)
 };
 
+// KL early stop of ppo.jl:235-238, decided BEFORE the step is applied, from the reduced statistics in g[n_params..]
+__device__ __forceinline__ int adam_stop(const AdamArgs& a) {
+    const float kl = a.g[a.n_params + 4] * (float)(1.0 / a.global_count);
+    return (a.apply_stats && a.hp.target_kl >= 0.f && kl > 1.5f * a.hp.target_kl) ? 1 : 0;
+}
+// The per-iteration accumulators (learn_stats sums, applied-step count, running beta^t, step counter, stop flag):
+// threads 0..15 of ONE CTA, independent global round trips.  s_f[0..1] receive the Adam bias corrections 1 - beta^t.
+__device__ __forceinline__ void adam_accumulate(const AdamArgs& a, float norm, int stop, int tid, float* s_f) {
+    if (tid >= 16) return;
+    const float* st = a.g + a.n_params;
+    const float invB = (float)(1.0 / a.global_count);
+    if (a.apply_stats) {
+        const float p_loss = st[0] * invB, v_loss = st[1] * invB, ent = st[2] * invB;
+        const float ent_loss = -ent;
+        double add = 0.0;
+        bool on_apply = true;
+        switch (tid) {
+            case 0: add = p_loss; break;
+            case 1: add = v_loss; break;
+            case 2: add = ent_loss; break;
+            case 3: add = st[3] * invB; break;
+            case 4: add = st[4] * invB; break;
+            case 5: add = ent; break;
+            case 6: add = st[5] * invB; break;
+            case 7: add = p_loss + a.hp.ent_coef * ent_loss + a.hp.vf_coef * v_loss; break;
+            case 8: add = norm; on_apply = false; break;     // grad_norms gets the PRE-clip norm before the KL check (ppo.jl:216-223)
+            case 9: add = 1.0; break;
+            case 10: add = 1.0; on_apply = false; break;
+            default: add = 0.0; on_apply = false; break;
+        }
+        if (tid <= 10 && (!on_apply || !stop)) a.iter_acc[tid] += add;
+    } else if (tid == 8) {
+        a.iter_acc[8] = (double)norm;
+    }
+    if (!stop && (tid == 12 || tid == 13)) {
+        double b = tid == 12 ? (double)a.hp.beta1 : (double)a.hp.beta2;
+        double pw = a.iter_acc[tid] * b;
+        a.iter_acc[tid] = pw;
+        if (s_f) s_f[tid - 12] = (float)(1.0 - pw);
+    }
+    if (tid == 14) {
+        if (stop) *a.stop_flag = 1; else *a.step += 1;
+    }
+}
+// Adam (Optimisers.Adam, eps 1e-5: ppo.jl:64-66) on one parameter + refresh of its packed copies
+__device__ __forceinline__ void adam_param(const AdamArgs& a, int p, float scale, float c1, float c2) {
+    const float b1 = a.hp.beta1, b2 = a.hp.beta2;
+    float g = __fmul_rn(a.g[p], scale);
+    float m = __fadd_rn(__fmul_rn(b1, a.m[p]), __fmul_rn(__fsub_rn(1.0f, b1), g));
+    float v = __fadd_rn(__fmul_rn(b2, a.v[p]), __fmul_rn(__fmul_rn(__fsub_rn(1.0f, b2), g), g));
+    float upd = __fmul_rn(__fdiv_rn(__fdiv_rn(m, c1), __fadd_rn(__fsqrt_rn(__fdiv_rn(v, c2)), a.hp.adam_eps)), a.hp.lr);
+    float w = __fsub_rn(a.flat[p], upd);
+    int ip = a.flat2pack[p];
+    int it = a.flat2packT[p];
+    a.m[p] = m; a.v[p] = v; a.flat[p] = w;
+    if (ip >= 0) a.pack[ip] = w;
+    if (it >= 0) a.pack[it] = w;
+}
+
 // One CTA: (given sum of squares q) clip scale -> KL stop -> statistics -> Adam -> refresh packed layouts.
-// The twelve accumulator updates run on twelve threads (independent global round trips).
 __device__ __forceinline__ void adam_apply(const AdamArgs& a, double q, float* s_f, int* s_i) {
     const int tid = threadIdx.x;
     const float norm = (float)sqrt(q);
-    const float* st = a.g + a.n_params;
-    const float invB = (float)(1.0 / a.global_count);
-    const float kl = st[4] * invB;
-    const int stop = (a.apply_stats && a.hp.target_kl >= 0.f && kl > 1.5f * a.hp.target_kl) ? 1 : 0;   // ppo.jl:235-238: BEFORE applying
-    if (tid < 16) {
-        if (a.apply_stats) {
-            const float p_loss = st[0] * invB, v_loss = st[1] * invB, ent = st[2] * invB;
-            const float ent_loss = -ent;
-            double add = 0.0;
-            bool on_apply = true;
-            switch (tid) {
-                case 0: add = p_loss; break;
-                case 1: add = v_loss; break;
-                case 2: add = ent_loss; break;
-                case 3: add = st[3] * invB; break;
-                case 4: add = kl; break;
-                case 5: add = ent; break;
-                case 6: add = st[5] * invB; break;
-                case 7: add = p_loss + a.hp.ent_coef * ent_loss + a.hp.vf_coef * v_loss; break;
-                case 8: add = norm; on_apply = false; break;     // grad_norms gets the PRE-clip norm before the KL check (ppo.jl:216-223)
-                case 9: add = 1.0; break;
-                case 10: add = 1.0; on_apply = false; break;
-                default: add = 0.0; on_apply = false; break;
-            }
-            if (tid <= 10 && (!on_apply || !stop)) a.iter_acc[tid] += add;
-        } else if (tid == 8) {
-            a.iter_acc[8] = (double)norm;
-        }
-        if (!stop && (tid == 12 || tid == 13)) {
-            double b = tid == 12 ? (double)a.hp.beta1 : (double)a.hp.beta2;
-            double pw = a.iter_acc[tid] * b;
-            a.iter_acc[tid] = pw;
-            s_f[tid - 12] = (float)(1.0 - pw);
-        }
-        if (tid == 14) {
-            if (stop) *a.stop_flag = 1; else *a.step += 1;
-            *s_i = stop;
-        }
-    }
+    const int stop = adam_stop(a);
+    adam_accumulate(a, norm, stop, tid, s_f);
+    if (tid == 14) *s_i = stop;
     __syncthreads();
     if (stop) return;
     float scale = 1.f;
     if (a.hp.max_grad_norm >= 0.f && norm > a.hp.max_grad_norm) scale = a.hp.max_grad_norm / norm;   // no epsilon (optimization_utils.jl:99-107)
     const float c1 = s_f[0], c2 = s_f[1];
-    const float b1 = a.hp.beta1, b2 = a.hp.beta2;
-    const float* __restrict__ gsrc = a.g;
-    float* __restrict__ pm = a.m;
-    float* __restrict__ pv = a.v;
-    float* __restrict__ pw = a.flat;
-    float* __restrict__ pk = a.pack;
-    const int* __restrict__ f2p = a.flat2pack;
-    const int* __restrict__ f2t = a.flat2packT;
 #pragma unroll 4
-    for (int p = tid; p < a.n_params; p += blockDim.x) {
-        float g = __fmul_rn(gsrc[p], scale);
-        float m = __fadd_rn(__fmul_rn(b1, pm[p]), __fmul_rn(__fsub_rn(1.0f, b1), g));
-        float v = __fadd_rn(__fmul_rn(b2, pv[p]), __fmul_rn(__fmul_rn(__fsub_rn(1.0f, b2), g), g));
-        float upd = __fmul_rn(__fdiv_rn(__fdiv_rn(m, c1), __fadd_rn(__fsqrt_rn(__fdiv_rn(v, c2)), a.hp.adam_eps)), a.hp.lr);
-        float w = __fsub_rn(pw[p], upd);
-        int ip = f2p[p];
-        int it = f2t[p];
-        pm[p] = m; pv[p] = v; pw[p] = w;
-        if (ip >= 0) pk[ip] = w;
-        if (it >= 0) pk[it] = w;
-    }
+    for (int p = tid; p < a.n_params; p += blockDim.x) adam_param(a, p, scale, c1, c2);
 }
 
 // stand-alone (multi-GPU path after the NCCL allreduce, and the dril_optimizer_step parity entry)

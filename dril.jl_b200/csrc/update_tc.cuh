@@ -25,6 +25,7 @@
 // instruction at M = 128.  Descriptor recipes are the ones verified on hardware by tools/tc_probe*.cu
 // (profiles/r01_tcgen05_probe.txt).  One pass over the minibatch per net (actor, then critic).
 #pragma once
+#include <cooperative_groups.h>
 #include "update.cuh"
 
 #define TC_M 128
@@ -582,11 +583,123 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) ppo_loss_grad_tc_kernel(const __grid_constant__ LossArgs a) {
+// ---------------------------------------------------------------------------------------------------------
+// Fused tail (cooperative launch): reduction of the per-CTA partials, (multi-GPU: one-shot exchange over NVLink peer
+// memory,) global gradient norm, clip, KL stop, statistics and the Adam step, inside the loss/grad kernel.  Every CTA
+// owns a contiguous slice of the flat gradient; grid barriers separate "partials written" / "slices reduced (and
+// published to the peers)" / "sums of squares written".  Replaces reduce_adam_kernel (+ p2p_sum_adam_kernel).
+// ---------------------------------------------------------------------------------------------------------
+struct TailArgs {
+    int mode;                       // 0: none (caller reduces), 1: single GPU, 2: peer-memory allreduce
+    const int* flat2g;
+    const unsigned char* f2planes;
+    int stats_off;
+    double* sq_part;                // [>= gridDim.x]
+    AdamArgs adam;
+    P2PDev pp;
+};
+
+__device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs& tl, float* s_red /* [8][64] */, double* scratch,
+                                              float* s_f) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const AdamArgs& ad = tl.adam;
+    const int tid = threadIdx.x, nb = (int)gridDim.x;
+    const int n = ad.n_params + 6;
+    const int per = (n + nb - 1) / nb;
+    const int p_lo = min(n, (int)blockIdx.x * per), p_hi = min(n, p_lo + per);
+    const int gpack = a.pd.gpack;
+    __threadfence();
+    grid.sync();                                             // every CTA's partial planes are visible
+    const double bp1 = ad.iter_acc[12], bp2 = ad.iter_acc[13];   // running beta^t BEFORE this step (CTA 0 updates them at the end)
+    const unsigned long long seq = tl.mode == 2 ? *tl.pp.local_seq + 1ull : 0ull;
+    double sq = 0.0;
+    for (int base = p_lo; base < p_hi; base += 64) {
+        const int lp = tid & 63, grp = tid >> 6, p = base + lp;
+        float part = 0.f;
+        if (p < p_hi) {
+            const int idx = p < ad.n_params ? tl.flat2g[p] : tl.stats_off + (p - ad.n_params);
+            const int planes = p < ad.n_params ? tl.f2planes[p] : 1;
+            for (int pl = 0; pl < planes; ++pl) {
+                const float* src = a.gpart + (size_t)pl * a.half_stride * gpack + idx;
+                float v[8];
+                for (int c0 = grp; c0 < nb; c0 += 64) {          // 8 independent loads in flight per thread
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int c = c0 + j * 8;
+                        v[j] = c < nb ? __ldcg(src + (size_t)c * gpack) : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) part += v[j];
+                }
+            }
+        }
+        s_red[grp * 64 + lp] = part;
+        __syncthreads();
+        if (grp == 0 && p < p_hi) {
+            float gs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gs += s_red[j * 64 + lp];
+            if (tl.mode == 2) {
+                tl.pp.local_gbuf[(size_t)(seq & 1ull) * tl.pp.n_slots + p] = gs;
+            } else {
+                ad.g[p] = gs;
+                if (p < ad.n_params) sq += (double)gs * (double)gs;
+            }
+        }
+        __syncthreads();
+    }
+    if (tl.mode == 2) {
+        __threadfence();
+        grid.sync();                                         // this rank's whole gradient is in its peer-visible buffer
+        if (blockIdx.x == 0 && tid == 0) {
+            __threadfence_system();
+            *tl.pp.local_seq = seq;
+            *tl.pp.local_flag = seq;
+            __threadfence_system();
+        }
+        if (tid < tl.pp.nranks) {
+            const volatile unsigned long long* f = tl.pp.peer_flag[tid];
+            long long spins = 0;
+            while (*f < seq) {
+                __nanosleep(64);
+                if (++spins > (1ll << 24)) { atomicExch(tl.pp.err, 1); break; }
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+        // sum of the peers' slices in rank order (identical on every rank => bit-identical parameters)
+        for (int p = p_lo + tid; p < p_hi; p += blockDim.x) {
+            const size_t off = (size_t)(seq & 1ull) * tl.pp.n_slots + p;
+            float gs = 0.f;
+            for (int r = 0; r < tl.pp.nranks; ++r) gs += __ldcv(tl.pp.peer_gbuf[r] + off);
+            ad.g[p] = gs;
+            if (p < ad.n_params) sq += (double)gs * (double)gs;
+        }
+    }
+    sq = block_sum(sq, scratch);
+    if (tid == 0) tl.sq_part[blockIdx.x] = sq;
+    __threadfence();
+    grid.sync();                                             // all slices of g and all sums of squares are visible
+    double q = 0.0;
+    for (int b = tid; b < nb; b += blockDim.x) q += __ldcg(tl.sq_part + b);
+    q = block_sum(q, scratch);
+    const float norm = (float)sqrt(q);
+    const int stop = adam_stop(ad);
+    if (blockIdx.x == 0) adam_accumulate(ad, norm, stop, tid, s_f);
+    if (stop) return;
+    float scale = 1.f;
+    if (ad.hp.max_grad_norm >= 0.f && norm > ad.hp.max_grad_norm) scale = ad.hp.max_grad_norm / norm;
+    const float c1 = (float)(1.0 - bp1 * (double)ad.hp.beta1), c2 = (float)(1.0 - bp2 * (double)ad.hp.beta2);
+    for (int p = p_lo + tid; p < min(p_hi, ad.n_params); p += blockDim.x) adam_param(ad, p, scale, c1, c2);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) ppo_loss_grad_tc_kernel(const __grid_constant__ LossArgs a, const __grid_constant__ TailArgs tl) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     __shared__ __align__(8) uint64_t bars[6];
     __shared__ uint32_t tmem_base_s;
     __shared__ double scratch[32];
+    __shared__ float s_f2[2];
     if (*a.stop_flag) return;
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), g = warp >> 3;
     const uint32_t raw = tc_smem_u32(tc_smem_raw);
@@ -634,4 +747,5 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_loss_grad_tc_kernel(const _
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(TC_TMEM_COLS));
+    if (tl.mode) tc_fused_tail(a, tl, reinterpret_cast<float*>(sm + TC_OFF_H0CAT), scratch, s_f2);
 }
