@@ -13,6 +13,7 @@
 #include "rollout.cuh"
 #include "update.cuh"
 #include "update_tc.cuh"
+#include "rollout_tc.cuh"
 
 #define DRIL_SMEM_MAX 232448  // 227 KB opt-in per CTA on sm_100
 #define DRIL_RESULT_SLOTS 4   // iterations that may be enqueued before their results are read
@@ -34,11 +35,13 @@ extern "C" int32_t dril_version(void) { return 100; }
 // options
 // ---------------------------------------------------------------------------------------
 static int g_opt_tc = getenv("DRIL_TC") ? atoi(getenv("DRIL_TC")) : 1;
+static int g_opt_tc_rollout = getenv("DRIL_TC_ROLLOUT") ? atoi(getenv("DRIL_TC_ROLLOUT")) : 1;   // tensor-core rollout (CartPole, [64,64])
 static int g_opt_tail = getenv("DRIL_TAIL") ? atoi(getenv("DRIL_TAIL")) : 1;   // fused reduce/clip/Adam tail of the TC kernel
 extern "C" int32_t dril_set_option(const char* key, int32_t value) {
     DRIL_REQUIRE(key, "key is NULL");
     if (!strcmp(key, "tc")) { g_opt_tc = value; return DRIL_OK; }
     if (!strcmp(key, "fused_tail")) { g_opt_tail = value; return DRIL_OK; }
+    if (!strcmp(key, "tc_rollout")) { g_opt_tc_rollout = value; return DRIL_OK; }
     dril_set_error("unknown option '%s'", key);
     return DRIL_ERR_INVALID;
 }
@@ -142,6 +145,8 @@ struct dril_buffer {
     void* slab = nullptr;
     BufDev d;
     int act_elems;  // per-sample action elements
+    TcRolloutScratch tcs = {nullptr, nullptr, nullptr, nullptr, 0};   // tensor-core rollout: inputs of the batched critic pass
+    void* tcs_slab = nullptr;
 };
 
 struct dril_env {
@@ -471,6 +476,7 @@ extern "C" int32_t dril_buffer_destroy(dril_buffer* b) {
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     cudaFree(b->slab);
+    if (b->tcs_slab) cudaFree(b->tcs_slab);
     delete b;
     return DRIL_OK;
 }
@@ -943,6 +949,37 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
     const bool upd = d.normalize && d.training && (d.norm_obs || d.norm_reward);
     if (upd) flags |= RO_GRID_SYNC;
     const long long N = d.n_envs;
+    if (has_policy && g_opt_tc_rollout && !d.normalize && d.kind == DRIL_ENV_CARTPOLE && d.obs_dim == 4 && T > 0 && tc_eligible(a.pd) &&
+        T == b->d.T) {
+        // tensor-core path: actor-only step loop (64 envs per CTA) + one batched critic pass for values / bootstrap values
+        if (!b->tcs_slab) {
+            const size_t cap = (size_t)b->d.T * b->d.N;
+            auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+            const size_t o_last = 0, o_tobs = o_last + al((size_t)N * 16), o_tidx = o_tobs + al(cap * 16), o_cnt = o_tidx + al(cap * 8);
+            DRIL_CUDA(cudaMalloc(&b->tcs_slab, o_cnt + 256));
+            char* base = (char*)b->tcs_slab;
+            b->tcs.last_obs = (float*)(base + o_last); b->tcs.trunc_obs = (float*)(base + o_tobs);
+            b->tcs.trunc_idx = (long long*)(base + o_tidx); b->tcs.trunc_count = (unsigned int*)(base + o_cnt);
+            b->tcs.cap = (unsigned int)std::min<size_t>(cap, 0x7fffffffu);
+        }
+        DRIL_CUDA(cudaMemsetAsync(b->tcs.trunc_count, 0, 4, c->stream));
+        a.flags = flags; a.M4 = RT_ENVS;
+        a.n_tiles = (int)((N + RT_ENVS - 1) / RT_ENVS);
+        {
+            Span sp(c, DRIL_K_ROLLOUT);
+            const int grid = std::min(a.n_tiles, 2 * c->sm_count);
+            rollout_tc_kernel<<<grid, RT_THREADS, RT_SMEM_BYTES, c->stream>>>(a, b->tcs);
+            DRIL_CUDA(cudaGetLastError());
+        }
+        {
+            Span sp(c, DRIL_K_ROLLOUT);
+            const long long tiles = ((long long)b->d.T * N + N + 127) / 128 + 8;
+            const int grid = (int)std::min<long long>(tiles, 2ll * c->sm_count);
+            critic_values_tc_kernel<<<grid, CV_THREADS, RT_SMEM_BYTES, c->stream>>>(a.pd, a.pack, b->d, b->tcs);
+            DRIL_CUDA(cudaGetLastError());
+        }
+        return DRIL_OK;
+    }
     static const int env_nofast = getenv("DRIL_ROLLOUT_NO_FAST") ? atoi(getenv("DRIL_ROLLOUT_NO_FAST")) : 0;
     if (has_policy && !upd && !env_nofast && d.kind != DRIL_ENV_SYNTHETIC && a.pd.act_n <= RF_MAX_OUT - 1 && T > 0 &&
         (a.pd.act_kind == DRIL_ACT_DISCRETE || a.pd.act_n == 1)) {

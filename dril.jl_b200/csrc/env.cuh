@@ -43,16 +43,15 @@ __device__ __forceinline__ void env_reset_state(int kind, uint32_t gid, uint32_t
     }
 }
 
-// CartPole-v1 Euler step. a01: 0 = push left, 1 = push right. Returns reward; sets terminated.
-__device__ __forceinline__ float cartpole_step(float* st, int a01, bool* terminated) {
+// CartPole-v1 Euler step with the (correctly rounded) sin/cos of the pole angle supplied by the caller.
+// a01: 0 = push left, 1 = push right. Returns reward; sets terminated.
+__device__ __forceinline__ float cartpole_step_sc(float* st, int a01, float sinth, float costh, bool* terminated) {
     const float GRAVITY = 9.8f, MASSPOLE = 0.1f, LENGTH = 0.5f, FORCE_MAG = 10.0f, TAU = 0.02f;
     const float TOTAL_MASS = __fadd_rn(0.1f, 1.0f);
     const float PML = __fmul_rn(0.1f, 0.5f);
     const float THETA_THR = 0.20943951023931953f, X_THR = 2.4f, FOUR_THIRDS = 1.3333333333333333f;
     float x = st[0], x_dot = st[1], th = st[2], th_dot = st[3];
     float force = (a01 == 1) ? FORCE_MAG : -FORCE_MAG;
-    float sinth, costh;
-    sincos_rn(th, &sinth, &costh);
     float temp = __fdiv_rn(__fadd_rn(force, __fmul_rn(__fmul_rn(PML, __fmul_rn(th_dot, th_dot)), sinth)), TOTAL_MASS);
     float den = __fmul_rn(LENGTH, __fsub_rn(FOUR_THIRDS, __fdiv_rn(__fmul_rn(MASSPOLE, __fmul_rn(costh, costh)), TOTAL_MASS)));
     float thetaacc = __fdiv_rn(__fsub_rn(__fmul_rn(GRAVITY, sinth), __fmul_rn(costh, temp)), den);
@@ -64,6 +63,11 @@ __device__ __forceinline__ float cartpole_step(float* st, int a01, bool* termina
     st[0] = xn; st[1] = xdn; st[2] = thn; st[3] = thdn;
     *terminated = (xn < -X_THR) || (xn > X_THR) || (thn < -THETA_THR) || (thn > THETA_THR);
     return 1.0f;
+}
+__device__ __forceinline__ float cartpole_step(float* st, int a01, bool* terminated) {
+    float sinth, costh;
+    sincos_rn(st[2], &sinth, &costh);
+    return cartpole_step_sc(st, a01, sinth, costh, terminated);
 }
 
 // Pendulum-v1 step (g = 10, m = l = 1). u: env-space torque (clipped again like Gymnasium).

@@ -1,0 +1,386 @@
+// Tensor-core variant of the fused rollout for the reference's default CartPole setup (hidden_dims = [64, 64],
+// Discrete(<= 2), obs_dim = 4, no normaliser): the n_steps loop of collect_trajectories (buffers/trajectory.jl:25-73,
+// rollout_buffer.jl:46-90) with the actor's 64x64 layer on tcgen05.mma (3xTF32, same split as update_tc.cuh).
+//
+// The per-step chain (observe -> actor -> sample -> dynamics) is latency bound, so it is cut to the minimum:
+//  * only the ACTOR runs inside the step loop.  Values are not needed to choose actions: V(s_t), the bootstrap value of
+//    the final observation and V(terminal_obs) of truncated steps (trajectory.jl:57-70) are computed afterwards in one
+//    batched tensor-core pass over all n_steps x n_envs observations (critic_values_tc_kernel);
+//  * 64 envs per CTA (TMEM lanes 0..63), four threads per env (16 hidden features each) that all keep the env state in
+//    registers and step it redundantly, so a step needs two 256-thread barriers; the correctly rounded fp64 sin/cos of
+//    the dynamics is computed by one of the four threads while the MMAs run;
+//  * per step: layer 0 (K = 4) on CUDA cores -> hi/lo to TMEM -> 24 tcgen05.mma (M = 128 rows, 64 used; N = 64; K = 8)
+//    -> tanh + output layer partials -> softmax, Philox inverse-CDF sample, log-prob, dynamics, monitor, auto-reset.
+// Warps whose TMEM lane quadrant holds no envs (warp % 4 >= 2) only help staging the weights and exit.
+#pragma once
+#include "rollout.cuh"
+#include "update_tc.cuh"
+
+#define RT_ENVS 64
+#define RT_THREADS 512
+#define RT_COL_D 0
+#define RT_COL_HI 64
+#define RT_COL_LO 128
+#define RT_TMEM_COLS 256
+#define RT_OFF_WT_HI 0
+#define RT_OFF_WT_LO 16384
+#define RT_OFF_SMALL 32768
+#define RT_SMALL_FLOATS 1664
+#define RT_SMEM_BYTES (RT_OFF_SMALL + RT_SMALL_FLOATS * 4 + 1024)
+
+struct TcRolloutScratch {
+    float* last_obs;          // [N][4] observation after the final step
+    float* trunc_obs;         // [cap][4] terminal observations of truncated steps
+    long long* trunc_idx;     // [cap] buffer sample index of each entry
+    unsigned int* trunc_count;
+    unsigned int cap;
+};
+
+__device__ __forceinline__ void rt_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* r) {
+    uint32_t u[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+                   "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = __uint_as_float(u[j]);
+}
+
+// stage W1^T of one net as K-major no-swizzle hi/lo images (B operand of H1pre = H0 W1)
+__device__ __forceinline__ void rt_stage_w1(const float* __restrict__ pack, const LayerDesc& L1, unsigned char* sm, int tid, int nthreads) {
+    float* hi_img = reinterpret_cast<float*>(sm + RT_OFF_WT_HI);
+    float* lo_img = reinterpret_cast<float*>(sm + RT_OFF_WT_LO);
+    for (int i = tid; i < 64 * 64; i += nthreads) {
+        const int k = i >> 6, n = i & 63;
+        const float w = pack[L1.pw_off + i];
+        const float hi = tc_hi(w);
+        hi_img[tc_core_index(n, k, 64)] = hi;
+        lo_img[tc_core_index(n, k, 64)] = w - hi;
+    }
+}
+
+__global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_constant__ RolloutArgs a, const TcRolloutScratch sc) {
+    extern __shared__ __align__(1024) unsigned char rt_smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const EnvDev& env = a.env;
+    const BufDev& buf = a.buf;
+    const PolicyDesc& pd = a.pd;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int lane = tid & 31;
+    const uint32_t raw = tc_smem_u32(rt_smem_raw);
+    const uint32_t sm_base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = rt_smem_raw + (sm_base - raw);
+    float* sSmall = reinterpret_cast<float*>(sm + RT_OFF_SMALL);
+    float* sW0 = sSmall;            // [4][64]
+    float* sb0 = sW0 + 256;         // [64]
+    float* sb1 = sb0 + 64;          // [64]
+    float* sW2 = sb1 + 64;          // [64][4]
+    float* sb2 = sW2 + 256;         // [4]
+    float* sPart = sb2 + 8;         // [4 feature quarters][2][64] partial logits
+    float* sSC = sPart + 512;       // [64][2] sin, cos of the pole angle
+    const LayerDesc& L0 = pd.L[0][0];
+    const LayerDesc& L1 = pd.L[0][1];
+    const LayerDesc& L2 = pd.L[0][2];
+    rt_stage_w1(a.pack, L1, sm, tid, RT_THREADS);
+    for (int i = tid; i < 256; i += RT_THREADS) { sW0[i] = a.pack[L0.pw_off + i]; sW2[i] = a.pack[L2.pw_off + i]; }
+    if (tid < 64) { sb0[tid] = a.pack[L0.pb_off + tid]; sb1[tid] = a.pack[L1.pb_off + tid]; }
+    if (tid < 4) sb2[tid] = a.pack[L2.pb_off + tid];
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_s)), "r"(RT_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if ((warp & 3) >= 2) return;                      // no envs in TMEM lanes 64..127
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+    const int q = warp & 3, fq = warp >> 2, f0 = fq * 16;
+    const int e = q * 32 + lane;                      // env slot == TMEM lane
+    const uint32_t my = tb + ((uint32_t)(q * 32) << 16);
+    const uint32_t idesc = tc_idesc(128, 64, 0, 0);
+    const long long N = env.n_envs;
+    const int A = pd.act_n;
+    uint32_t nbar = 0;
+    for (long long tile = blockIdx.x; tile * RT_ENVS < N; tile += gridDim.x) {
+        const long long n = tile * RT_ENVS + e;
+        const bool mine = n < N;
+        const bool writer = mine && fq == 0;
+        const uint32_t gid = (uint32_t)(env.gid_offset + n);
+        float st[4] = {0.f, 0.f, 0.f, 0.f};
+        int steps = 0, ep_len = 0;
+        float ep_ret = 0.f;
+        uint32_t episode = 0;
+        if (mine) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) st[k] = env.state[(size_t)k * N + n];
+            steps = env.steps[n];
+            episode = env.episode[n];
+            if (env.monitor) { ep_ret = env.ep_ret[n]; ep_len = env.ep_len[n]; }
+        }
+        for (int t = 0; t < a.T; ++t) {
+            const size_t row = (size_t)t * N;
+            if (writer) *reinterpret_cast<float4*>(buf.obs + (row + n) * 4) = make_float4(st[0], st[1], st[2], st[3]);
+            // ---- layer 0 (own 16 features) -> hi/lo -> TMEM ---------------------------------------------------------
+#pragma unroll
+            for (int c0 = 0; c0 < 16; c0 += 8) {
+                float h[8], hi[8], lo[8];
+                {
+                    const float4 ba = *reinterpret_cast<const float4*>(sb0 + f0 + c0);
+                    const float4 bb = *reinterpret_cast<const float4*>(sb0 + f0 + c0 + 4);
+                    h[0] = ba.x; h[1] = ba.y; h[2] = ba.z; h[3] = ba.w; h[4] = bb.x; h[5] = bb.y; h[6] = bb.z; h[7] = bb.w;
+                }
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(sW0 + d * 64 + f0 + c0);
+                    const float4 w1 = *reinterpret_cast<const float4*>(sW0 + d * 64 + f0 + c0 + 4);
+                    h[0] = fmaf(st[d], w0.x, h[0]); h[1] = fmaf(st[d], w0.y, h[1]); h[2] = fmaf(st[d], w0.z, h[2]); h[3] = fmaf(st[d], w0.w, h[3]);
+                    h[4] = fmaf(st[d], w1.x, h[4]); h[5] = fmaf(st[d], w1.y, h[5]); h[6] = fmaf(st[d], w1.z, h[6]); h[7] = fmaf(st[d], w1.w, h[7]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { h[j] = fast_tanh(h[j]); hi[j] = tc_hi(h[j]); lo[j] = h[j] - hi[j]; }
+                tc_st8(my + RT_COL_HI + f0 + c0, hi);
+                tc_st8(my + RT_COL_LO + f0 + c0, lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            rt_sync();
+            // ---- H1pre = H0 W1 on the tensor cores; meanwhile one thread per env evaluates sin/cos in fp64 ---------------
+            if (warp == 0 && tc_elect_one()) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int ps = 0; ps < 3; ++ps) {
+                    const uint32_t acol = tb + (ps == 1 ? RT_COL_LO : RT_COL_HI);
+                    const uint32_t bimg = sm_base + (ps == 2 ? RT_OFF_WT_LO : RT_OFF_WT_HI);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        tc_mma_ts(tb + RT_COL_D, acol + kk * 8, tc_desc(bimg + kk * 256, 128, 2048, 0), idesc, (ps | kk) ? 1u : 0u);
+                }
+                tc_commit(&bar);
+            }
+            if (fq == 0) {
+                float s_, c_;
+                sincos_rn(st[2], &s_, &c_);
+                *reinterpret_cast<float2*>(sSC + e * 2) = make_float2(s_, c_);
+            }
+            tc_wait(&bar, nbar & 1u);
+            ++nbar;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // ---- H1 = tanh(. + b1), partial logits over the own 16 features ---------------------------------------------
+            {
+                float h1[16];
+                tc_ld16(my + RT_COL_D + f0, h1);
+                float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float hv = fast_tanh(h1[k] + sb1[f0 + k]);
+                    const float4 w = *reinterpret_cast<const float4*>(sW2 + (f0 + k) * 4);
+                    p0 = fmaf(hv, w.x, p0);
+                    p1 = fmaf(hv, w.y, p1);
+                }
+                sPart[(fq * 2 + 0) * 64 + e] = p0;
+                sPart[(fq * 2 + 1) * 64 + e] = p1;
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            rt_sync();
+            // ---- all four threads of an env: softmax, sample, log-prob, dynamics, monitor, auto-reset (identical results) ----
+            if (mine) {
+                float z0 = sb2[0], z1 = sb2[1];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { z0 += sPart[(k * 2 + 0) * 64 + e]; z1 += sPart[(k * 2 + 1) * 64 + e]; }
+                float logp;
+                int idx;
+                if (A == 1) {
+                    idx = 0;                                              // Discrete(1): probs = [1]
+                    logp = 0.f;
+                } else {
+                    const float m = fmaxf(z0, z1);
+                    const float e0 = expf(z0 - m), e1 = expf(z1 - m);
+                    const float ssum = e0 + e1;
+                    idx = 1;
+                    if (a.forced) {
+                        idx = reinterpret_cast<const int*>(a.forced)[row + n] - pd.act_start;
+                        idx = idx < 0 ? 0 : (idx > 1 ? 1 : idx);
+                    } else {
+                        uint32_t x[4];
+                        philox4x32(gid, a.step0 + (uint32_t)t, 0u, DRIL_TAG_SAMPLE, a.pseed, x);
+                        const double u = u01_f64(x[0], x[1]);
+                        const float cum0 = e0 / ssum;                    // fp32 cumsum vs Float64 u (categorical.jl:45-47)
+                        if ((double)cum0 >= u) idx = 0;
+                    }
+                    logp = logf((idx == 0 ? e0 : e1) / ssum);
+                }
+                const float2 scv = *reinterpret_cast<const float2*>(sSC + e * 2);
+                bool term = false;
+                const float r = cartpole_step_sc(st, idx, scv.x, scv.y, &term);
+                steps += 1;
+                const bool trunc = steps >= env.max_steps;
+                const bool done = term || trunc;
+                if (env.monitor) { ep_ret = __fadd_rn(ep_ret, r); ep_len += 1; }
+                if (writer) {
+                    reinterpret_cast<int*>(buf.actions)[row + n] = idx + pd.act_start;
+                    buf.logprobs[row + n] = logp;
+                    buf.flags[row + n] = (unsigned char)((term ? 1 : 0) | (trunc ? 2 : 0));
+                    buf.rewards[row + n] = r;
+                    if (env.monitor && done) {
+                        buf.episode_r[row + n] = ep_ret;
+                        buf.episode_l[row + n] = ep_len;
+                        atomicAdd(&buf.done_count[t], 1);
+                        atomicAdd(&env.roll_sums[0], (double)ep_ret);
+                        atomicAdd(&env.roll_sums[1], (double)ep_len);
+                        atomicAdd(env.roll_eps, 1ull);
+                    }
+                    if (trunc) {                                          // V(terminal_obs) is evaluated by the critic pass
+                        const unsigned int k = atomicAdd(sc.trunc_count, 1u);
+                        if (k < sc.cap) {
+                            *reinterpret_cast<float4*>(sc.trunc_obs + (size_t)k * 4) = make_float4(st[0], st[1], st[2], st[3]);
+                            sc.trunc_idx[k] = (long long)(row + n);
+                        }
+                    }
+                }
+                if (done) {
+                    if (env.monitor) { ep_ret = 0.f; ep_len = 0; }
+                    env_reset_state(env.kind, gid, episode, env.seed, st);
+                    episode += 1;
+                    steps = 0;
+                }
+            }
+        }
+        if (writer) {
+            *reinterpret_cast<float4*>(sc.last_obs + (size_t)n * 4) = make_float4(st[0], st[1], st[2], st[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) env.state[(size_t)k * N + n] = st[k];
+            env.steps[n] = steps;
+            env.episode[n] = episode;
+            if (env.monitor) { env.ep_ret[n] = ep_ret; env.ep_len[n] = ep_len; }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    rt_sync();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(RT_TMEM_COLS));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Batched critic: values of all T*N buffer observations, of the N final observations (bootstrap, trajectory.jl:65-70)
+// and of the terminal observations of truncated steps (trajectory.jl:57-61).  128 samples per tile, two threads per
+// sample (32 hidden features each), hidden layer on tcgen05 (3xTF32).  2 CTAs per SM (256 TMEM columns each).
+// ---------------------------------------------------------------------------------------------------------
+#define CV_THREADS 256
+__global__ void __launch_bounds__(CV_THREADS, 2) critic_values_tc_kernel(const PolicyDesc pd, const float* __restrict__ pack, BufDev buf,
+                                                                        const TcRolloutScratch sc) {
+    extern __shared__ __align__(1024) unsigned char rt_smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const uint32_t raw = tc_smem_u32(rt_smem_raw);
+    const uint32_t sm_base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = rt_smem_raw + (sm_base - raw);
+    float* sSmall = reinterpret_cast<float*>(sm + RT_OFF_SMALL);
+    float* sW0 = sSmall;
+    float* sb0 = sW0 + 256;
+    float* sb1 = sb0 + 64;
+    float* sW2 = sb1 + 64;
+    float* sb2 = sW2 + 256;
+    float* sPart = sb2 + 8;         // [2 halves][128]
+    const LayerDesc& L0 = pd.L[1][0];
+    const LayerDesc& L1 = pd.L[1][1];
+    const LayerDesc& L2 = pd.L[1][2];
+    rt_stage_w1(pack, L1, sm, tid, CV_THREADS);
+    for (int i = tid; i < 256; i += CV_THREADS) { sW0[i] = pack[L0.pw_off + i]; sW2[i] = pack[L2.pw_off + i]; }
+    if (tid < 64) { sb0[tid] = pack[L0.pb_off + tid]; sb1[tid] = pack[L1.pb_off + tid]; }
+    if (tid < 4) sb2[tid] = pack[L2.pb_off + tid];
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_s)), "r"(RT_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+    const int m = tid & 127, half = (warp >> 2) & 1, f0 = half * 32;
+    const uint32_t my = tb + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t idesc = tc_idesc(128, 64, 0, 0);
+    const long long TN = buf.T * buf.N;
+    const unsigned int ntr = min(*sc.trunc_count, sc.cap);
+    const long long total = TN + buf.N + (long long)ntr;
+    const long long n_tiles = (total + 127) / 128;
+    uint32_t nbar = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long v = tile * 128 + m;
+        const bool valid = v < total;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* dst = nullptr;
+        if (valid) {
+            if (v < TN) { x = *reinterpret_cast<const float4*>(buf.obs + v * 4); dst = buf.values + v; }
+            else if (v < TN + buf.N) { x = *reinterpret_cast<const float4*>(sc.last_obs + (v - TN) * 4); dst = buf.last_values + (v - TN); }
+            else { const long long k = v - TN - buf.N; x = *reinterpret_cast<const float4*>(sc.trunc_obs + k * 4); dst = buf.boot + sc.trunc_idx[k]; }
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 8) {
+            float h[8], hi[8], lo[8];
+            {
+                const float4 ba = *reinterpret_cast<const float4*>(sb0 + f0 + c0);
+                const float4 bb = *reinterpret_cast<const float4*>(sb0 + f0 + c0 + 4);
+                h[0] = ba.x; h[1] = ba.y; h[2] = ba.z; h[3] = ba.w; h[4] = bb.x; h[5] = bb.y; h[6] = bb.z; h[7] = bb.w;
+            }
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const float xd = d == 0 ? x.x : (d == 1 ? x.y : (d == 2 ? x.z : x.w));
+                const float4 w0 = *reinterpret_cast<const float4*>(sW0 + d * 64 + f0 + c0);
+                const float4 w1 = *reinterpret_cast<const float4*>(sW0 + d * 64 + f0 + c0 + 4);
+                h[0] = fmaf(xd, w0.x, h[0]); h[1] = fmaf(xd, w0.y, h[1]); h[2] = fmaf(xd, w0.z, h[2]); h[3] = fmaf(xd, w0.w, h[3]);
+                h[4] = fmaf(xd, w1.x, h[4]); h[5] = fmaf(xd, w1.y, h[5]); h[6] = fmaf(xd, w1.z, h[6]); h[7] = fmaf(xd, w1.w, h[7]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { h[j] = fast_tanh(h[j]); hi[j] = tc_hi(h[j]); lo[j] = h[j] - hi[j]; }
+            tc_st8(my + RT_COL_HI + f0 + c0, hi);
+            tc_st8(my + RT_COL_LO + f0 + c0, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0 && tc_elect_one()) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int ps = 0; ps < 3; ++ps) {
+                const uint32_t acol = tb + (ps == 1 ? RT_COL_LO : RT_COL_HI);
+                const uint32_t bimg = sm_base + (ps == 2 ? RT_OFF_WT_LO : RT_OFF_WT_HI);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    tc_mma_ts(tb + RT_COL_D, acol + kk * 8, tc_desc(bimg + kk * 256, 128, 2048, 0), idesc, (ps | kk) ? 1u : 0u);
+            }
+            tc_commit(&bar);
+        }
+        tc_wait(&bar, nbar & 1u);
+        ++nbar;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            float h1[32];
+            tc_ld32(my + RT_COL_D + f0, h1);
+            float p0 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) p0 = fmaf(fast_tanh(h1[k] + sb1[f0 + k]), sW2[(f0 + k) * 4], p0);
+            sPart[half * 128 + m] = p0;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (half == 0 && valid) *dst = sb2[0] + (sPart[m] + sPart[128 + m]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(RT_TMEM_COLS));
+}
