@@ -1727,6 +1727,11 @@ extern "C" int32_t dril_optimizer_step(dril_policy* p, const float* grads, int64
 }
 
 #ifdef TC_TRACE
+extern "C" int32_t dril_debug_rt_trace(long long* out) {
+    DRIL_CUDA(cudaDeviceSynchronize());
+    DRIL_CUDA(cudaMemcpyFromSymbol(out, g_rt_trace, sizeof(long long) * 4 * 8 * 8));
+    return DRIL_OK;
+}
 extern "C" int32_t dril_debug_tc_trace(long long* out) {
     DRIL_CUDA(cudaDeviceSynchronize());
     DRIL_CUDA(cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(long long) * 2 * 32 * 16));

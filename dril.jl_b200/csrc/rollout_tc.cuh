@@ -6,17 +6,21 @@
 //  * only the ACTOR runs inside the step loop.  Values are not needed to choose actions: V(s_t), the bootstrap value of
 //    the final observation and V(terminal_obs) of truncated steps (trajectory.jl:57-70) are computed afterwards in one
 //    batched tensor-core pass over all n_steps x n_envs observations (critic_values_tc_kernel);
-//  * 64 envs per CTA (TMEM lanes 0..63), four threads per env (16 hidden features each) that all keep the env state in
-//    registers and step it redundantly, so a step needs two 256-thread barriers; the correctly rounded fp64 sin/cos of
-//    the dynamics is computed by one of the four threads while the MMAs run;
+//  * 32 envs per CTA (TMEM lanes 0..31; 128 CTAs for 4096 envs), four threads per env (16 hidden features each, warps
+//    0/4/8/12) that all keep the env state in registers, so a step needs two 128-thread barriers;
+//  * everything that does not depend on the sampled action is done while the MMAs run, one role per warp: the Euler step
+//    for BOTH pushes (in CartPole the new positions, the termination test and the reset are action independent, only
+//    the two velocities differ), the Philox uniform, the start state of the env's next episode, the correctly rounded
+//    fp64 sin/cos of the next pole angle (one step ahead), and the buffer/monitor bookkeeping of the previous step.
+//    After the logits only softmax -> compare -> select remains;
 //  * per step: layer 0 (K = 4) on CUDA cores -> hi/lo to TMEM -> 24 tcgen05.mma (M = 128 rows, 64 used; N = 64; K = 8)
 //    -> tanh + output layer partials -> softmax, Philox inverse-CDF sample, log-prob, dynamics, monitor, auto-reset.
-// Warps whose TMEM lane quadrant holds no envs (warp % 4 >= 2) only help staging the weights and exit.
+// Warps whose TMEM lane quadrant holds no envs (warp % 4 != 0) only help staging the weights and exit.
 #pragma once
 #include "rollout.cuh"
 #include "update_tc.cuh"
 
-#define RT_ENVS 64
+#define RT_ENVS 32
 #define RT_THREADS 512
 #define RT_COL_D 0
 #define RT_COL_HI 64
@@ -25,7 +29,7 @@
 #define RT_OFF_WT_HI 0
 #define RT_OFF_WT_LO 16384
 #define RT_OFF_SMALL 32768
-#define RT_SMALL_FLOATS 1664
+#define RT_SMALL_FLOATS 1920
 #define RT_SMEM_BYTES (RT_OFF_SMALL + RT_SMALL_FLOATS * 4 + 1024)
 
 struct TcRolloutScratch {
@@ -36,7 +40,13 @@ struct TcRolloutScratch {
     unsigned int cap;
 };
 
-__device__ __forceinline__ void rt_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+#ifdef TC_TRACE
+__device__ long long g_rt_trace[4][8][8];     // [feature quarter][step - 8][point], CTA 0, lane 0 of the quarter's first warp
+#define RT_MARK(pt) do { if (blockIdx.x == 0 && lane == 0 && t >= 8 && t < 16) g_rt_trace[fq][t - 8][pt] = clock64(); } while (0)
+#else
+#define RT_MARK(pt) do { } while (0)
+#endif
+__device__ __forceinline__ void rt_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* r) {
     uint32_t u[16];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -80,8 +90,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
     float* sb1 = sb0 + 64;          // [64]
     float* sW2 = sb1 + 64;          // [64][4]
     float* sb2 = sW2 + 256;         // [4]
-    float* sPart = sb2 + 8;         // [4 feature quarters][2][64] partial logits
-    float* sSC = sPart + 512;       // [64][2] sin, cos of the pole angle
+    float* sPart = sb2 + 8;         // [4 feature quarters][2][32] partial logits
+    float* sCand = sPart + 256;     // [32][8] next-state candidates: xn, thn, xd(0), thd(0), xd(1), thd(1)
+    float* sReset = sCand + 256;    // [32][8] state of the env's next episode + sin/cos of its pole angle
+    float* sSCn = sReset + 256;     // [32][2] sin/cos of the next pole angle if the episode continues
+    double* sU = reinterpret_cast<double*>(sSCn + 64);   // [32] uniform of the step's action sample
     const LayerDesc& L0 = pd.L[0][0];
     const LayerDesc& L1 = pd.L[0][1];
     const LayerDesc& L2 = pd.L[0][2];
@@ -101,24 +114,27 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if ((warp & 3) >= 2) return;                      // no envs in TMEM lanes 64..127
+    if ((warp & 3) != 0) return;                      // the envs live in TMEM lanes 0..31: only warps 0, 4, 8, 12 can reach them
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base_s, 0);
-    const int q = warp & 3, fq = warp >> 2, f0 = fq * 16;
-    const int e = q * 32 + lane;                      // env slot == TMEM lane
-    const uint32_t my = tb + ((uint32_t)(q * 32) << 16);
+    const int fq = warp >> 2, f0 = fq * 16;           // feature quarter == role in the MMA window
+    const int e = lane;                               // env slot == TMEM lane
+    const uint32_t my = tb;
     const uint32_t idesc = tc_idesc(128, 64, 0, 0);
     const long long N = env.n_envs;
     const int A = pd.act_n;
+    const float TAU = 0.02f;
     uint32_t nbar = 0;
     for (long long tile = blockIdx.x; tile * RT_ENVS < N; tile += gridDim.x) {
         const long long n = tile * RT_ENVS + e;
         const bool mine = n < N;
-        const bool writer = mine && fq == 0;
+        const bool writer = mine && fq == 3;
         const uint32_t gid = (uint32_t)(env.gid_offset + n);
         float st[4] = {0.f, 0.f, 0.f, 0.f};
         int steps = 0, ep_len = 0;
         float ep_ret = 0.f;
         uint32_t episode = 0;
+        float sn = 0.f, cs = 1.f;                     // fq 0: sin/cos of the current pole angle
+        bool need_reset_calc = true;                  // fq 2: sReset[e] must be (re)computed for `episode`
         if (mine) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) st[k] = env.state[(size_t)k * N + n];
@@ -126,8 +142,41 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
             episode = env.episode[n];
             if (env.monitor) { ep_ret = env.ep_ret[n]; ep_len = env.ep_len[n]; }
         }
+        if (fq == 0) sincos_rn(st[2], &sn, &cs);
+        // bookkeeping of a finished step (log-prob, buffer row, monitor, truncation list): done by the env's writer thread
+        // one step late, while the next step's MMAs run, so that it is off the per-step critical path
+        struct Pending { float pe, ssum, ep_ret; float4 tobs; int idx, ep_len, t; bool term, trunc, live; } pend;
+        pend.live = false; pend.pe = pend.ssum = 1.f; pend.ep_ret = 0.f; pend.tobs = make_float4(0.f, 0.f, 0.f, 0.f);
+        pend.idx = 0; pend.ep_len = 0; pend.t = 0; pend.term = pend.trunc = false;
+        auto flush = [&]() {
+            if (!pend.live) return;
+            const size_t r = (size_t)pend.t * N + n;
+            reinterpret_cast<int*>(buf.actions)[r] = pend.idx + pd.act_start;
+            buf.logprobs[r] = A == 1 ? 0.f : logf(pend.pe / pend.ssum);
+            buf.flags[r] = (unsigned char)((pend.term ? 1 : 0) | (pend.trunc ? 2 : 0));
+            buf.rewards[r] = 1.0f;
+            if (env.monitor && (pend.term || pend.trunc)) {
+                buf.episode_r[r] = pend.ep_ret;
+                buf.episode_l[r] = pend.ep_len;
+                atomicAdd(&buf.done_count[pend.t], 1);
+                atomicAdd(&env.roll_sums[0], (double)pend.ep_ret);
+                atomicAdd(&env.roll_sums[1], (double)pend.ep_len);
+                atomicAdd(env.roll_eps, 1ull);
+            }
+            if (pend.trunc) {                                             // V(terminal_obs) is evaluated by the critic pass
+                const unsigned int k = atomicAdd(sc.trunc_count, 1u);
+                if (k < sc.cap) {
+                    *reinterpret_cast<float4*>(sc.trunc_obs + (size_t)k * 4) = pend.tobs;
+                    sc.trunc_idx[k] = (long long)r;
+                }
+            }
+            pend.live = false;
+        };
         for (int t = 0; t < a.T; ++t) {
             const size_t row = (size_t)t * N;
+            RT_MARK(0);
+            int forced_a = 0;
+            if (a.forced && mine) forced_a = reinterpret_cast<const int*>(a.forced)[row + n];
             if (writer) *reinterpret_cast<float4*>(buf.obs + (row + n) * 4) = make_float4(st[0], st[1], st[2], st[3]);
             // ---- layer 0 (own 16 features) -> hi/lo -> TMEM ---------------------------------------------------------
 #pragma unroll
@@ -150,10 +199,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
                 tc_st8(my + RT_COL_HI + f0 + c0, hi);
                 tc_st8(my + RT_COL_LO + f0 + c0, lo);
             }
+            RT_MARK(1);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             rt_sync();
-            // ---- H1pre = H0 W1 on the tensor cores; meanwhile one thread per env evaluates sin/cos in fp64 ---------------
+            // ---- H1pre = H0 W1 on the tensor cores ------------------------------------------------------------------------
             if (warp == 0 && tc_elect_one()) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -166,14 +216,40 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
                 }
                 tc_commit(&bar);
             }
+            RT_MARK(2);
+            // ---- while the MMAs run: everything that does not depend on the action, one role per feature quarter ----------
             if (fq == 0) {
-                float s_, c_;
-                sincos_rn(st[2], &s_, &c_);
-                *reinterpret_cast<float2*>(sSC + e * 2) = make_float2(s_, c_);
+                // Euler step for BOTH pushes: positions, termination and the reset do not depend on the action
+                float s0[4] = {st[0], st[1], st[2], st[3]}, s1[4] = {st[0], st[1], st[2], st[3]};
+                bool t0, t1;
+                cartpole_step_sc(s0, 0, sn, cs, &t0);
+                cartpole_step_sc(s1, 1, sn, cs, &t1);
+                *reinterpret_cast<float4*>(sCand + e * 8) = make_float4(s0[0], s0[2], s0[1], s0[3]);     // xn, thn, xd(0), thd(0)
+                *reinterpret_cast<float2*>(sCand + e * 8 + 4) = make_float2(s1[1], s1[3]);              // xd(1), thd(1)
+            } else if (fq == 1) {
+                uint32_t x[4];
+                philox4x32(gid, a.step0 + (uint32_t)t, 0u, DRIL_TAG_SAMPLE, a.pseed, x);
+                sU[e] = u01_f64(x[0], x[1]);
+            } else if (fq == 2) {
+                if (need_reset_calc) {                    // start state of the env's next episode and sin/cos of its pole angle
+                    float rs[4], s_, c_;
+                    env_reset_state(env.kind, gid, episode, env.seed, rs);
+                    sincos_rn(rs[2], &s_, &c_);
+                    *reinterpret_cast<float4*>(sReset + e * 8) = make_float4(rs[0], rs[1], rs[2], rs[3]);
+                    *reinterpret_cast<float2*>(sReset + e * 8 + 4) = make_float2(s_, c_);
+                    need_reset_calc = false;
+                }
+            } else {
+                float s_, c_;                            // correctly rounded sin/cos of the next pole angle (if no reset)
+                sincos_rn(__fadd_rn(st[2], __fmul_rn(TAU, st[3])), &s_, &c_);
+                *reinterpret_cast<float2*>(sSCn + e * 2) = make_float2(s_, c_);
+                flush();
             }
+            RT_MARK(3);
             tc_wait(&bar, nbar & 1u);
             ++nbar;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            RT_MARK(4);
             // ---- H1 = tanh(. + b1), partial logits over the own 16 features ---------------------------------------------
             {
                 float h1[16];
@@ -186,74 +262,64 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
                     p0 = fmaf(hv, w.x, p0);
                     p1 = fmaf(hv, w.y, p1);
                 }
-                sPart[(fq * 2 + 0) * 64 + e] = p0;
-                sPart[(fq * 2 + 1) * 64 + e] = p1;
+                sPart[(fq * 2 + 0) * 32 + e] = p0;
+                sPart[(fq * 2 + 1) * 32 + e] = p1;
             }
+            RT_MARK(5);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             rt_sync();
-            // ---- all four threads of an env: softmax, sample, log-prob, dynamics, monitor, auto-reset (identical results) ----
+            RT_MARK(6);
+            // ---- all four threads of an env: softmax, inverse-CDF sample, select the pre-computed next state / reset ----------
             if (mine) {
                 float z0 = sb2[0], z1 = sb2[1];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { z0 += sPart[(k * 2 + 0) * 64 + e]; z1 += sPart[(k * 2 + 1) * 64 + e]; }
-                float logp;
-                int idx;
-                if (A == 1) {
-                    idx = 0;                                              // Discrete(1): probs = [1]
-                    logp = 0.f;
-                } else {
+                for (int k = 0; k < 4; ++k) { z0 += sPart[(k * 2 + 0) * 32 + e]; z1 += sPart[(k * 2 + 1) * 32 + e]; }
+                int idx = 0;
+                float pe = 1.f, ssum = 1.f;
+                if (A > 1) {
                     const float m = fmaxf(z0, z1);
                     const float e0 = expf(z0 - m), e1 = expf(z1 - m);
-                    const float ssum = e0 + e1;
+                    ssum = e0 + e1;
                     idx = 1;
                     if (a.forced) {
-                        idx = reinterpret_cast<const int*>(a.forced)[row + n] - pd.act_start;
+                        idx = forced_a - pd.act_start;
                         idx = idx < 0 ? 0 : (idx > 1 ? 1 : idx);
                     } else {
-                        uint32_t x[4];
-                        philox4x32(gid, a.step0 + (uint32_t)t, 0u, DRIL_TAG_SAMPLE, a.pseed, x);
-                        const double u = u01_f64(x[0], x[1]);
                         const float cum0 = e0 / ssum;                    // fp32 cumsum vs Float64 u (categorical.jl:45-47)
-                        if ((double)cum0 >= u) idx = 0;
+                        if ((double)cum0 >= sU[e]) idx = 0;
                     }
-                    logp = logf((idx == 0 ? e0 : e1) / ssum);
+                    pe = idx == 0 ? e0 : e1;
                 }
-                const float2 scv = *reinterpret_cast<const float2*>(sSC + e * 2);
-                bool term = false;
-                const float r = cartpole_step_sc(st, idx, scv.x, scv.y, &term);
+                const float4 c4 = *reinterpret_cast<const float4*>(sCand + e * 8);
+                const float2 c2 = *reinterpret_cast<const float2*>(sCand + e * 8 + 4);
+                st[0] = c4.x; st[2] = c4.y;
+                st[1] = idx == 1 ? c2.x : c4.z;
+                st[3] = idx == 1 ? c2.y : c4.w;
+                const bool term = (st[0] < -2.4f) || (st[0] > 2.4f) || (st[2] < -0.20943951023931953f) || (st[2] > 0.20943951023931953f);
                 steps += 1;
                 const bool trunc = steps >= env.max_steps;
                 const bool done = term || trunc;
-                if (env.monitor) { ep_ret = __fadd_rn(ep_ret, r); ep_len += 1; }
-                if (writer) {
-                    reinterpret_cast<int*>(buf.actions)[row + n] = idx + pd.act_start;
-                    buf.logprobs[row + n] = logp;
-                    buf.flags[row + n] = (unsigned char)((term ? 1 : 0) | (trunc ? 2 : 0));
-                    buf.rewards[row + n] = r;
-                    if (env.monitor && done) {
-                        buf.episode_r[row + n] = ep_ret;
-                        buf.episode_l[row + n] = ep_len;
-                        atomicAdd(&buf.done_count[t], 1);
-                        atomicAdd(&env.roll_sums[0], (double)ep_ret);
-                        atomicAdd(&env.roll_sums[1], (double)ep_len);
-                        atomicAdd(env.roll_eps, 1ull);
-                    }
-                    if (trunc) {                                          // V(terminal_obs) is evaluated by the critic pass
-                        const unsigned int k = atomicAdd(sc.trunc_count, 1u);
-                        if (k < sc.cap) {
-                            *reinterpret_cast<float4*>(sc.trunc_obs + (size_t)k * 4) = make_float4(st[0], st[1], st[2], st[3]);
-                            sc.trunc_idx[k] = (long long)(row + n);
-                        }
-                    }
+                if (fq == 3) {
+                    if (env.monitor) { ep_ret = __fadd_rn(ep_ret, 1.0f); ep_len += 1; }
+                    pend.live = true; pend.t = t; pend.idx = idx; pend.pe = pe; pend.ssum = ssum; pend.term = term; pend.trunc = trunc;
+                    pend.ep_ret = ep_ret; pend.ep_len = ep_len;
+                    if (trunc) pend.tobs = make_float4(st[0], st[1], st[2], st[3]);
+                    if (done && env.monitor) { ep_ret = 0.f; ep_len = 0; }
                 }
                 if (done) {
-                    if (env.monitor) { ep_ret = 0.f; ep_len = 0; }
-                    env_reset_state(env.kind, gid, episode, env.seed, st);
+                    const float4 r4 = *reinterpret_cast<const float4*>(sReset + e * 8);
+                    st[0] = r4.x; st[1] = r4.y; st[2] = r4.z; st[3] = r4.w;
                     episode += 1;
                     steps = 0;
+                    need_reset_calc = true;
+                }
+                if (fq == 0) {
+                    const float2 scn = done ? *reinterpret_cast<const float2*>(sReset + e * 8 + 4) : *reinterpret_cast<const float2*>(sSCn + e * 2);
+                    sn = scn.x; cs = scn.y;
                 }
             }
         }
+        if (fq == 3) flush();
         if (writer) {
             *reinterpret_cast<float4*>(sc.last_obs + (size_t)n * 4) = make_float4(st[0], st[1], st[2], st[3]);
 #pragma unroll
@@ -262,6 +328,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
             env.episode[n] = episode;
             if (env.monitor) { env.ep_ret[n] = ep_ret; env.ep_len[n] = ep_len; }
         }
+        rt_sync();                                    // the next tile's windows reuse sReset / sCand
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     rt_sync();
