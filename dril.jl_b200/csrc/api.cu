@@ -384,13 +384,16 @@ extern "C" int32_t dril_comm_destroy(dril_ctx* c) {
     return DRIL_OK;
 }
 #define P2P_HDR_BYTES 256   // [0] flag (u64), [8] seq (u64), [16] err (int)
+#define P2P_MAX_CTA 256
 extern "C" int32_t dril_comm_p2p_export(dril_ctx* c, int64_t n_slots, uint8_t handle_out[64]) {
     DRIL_REQUIRE(c && handle_out && n_slots >= 1, "bad p2p arguments");
     DRIL_REQUIRE(c->nranks >= 1 && c->nranks <= DRIL_MAX_RANKS, "p2p allreduce supports up to %d ranks", DRIL_MAX_RANKS);
     DRIL_CUDA(cudaSetDevice(c->device));
     if (c->p2p_region) { cudaFree(c->p2p_region); c->p2p_region = nullptr; c->p2p_enabled = false; }
     size_t slots = ((size_t)n_slots + 63) & ~(size_t)63;
-    size_t bytes = P2P_HDR_BYTES + 2 * slots * sizeof(float);
+    // [header | gbuf[2][slots] (pull exchange) | recv[2][nranks][slots] (push exchange) | cflag[nranks][P2P_MAX_CTA]]
+    size_t bytes = P2P_HDR_BYTES + 2 * slots * sizeof(float) + 2 * (size_t)c->nranks * slots * sizeof(float) +
+                   (size_t)c->nranks * P2P_MAX_CTA * sizeof(unsigned long long);
     DRIL_CUDA(cudaMalloc(&c->p2p_region, bytes));
     DRIL_CUDA(cudaMemset(c->p2p_region, 0, bytes));
     memset(&c->p2p, 0, sizeof(c->p2p));
@@ -416,7 +419,13 @@ extern "C" int32_t dril_comm_p2p_import(dril_ctx* c, const uint8_t* handles) {
         c->p2p_peer_base[r] = base;
         c->p2p.peer_flag[r] = (const volatile unsigned long long*)base;
         c->p2p.peer_gbuf[r] = (const float*)((char*)base + P2P_HDR_BYTES);
+        char* recv = (char*)base + P2P_HDR_BYTES + 2 * (size_t)c->p2p.n_slots * sizeof(float);
+        c->p2p.peer_recv[r] = (float*)recv;
+        c->p2p.peer_cflag[r] = (unsigned long long*)(recv + 2 * (size_t)c->nranks * c->p2p.n_slots * sizeof(float));
     }
+    c->p2p.local_recv = c->p2p.peer_recv[c->rank];
+    c->p2p.local_cflag = c->p2p.peer_cflag[c->rank];
+    c->p2p.max_cta = P2P_MAX_CTA;
     c->p2p.local_flag = (volatile unsigned long long*)local;
     c->p2p.local_seq = (unsigned long long*)(local + 8);
     c->p2p.err = (int*)(local + 16);
@@ -1361,7 +1370,7 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
     const bool fused = apply && c->nranks == 1;
     const bool p2p = apply && c->nranks > 1 && c->p2p_enabled && n <= c->p2p.n_slots;
     // tensor-core path: reduction (+ peer-memory exchange) + clip + Adam run as the tail of the loss/grad kernel
-    const bool tail = tc && g_opt_tail && (fused || p2p) && grid <= c->sm_count;
+    const bool tail = tc && g_opt_tail && (fused || p2p) && grid <= c->sm_count && grid <= P2P_MAX_CTA;
     {
         Span sp(c, DRIL_K_LOSS_GRAD);
         if (tc) {

@@ -767,6 +767,14 @@ struct P2PDev {
     const volatile unsigned long long* peer_flag[DRIL_MAX_RANKS];
     int* err;
     int n_slots, nranks, rank;
+    // push exchange (fused tail of the tensor-core kernel): every rank owns recv[2][nranks][n_slots] and per-(source rank,
+    // CTA) arrival flags; rank r's CTA b stores its reduced slice into EVERY rank's recv[parity][r] and then raises
+    // that rank's cflag[r][b], so a receiver only polls and reads its own memory (one NVLink one-way latency)
+    float* peer_recv[DRIL_MAX_RANKS];
+    unsigned long long* peer_cflag[DRIL_MAX_RANKS];
+    const float* local_recv;
+    const volatile unsigned long long* local_cflag;
+    int max_cta;
 };
 
 __global__ void __launch_bounds__(1024) p2p_sum_adam_kernel(P2PDev pp, double* __restrict__ sq_part,

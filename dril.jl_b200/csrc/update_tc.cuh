@@ -613,6 +613,7 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
     grid.sync();                                             // every CTA's partial planes are visible
     const double bp1 = ad.iter_acc[12], bp2 = ad.iter_acc[13];   // running beta^t BEFORE this step (CTA 0 updates them at the end)
     const unsigned long long seq = tl.mode == 2 ? *tl.pp.local_seq + 1ull : 0ull;
+    const size_t par_off = (size_t)(seq & 1ull) * tl.pp.nranks * tl.pp.n_slots;      // parity half of recv[2][nranks][n_slots]
     double sq = 0.0;
     for (int base = p_lo; base < p_hi; base += 64) {
         const int lp = tid & 63, grp = tid >> 6, p = base + lp;
@@ -641,7 +642,9 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
 #pragma unroll
             for (int j = 0; j < 8; ++j) gs += s_red[j * 64 + lp];
             if (tl.mode == 2) {
-                tl.pp.local_gbuf[(size_t)(seq & 1ull) * tl.pp.n_slots + p] = gs;
+                // push this rank's reduced slice into every rank's receive buffer (own one included)
+                const size_t off = par_off + (size_t)tl.pp.rank * tl.pp.n_slots + p;
+                for (int r = 0; r < tl.pp.nranks; ++r) tl.pp.peer_recv[r][off] = gs;
             } else {
                 ad.g[p] = gs;
                 if (p < ad.n_params) sq += (double)gs * (double)gs;
@@ -650,29 +653,26 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
         __syncthreads();
     }
     if (tl.mode == 2) {
-        __threadfence();
-        grid.sync();                                         // this rank's whole gradient is in its peer-visible buffer
-        if (blockIdx.x == 0 && tid == 0) {
+        // raise this CTA's arrival flag at every rank, then wait for every rank's CTA with the same slice
+        if (tid == 0) {
             __threadfence_system();
-            *tl.pp.local_seq = seq;
-            *tl.pp.local_flag = seq;
-            __threadfence_system();
+            for (int r = 0; r < tl.pp.nranks; ++r)
+                *reinterpret_cast<volatile unsigned long long*>(tl.pp.peer_cflag[r] + (size_t)tl.pp.rank * tl.pp.max_cta + blockIdx.x) = seq;
         }
         if (tid < tl.pp.nranks) {
-            const volatile unsigned long long* f = tl.pp.peer_flag[tid];
+            const volatile unsigned long long* f = tl.pp.local_cflag + (size_t)tid * tl.pp.max_cta + blockIdx.x;
             long long spins = 0;
             while (*f < seq) {
-                __nanosleep(64);
+                __nanosleep(32);
                 if (++spins > (1ll << 24)) { atomicExch(tl.pp.err, 1); break; }
             }
             __threadfence_system();
         }
         __syncthreads();
-        // sum of the peers' slices in rank order (identical on every rank => bit-identical parameters)
+        // sum of all ranks' slices in rank order (identical on every rank => bit-identical parameters)
         for (int p = p_lo + tid; p < p_hi; p += blockDim.x) {
-            const size_t off = (size_t)(seq & 1ull) * tl.pp.n_slots + p;
             float gs = 0.f;
-            for (int r = 0; r < tl.pp.nranks; ++r) gs += __ldcv(tl.pp.peer_gbuf[r] + off);
+            for (int r = 0; r < tl.pp.nranks; ++r) gs += __ldcv(tl.pp.local_recv + par_off + (size_t)r * tl.pp.n_slots + p);
             ad.g[p] = gs;
             if (p < ad.n_params) sq += (double)gs * (double)gs;
         }
@@ -687,6 +687,7 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
     const float norm = (float)sqrt(q);
     const int stop = adam_stop(ad);
     if (blockIdx.x == 0) adam_accumulate(ad, norm, stop, tid, s_f);
+    if (tl.mode == 2 && blockIdx.x == 0 && tid == 32) *tl.pp.local_seq = seq;       // every CTA read the old value before the barrier
     if (stop) return;
     float scale = 1.f;
     if (ad.hp.max_grad_norm >= 0.f && norm > ad.hp.max_grad_norm) scale = ad.hp.max_grad_norm / norm;
