@@ -299,7 +299,10 @@ def run_ours(args):
     else:
         note = ("fp32 CUDA-core kernels; frac is against the tensor peak by contract, frac_of_fp32_fma_peak is the pipe it actually "
                 "runs on")
-    roof.update({"kernel": dominant, "traffic": None, "peak_source": pk["source"] + (" sustained bf16" if roof["bound"] == "tensor" else " copy"),
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of workload C2
+    # (profiles/r01_lossgrad_tc_final_summary.txt, profiles/r01_rollout_tc_final_summary.txt); null for other workloads
+    traffic_c2 = {"loss_grad": 14.16e6 + 0.06e6, "rollout": 192.3e3} if (args.workload == "c2" and lg_path == "tensor") else {}
+    roof.update({"kernel": dominant, "traffic": traffic_c2.get(dominant), "peak_source": pk["source"] + (" sustained bf16" if roof["bound"] == "tensor" else " copy"),
                  "note": note})
 
     line = {

@@ -5,13 +5,13 @@ import csv, subprocess, sys, io
 rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-h, v = rows[0], rows[2]
+h, u, v = rows[0], rows[1], rows[2]
 want = ['gpu__time_duration.sum', 'sm__cycles_elapsed.max', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'launch__registers_per_thread', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg',
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'sm__inst_executed_pipe_xu.sum', 'smsp__inst_executed_pipe_xu.sum',
         'sm__warps_active.avg.per_cycle_active', 'launch__grid_size', 'launch__block_size']
-for a, b in zip(h, v):
-    if any(a.endswith(w) for w in want): print(f'{a} = {b}')
+for a, b, c in zip(h, v, u):
+    if any(a.endswith(w) for w in want): print(f'{a} = {b} {c}')
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]; data = rows[2:]
