@@ -279,6 +279,7 @@ extern "C" int32_t dril_ctx_create(int32_t device, uint64_t seed, dril_ctx** out
     DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
     DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
     DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    DRIL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM_BYTES));
     *out = c;
     return DRIL_OK;
 }
@@ -984,7 +985,7 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
             Span sp(c, DRIL_K_ROLLOUT);
             const long long tiles = ((long long)b->d.T * N + N + 127) / 128 + 8;
             const int grid = (int)std::min<long long>(tiles, 2ll * c->sm_count);
-            critic_values_tc_kernel<<<grid, CV_THREADS, RT_SMEM_BYTES, c->stream>>>(a.pd, a.pack, b->d, b->tcs);
+            critic_values_tc_kernel<<<grid, CV_THREADS, CV_SMEM_BYTES, c->stream>>>(a.pd, a.pack, b->d, b->tcs);
             DRIL_CUDA(cudaGetLastError());
         }
         return DRIL_OK;

@@ -6,8 +6,11 @@
 //  * only the ACTOR runs inside the step loop.  Values are not needed to choose actions: V(s_t), the bootstrap value of
 //    the final observation and V(terminal_obs) of truncated steps (trajectory.jl:57-70) are computed afterwards in one
 //    batched tensor-core pass over all n_steps x n_envs observations (critic_values_tc_kernel);
-//  * 32 envs per CTA (TMEM lanes 0..31; 128 CTAs for 4096 envs), four threads per env (16 hidden features each, warps
-//    0/4/8/12) that all keep the env state in registers, so a step needs two 128-thread barriers;
+//  * 32 envs per CTA (128 CTAs for 4096 envs), sixteen threads per env (warp w owns hidden features 4w..4w+3 of all 32
+//    envs, its slices of W0/b0/b1/W2 stay in registers) that all keep the env state in registers.  A warp can only
+//    reach the TMEM lane quadrant warp % 4, which is also its scheduler, so both MMA operands come from shared memory
+//    (SS mode) and only four warps copy the 32x64 accumulator back to shared memory: the CUDA-core work is spread over
+//    all four schedulers instead of one;
 //  * everything that does not depend on the sampled action is done while the MMAs run, one role per warp: the Euler step
 //    for BOTH pushes (in CartPole the new positions, the termination test and the reset are action independent, only
 //    the two velocities differ), the Philox uniform, the start state of the env's next episode, the correctly rounded
@@ -15,7 +18,6 @@
 //    After the logits only softmax -> compare -> select remains;
 //  * per step: layer 0 (K = 4) on CUDA cores -> hi/lo to TMEM -> 24 tcgen05.mma (M = 128 rows, 64 used; N = 64; K = 8)
 //    -> tanh + output layer partials -> softmax, Philox inverse-CDF sample, log-prob, dynamics, monitor, auto-reset.
-// Warps whose TMEM lane quadrant holds no envs (warp % 4 != 0) only help staging the weights and exit.
 #pragma once
 #include "rollout.cuh"
 #include "update_tc.cuh"
@@ -25,12 +27,17 @@
 #define RT_COL_D 0
 #define RT_COL_HI 64
 #define RT_COL_LO 128
-#define RT_TMEM_COLS 256
-#define RT_OFF_WT_HI 0
+#define RT_TMEM_COLS 64
+#define RT_OFF_WT_HI 0           // W1^T hi / lo, K-major no-swizzle images (B operand)
 #define RT_OFF_WT_LO 16384
-#define RT_OFF_SMALL 32768
-#define RT_SMALL_FLOATS 1920
+#define RT_OFF_A_HI 32768        // rollout kernel: H0 hi / lo, 128 rows x 64 K-major no-swizzle (A operand, rows 0..31 used)
+#define RT_OFF_A_LO 65536
+#define RT_OFF_SMALL 98304
+#define RT_SMALL_FLOATS 4096
 #define RT_SMEM_BYTES (RT_OFF_SMALL + RT_SMALL_FLOATS * 4 + 1024)
+#define CV_OFF_SMALL 32768       // critic kernel: small arrays right after the W1 images
+#define CV_SMALL_FLOATS 1024
+#define CV_SMEM_BYTES (CV_OFF_SMALL + CV_SMALL_FLOATS * 4 + 1024)
 
 struct TcRolloutScratch {
     float* last_obs;          // [N][4] observation after the final step
@@ -42,7 +49,7 @@ struct TcRolloutScratch {
 
 #ifdef TC_TRACE
 __device__ long long g_rt_trace[4][8][8];     // [feature quarter][step - 8][point], CTA 0, lane 0 of the quarter's first warp
-#define RT_MARK(pt) do { if (blockIdx.x == 0 && lane == 0 && t >= 8 && t < 16) g_rt_trace[fq][t - 8][pt] = clock64(); } while (0)
+#define RT_MARK(pt) do { if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5 || warp == 6 || warp == 7) && t >= 8 && t < 16) g_rt_trace[warp == 0 ? 0 : warp - 4][t - 8][pt] = clock64(); } while (0)
 #else
 #define RT_MARK(pt) do { } while (0)
 #endif
@@ -84,24 +91,33 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
     const uint32_t raw = tc_smem_u32(rt_smem_raw);
     const uint32_t sm_base = (raw + 1023u) & ~1023u;
     unsigned char* sm = rt_smem_raw + (sm_base - raw);
+    float* sAhi = reinterpret_cast<float*>(sm + RT_OFF_A_HI);
+    float* sAlo = reinterpret_cast<float*>(sm + RT_OFF_A_LO);
     float* sSmall = reinterpret_cast<float*>(sm + RT_OFF_SMALL);
-    float* sW0 = sSmall;            // [4][64]
-    float* sb0 = sW0 + 256;         // [64]
-    float* sb1 = sb0 + 64;          // [64]
-    float* sW2 = sb1 + 64;          // [64][4]
-    float* sb2 = sW2 + 256;         // [4]
-    float* sPart = sb2 + 8;         // [4 feature quarters][2][32] partial logits
-    float* sCand = sPart + 256;     // [32][8] next-state candidates: xn, thn, xd(0), thd(0), xd(1), thd(1)
-    float* sReset = sCand + 256;    // [32][8] state of the env's next episode + sin/cos of its pole angle
-    float* sSCn = sReset + 256;     // [32][2] sin/cos of the next pole angle if the episode continues
+    float* sD = sSmall;                 // [32][68] pre-activations of the hidden layer (copied out of TMEM)
+    float* sPart = sD + 32 * 68;        // [16 feature groups][32][2] partial logits
+    float* sCand = sPart + 1024;        // [32][8] next-state candidates: xn, thn, xd(0), thd(0), xd(1), thd(1)
+    float* sReset = sCand + 256;        // [32][8] state of the env's next episode + sin/cos of its pole angle
+    float* sSCn = sReset + 256;         // [32][2] sin/cos of the next pole angle if the episode continues
     double* sU = reinterpret_cast<double*>(sSCn + 64);   // [32] uniform of the step's action sample
     const LayerDesc& L0 = pd.L[0][0];
     const LayerDesc& L1 = pd.L[0][1];
     const LayerDesc& L2 = pd.L[0][2];
     rt_stage_w1(a.pack, L1, sm, tid, RT_THREADS);
-    for (int i = tid; i < 256; i += RT_THREADS) { sW0[i] = a.pack[L0.pw_off + i]; sW2[i] = a.pack[L2.pw_off + i]; }
-    if (tid < 64) { sb0[tid] = a.pack[L0.pb_off + tid]; sb1[tid] = a.pack[L1.pb_off + tid]; }
-    if (tid < 4) sb2[tid] = a.pack[L2.pb_off + tid];
+    const int e = lane;                               // env slot == row of the MMA == TMEM lane
+    const int fg = warp, f0 = fg * 4;                 // this thread's 4 hidden features
+    // this thread's slices of the thin layers live in registers for the whole rollout
+    float w0r[4][4], b0r[4], b1r[4], w2r[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d) w0r[d][j] = a.pack[L0.pw_off + d * 64 + f0 + j];
+        b0r[j] = a.pack[L0.pb_off + f0 + j];
+        b1r[j] = a.pack[L1.pb_off + f0 + j];
+        w2r[j][0] = a.pack[L2.pw_off + (f0 + j) * 4];
+        w2r[j][1] = a.pack[L2.pw_off + (f0 + j) * 4 + 1];
+    }
+    const float b2_0 = a.pack[L2.pb_off], b2_1 = a.pack[L2.pb_off + 1];
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_s)), "r"(RT_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -114,27 +130,27 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if ((warp & 3) != 0) return;                      // the envs live in TMEM lanes 0..31: only warps 0, 4, 8, 12 can reach them
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base_s, 0);
-    const int fq = warp >> 2, f0 = fq * 16;           // feature quarter == role in the MMA window
-    const int e = lane;                               // env slot == TMEM lane
-    const uint32_t my = tb;
     const uint32_t idesc = tc_idesc(128, 64, 0, 0);
     const long long N = env.n_envs;
     const int A = pd.act_n;
     const float TAU = 0.02f;
+    const int a_off = ((e >> 3) * 16 + fg) * 32 + (e & 7) * 4;      // K-major no-swizzle core layout: row e, columns f0..f0+3
+    // roles in the MMA window (warps on different schedulers)
+    const bool r_cand = warp == 1, r_philox = warp == 2, r_reset = warp == 3, r_sincos = warp == 5, r_writer = warp == 6;
+    const bool r_copy = (warp & 3) == 0;              // TMEM lanes 0..31 are reachable from warps 0, 4, 8, 12 only
     uint32_t nbar = 0;
     for (long long tile = blockIdx.x; tile * RT_ENVS < N; tile += gridDim.x) {
         const long long n = tile * RT_ENVS + e;
         const bool mine = n < N;
-        const bool writer = mine && fq == 3;
+        const bool writer = mine && r_writer;
         const uint32_t gid = (uint32_t)(env.gid_offset + n);
         float st[4] = {0.f, 0.f, 0.f, 0.f};
         int steps = 0, ep_len = 0;
         float ep_ret = 0.f;
         uint32_t episode = 0;
-        float sn = 0.f, cs = 1.f;                     // fq 0: sin/cos of the current pole angle
-        bool need_reset_calc = true;                  // fq 2: sReset[e] must be (re)computed for `episode`
+        float sn = 0.f, cs = 1.f;                     // r_cand: sin/cos of the current pole angle
+        bool need_reset_calc = true;                  // r_reset: sReset[e] must be (re)computed for `episode`
         if (mine) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) st[k] = env.state[(size_t)k * N + n];
@@ -142,7 +158,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
             episode = env.episode[n];
             if (env.monitor) { ep_ret = env.ep_ret[n]; ep_len = env.ep_len[n]; }
         }
-        if (fq == 0) sincos_rn(st[2], &sn, &cs);
+        if (r_cand) sincos_rn(st[2], &sn, &cs);
         // bookkeeping of a finished step (log-prob, buffer row, monitor, truncation list): done by the env's writer thread
         // one step late, while the next step's MMAs run, so that it is off the per-step critical path
         struct Pending { float pe, ssum, ep_ret; float4 tobs; int idx, ep_len, t; bool term, trunc, live; } pend;
@@ -178,47 +194,41 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
             int forced_a = 0;
             if (a.forced && mine) forced_a = reinterpret_cast<const int*>(a.forced)[row + n];
             if (writer) *reinterpret_cast<float4*>(buf.obs + (row + n) * 4) = make_float4(st[0], st[1], st[2], st[3]);
-            // ---- layer 0 (own 16 features) -> hi/lo -> TMEM ---------------------------------------------------------
+            // ---- layer 0 (own 4 features) -> hi/lo -> A operand images in shared memory -----------------------------------
+            {
+                float hi[4], lo[4];
 #pragma unroll
-            for (int c0 = 0; c0 < 16; c0 += 8) {
-                float h[8], hi[8], lo[8];
-                {
-                    const float4 ba = *reinterpret_cast<const float4*>(sb0 + f0 + c0);
-                    const float4 bb = *reinterpret_cast<const float4*>(sb0 + f0 + c0 + 4);
-                    h[0] = ba.x; h[1] = ba.y; h[2] = ba.z; h[3] = ba.w; h[4] = bb.x; h[5] = bb.y; h[6] = bb.z; h[7] = bb.w;
+                for (int j = 0; j < 4; ++j) {
+                    float h = b0r[j];
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) h = fmaf(st[d], w0r[d][j], h);
+                    h = fast_tanh(h);
+                    hi[j] = tc_hi(h); lo[j] = h - hi[j];
                 }
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(sW0 + d * 64 + f0 + c0);
-                    const float4 w1 = *reinterpret_cast<const float4*>(sW0 + d * 64 + f0 + c0 + 4);
-                    h[0] = fmaf(st[d], w0.x, h[0]); h[1] = fmaf(st[d], w0.y, h[1]); h[2] = fmaf(st[d], w0.z, h[2]); h[3] = fmaf(st[d], w0.w, h[3]);
-                    h[4] = fmaf(st[d], w1.x, h[4]); h[5] = fmaf(st[d], w1.y, h[5]); h[6] = fmaf(st[d], w1.z, h[6]); h[7] = fmaf(st[d], w1.w, h[7]);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { h[j] = fast_tanh(h[j]); hi[j] = tc_hi(h[j]); lo[j] = h[j] - hi[j]; }
-                tc_st8(my + RT_COL_HI + f0 + c0, hi);
-                tc_st8(my + RT_COL_LO + f0 + c0, lo);
+                *reinterpret_cast<float4*>(sAhi + a_off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(sAlo + a_off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
             RT_MARK(1);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            rt_sync();
-            // ---- H1pre = H0 W1 on the tensor cores ------------------------------------------------------------------------
+            __syncthreads();
+            // ---- H1pre = H0 W1 on the tensor cores (both operands from shared memory) ---------------------------------------
             if (warp == 0 && tc_elect_one()) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int ps = 0; ps < 3; ++ps) {
-                    const uint32_t acol = tb + (ps == 1 ? RT_COL_LO : RT_COL_HI);
+                    const uint32_t aimg = sm_base + (ps == 1 ? RT_OFF_A_LO : RT_OFF_A_HI);
                     const uint32_t bimg = sm_base + (ps == 2 ? RT_OFF_WT_LO : RT_OFF_WT_HI);
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk)
-                        tc_mma_ts(tb + RT_COL_D, acol + kk * 8, tc_desc(bimg + kk * 256, 128, 2048, 0), idesc, (ps | kk) ? 1u : 0u);
+                        tc_mma_ss(tb + RT_COL_D, tc_desc(aimg + kk * 256, 128, 2048, 0), tc_desc(bimg + kk * 256, 128, 2048, 0), idesc,
+                                  (ps | kk) ? 1u : 0u);
                 }
                 tc_commit(&bar);
             }
             RT_MARK(2);
-            // ---- while the MMAs run: everything that does not depend on the action, one role per feature quarter ----------
-            if (fq == 0) {
+            // ---- while the MMAs run: everything that does not depend on the action, one role per warp --------------------
+            if (r_cand) {
                 // Euler step for BOTH pushes: positions, termination and the reset do not depend on the action
                 float s0[4] = {st[0], st[1], st[2], st[3]}, s1[4] = {st[0], st[1], st[2], st[3]};
                 bool t0, t1;
@@ -226,54 +236,61 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
                 cartpole_step_sc(s1, 1, sn, cs, &t1);
                 *reinterpret_cast<float4*>(sCand + e * 8) = make_float4(s0[0], s0[2], s0[1], s0[3]);     // xn, thn, xd(0), thd(0)
                 *reinterpret_cast<float2*>(sCand + e * 8 + 4) = make_float2(s1[1], s1[3]);              // xd(1), thd(1)
-            } else if (fq == 1) {
+            } else if (r_philox) {
                 uint32_t x[4];
                 philox4x32(gid, a.step0 + (uint32_t)t, 0u, DRIL_TAG_SAMPLE, a.pseed, x);
                 sU[e] = u01_f64(x[0], x[1]);
-            } else if (fq == 2) {
+            } else if (r_reset) {
                 if (need_reset_calc) {                    // start state of the env's next episode and sin/cos of its pole angle
                     float rs[4], s_, c_;
                     env_reset_state(env.kind, gid, episode, env.seed, rs);
                     sincos_rn(rs[2], &s_, &c_);
                     *reinterpret_cast<float4*>(sReset + e * 8) = make_float4(rs[0], rs[1], rs[2], rs[3]);
                     *reinterpret_cast<float2*>(sReset + e * 8 + 4) = make_float2(s_, c_);
-                    need_reset_calc = false;
                 }
-            } else {
+            } else if (r_sincos) {
                 float s_, c_;                            // correctly rounded sin/cos of the next pole angle (if no reset)
                 sincos_rn(__fadd_rn(st[2], __fmul_rn(TAU, st[3])), &s_, &c_);
                 *reinterpret_cast<float2*>(sSCn + e * 2) = make_float2(s_, c_);
+            } else if (r_writer) {
                 flush();
             }
+            need_reset_calc = false;
             RT_MARK(3);
-            tc_wait(&bar, nbar & 1u);
-            ++nbar;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            RT_MARK(4);
-            // ---- H1 = tanh(. + b1), partial logits over the own 16 features ---------------------------------------------
-            {
-                float h1[16];
-                tc_ld16(my + RT_COL_D + f0, h1);
-                float p0 = 0.f, p1 = 0.f;
+            // ---- warps 0/4/8/12 copy the accumulator (16 columns each) out of TMEM -----------------------------------------
+            if (r_copy) {
+                tc_wait(&bar, nbar & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                float d[16];
+                const int c0 = (warp >> 2) * 16;
+                tc_ld16(tb + RT_COL_D + c0, d);
+                float* dst = sD + e * 68 + c0;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const float hv = fast_tanh(h1[k] + sb1[f0 + k]);
-                    const float4 w = *reinterpret_cast<const float4*>(sW2 + (f0 + k) * 4);
-                    p0 = fmaf(hv, w.x, p0);
-                    p1 = fmaf(hv, w.y, p1);
-                }
-                sPart[(fq * 2 + 0) * 32 + e] = p0;
-                sPart[(fq * 2 + 1) * 32 + e] = p1;
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
+            ++nbar;
+            RT_MARK(4);
+            __syncthreads();
+            // ---- H1 = tanh(. + b1), partial logits over the own 4 features --------------------------------------------------
+            {
+                const float4 z = *reinterpret_cast<const float4*>(sD + e * 68 + f0);
+                const float h0 = fast_tanh(z.x + b1r[0]), h1 = fast_tanh(z.y + b1r[1]), h2 = fast_tanh(z.z + b1r[2]), h3 = fast_tanh(z.w + b1r[3]);
+                const float p0 = fmaf(h3, w2r[3][0], fmaf(h2, w2r[2][0], fmaf(h1, w2r[1][0], h0 * w2r[0][0])));
+                const float p1 = fmaf(h3, w2r[3][1], fmaf(h2, w2r[2][1], fmaf(h1, w2r[1][1], h0 * w2r[0][1])));
+                *reinterpret_cast<float2*>(sPart + (fg * 32 + e) * 2) = make_float2(p0, p1);
             }
             RT_MARK(5);
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            rt_sync();
+            __syncthreads();
             RT_MARK(6);
-            // ---- all four threads of an env: softmax, inverse-CDF sample, select the pre-computed next state / reset ----------
+            // ---- every thread of an env: logits, softmax, inverse-CDF sample, select the pre-computed next state / reset -------
             if (mine) {
-                float z0 = sb2[0], z1 = sb2[1];
+                float z0 = b2_0, z1 = b2_1;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { z0 += sPart[(k * 2 + 0) * 32 + e]; z1 += sPart[(k * 2 + 1) * 32 + e]; }
+                for (int k = 0; k < 16; ++k) {
+                    const float2 pp = *reinterpret_cast<const float2*>(sPart + (k * 32 + e) * 2);
+                    z0 += pp.x; z1 += pp.y;
+                }
                 int idx = 0;
                 float pe = 1.f, ssum = 1.f;
                 if (A > 1) {
@@ -299,7 +316,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
                 steps += 1;
                 const bool trunc = steps >= env.max_steps;
                 const bool done = term || trunc;
-                if (fq == 3) {
+                if (r_writer) {
                     if (env.monitor) { ep_ret = __fadd_rn(ep_ret, 1.0f); ep_len += 1; }
                     pend.live = true; pend.t = t; pend.idx = idx; pend.pe = pe; pend.ssum = ssum; pend.term = term; pend.trunc = trunc;
                     pend.ep_ret = ep_ret; pend.ep_len = ep_len;
@@ -313,13 +330,13 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
                     steps = 0;
                     need_reset_calc = true;
                 }
-                if (fq == 0) {
+                if (r_cand) {
                     const float2 scn = done ? *reinterpret_cast<const float2*>(sReset + e * 8 + 4) : *reinterpret_cast<const float2*>(sSCn + e * 2);
                     sn = scn.x; cs = scn.y;
                 }
             }
         }
-        if (fq == 3) flush();
+        if (r_writer) flush();
         if (writer) {
             *reinterpret_cast<float4*>(sc.last_obs + (size_t)n * 4) = make_float4(st[0], st[1], st[2], st[3]);
 #pragma unroll
@@ -328,10 +345,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
             env.episode[n] = episode;
             if (env.monitor) { env.ep_ret[n] = ep_ret; env.ep_len[n] = ep_len; }
         }
-        rt_sync();                                    // the next tile's windows reuse sReset / sCand
+        __syncthreads();                              // the next tile's windows reuse sReset / sCand
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    rt_sync();
+    __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(RT_TMEM_COLS));
 }
 
@@ -341,6 +358,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
 // sample (32 hidden features each), hidden layer on tcgen05 (3xTF32).  2 CTAs per SM (256 TMEM columns each).
 // ---------------------------------------------------------------------------------------------------------
 #define CV_THREADS 256
+#define CV_TMEM_COLS 256
 __global__ void __launch_bounds__(CV_THREADS, 2) critic_values_tc_kernel(const PolicyDesc pd, const float* __restrict__ pack, BufDev buf,
                                                                         const TcRolloutScratch sc) {
     extern __shared__ __align__(1024) unsigned char rt_smem_raw[];
@@ -351,7 +369,7 @@ __global__ void __launch_bounds__(CV_THREADS, 2) critic_values_tc_kernel(const P
     const uint32_t raw = tc_smem_u32(rt_smem_raw);
     const uint32_t sm_base = (raw + 1023u) & ~1023u;
     unsigned char* sm = rt_smem_raw + (sm_base - raw);
-    float* sSmall = reinterpret_cast<float*>(sm + RT_OFF_SMALL);
+    float* sSmall = reinterpret_cast<float*>(sm + CV_OFF_SMALL);
     float* sW0 = sSmall;
     float* sb0 = sW0 + 256;
     float* sb1 = sb0 + 64;
@@ -366,7 +384,7 @@ __global__ void __launch_bounds__(CV_THREADS, 2) critic_values_tc_kernel(const P
     if (tid < 64) { sb0[tid] = pack[L0.pb_off + tid]; sb1[tid] = pack[L1.pb_off + tid]; }
     if (tid < 4) sb2[tid] = pack[L2.pb_off + tid];
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_s)), "r"(RT_TMEM_COLS));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_s)), "r"(CV_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
@@ -449,5 +467,5 @@ __global__ void __launch_bounds__(CV_THREADS, 2) critic_values_tc_kernel(const P
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(RT_TMEM_COLS));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(CV_TMEM_COLS));
 }
