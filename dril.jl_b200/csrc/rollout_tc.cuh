@@ -285,12 +285,15 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
             RT_MARK(6);
             // ---- every thread of an env: logits, softmax, inverse-CDF sample, select the pre-computed next state / reset -------
             if (mine) {
-                float z0 = b2_0, z1 = b2_1;
+                // logits: fixed-order tree over the 16 partials (4 independent chains)
+                float za[4] = {0.f, 0.f, 0.f, 0.f}, zb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const float2 pp = *reinterpret_cast<const float2*>(sPart + (k * 32 + e) * 2);
-                    z0 += pp.x; z1 += pp.y;
+                    za[k & 3] += pp.x; zb[k & 3] += pp.y;
                 }
+                const float z0 = b2_0 + ((za[0] + za[1]) + (za[2] + za[3]));
+                const float z1 = b2_1 + ((zb[0] + zb[1]) + (zb[2] + zb[3]));
                 int idx = 0;
                 float pe = 1.f, ssum = 1.f;
                 if (A > 1) {
@@ -307,6 +310,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
                     }
                     pe = idx == 0 ? e0 : e1;
                 }
+                RT_MARK(7);
                 const float4 c4 = *reinterpret_cast<const float4*>(sCand + e * 8);
                 const float2 c2 = *reinterpret_cast<const float2*>(sCand + e * 8 + 4);
                 st[0] = c4.x; st[2] = c4.y;

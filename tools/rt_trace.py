@@ -19,10 +19,10 @@ out = (C.c_longlong * (4 * 8 * 8))()
 ctx.lib.dril_debug_rt_trace.argtypes = [C.c_void_p]
 L.check(ctx.lib.dril_debug_rt_trace(out))
 tr = np.array(out).reshape(4, 8, 8)
-names = ["L0+st", "sync A+issue", "window work", "MMA wait", "ld+tanh+dot", "sync B", "to next step"]
+names = ["L0", "sync1+issue", "window", "wait+copy", "sync2+head", "sync3", "decide", "select+reset"]
 for fq in range(4):
     for st in range(2, 5):
-        row = tr[fq, st, :7]
+        row = tr[fq, st, :8]
         nxt = tr[fq, st + 1, 0]
-        seg = [row[i + 1] - row[i] for i in range(6)] + [nxt - row[6]]
-        print(f"fq{fq} step{8 + st}: " + " ".join(f"{names[i]}={seg[i]}" for i in range(7)) + f" | step total {nxt - row[0]}")
+        seg = [row[i + 1] - row[i] for i in range(7)] + [nxt - row[7]]
+        print(f"warp{[0, 5, 6, 7][fq]} step{8 + st}: " + " ".join(f"{names[i]}={seg[i]}" for i in range(8)) + f" | step total {nxt - row[0]}")
