@@ -121,8 +121,11 @@ const char* dril_last_error(void);
 int32_t dril_version(void);
 /* 0 if a CUDA device is usable, else an error (used by hosts to fail loudly, never to fall back) */
 int32_t dril_device_count(int32_t* count);
-/* process-wide tuning switches, e.g. ("tc", 1): tensor-core (tcgen05, 3xTF32) variant of the fused loss/grad
- * kernel for hidden_dims = [64, 64] networks. Unknown keys are an error. */
+/* process-wide kernel-path switches (all default 1; every combination meets the same parity bounds, tests/
+ * test_gpu_parity.py::test_kernel_paths_vs_oracle).  Unknown keys are an error.
+ *   "tc"          tensor-core (tcgen05, 3xTF32) loss/grad kernel for hidden_dims = [64, 64], obs_dim <= 4, Discrete(<= 2)
+ *   "fused_tail"  partial reduction + (peer-memory allreduce) + clip + KL stop + Adam inside that kernel (cooperative launch)
+ *   "tc_rollout"  tensor-core rollout for CartPole with such a policy (actor-only step loop + batched critic pass) */
 int32_t dril_set_option(const char* key, int32_t value);
 
 /* ---- context ---------------------------------------------------------------------------- */

@@ -484,3 +484,56 @@ def test_full_size_properties(D):
     obs = buf.download("obs")
     assert (np.abs(obs[..., 0]) <= 2.4 + 0.2).all() and (np.abs(obs[..., 2]) <= 0.21 + 0.2).all()
     buf.close()
+
+
+# ------------------------------------------------------------------------------------------
+# kernel-path switches: every combination must agree with the oracle (and hence with each other)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tc,tail,tc_rollout", [(1, 1, 1), (1, 0, 1), (0, 0, 0), (1, 1, 0), (0, 0, 1)])
+def test_kernel_paths_vs_oracle(D, tc, tail, tc_rollout):
+    """The tensor-core loss/grad kernel (with and without its fused reduce/clip/Adam tail), the fp32 CUDA-core kernel,
+    the tensor-core rollout and the general rollout are interchangeable: same buffer, same updated parameters."""
+    opts = {"tc": tc, "fused_tail": tail, "tc_rollout": tc_rollout}
+    try:
+        for k, v in opts.items():
+            D.set_option(k, v)
+        n, T = 96, 20
+        env, oenv, spec = _mk(D, "cartpole", n, 31, 12, True, False)
+        rng = np.random.default_rng(5)
+        flat = (OP.init_params(spec, seed=6) + rng.normal(size=spec.n_params()).astype(f32) * 0.02).astype(f32)
+        forced = rng.integers(1, 3, (T, n))
+        layer = D.ActorCriticLayer(env.observation_space(), env.action_space(), hidden_dims=spec.hidden)
+        alg = D.PPO(n_steps=T, batch_size=500, epochs=2, ent_coef=0.01)
+        agent = D.Agent(layer, alg, rng=np.random.default_rng(0))
+        agent.set_parameters(flat)
+        assert agent.device.update_path() == ("tensor" if tc else "fp32")
+        buf = D.RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, T, n)
+        D.collect_rollout(buf, agent, alg, env, forced_actions=forced)
+        exp = OO.collect_rollout_timemajor(oenv, spec, flat, T, forced_actions=forced)
+        te, tr = _flags(buf)
+        np.testing.assert_array_equal(te, exp["term"])
+        np.testing.assert_array_equal(tr, exp["trunc"])
+        assert tr.any()
+        np.testing.assert_allclose(buf.download("obs"), exp["obs"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(buf.download("values"), exp["values"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(buf.download("logprobs"), exp["logprobs"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(np.where(tr, buf.download("boot"), 0), exp["boot"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(buf.download("last_values"), exp["last_values"], rtol=1e-5, atol=1e-5)
+        ob = {k: buf.download(k) for k in ("obs", "actions", "rewards", "values", "logprobs", "advantages", "returns")}
+        import ctypes as C
+        from dril_b200 import _lib as L
+        st = D.IterStats()
+        h = alg.hyper()
+        L.check(agent.ctx.lib.dril_ppo_update(agent.device.h, buf.h, C.byref(h), alg.epochs, alg.batch_size, 99, 0, C.byref(st)))
+        cfg = OO.PPOConfig(n_steps=T, batch_size=500, epochs=2, ent_coef=0.01)
+        opt = OO.Adam(flat.size, lr=cfg.learning_rate)
+        new_flat, means, _ = OO.ppo_update(spec, flat, opt, ob, cfg, shuffle_seed=99, epoch_counter0=0)
+        got = agent.device.get_params()
+        np.testing.assert_allclose(got, new_flat, rtol=1e-4, atol=2e-6)
+        assert st.n_minibatch_steps == 2 * 4
+        for k in ("policy_loss", "value_loss", "loss", "grad_norm"):
+            assert abs(getattr(st, k) - means[k]) <= 2e-4 * max(1.0, abs(means[k])), (k, getattr(st, k), means[k])
+        buf.close()
+    finally:
+        for k in opts:
+            D.set_option(k, 1)
