@@ -977,7 +977,12 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
         a.n_tiles = (int)((N + RT_ENVS - 1) / RT_ENVS);
         {
             Span sp(c, DRIL_K_ROLLOUT);
-            const int grid = std::min(a.n_tiles, 2 * c->sm_count);
+            static int per_sm = 0;                                       // registers allow one 512-thread CTA per SM today
+            if (!per_sm) {
+                DRIL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_tc_kernel, RT_THREADS, RT_SMEM_BYTES));
+                per_sm = std::max(per_sm, 1);
+            }
+            const int grid = std::min(a.n_tiles, per_sm * c->sm_count);
             rollout_tc_kernel<<<grid, RT_THREADS, RT_SMEM_BYTES, c->stream>>>(a, b->tcs);
             DRIL_CUDA(cudaGetLastError());
         }

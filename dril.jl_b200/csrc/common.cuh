@@ -177,9 +177,13 @@ __host__ __device__ __forceinline__ long long feistel_permute(long long i, long 
 // ---------------------------------------------------------------------------------------
 // tanh with ~1e-7 absolute error from ex2.approx + fast divide (Lux tanh on fp32 is
 // itself a ~1 ulp polynomial; the tolerance budget is 1e-6 on values, 1e-5 on logprobs).
+// tanh(x) = 1 - 2 / (1 + e^(2x)) in five instructions (FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA); absolute error ~1e-7.
+// x -> +inf: e = inf, rcp = 0, result 1; x -> -inf: e = 0, result -1.
 __device__ __forceinline__ float fast_tanh(float x) {
-    float e = __expf(2.0f * x);
-    return 1.0f - __fdividef(2.0f, e + 1.0f);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));      // 2 * log2(e)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

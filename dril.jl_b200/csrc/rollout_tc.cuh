@@ -30,11 +30,14 @@
 #define RT_TMEM_COLS 64
 #define RT_OFF_WT_HI 0           // W1^T hi / lo, K-major no-swizzle images (B operand)
 #define RT_OFF_WT_LO 16384
-#define RT_OFF_A_HI 32768        // rollout kernel: H0 hi / lo, 128 rows x 64 K-major no-swizzle (A operand, rows 0..31 used)
-#define RT_OFF_A_LO 65536
-#define RT_OFF_SMALL 98304
+// rollout kernel: H0 hi / lo as K-major no-swizzle A operand images.  The M = 128 instruction reads 16 row groups
+// (32 KB) from each base but only rows 0..31 (8 KB) hold envs: the images are packed 8 KB apart and the reads of the
+// unused rows run over whatever follows (their accumulator rows are never read); the allocation covers the last read.
+#define RT_OFF_A_HI 32768
+#define RT_OFF_A_LO 40960
+#define RT_OFF_SMALL 49152
 #define RT_SMALL_FLOATS 4096
-#define RT_SMEM_BYTES (RT_OFF_SMALL + RT_SMALL_FLOATS * 4 + 1024)
+#define RT_SMEM_BYTES (RT_OFF_A_LO + 32768 + 1024)
 #define CV_OFF_SMALL 32768       // critic kernel: small arrays right after the W1 images
 #define CV_SMALL_FLOATS 1024
 #define CV_SMEM_BYTES (CV_OFF_SMALL + CV_SMALL_FLOATS * 4 + 1024)
@@ -100,6 +103,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
     float* sReset = sCand + 256;        // [32][8] state of the env's next episode + sin/cos of its pole angle
     float* sSCn = sReset + 256;         // [32][2] sin/cos of the next pole angle if the episode continues
     double* sU = reinterpret_cast<double*>(sSCn + 64);   // [32] uniform of the step's action sample
+    float* sState = reinterpret_cast<float*>(sU + 32);   // [32][4] current env state (owned by the decision warp)
+    float* sSCcur = sState + 128;       // [32][2] sin/cos of the current pole angle
+    int* sNeed = reinterpret_cast<int*>(sSCcur + 64);    // [32] episode whose start state must be prepared, or -1
     const LayerDesc& L0 = pd.L[0][0];
     const LayerDesc& L1 = pd.L[0][1];
     const LayerDesc& L2 = pd.L[0][2];
@@ -137,33 +143,23 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
     const float TAU = 0.02f;
     const int a_off = ((e >> 3) * 16 + fg) * 32 + (e & 7) * 4;      // K-major no-swizzle core layout: row e, columns f0..f0+3
     // roles in the MMA window (warps on different schedulers)
-    const bool r_cand = warp == 1, r_philox = warp == 2, r_reset = warp == 3, r_sincos = warp == 5, r_writer = warp == 6;
+    const bool r_cand = warp == 1, r_philox = warp == 2, r_reset = warp == 3, r_sincos = warp == 5, r_dec = warp == 6;
     const bool r_copy = (warp & 3) == 0;              // TMEM lanes 0..31 are reachable from warps 0, 4, 8, 12 only
     uint32_t nbar = 0;
     for (long long tile = blockIdx.x; tile * RT_ENVS < N; tile += gridDim.x) {
         const long long n = tile * RT_ENVS + e;
         const bool mine = n < N;
-        const bool writer = mine && r_writer;
         const uint32_t gid = (uint32_t)(env.gid_offset + n);
+        // the decision warp owns the env: state, counters, monitor accumulators; everybody else reads sState
         float st[4] = {0.f, 0.f, 0.f, 0.f};
         int steps = 0, ep_len = 0;
         float ep_ret = 0.f;
         uint32_t episode = 0;
-        float sn = 0.f, cs = 1.f;                     // r_cand: sin/cos of the current pole angle
-        bool need_reset_calc = true;                  // r_reset: sReset[e] must be (re)computed for `episode`
-        if (mine) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) st[k] = env.state[(size_t)k * N + n];
-            steps = env.steps[n];
-            episode = env.episode[n];
-            if (env.monitor) { ep_ret = env.ep_ret[n]; ep_len = env.ep_len[n]; }
-        }
-        if (r_cand) sincos_rn(st[2], &sn, &cs);
-        // bookkeeping of a finished step (log-prob, buffer row, monitor, truncation list): done by the env's writer thread
-        // one step late, while the next step's MMAs run, so that it is off the per-step critical path
         struct Pending { float pe, ssum, ep_ret; float4 tobs; int idx, ep_len, t; bool term, trunc, live; } pend;
         pend.live = false; pend.pe = pend.ssum = 1.f; pend.ep_ret = 0.f; pend.tobs = make_float4(0.f, 0.f, 0.f, 0.f);
         pend.idx = 0; pend.ep_len = 0; pend.t = 0; pend.term = pend.trunc = false;
+        // bookkeeping of a finished step (log-prob, buffer row, monitor, truncation list): done one step late, while the
+        // next step's MMAs run, so that it is off the per-step critical path
         auto flush = [&]() {
             if (!pend.live) return;
             const size_t r = (size_t)pend.t * N + n;
@@ -188,20 +184,31 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
             }
             pend.live = false;
         };
+        if (r_dec) {
+            if (mine) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) st[k] = env.state[(size_t)k * N + n];
+                steps = env.steps[n];
+                episode = env.episode[n];
+                if (env.monitor) { ep_ret = env.ep_ret[n]; ep_len = env.ep_len[n]; }
+            }
+            float s_, c_;
+            sincos_rn(st[2], &s_, &c_);
+            *reinterpret_cast<float4*>(sState + e * 4) = make_float4(st[0], st[1], st[2], st[3]);
+            *reinterpret_cast<float2*>(sSCcur + e * 2) = make_float2(s_, c_);
+            sNeed[e] = (int)episode;
+        }
+        __syncthreads();
         for (int t = 0; t < a.T; ++t) {
             const size_t row = (size_t)t * N;
             RT_MARK(0);
-            int forced_a = 0;
-            if (a.forced && mine) forced_a = reinterpret_cast<const int*>(a.forced)[row + n];
-            if (writer) *reinterpret_cast<float4*>(buf.obs + (row + n) * 4) = make_float4(st[0], st[1], st[2], st[3]);
+            const float4 s4 = *reinterpret_cast<const float4*>(sState + e * 4);
             // ---- layer 0 (own 4 features) -> hi/lo -> A operand images in shared memory -----------------------------------
             {
                 float hi[4], lo[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float h = b0r[j];
-#pragma unroll
-                    for (int d = 0; d < 4; ++d) h = fmaf(st[d], w0r[d][j], h);
+                    float h = fmaf(s4.w, w0r[3][j], fmaf(s4.z, w0r[2][j], fmaf(s4.y, w0r[1][j], fmaf(s4.x, w0r[0][j], b0r[j]))));
                     h = fast_tanh(h);
                     hi[j] = tc_hi(h); lo[j] = h - hi[j];
                 }
@@ -230,10 +237,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
             // ---- while the MMAs run: everything that does not depend on the action, one role per warp --------------------
             if (r_cand) {
                 // Euler step for BOTH pushes: positions, termination and the reset do not depend on the action
-                float s0[4] = {st[0], st[1], st[2], st[3]}, s1[4] = {st[0], st[1], st[2], st[3]};
+                const float2 scv = *reinterpret_cast<const float2*>(sSCcur + e * 2);
+                float s0[4] = {s4.x, s4.y, s4.z, s4.w}, s1[4] = {s4.x, s4.y, s4.z, s4.w};
                 bool t0, t1;
-                cartpole_step_sc(s0, 0, sn, cs, &t0);
-                cartpole_step_sc(s1, 1, sn, cs, &t1);
+                cartpole_step_sc(s0, 0, scv.x, scv.y, &t0);
+                cartpole_step_sc(s1, 1, scv.x, scv.y, &t1);
                 *reinterpret_cast<float4*>(sCand + e * 8) = make_float4(s0[0], s0[2], s0[1], s0[3]);     // xn, thn, xd(0), thd(0)
                 *reinterpret_cast<float2*>(sCand + e * 8 + 4) = make_float2(s1[1], s1[3]);              // xd(1), thd(1)
             } else if (r_philox) {
@@ -241,21 +249,22 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
                 philox4x32(gid, a.step0 + (uint32_t)t, 0u, DRIL_TAG_SAMPLE, a.pseed, x);
                 sU[e] = u01_f64(x[0], x[1]);
             } else if (r_reset) {
-                if (need_reset_calc) {                    // start state of the env's next episode and sin/cos of its pole angle
+                const int ep = sNeed[e];
+                if (ep >= 0) {                            // start state of the env's next episode and sin/cos of its pole angle
                     float rs[4], s_, c_;
-                    env_reset_state(env.kind, gid, episode, env.seed, rs);
+                    env_reset_state(env.kind, gid, (uint32_t)ep, env.seed, rs);
                     sincos_rn(rs[2], &s_, &c_);
                     *reinterpret_cast<float4*>(sReset + e * 8) = make_float4(rs[0], rs[1], rs[2], rs[3]);
                     *reinterpret_cast<float2*>(sReset + e * 8 + 4) = make_float2(s_, c_);
                 }
             } else if (r_sincos) {
                 float s_, c_;                            // correctly rounded sin/cos of the next pole angle (if no reset)
-                sincos_rn(__fadd_rn(st[2], __fmul_rn(TAU, st[3])), &s_, &c_);
+                sincos_rn(__fadd_rn(s4.z, __fmul_rn(TAU, s4.w)), &s_, &c_);
                 *reinterpret_cast<float2*>(sSCn + e * 2) = make_float2(s_, c_);
-            } else if (r_writer) {
+            } else if (r_dec) {
+                if (mine) *reinterpret_cast<float4*>(buf.obs + (row + n) * 4) = s4;
                 flush();
             }
-            need_reset_calc = false;
             RT_MARK(3);
             // ---- warps 0/4/8/12 copy the accumulator (16 columns each) out of TMEM -----------------------------------------
             if (r_copy) {
@@ -283,8 +292,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
             RT_MARK(5);
             __syncthreads();
             RT_MARK(6);
-            // ---- every thread of an env: logits, softmax, inverse-CDF sample, select the pre-computed next state / reset -------
-            if (mine) {
+            // ---- the decision warp: logits, softmax, inverse-CDF sample, select the pre-computed next state / reset -----------
+            if (r_dec && mine) {
+                int forced_a = 0;
+                if (a.forced) forced_a = reinterpret_cast<const int*>(a.forced)[row + n];
                 // logits: fixed-order tree over the 16 partials (4 independent chains)
                 float za[4] = {0.f, 0.f, 0.f, 0.f}, zb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -320,36 +331,40 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
                 steps += 1;
                 const bool trunc = steps >= env.max_steps;
                 const bool done = term || trunc;
-                if (r_writer) {
-                    if (env.monitor) { ep_ret = __fadd_rn(ep_ret, 1.0f); ep_len += 1; }
-                    pend.live = true; pend.t = t; pend.idx = idx; pend.pe = pe; pend.ssum = ssum; pend.term = term; pend.trunc = trunc;
-                    pend.ep_ret = ep_ret; pend.ep_len = ep_len;
-                    if (trunc) pend.tobs = make_float4(st[0], st[1], st[2], st[3]);
-                    if (done && env.monitor) { ep_ret = 0.f; ep_len = 0; }
-                }
+                if (env.monitor) { ep_ret = __fadd_rn(ep_ret, 1.0f); ep_len += 1; }
+                pend.live = true; pend.t = t; pend.idx = idx; pend.pe = pe; pend.ssum = ssum; pend.term = term; pend.trunc = trunc;
+                pend.ep_ret = ep_ret; pend.ep_len = ep_len;
+                if (trunc) pend.tobs = make_float4(st[0], st[1], st[2], st[3]);
+                float2 scn;
                 if (done) {
+                    if (env.monitor) { ep_ret = 0.f; ep_len = 0; }
                     const float4 r4 = *reinterpret_cast<const float4*>(sReset + e * 8);
+                    scn = *reinterpret_cast<const float2*>(sReset + e * 8 + 4);
                     st[0] = r4.x; st[1] = r4.y; st[2] = r4.z; st[3] = r4.w;
                     episode += 1;
                     steps = 0;
-                    need_reset_calc = true;
+                    sNeed[e] = (int)episode;
+                } else {
+                    scn = *reinterpret_cast<const float2*>(sSCn + e * 2);
+                    sNeed[e] = -1;
                 }
-                if (r_cand) {
-                    const float2 scn = done ? *reinterpret_cast<const float2*>(sReset + e * 8 + 4) : *reinterpret_cast<const float2*>(sSCn + e * 2);
-                    sn = scn.x; cs = scn.y;
-                }
+                *reinterpret_cast<float4*>(sState + e * 4) = make_float4(st[0], st[1], st[2], st[3]);
+                *reinterpret_cast<float2*>(sSCcur + e * 2) = scn;
+            }
+            __syncthreads();
+        }
+        if (r_dec) {
+            flush();
+            if (mine) {
+                *reinterpret_cast<float4*>(sc.last_obs + (size_t)n * 4) = make_float4(st[0], st[1], st[2], st[3]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) env.state[(size_t)k * N + n] = st[k];
+                env.steps[n] = steps;
+                env.episode[n] = episode;
+                if (env.monitor) { env.ep_ret[n] = ep_ret; env.ep_len[n] = ep_len; }
             }
         }
-        if (r_writer) flush();
-        if (writer) {
-            *reinterpret_cast<float4*>(sc.last_obs + (size_t)n * 4) = make_float4(st[0], st[1], st[2], st[3]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) env.state[(size_t)k * N + n] = st[k];
-            env.steps[n] = steps;
-            env.episode[n] = episode;
-            if (env.monitor) { env.ep_ret[n] = ep_ret; env.ep_len[n] = ep_len; }
-        }
-        __syncthreads();                              // the next tile's windows reuse sReset / sCand
+        __syncthreads();                              // the next tile reuses the shared arrays
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
