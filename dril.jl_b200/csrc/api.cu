@@ -392,9 +392,11 @@ extern "C" int32_t dril_comm_p2p_export(dril_ctx* c, int64_t n_slots, uint8_t ha
     DRIL_CUDA(cudaSetDevice(c->device));
     if (c->p2p_region) { cudaFree(c->p2p_region); c->p2p_region = nullptr; c->p2p_enabled = false; }
     size_t slots = ((size_t)n_slots + 63) & ~(size_t)63;
-    // [header | gbuf[2][slots] (pull exchange) | recv[2][nranks][slots] (push exchange) | cflag[nranks][P2P_MAX_CTA]]
+    // [header | gbuf[2][slots] (pull exchange) | recv[2][nranks][slots] (push exchange) | cflag[nranks][P2P_MAX_CTA] |
+    //  srecv[2][nranks][P2P_SMALL_MAX] doubles | sflag[DRIL_MAX_RANKS]]; header: [0] flag, [8] seq, [16] err, [24] small_seq
     size_t bytes = P2P_HDR_BYTES + 2 * slots * sizeof(float) + 2 * (size_t)c->nranks * slots * sizeof(float) +
-                   (size_t)c->nranks * P2P_MAX_CTA * sizeof(unsigned long long);
+                   (size_t)c->nranks * P2P_MAX_CTA * sizeof(unsigned long long) +
+                   2 * (size_t)c->nranks * P2P_SMALL_MAX * sizeof(double) + DRIL_MAX_RANKS * sizeof(unsigned long long);
     DRIL_CUDA(cudaMalloc(&c->p2p_region, bytes));
     DRIL_CUDA(cudaMemset(c->p2p_region, 0, bytes));
     memset(&c->p2p, 0, sizeof(c->p2p));
@@ -423,7 +425,13 @@ extern "C" int32_t dril_comm_p2p_import(dril_ctx* c, const uint8_t* handles) {
         char* recv = (char*)base + P2P_HDR_BYTES + 2 * (size_t)c->p2p.n_slots * sizeof(float);
         c->p2p.peer_recv[r] = (float*)recv;
         c->p2p.peer_cflag[r] = (unsigned long long*)(recv + 2 * (size_t)c->nranks * c->p2p.n_slots * sizeof(float));
+        char* small = (char*)c->p2p.peer_cflag[r] + (size_t)c->nranks * P2P_MAX_CTA * sizeof(unsigned long long);
+        c->p2p.peer_srecv[r] = (double*)small;
+        c->p2p.peer_sflag[r] = (unsigned long long*)(small + 2 * (size_t)c->nranks * P2P_SMALL_MAX * sizeof(double));
     }
+    c->p2p.local_srecv = c->p2p.peer_srecv[c->rank];
+    c->p2p.local_sflag = c->p2p.peer_sflag[c->rank];
+    c->p2p.small_seq = (unsigned long long*)(local + 24);
     c->p2p.local_recv = c->p2p.peer_recv[c->rank];
     c->p2p.local_cflag = c->p2p.peer_cflag[c->rank];
     c->p2p.max_cta = P2P_MAX_CTA;
@@ -439,6 +447,20 @@ static int32_t allreduce_sum(dril_ctx* c, void* buf, size_t count, bool is_doubl
     if (!c->comm || c->nranks == 1) return DRIL_OK;
     Span sp(c, DRIL_K_ALLREDUCE);
     DRIL_NCCL(g_nccl.AllReduce(buf, buf, count, is_double ? NCCL_FLOAT64 : NCCL_FLOAT32, NCCL_SUM, c->comm, c->stream));
+    return DRIL_OK;
+}
+
+// in-place sum over ranks of two small fp64 arrays (either may be empty): peer memory if available, else NCCL
+static int32_t allreduce_small(dril_ctx* c, double* a, int na, double* b, int nb) {
+    if (c->nranks == 1 || na + nb == 0) return DRIL_OK;
+    if (c->p2p_enabled && na + nb <= P2P_SMALL_MAX) {
+        Span sp(c, DRIL_K_ALLREDUCE);
+        p2p_small_allreduce_kernel<<<1, P2P_SMALL_MAX, 0, c->stream>>>(c->p2p, a, na, b, nb);
+        DRIL_CUDA(cudaGetLastError());
+        return DRIL_OK;
+    }
+    if (na) DRIL_TRY(allreduce_sum(c, a, (size_t)na, true));
+    if (nb) DRIL_TRY(allreduce_sum(c, b, (size_t)nb, true));
     return DRIL_OK;
 }
 
@@ -1438,8 +1460,9 @@ static int32_t ensure_mbstats(dril_policy* p, int n_mb, int blocks_per_mb) {
     return DRIL_OK;
 }
 
+// extra / n_extra: a second small fp64 array summed over ranks together with the first batch of advantage moments
 static int32_t update_async(dril_policy* p, dril_buffer* b, const dril_ppo_hyper* h, int epochs, int64_t batch_size,
-                            uint64_t shuffle_seed, uint64_t epoch_counter) {
+                            uint64_t shuffle_seed, uint64_t epoch_counter, double* extra = nullptr, int n_extra = 0) {
     dril_ctx* c = p->ctx;
     const long long n_total = b->d.T * b->d.N;
     DRIL_REQUIRE(batch_size >= 1, "batch_size must be positive");
@@ -1469,7 +1492,8 @@ static int32_t update_async(dril_policy* p, dril_buffer* b, const dril_ppo_hyper
                 adv_stats_finalize_kernel<<<(n_mb * ne * 2 + 127) / 128, 128, 0, c->stream>>>(p->adv_partial, bpm, n_mb * ne, p->mbstats);
                 DRIL_CUDA(cudaGetLastError());
             }
-            DRIL_TRY(allreduce_sum(c, p->mbstats, (size_t)n_mb * ne * 2, true));
+            DRIL_TRY(allreduce_small(c, p->mbstats, n_mb * ne * 2, extra, n_extra));
+            n_extra = 0;
         }
         for (int e = 0; e < ne; ++e) {
             for (int i = 0; i < n_mb; ++i) {
@@ -1482,6 +1506,7 @@ static int32_t update_async(dril_policy* p, dril_buffer* b, const dril_ppo_hyper
             }
         }
     }
+    if (n_extra) DRIL_TRY(allreduce_small(c, nullptr, 0, extra, n_extra));   // no advantage moments were exchanged
     return DRIL_OK;
 }
 
@@ -1611,8 +1636,7 @@ extern "C" int32_t dril_ppo_iteration_async(dril_env* e, dril_policy* p, dril_bu
     DRIL_TRY(launch_monitor_finalize(e, b));
     DRIL_CUDA(cudaEventRecord(sl.ev[1], c->stream));
     DRIL_TRY(ev_async(p, b));   // explained variance uses the rollout's values/returns (ppo.jl:256)
-    DRIL_TRY(allreduce_sum(c, p->ev_acc, 4, true));
-    DRIL_TRY(update_async(p, b, h, epochs, batch_size, shuffle_seed, epoch_counter));
+    DRIL_TRY(update_async(p, b, h, epochs, batch_size, shuffle_seed, epoch_counter, p->ev_acc, 4));
     DRIL_CUDA(cudaEventRecord(sl.ev[2], c->stream));
     {
         IterRecordSrc src;

@@ -775,7 +775,49 @@ struct P2PDev {
     const float* local_recv;
     const volatile unsigned long long* local_cflag;
     int max_cta;
+    // small fp64 allreduce (minibatch advantage moments, explained-variance moments): srecv[2][nranks][P2P_SMALL_MAX]
+    double* peer_srecv[DRIL_MAX_RANKS];
+    unsigned long long* peer_sflag[DRIL_MAX_RANKS];     // [nranks]
+    const double* local_srecv;
+    const volatile unsigned long long* local_sflag;
+    unsigned long long* small_seq;
 };
+#define P2P_SMALL_MAX 256
+
+// In-place sum over ranks of up to P2P_SMALL_MAX doubles (two arrays back to back), as a push over peer memory:
+// one CTA; every rank stores its values into every rank's srecv[parity][rank], raises sflag[rank], waits for all
+// ranks' flags in its own memory and sums in rank order (bit-identical on every rank).  ~5 us instead of ~30 us NCCL.
+__global__ void __launch_bounds__(P2P_SMALL_MAX) p2p_small_allreduce_kernel(P2PDev pp, double* __restrict__ a, int na,
+                                                                            double* __restrict__ b, int nb) {
+    const int tid = threadIdx.x, n = na + nb;
+    const unsigned long long seq = *pp.small_seq + 1ull;
+    const size_t par_off = (size_t)(seq & 1ull) * pp.nranks * P2P_SMALL_MAX;
+    if (tid < n) {
+        const double v = tid < na ? a[tid] : b[tid - na];
+        for (int r = 0; r < pp.nranks; ++r) pp.peer_srecv[r][par_off + (size_t)pp.rank * P2P_SMALL_MAX + tid] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();
+        for (int r = 0; r < pp.nranks; ++r) *reinterpret_cast<volatile unsigned long long*>(pp.peer_sflag[r] + pp.rank) = seq;
+    }
+    if (tid < pp.nranks) {
+        const volatile unsigned long long* f = pp.local_sflag + tid;
+        long long spins = 0;
+        while (*f < seq) {
+            __nanosleep(32);
+            if (++spins > (1ll << 24)) { atomicExch(pp.err, 1); break; }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (tid < n) {
+        double s = 0.0;
+        for (int r = 0; r < pp.nranks; ++r) s += __ldcv(pp.local_srecv + par_off + (size_t)r * P2P_SMALL_MAX + tid);
+        if (tid < na) a[tid] = s; else b[tid - na] = s;
+    }
+    if (tid == 0) *pp.small_seq = seq;
+}
 
 __global__ void __launch_bounds__(1024) p2p_sum_adam_kernel(P2PDev pp, double* __restrict__ sq_part,
                                                            unsigned int* __restrict__ ticket, AdamArgs a) {
