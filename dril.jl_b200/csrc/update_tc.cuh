@@ -227,10 +227,11 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
     float* sX = sGrp + 768;         // per group: [128][4] observations
     float* sStageB = reinterpret_cast<float*>(sm + TC_OFF_Z1_HI);   // [128][68] staging of dZ0 once G3 has consumed the dZ1 images
     float* sRed = reinterpret_cast<float*>(sm + TC_OFF_H0CAT);      // end-of-pass scratch [8 slots][8 sums][64]
-    uint64_t* bar1 = bars + g * 3;
-    uint64_t* bar2 = bars + g * 3 + 1;
-    uint64_t* bfree = bars + g * 3 + 2;
-    uint64_t* obfree = bars + (g ^ 1) * 3 + 2;
+    uint64_t* bar1 = bars + g * 4;
+    uint64_t* bar2 = bars + g * 4 + 1;      // G2 complete
+    uint64_t* bfree = bars + g * 4 + 2;
+    uint64_t* bar3 = bars + g * 4 + 3;      // G3 complete
+    uint64_t* obfree = bars + (g ^ 1) * 4 + 2;
     const uint32_t gcol = tb + (uint32_t)g * TC_COL_GROUP;
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t my = gcol + lane_base;       // this thread's lane, this group's columns
@@ -484,6 +485,7 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
                 for (int kk = 0; kk < 8; ++kk)
                     tc_mma_ts(gcol + TC_COL_D, acol + kk * 8, tc_desc(bimg + kk * 256, 128, 2048, 0), idesc_k, (ps | kk) ? 1u : 0u);
             }
+            tc_commit(bar2);                 // the layer-0 delta only needs G2; G3 keeps running underneath it
 #pragma unroll
             for (int ps = 0; ps < 2; ++ps) {
                 const uint32_t bimg = sm_base + (ps ? TC_OFF_Z1_LO : TC_OFF_Z1_HI);
@@ -492,7 +494,7 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
                     tc_mma_ss(tb + TC_COL_D3, tc_desc(sm_base + TC_OFF_H0CAT + kk * 4096, 512, 2048, 1),
                               tc_desc(bimg + kk * 2048, 512, 1024, 1), idesc_mn, 1u);
             }
-            tc_commit(bar2);
+            tc_commit(bar3);
         }
         TC_MARK(9);
         tc_wait(bar2, phase);
@@ -514,6 +516,8 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dz0[c0 + j] *= (1.0f - h0[j] * h0[j]);
             }
+            tc_wait(bar3, phase);            // G3 has consumed the dZ1 images: their space becomes the staging buffer
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float* rb = sStageB + m * TC_STAGE_LD + f0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(rb + j) = make_float4(dz0[j], dz0[j + 1], dz0[j + 2], dz0[j + 3]);
@@ -697,7 +701,7 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
 
 __global__ void __launch_bounds__(TC_THREADS, 1) ppo_loss_grad_tc_kernel(const __grid_constant__ LossArgs a, const __grid_constant__ TailArgs tl) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-    __shared__ __align__(8) uint64_t bars[6];
+    __shared__ __align__(8) uint64_t bars[8];
     __shared__ uint32_t tmem_base_s;
     __shared__ double scratch[32];
     __shared__ float s_f2[2];
@@ -712,7 +716,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_loss_grad_tc_kernel(const _
     }
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[i])));
+        for (int i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[i])));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
