@@ -537,3 +537,37 @@ def test_kernel_paths_vs_oracle(D, tc, tail, tc_rollout):
     finally:
         for k in opts:
             D.set_option(k, 1)
+
+
+def test_c1_shape_update_vs_oracle(D):
+    """BASELINE config C1 (the reference's own CPU-runnable case): 4 envs, n_steps 2048, batch 64 -> 128 Adam steps per
+    epoch on half-filled 128-sample tiles, one CTA per launch.  Parameters after one epoch must match the oracle."""
+    n, T = 4, 2048
+    env, oenv, spec = _mk(D, "cartpole", n, 3, 500, True, False)
+    flat = OP.init_params(spec, seed=11)
+    layer = D.ActorCriticLayer(env.observation_space(), env.action_space(), hidden_dims=spec.hidden)
+    alg = D.PPO(n_steps=T, batch_size=64, epochs=1)
+    agent = D.Agent(layer, alg, rng=np.random.default_rng(0))
+    agent.set_parameters(flat)
+    buf = D.RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, T, n)
+    D.collect_rollout(buf, agent, alg, env)
+    ob = {k: buf.download(k) for k in ("obs", "actions", "rewards", "values", "logprobs", "advantages", "returns")}
+    # the rollout itself: stored log-probs / values equal evaluate_actions on the stored (obs, actions)
+    v, lp, _ = OP.evaluate_actions(spec, flat, ob["obs"].reshape(T * n, -1), ob["actions"].reshape(T * n, -1))
+    np.testing.assert_allclose(ob["logprobs"].reshape(-1), lp, atol=1e-5)
+    np.testing.assert_allclose(ob["values"].reshape(-1), v, atol=1e-5)
+    import ctypes as C
+    from dril_b200 import _lib as L
+    st = D.IterStats()
+    h = alg.hyper()
+    L.check(agent.ctx.lib.dril_ppo_update(agent.device.h, buf.h, C.byref(h), alg.epochs, alg.batch_size, 5, 0, C.byref(st)))
+    cfg = OO.PPOConfig(n_steps=T, batch_size=64, epochs=1)
+    opt = OO.Adam(flat.size, lr=cfg.learning_rate)
+    new_flat, means, _ = OO.ppo_update(spec, flat, opt, ob, cfg, shuffle_seed=5, epoch_counter0=0)
+    got = agent.device.get_params()
+    assert st.n_minibatch_steps == 128
+    np.testing.assert_allclose(got, new_flat, rtol=2e-3, atol=2e-4)
+    assert _relerr(got - flat, new_flat - flat) < 2e-2
+    for k in ("policy_loss", "value_loss", "loss"):
+        assert abs(getattr(st, k) - means[k]) <= 1e-3 * max(1.0, abs(means[k])), (k, getattr(st, k), means[k])
+    buf.close()
