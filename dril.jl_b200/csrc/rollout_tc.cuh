@@ -30,14 +30,14 @@
 #define RT_TMEM_COLS 64
 #define RT_OFF_WT_HI 0           // W1^T hi / lo, K-major no-swizzle images (B operand)
 #define RT_OFF_WT_LO 16384
-// rollout kernel: H0 hi / lo as K-major no-swizzle A operand images.  The M = 128 instruction reads 16 row groups
-// (32 KB) from each base but only rows 0..31 (8 KB) hold envs: the images are packed 8 KB apart and the reads of the
-// unused rows run over whatever follows (their accumulator rows are never read); the allocation covers the last read.
+// rollout kernel: H0 hi / lo as K-major no-swizzle A operand images.  The M = 64 instruction reads 8 row groups
+// (16 KB) from each base but only rows 0..31 (8 KB) hold envs: the images are packed 8 KB apart and the reads of the
+// unused rows run over whatever follows (their accumulator rows are never read).
 #define RT_OFF_A_HI 32768
 #define RT_OFF_A_LO 40960
 #define RT_OFF_SMALL 49152
 #define RT_SMALL_FLOATS 4096
-#define RT_SMEM_BYTES (RT_OFF_A_LO + 32768 + 1024)
+#define RT_SMEM_BYTES (RT_OFF_SMALL + RT_SMALL_FLOATS * 4 + 1024)   // the M = 64 instruction reads 8 row groups (16 KB) per image
 #define CV_OFF_SMALL 32768       // critic kernel: small arrays right after the W1 images
 #define CV_SMALL_FLOATS 1024
 #define CV_SMEM_BYTES (CV_OFF_SMALL + CV_SMALL_FLOATS * 4 + 1024)
@@ -137,14 +137,16 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base_s, 0);
-    const uint32_t idesc = tc_idesc(128, 64, 0, 0);
+    const uint32_t idesc = tc_idesc(64, 64, 0, 0);
     const long long N = env.n_envs;
     const int A = pd.act_n;
     const float TAU = 0.02f;
     const int a_off = ((e >> 3) * 16 + fg) * 32 + (e & 7) * 4;      // K-major no-swizzle core layout: row e, columns f0..f0+3
     // roles in the MMA window (warps on different schedulers)
-    const bool r_cand = warp == 1, r_philox = warp == 2, r_reset = warp == 3, r_sincos = warp == 5, r_dec = warp == 6;
-    const bool r_copy = (warp & 3) == 0;              // TMEM lanes 0..31 are reachable from warps 0, 4, 8, 12 only
+    const bool r_cand = warp == 10, r_philox = warp == 2, r_reset = warp == 3, r_sin = warp == 7, r_cos = warp == 11, r_dec = warp == 6;
+    // M = 64: accumulator row i sits in TMEM lane 32 * (i / 16) + i % 16, so envs 0..15 are in quadrant 0 (warps 0, 4, 8, 12)
+    // and envs 16..31 in quadrant 1 (warps 1, 5, 9, 13), lanes 0..15 of each
+    const bool r_copy = (warp & 3) < 2;
     uint32_t nbar = 0;
     for (long long tile = blockIdx.x; tile * RT_ENVS < N; tile += gridDim.x) {
         const long long n = tile * RT_ENVS + e;
@@ -257,10 +259,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
                     *reinterpret_cast<float4*>(sReset + e * 8) = make_float4(rs[0], rs[1], rs[2], rs[3]);
                     *reinterpret_cast<float2*>(sReset + e * 8 + 4) = make_float2(s_, c_);
                 }
-            } else if (r_sincos) {
-                float s_, c_;                            // correctly rounded sin/cos of the next pole angle (if no reset)
-                sincos_rn(__fadd_rn(s4.z, __fmul_rn(TAU, s4.w)), &s_, &c_);
-                *reinterpret_cast<float2*>(sSCn + e * 2) = make_float2(s_, c_);
+            } else if (r_sin || r_cos) {
+                // correctly rounded sin / cos of the next pole angle (if no reset); the two fp64 evaluations are dependent
+                // chains of slow instructions, so they run on two warps
+                const double th = (double)__fadd_rn(s4.z, __fmul_rn(TAU, s4.w));
+                sSCn[e * 2 + (r_cos ? 1 : 0)] = (float)(r_cos ? cos(th) : sin(th));
             } else if (r_dec) {
                 if (mine) *reinterpret_cast<float4*>(buf.obs + (row + n) * 4) = s4;
                 flush();
@@ -271,11 +274,13 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
                 tc_wait(&bar, nbar & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 float d[16];
-                const int c0 = (warp >> 2) * 16;
-                tc_ld16(tb + RT_COL_D + c0, d);
-                float* dst = sD + e * 68 + c0;
+                const int c0 = (warp >> 2) * 16, qd = warp & 3;
+                tc_ld16(tb + ((uint32_t)(qd * 32) << 16) + RT_COL_D + c0, d);
+                if (lane < 16) {
+                    float* dst = sD + (qd * 16 + lane) * 68 + c0;
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
+                }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             }
             ++nbar;
