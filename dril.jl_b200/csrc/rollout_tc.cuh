@@ -20,6 +20,7 @@
 //    -> tanh + output layer partials -> softmax, Philox inverse-CDF sample, log-prob, dynamics, monitor, auto-reset.
 #pragma once
 #include "rollout.cuh"
+#include <cuda_fp16.h>
 #include "update_tc.cuh"
 
 #define RT_ENVS 32
@@ -81,6 +82,32 @@ __device__ __forceinline__ void rt_stage_w1(const float* __restrict__ pack, cons
     }
 }
 
+// fp16 split used by the rollout kernel's MMAs: x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (22 significant bits;
+// fp16 subnormals keep tiny values to an absolute 3e-8).  Safe here because both operands are bounded: H0 = tanh(.)
+// and the layer weights (|w| < 65504).  Products hi*hi + lo*hi + hi*lo on kind::f16 with fp32 accumulation: K = 16 per
+// instruction, i.e. half the instructions of the 3xTF32 scheme at the same accuracy.
+__device__ __forceinline__ void rt_split_f16(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+// [R][C] fp16 matrix in the no-swizzle K-major core layout: cores of 8 rows x 8 columns (16-byte rows), ordered [r/8][c/8]
+__device__ __forceinline__ int rt_core_index_f16(int r, int c, int C) { return ((r >> 3) * (C >> 3) + (c >> 3)) * 64 + (r & 7) * 8 + (c & 7); }
+__device__ __forceinline__ void rt_stage_w1_f16(const float* __restrict__ pack, const LayerDesc& L1, unsigned char* sm, int tid, int nthreads) {
+    __half* hi_img = reinterpret_cast<__half*>(sm + RT_OFF_WT_HI);
+    __half* lo_img = reinterpret_cast<__half*>(sm + RT_OFF_WT_LO);
+    for (int i = tid; i < 64 * 64; i += nthreads) {
+        const int k = i >> 6, n = i & 63;
+        __half hi, lo;
+        rt_split_f16(pack[L1.pw_off + i], hi, lo);
+        hi_img[rt_core_index_f16(n, k, 64)] = hi;
+        lo_img[rt_core_index_f16(n, k, 64)] = lo;
+    }
+}
+__device__ __forceinline__ void rt_mma_f16_ss(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
+                 "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+
 __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_constant__ RolloutArgs a, const TcRolloutScratch sc) {
     extern __shared__ __align__(1024) unsigned char rt_smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -94,8 +121,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
     const uint32_t raw = tc_smem_u32(rt_smem_raw);
     const uint32_t sm_base = (raw + 1023u) & ~1023u;
     unsigned char* sm = rt_smem_raw + (sm_base - raw);
-    float* sAhi = reinterpret_cast<float*>(sm + RT_OFF_A_HI);
-    float* sAlo = reinterpret_cast<float*>(sm + RT_OFF_A_LO);
+    __half* sAhi = reinterpret_cast<__half*>(sm + RT_OFF_A_HI);
+    __half* sAlo = reinterpret_cast<__half*>(sm + RT_OFF_A_LO);
     float* sSmall = reinterpret_cast<float*>(sm + RT_OFF_SMALL);
     float* sD = sSmall;                 // [32][68] pre-activations of the hidden layer (copied out of TMEM)
     float* sPart = sD + 32 * 68;        // [16 feature groups][32][2] partial logits
@@ -109,7 +136,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
     const LayerDesc& L0 = pd.L[0][0];
     const LayerDesc& L1 = pd.L[0][1];
     const LayerDesc& L2 = pd.L[0][2];
-    rt_stage_w1(a.pack, L1, sm, tid, RT_THREADS);
+    rt_stage_w1_f16(a.pack, L1, sm, tid, RT_THREADS);
     const int e = lane;                               // env slot == row of the MMA == TMEM lane
     const int fg = warp, f0 = fg * 4;                 // this thread's 4 hidden features
     // this thread's slices of the thin layers live in registers for the whole rollout
@@ -137,11 +164,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base_s, 0);
-    const uint32_t idesc = tc_idesc(64, 64, 0, 0);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);   // kind::f16: F16 x F16 -> F32, M = 64, N = 64, K-major
     const long long N = env.n_envs;
     const int A = pd.act_n;
     const float TAU = 0.02f;
-    const int a_off = ((e >> 3) * 16 + fg) * 32 + (e & 7) * 4;      // K-major no-swizzle core layout: row e, columns f0..f0+3
+    const int a_off = rt_core_index_f16(e, f0, 64);                // K-major no-swizzle core layout: row e, columns f0..f0+3 (8 bytes)
     // roles in the MMA window (warps on different schedulers)
     const bool r_cand = warp == 10, r_philox = warp == 2, r_reset = warp == 3, r_sin = warp == 7, r_cos = warp == 11, r_dec = warp == 6;
     // M = 64: accumulator row i sits in TMEM lane 32 * (i / 16) + i % 16, so envs 0..15 are in quadrant 0 (warps 0, 4, 8, 12)
@@ -207,15 +234,19 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
             const float4 s4 = *reinterpret_cast<const float4*>(sState + e * 4);
             // ---- layer 0 (own 4 features) -> hi/lo -> A operand images in shared memory -----------------------------------
             {
-                float hi[4], lo[4];
+                __half hi[4], lo[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float h = fmaf(s4.w, w0r[3][j], fmaf(s4.z, w0r[2][j], fmaf(s4.y, w0r[1][j], fmaf(s4.x, w0r[0][j], b0r[j]))));
-                    h = fast_tanh(h);
-                    hi[j] = tc_hi(h); lo[j] = h - hi[j];
+                    rt_split_f16(fast_tanh(h), hi[j], lo[j]);
                 }
-                *reinterpret_cast<float4*>(sAhi + a_off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(sAlo + a_off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                __half2 h01 = __halves2half2(hi[0], hi[1]), h23 = __halves2half2(hi[2], hi[3]);
+                __half2 l01 = __halves2half2(lo[0], lo[1]), l23 = __halves2half2(lo[2], lo[3]);
+                uint2 uh, ul;
+                uh.x = *reinterpret_cast<uint32_t*>(&h01); uh.y = *reinterpret_cast<uint32_t*>(&h23);
+                ul.x = *reinterpret_cast<uint32_t*>(&l01); ul.y = *reinterpret_cast<uint32_t*>(&l23);
+                *reinterpret_cast<uint2*>(sAhi + a_off) = uh;
+                *reinterpret_cast<uint2*>(sAlo + a_off) = ul;
             }
             RT_MARK(1);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -229,9 +260,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_
                     const uint32_t aimg = sm_base + (ps == 1 ? RT_OFF_A_LO : RT_OFF_A_HI);
                     const uint32_t bimg = sm_base + (ps == 2 ? RT_OFF_WT_LO : RT_OFF_WT_HI);
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                        tc_mma_ss(tb + RT_COL_D, tc_desc(aimg + kk * 256, 128, 2048, 0), tc_desc(bimg + kk * 256, 128, 2048, 0), idesc,
-                                  (ps | kk) ? 1u : 0u);
+                    for (int kk = 0; kk < 4; ++kk)          // K = 16 per instruction: two 16-byte cores, 128 B apart; row groups 1 KB apart
+                        rt_mma_f16_ss(tb + RT_COL_D, tc_desc(aimg + kk * 256, 128, 1024, 0), tc_desc(bimg + kk * 256, 128, 1024, 0), idesc,
+                                      (ps | kk) ? 1u : 0u);
                 }
                 tc_commit(&bar);
             }
