@@ -146,6 +146,11 @@ __device__ long long g_tc_trace[2][32][16];
 #else
 #define TC_MARK(pt) do { } while (0)
 #endif
+#ifdef TC_TRACE
+#define TAIL_MARK(pt) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_tc_trace[1][31][pt] = clock64(); } while (0)
+#else
+#define TAIL_MARK(pt) do { } while (0)
+#endif
 __device__ __forceinline__ bool tc_elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
@@ -613,30 +618,41 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
     const int per = (n + nb - 1) / nb;
     const int p_lo = min(n, (int)blockIdx.x * per), p_hi = min(n, p_lo + per);
     const int gpack = a.pd.gpack;
+    TAIL_MARK(0);
     __threadfence();
     grid.sync();                                             // every CTA's partial planes are visible
+    TAIL_MARK(1);
     const double bp1 = ad.iter_acc[12], bp2 = ad.iter_acc[13];   // running beta^t BEFORE this step (CTA 0 updates them at the end)
     const unsigned long long seq = tl.mode == 2 ? *tl.pp.local_seq + 1ull : 0ull;
     const size_t par_off = (size_t)(seq & 1ull) * tl.pp.nranks * tl.pp.n_slots;      // parity half of recv[2][nranks][n_slots]
     double sq = 0.0;
+    float g_own = 0.f;                                         // reduced gradient of parameter p_lo + tid (first 64 of the slice)
     for (int base = p_lo; base < p_hi; base += 64) {
         const int lp = tid & 63, grp = tid >> 6, p = base + lp;
         float part = 0.f;
         if (p < p_hi) {
             const int idx = p < ad.n_params ? tl.flat2g[p] : tl.stats_off + (p - ad.n_params);
             const int planes = p < ad.n_params ? tl.f2planes[p] : 1;
-            for (int pl = 0; pl < planes; ++pl) {
-                const float* src = a.gpart + (size_t)pl * a.half_stride * gpack + idx;
-                float v[8];
-                for (int c0 = grp; c0 < nb; c0 += 64) {          // 8 independent loads in flight per thread
+            // all loads of this thread's share (every 8th CTA of up to 2 planes) are issued before the first add: one L2
+            // round trip instead of one per batch of 8
+            const float* src0 = a.gpart + idx;
+            const float* src1 = a.gpart + (size_t)a.half_stride * gpack + idx;
+            for (int c0 = grp; c0 < nb; c0 += 8 * 20) {
+                float v0[20], v1[20];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int c = c0 + j * 8;
-                        v[j] = c < nb ? __ldcg(src + (size_t)c * gpack) : 0.f;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) part += v[j];
+                for (int j = 0; j < 20; ++j) {
+                    const int c = c0 + j * 8;
+                    v0[j] = c < nb ? __ldcg(src0 + (size_t)c * gpack) : 0.f;
+                    v1[j] = (planes > 1 && c < nb) ? __ldcg(src1 + (size_t)c * gpack) : 0.f;
                 }
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 20; ++j) { s0 += v0[j]; s1 += v1[j]; }
+                part += s0 + s1;
+            }
+            for (int pl = 2; pl < planes; ++pl) {                  // (the tensor-core kernel writes at most 2 planes)
+                const float* src = a.gpart + (size_t)pl * a.half_stride * gpack + idx;
+                for (int c = grp; c < nb; c += 8) part += __ldcg(src + (size_t)c * gpack);
             }
         }
         s_red[grp * 64 + lp] = part;
@@ -651,6 +667,7 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
                 for (int r = 0; r < tl.pp.nranks; ++r) tl.pp.peer_recv[r][off] = gs;
             } else {
                 ad.g[p] = gs;
+                if (base == p_lo) g_own = gs;
                 if (p < ad.n_params) sq += (double)gs * (double)gs;
             }
         }
@@ -678,13 +695,22 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
             float gs = 0.f;
             for (int r = 0; r < tl.pp.nranks; ++r) gs += __ldcv(tl.pp.local_recv + par_off + (size_t)r * tl.pp.n_slots + p);
             ad.g[p] = gs;
+            if (p == p_lo + tid && tid < 64) g_own = gs;
             if (p < ad.n_params) sq += (double)gs * (double)gs;
         }
     }
+    TAIL_MARK(2);
+    // Adam state of this thread's parameter is fetched before the barrier (it does not depend on the other CTAs)
+    const int p_own = p_lo + tid;
+    const bool own = tid < 64 && p_own < min(p_hi, ad.n_params);
+    float m_own = 0.f, v_own = 0.f, w_own = 0.f;
+    int ip_own = -1, it_own = -1;
+    if (own) { m_own = ad.m[p_own]; v_own = ad.v[p_own]; w_own = ad.flat[p_own]; ip_own = ad.flat2pack[p_own]; it_own = ad.flat2packT[p_own]; }
     sq = block_sum(sq, scratch);
     if (tid == 0) tl.sq_part[blockIdx.x] = sq;
     __threadfence();
     grid.sync();                                             // all slices of g and all sums of squares are visible
+    TAIL_MARK(3);
     double q = 0.0;
     for (int b = tid; b < nb; b += blockDim.x) q += __ldcg(tl.sq_part + b);
     q = block_sum(q, scratch);
@@ -696,7 +722,19 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
     float scale = 1.f;
     if (ad.hp.max_grad_norm >= 0.f && norm > ad.hp.max_grad_norm) scale = ad.hp.max_grad_norm / norm;
     const float c1 = (float)(1.0 - bp1 * (double)ad.hp.beta1), c2 = (float)(1.0 - bp2 * (double)ad.hp.beta2);
-    for (int p = p_lo + tid; p < min(p_hi, ad.n_params); p += blockDim.x) adam_param(ad, p, scale, c1, c2);
+    if (own) {                                               // same arithmetic as adam_param, operands already in registers
+        const float b1 = ad.hp.beta1, b2 = ad.hp.beta2;
+        const float gg = __fmul_rn(g_own, scale);
+        const float mm = __fadd_rn(__fmul_rn(b1, m_own), __fmul_rn(__fsub_rn(1.0f, b1), gg));
+        const float vv = __fadd_rn(__fmul_rn(b2, v_own), __fmul_rn(__fmul_rn(__fsub_rn(1.0f, b2), gg), gg));
+        const float upd = __fmul_rn(__fdiv_rn(__fdiv_rn(mm, c1), __fadd_rn(__fsqrt_rn(__fdiv_rn(vv, c2)), ad.hp.adam_eps)), ad.hp.lr);
+        const float w = __fsub_rn(w_own, upd);
+        ad.m[p_own] = mm; ad.v[p_own] = vv; ad.flat[p_own] = w;
+        if (ip_own >= 0) ad.pack[ip_own] = w;
+        if (it_own >= 0) ad.pack[it_own] = w;
+    }
+    for (int p = p_lo + 64 + tid; p < min(p_hi, ad.n_params); p += blockDim.x) adam_param(ad, p, scale, c1, c2);   // slices wider than 64
+    TAIL_MARK(4);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) ppo_loss_grad_tc_kernel(const __grid_constant__ LossArgs a, const __grid_constant__ TailArgs tl) {

@@ -31,3 +31,7 @@ for ps, nm in ((0, "actor"), (16, "critic")):
             rel = row - t0
             print(f"{nm} g{g} tile{it}: start {rel[0]:7d} | " + " ".join(f"{names[i + 1]}+{row[i + 1] - row[i]}" for i in range(12)) +
                   f" | total {row[12] - row[0]}")
+
+tl = tr[1, 31, :5]
+print("tail (CTA 0): wait for all CTAs + barrier 1 = %d, slice reduction = %d, block sum + barrier 2 = %d, norm/stats/Adam = %d cycles" %
+      (tl[1] - tl[0], tl[2] - tl[1], tl[3] - tl[2], tl[4] - tl[3]))
