@@ -8,7 +8,8 @@ updates, over synthetic env batches of the named shape with random-init weights.
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4]
 
 N > 1 is launched by the driver with torch.distributed.run (one rank per GPU): envs shard across
-ranks (weak scaling: per-GPU env count fixed), gradients are allreduced with NCCL per minibatch.
+ranks (weak scaling: per-GPU env count fixed), gradients are allreduced over NVLink peer memory per minibatch
+(NCCL fallback with DRIL_NO_P2P=1).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -154,8 +155,8 @@ def run_ours(args):
                 dist.all_gather_object(out, b)
                 return out
             ctx.comm_p2p_setup(all_gather, agent.device.n_params + 8)
-            comm = ("one-shot NVLink peer-memory allreduce of the flat gradient fused into the reduce/Adam kernels "
-                    "(NCCL only for the per-update advantage moments)")
+            comm = ("one-shot NVLink peer-memory allreduce (push) of the flat gradient inside the loss/grad kernel's fused tail; "
+                    "advantage / explained-variance moments through a second small peer-memory kernel; no NCCL on the data path")
     buf = D.RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, n_steps, n_envs, ctx=ctx)
     import ctypes as C
     from dril_b200 import _lib as L
@@ -194,9 +195,16 @@ def run_ours(args):
         ctx.synchronize()
 
     # ---- warm-up --------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    # at least W (>= 3) iterations, and at least 0.3 s of work so that a box that was idle reaches its sustained clocks
+    # and the pipelined enqueue path is in steady state before anything is timed
+    t_w = time.perf_counter()
+    n_w = 0
+    while n_w < max(args.warmup, 3) or time.perf_counter() - t_w < 0.3:
         iteration_async()
-        st = drain()
+        n_w += 1
+        if n_w % 3 == 0:
+            drain()
+    st = drain()
     # ---- value: K iterations resident on the device, CUDA events on the launching stream -----
     sampler = ClockSampler(local)
     barrier()
@@ -306,7 +314,7 @@ def run_ours(args):
                  "note": note})
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_w,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (on-device env batches of the named shape, orthogonal random-init weights, seed 0)",
         "config": {"workload": w["name"], "epochs": EPOCHS, "minibatches_per_epoch": N_MINIBATCHES, "batch_size_per_gpu": batch,
