@@ -520,33 +520,6 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
     }
 }
 
-// g_flat[p] = sum over the partial planes / CTAs of the packed partials (fixed order => deterministic)
-__device__ __forceinline__ float reduce_partials(const float* __restrict__ gpart, int n_cta, int half_stride, int gpack,
-                                                 int idx, int planes) {
-    float s = 0.f;
-    for (int pl = 0; pl < planes; ++pl) {
-        const float* base = gpart + (size_t)pl * half_stride * gpack + idx;
-        float sp = 0.f;
-#pragma unroll 4
-        for (int c = 0; c < n_cta; ++c) sp += base[(size_t)c * gpack];
-        s += sp;
-    }
-    return s;
-}
-
-__global__ void __launch_bounds__(256) grad_reduce_kernel(const float* __restrict__ gpart, int n_cta, int half_stride,
-                                                          int gpack, const int* __restrict__ flat2g,
-                                                          const unsigned char* __restrict__ f2planes, int n_params,
-                                                          int stats_off, float* __restrict__ g_flat /* [n_params + 8] */,
-                                                          const int* stop_flag) {
-    if (*stop_flag) return;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_params + 6) return;
-    int idx = p < n_params ? flat2g[p] : stats_off + (p - n_params);
-    int planes = p < n_params ? f2planes[p] : 1;
-    g_flat[p] = reduce_partials(gpart, n_cta, half_stride, gpack, idx, planes);
-}
-
 // iteration accumulators (device): [0..6] sums over applied minibatches of policy_loss, value_loss,
 // entropy_loss, clip_fraction, approx_kl, entropy, ratio; [7] loss; [8] grad_norm sum; [9] applied
 // count; [10] grad_norm count; [12],[13] running beta1^t, beta2^t

@@ -75,14 +75,6 @@ __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(done) : "r"(tc_smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, float* r) {
-    uint32_t u[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]) : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = __uint_as_float(u[j]);
-}
 __device__ __forceinline__ void tc_st8(uint32_t taddr, const float* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(__float_as_uint(r[0])),
                  "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])), "r"(__float_as_uint(r[3])), "r"(__float_as_uint(r[4])),
@@ -300,7 +292,7 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
         // sX of the previous tile was last read before the group barrier that ended that tile
         if (half == 0) *reinterpret_cast<float4*>(sX + m * 4) = make_float4(x0, x1, x2, x3);
         // ---- layer 0 on CUDA cores, H0 hi/lo -> TMEM (A operand of G1) ----------------------------------------------
-#pragma unroll
+#pragma unroll 2
         for (int c0 = 0; c0 < 32; c0 += 8) {
             float h[8], hi[8], lo[8];
             {
