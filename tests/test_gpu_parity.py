@@ -571,3 +571,37 @@ def test_c1_shape_update_vs_oracle(D):
     for k in ("policy_loss", "value_loss", "loss"):
         assert abs(getattr(st, k) - means[k]) <= 1e-3 * max(1.0, abs(means[k])), (k, getattr(st, k), means[k])
     buf.close()
+
+
+@pytest.mark.parametrize("n,T,ms", [(33, 6, 1), (64, 1, 500), (5, 40, 2), (1, 9, 3)])
+def test_fused_rollout_edge_shapes(D, n, T, ms):
+    """Edge cases of the (tensor-core) rollout against the oracle with replayed actions: every step truncates
+    (max_steps = 1: back-to-back resets, one terminal observation per sample), a single step, tiny env counts."""
+    env, oenv, spec = _mk(D, "cartpole", n, 17, ms, True, False)
+    rng = np.random.default_rng(2)
+    flat = (OP.init_params(spec, seed=1) + rng.normal(size=spec.n_params()).astype(f32) * 0.05).astype(f32)
+    forced = rng.integers(1, 3, (T, n))
+    layer = D.ActorCriticLayer(env.observation_space(), env.action_space(), hidden_dims=spec.hidden)
+    alg = D.PPO(n_steps=T, gamma=0.97, gae_lambda=0.9)
+    agent = D.Agent(layer, alg, rng=np.random.default_rng(0))
+    agent.set_parameters(flat)
+    for rollout in range(2):
+        buf = D.RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, T, n)
+        D.collect_rollout(buf, agent, alg, env, forced_actions=forced)
+        ob = OO.collect_rollout_timemajor(oenv, spec, flat, T, forced_actions=forced)
+        te, tr = _flags(buf)
+        np.testing.assert_array_equal(te, ob["term"])
+        np.testing.assert_array_equal(tr, ob["trunc"])
+        np.testing.assert_allclose(buf.download("obs"), ob["obs"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(buf.download("values"), ob["values"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(buf.download("logprobs"), ob["logprobs"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(buf.download("last_values"), ob["last_values"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(np.where(tr, buf.download("boot"), 0), ob["boot"], rtol=1e-5, atol=1e-5)
+        ea, er = OO.gae_timemajor(ob["rewards"], ob["values"], ob["term"], ob["trunc"], ob["boot"], ob["last_values"], 0.97, 0.9)
+        np.testing.assert_allclose(buf.download("advantages"), ea, rtol=1e-4, atol=1e-4)
+        done = te | tr
+        if done.any():
+            np.testing.assert_array_equal(buf.download("episode_l")[done], ob["episode_l"][done])
+        if ms == 1:
+            assert tr.all()
+        buf.close()
