@@ -1287,10 +1287,11 @@ extern "C" int32_t dril_rollout_collect(dril_env* e, dril_policy* p, dril_buffer
     return DRIL_OK;
 }
 
-static int32_t gae_async(dril_ctx* c, const BufDev& d, float gamma, float lambda) {
+// ev_acc4 (optional, zeroed by the caller): the explained-variance moments are accumulated in the same pass
+static int32_t gae_async(dril_ctx* c, const BufDev& d, float gamma, float lambda, double* ev_acc4 = nullptr) {
     Span sp(c, DRIL_K_GAE);
     gae_kernel<<<(unsigned)((d.N + 255) / 256), 256, 0, c->stream>>>(d.rewards, d.values, d.flags, d.boot, d.last_values,
-                                                                    d.advantages, d.returns, d.T, d.N, gamma, lambda);
+                                                                    d.advantages, d.returns, d.T, d.N, gamma, lambda, ev_acc4);
     DRIL_CUDA(cudaGetLastError());
     return DRIL_OK;
 }
@@ -1632,10 +1633,10 @@ extern "C" int32_t dril_ppo_iteration_async(dril_env* e, dril_policy* p, dril_bu
     p->last_env = e; p->last_buf = b; p->last_lr = h->learning_rate;
     DRIL_CUDA(cudaEventRecord(sl.ev[0], c->stream));
     DRIL_TRY(rollout_async(e, p, b, nullptr));
-    DRIL_TRY(gae_async(c, b->d, h->gamma, h->gae_lambda));
+    DRIL_CUDA(cudaMemsetAsync(p->ev_acc, 0, 32, c->stream));
+    DRIL_TRY(gae_async(c, b->d, h->gamma, h->gae_lambda, p->ev_acc));   // + explained-variance moments (ppo.jl:256)
     DRIL_TRY(launch_monitor_finalize(e, b));
     DRIL_CUDA(cudaEventRecord(sl.ev[1], c->stream));
-    DRIL_TRY(ev_async(p, b));   // explained variance uses the rollout's values/returns (ppo.jl:256)
     DRIL_TRY(update_async(p, b, h, epochs, batch_size, shuffle_seed, epoch_counter, p->ev_acc, 4));
     DRIL_CUDA(cudaEventRecord(sl.ev[2], c->stream));
     {

@@ -16,9 +16,12 @@ __global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewa
                                                   const unsigned char* __restrict__ flags,
                                                   const float* __restrict__ boot, const float* __restrict__ last_values,
                                                   float* __restrict__ adv, float* __restrict__ ret, long long T,
-                                                  long long N, float gamma, float lambda) {
+                                                  long long N, float gamma, float lambda, double* ev_acc4) {
+    __shared__ double scratch[32];
     long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+    const bool live = n < N;
+    if (!live) n = N - 1;          // keep the thread for the block sums of the fused explained-variance moments (no stores)
+    double sd = 0, sdd = 0, sr = 0, srr = 0;
     const float gl = __fmul_rn(gamma, lambda);
     float a_next = 0.f, v_next = 0.f;
     long long t = T - 1;
@@ -37,8 +40,13 @@ __global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewa
             float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(gamma, v_next)), v);
             a = __fadd_rn(delta, __fmul_rn(gl, a_next));
         }
-        adv[tt * N + n] = a;
-        ret[tt * N + n] = __fadd_rn(a, v);
+        const float rt = __fadd_rn(a, v);
+        if (live) {
+            adv[tt * N + n] = a;
+            ret[tt * N + n] = rt;
+            const double dv = (double)v - (double)rt, dr = (double)rt;
+            sd += dv; sdd += dv * dv; sr += dr; srr += dr * dr;
+        }
         a_next = a; v_next = v;
     };
     while (t >= GAE_UNROLL - 1) {
@@ -54,6 +62,14 @@ __global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewa
         t -= GAE_UNROLL;
     }
     for (; t >= 0; --t) step(t, rewards[t * N + n], values[t * N + n], flags[t * N + n]);
+    // explained_variance moments of the same rollout (algorithms/ppo.jl:256) without a second pass over the buffer
+    if (ev_acc4) {
+        sd = block_sum(sd, scratch); sdd = block_sum(sdd, scratch);
+        sr = block_sum(sr, scratch); srr = block_sum(srr, scratch);
+        if (threadIdx.x == 0) {
+            atomicAdd(&ev_acc4[0], sd); atomicAdd(&ev_acc4[1], sdd); atomicAdd(&ev_acc4[2], sr); atomicAdd(&ev_acc4[3], srr);
+        }
+    }
 }
 
 // explained_variance = 1 - var(values - returns) / var(returns) (algorithms/ppo.jl:256):
@@ -158,17 +174,20 @@ __global__ void iter_record_kernel(IterRecordSrc s, IterRecord* out) {
         out->stop = *s.stop;
         out->p2p_err = s.p2p_err ? *s.p2p_err : 0;
     }
-    if (t == 31) {
+    {   // window means: lane-strided partial sums, then a fixed-order butterfly (deterministic)
         long long cnt = 0;
         float sr = 0.f;
         double sl = 0.0;
         if (s.has_ring) {
             const long long head = *s.ring.head;
             cnt = head < s.ring.window ? head : s.ring.window;
-            for (long long i = 0; i < cnt; ++i) { sr += s.ring.ret[i]; sl += (double)s.ring.len[i]; }
+            for (long long i = t; i < cnt; i += 32) { sr += s.ring.ret[i]; sl += (double)s.ring.len[i]; }
         }
-        out->ring_count = cnt;
-        out->ring_rew_mean = cnt ? sr / (float)cnt : nanf("");
-        out->ring_len_mean = cnt ? (float)(sl / (double)cnt) : nanf("");
+        sr = warp_sum(sr); sl = warp_sum(sl);
+        if (t == 31) {
+            out->ring_count = cnt;
+            out->ring_rew_mean = cnt ? sr / (float)cnt : nanf("");
+            out->ring_len_mean = cnt ? (float)(sl / (double)cnt) : nanf("");
+        }
     }
 }

@@ -111,3 +111,19 @@ def test_pipelined_train_matches_sequential(D):
     assert len(s_a["losses"]) == 7
     assert m_a == m_b
     assert [v for _, v in l_a["env/ep_rew_mean"]] == [v for _, v in l_b["env/ep_rew_mean"]]
+
+
+def test_iteration_explained_variance_matches_buffer(D):
+    """The explained variance reported by a train! iteration (moments fused into the GAE pass) equals the value
+    computed from the buffer's stored values / returns (algorithms/ppo.jl:256), also from the NumPy formula."""
+    n, T = 300, 40
+    env = D.CudaBatchedEnv("cartpole", n, seed=11, monitor_window=100)
+    layer = D.ActorCriticLayer(env.observation_space(), env.action_space(), hidden_dims=[64, 64])
+    alg = D.PPO(n_steps=T, batch_size=T * n // 2, epochs=1)
+    agent = D.Agent(layer, alg, rng=np.random.default_rng(2))
+    out = D.train(agent, env, alg, n * T)
+    buf = next(iter(agent._roll_buffers.values()))
+    v, r = buf.download("values").astype(np.float64).ravel(), buf.download("returns").astype(np.float64).ravel()
+    ev = 1.0 - np.var(v - r, ddof=1) / np.var(r, ddof=1)
+    assert abs(out[0]["explained_variances"][0] - ev) < 1e-5
+    assert abs(buf.explained_variance() - ev) < 1e-5
