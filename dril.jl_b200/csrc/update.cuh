@@ -551,10 +551,14 @@ __device__ __forceinline__ int adam_stop(const AdamArgs& a) {
 // threads 0..15 of ONE CTA, independent global round trips.  s_f[0..1] receive the Adam bias corrections 1 - beta^t.
 __device__ __forceinline__ void adam_accumulate(const AdamArgs& a, float norm, int stop, int tid, float* s_f) {
     if (tid >= 16) return;
+    // all loads first and unconditionally (one round trip): the per-thread cases below are pure arithmetic, so the
+    // divergent switch does not serialise a global load per case
     const float* st = a.g + a.n_params;
+    const float st0 = st[0], st1 = st[1], st2 = st[2], st3 = st[3], st4 = st[4], st5 = st[5];
+    const double old = a.iter_acc[tid];
     const float invB = (float)(1.0 / a.global_count);
     if (a.apply_stats) {
-        const float p_loss = st[0] * invB, v_loss = st[1] * invB, ent = st[2] * invB;
+        const float p_loss = st0 * invB, v_loss = st1 * invB, ent = st2 * invB;
         const float ent_loss = -ent;
         double add = 0.0;
         bool on_apply = true;
@@ -562,23 +566,23 @@ __device__ __forceinline__ void adam_accumulate(const AdamArgs& a, float norm, i
             case 0: add = p_loss; break;
             case 1: add = v_loss; break;
             case 2: add = ent_loss; break;
-            case 3: add = st[3] * invB; break;
-            case 4: add = st[4] * invB; break;
+            case 3: add = st3 * invB; break;
+            case 4: add = st4 * invB; break;
             case 5: add = ent; break;
-            case 6: add = st[5] * invB; break;
+            case 6: add = st5 * invB; break;
             case 7: add = p_loss + a.hp.ent_coef * ent_loss + a.hp.vf_coef * v_loss; break;
             case 8: add = norm; on_apply = false; break;     // grad_norms gets the PRE-clip norm before the KL check (ppo.jl:216-223)
             case 9: add = 1.0; break;
             case 10: add = 1.0; on_apply = false; break;
             default: add = 0.0; on_apply = false; break;
         }
-        if (tid <= 10 && (!on_apply || !stop)) a.iter_acc[tid] += add;
+        if (tid <= 10 && (!on_apply || !stop)) a.iter_acc[tid] = old + add;
     } else if (tid == 8) {
         a.iter_acc[8] = (double)norm;
     }
     if (!stop && (tid == 12 || tid == 13)) {
         double b = tid == 12 ? (double)a.hp.beta1 : (double)a.hp.beta2;
-        double pw = a.iter_acc[tid] * b;
+        double pw = old * b;
         a.iter_acc[tid] = pw;
         if (s_f) s_f[tid - 12] = (float)(1.0 - pw);
     }

@@ -627,6 +627,7 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
             const int planes = p < ad.n_params ? tl.f2planes[p] : 1;
             // all loads of this thread's share (every 8th CTA of up to 2 planes) are issued before the first add: one L2
             // round trip instead of one per batch of 8
+            TAIL_MARK(5);
             const float* src0 = a.gpart + idx;
             const float* src1 = a.gpart + (size_t)a.half_stride * gpack + idx;
             for (int c0 = grp; c0 < nb; c0 += 8 * 20) {
@@ -647,8 +648,10 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
                 for (int c = grp; c < nb; c += 8) part += __ldcg(src + (size_t)c * gpack);
             }
         }
+        TAIL_MARK(6);
         s_red[grp * 64 + lp] = part;
         __syncthreads();
+        TAIL_MARK(7);
         if (grp == 0 && p < p_hi) {
             float gs = 0.f;
 #pragma unroll
@@ -706,9 +709,12 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
     double q = 0.0;
     for (int b = tid; b < nb; b += blockDim.x) q += __ldcg(tl.sq_part + b);
     q = block_sum(q, scratch);
+    TAIL_MARK(8);
     const float norm = (float)sqrt(q);
     const int stop = adam_stop(ad);
+    TAIL_MARK(9);
     if (blockIdx.x == 0) adam_accumulate(ad, norm, stop, tid, s_f);
+    TAIL_MARK(10);
     if (tl.mode == 2 && blockIdx.x == 0 && tid == 32) *tl.pp.local_seq = seq;       // every CTA read the old value before the barrier
     if (stop) return;
     float scale = 1.f;

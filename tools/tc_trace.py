@@ -32,6 +32,8 @@ for ps, nm in ((0, "actor"), (16, "critic")):
             print(f"{nm} g{g} tile{it}: start {rel[0]:7d} | " + " ".join(f"{names[i + 1]}+{row[i + 1] - row[i]}" for i in range(12)) +
                   f" | total {row[12] - row[0]}")
 
-tl = tr[1, 31, :5]
+tl = tr[1, 31, :11]
 print("tail (CTA 0): wait for all CTAs + barrier 1 = %d, slice reduction = %d, block sum + barrier 2 = %d, norm/stats/Adam = %d cycles" %
       (tl[1] - tl[0], tl[2] - tl[1], tl[3] - tl[2], tl[4] - tl[3]))
+print("  reduction: index loads %d, partial loads + sums %d, smem exchange %d, rest %d | after barrier 2: sq sum %d, stop flag %d, accumulators %d, Adam %d" %
+      (tl[5] - tl[1], tl[6] - tl[5], tl[7] - tl[6], tl[2] - tl[7], tl[8] - tl[3], tl[9] - tl[8], tl[10] - tl[9], tl[4] - tl[10]))
