@@ -167,7 +167,7 @@ struct dril_policy {
     float *flat = nullptr, *pack = nullptr, *m = nullptr, *v = nullptr, *g = nullptr, *gpart = nullptr;
     int *flat2pack = nullptr, *flat2packT = nullptr, *flat2g = nullptr;
     unsigned char* f2planes = nullptr;   // partial planes holding contributions to each parameter's gradient
-    unsigned char* f2planes_one = nullptr;   // tensor-core path: one partial plane per CTA, two (hi/lo part) for the hidden weights
+    unsigned char* f2planes_one = nullptr;   // tensor-core path: one partial plane per CTA
     double* sq_part = nullptr;
     unsigned int* ticket = nullptr;
     int loss_M4 = 0, loss_splits = 1;
@@ -660,11 +660,6 @@ extern "C" int32_t dril_policy_create(dril_ctx* c, int32_t obs_dim, int32_t n_hi
         DRIL_TRY(dmalloc(&p->f2planes, np));
         DRIL_CUDA(cudaMemcpy(p->f2planes, planes.data(), np, cudaMemcpyHostToDevice));
         std::vector<unsigned char> one_plane(np, 1);
-        if (tc_eligible(pd))
-            for (int net = 0; net < 2; ++net) {
-                const LayerDesc& L = pd.L[net][1];
-                for (int i = 0; i < L.K * L.N; ++i) one_plane[L.w_off + i] = 2;
-            }
         DRIL_TRY(dmalloc(&p->f2planes_one, np));
         DRIL_CUDA(cudaMemcpy(p->f2planes_one, one_plane.data(), np, cudaMemcpyHostToDevice));
         DRIL_TRY(dmalloc(&p->sq_part, 8192));

@@ -540,15 +540,19 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
         TC_MARK(12);
         if (t == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bfree)) : "memory");
     }
-    // ---- end of pass: dW1 from TMEM (M = 128: row i <-> lane i; rows 0..63 -> plane 0, rows 64..127 (lo part) -> plane 1) -----
+    // ---- end of pass: dW1 from TMEM (M = 128: row i <-> lane i; rows 0..63 hold the hi part of H0, rows 64..127 the lo
+    //      part: the two are added through shared memory so that one partial plane per CTA is enough) ---------------------
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float dw1[32];
+    float* sTmp = sRed + 8192;                                       // [64][68] lo-part rows (behind the sRed scratch)
     if (g == 0) {
-        float tt[32];
-        tc_ld32(tb + lane_base + TC_COL_D3 + f0, tt);
-        float* gw = gp + (size_t)(m >> 6) * a.half_stride * pd.gpack + L1.pw_off + (m & 63) * 64 + f0;
+        tc_ld32(tb + lane_base + TC_COL_D3 + f0, dw1);
+        if (m >= 64) {
+            float* d = sTmp + (m - 64) * TC_STAGE_LD + f0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(gw + j) = make_float4(tt[j], tt[j + 1], tt[j + 2], tt[j + 3]);
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(d + j) = make_float4(dw1[j], dw1[j + 1], dw1[j + 2], dw1[j + 3]);
+        }
     }
     // reducer partial sums -> sRed[slot = g*4 + rq][sum][f] -> fixed-order sum over the 8 slots
     {
@@ -564,6 +568,15 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
         }
     }
     __syncthreads();
+    if (g == 0 && m < 64) {
+        const float* d = sTmp + m * TC_STAGE_LD + f0;
+        float* gw = gp + L1.pw_off + m * 64 + f0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 lo4 = *reinterpret_cast<const float4*>(d + j);
+            *reinterpret_cast<float4*>(gw + j) = make_float4(dw1[j] + lo4.x, dw1[j + 1] + lo4.y, dw1[j + 2] + lo4.z, dw1[j + 3] + lo4.w);
+        }
+    }
     for (int i = tid; i < (6 + NOUT) * 64 + NOUT; i += TC_THREADS) {
         if (i < (6 + NOUT) * 64) {
             const int q = i >> 6, f = i & 63;
