@@ -12,18 +12,25 @@
 //                                                 across all tiles of the pass (rows 0..63 hi part, 64..127 lo part)
 // Everything else is CUDA-core code with two threads per sample (thread (m, half) <-> TMEM lane m, hidden features
 // [32 half, 32 half + 32)): layer 0 (K = obs_dim), the output layers, the loss head and the deltas.  The thin-layer
-// gradients (dW0, db0, db1, dW2) are sums over samples: the per-sample factors are staged in shared memory as
-// [sample][68] rows and thread (feature f, sample quarter) accumulates its 32 samples per tile in registers (no
-// shuffles); the partial sums are combined once at the end of the pass.
+// gradients are sums over samples: dW2 and db1 by a register shuffle transpose-reduce (outside the critical section
+// below), dW0 and db0 through a [sample][68] shared-memory staging buffer where thread (feature f, sample quarter)
+// accumulates its 32 samples per tile in registers; the partial sums are combined once at the end of the pass, where
+// the hi and lo rows of the dW1 accumulator are also added so that every CTA writes ONE partial plane.
 //
 // Two groups of 8 warps work on alternate 128-sample tiles of the CTA (ping-pong): while one group's MMAs run or
 // it waits, the other group is in a CUDA-core phase.  Each group owns 192 TMEM columns (D | A/Z hi | A/Z lo; the dZ1
-// operand overwrites the H0 operand once G1 has consumed it) and its own mbarriers; the dW1 accumulator (64
-// columns) and the 128 KB image region are shared.  A group holds the image region from the staging of its
-// output-layer factors until its layer-0 gradient sums are done (staging -> images -> G2/G3 -> layer-0 delta, which
-// re-reads H0 from the image -> staging) and then releases it through an mbarrier, so use strictly alternates.  tcgen05 rates measured on B200 by tools/tc_probe3.cu: max(44, N/2) cycles per tf32
-// instruction at M = 128.  Descriptor recipes are the ones verified on hardware by tools/tc_probe*.cu
-// (profiles/r01_tcgen05_probe.txt).  One pass over the minibatch per net (actor, then critic).
+// operand overwrites the H0 operand once G1 has consumed it) and its own mbarriers (G1 done, G2 done, G3 done,
+// region free); the dW1 accumulator (64 columns) and the 128 KB image region are shared.  A group takes the image
+// region when its deltas are ready (images -> G2, G3 -> layer-0 delta, which re-reads H0 from the image while G3 still
+// runs -> staging over the consumed dZ1 images -> layer-0 sums) and then releases it through an mbarrier, so use
+// strictly alternates.  MMAs are issued by one elected lane of a warp whose index is warp-uniform for the compiler;
+// the next tile's samples are gathered while G2/G3 run.
+//
+// The kernel ends with a cooperative tail (tc_fused_tail): reduction of the per-CTA partials, optional peer-memory
+// push exchange between GPUs, gradient norm, clip, KL stop, statistics and Adam.
+// tcgen05 rates measured on B200 by tools/tc_probe3.cu: max(44, N/2) cycles per tf32 instruction at M = 128.
+// Descriptor recipes are the ones verified on hardware by tools/tc_probe*.cu (profiles/r01_tcgen05_probe.txt).
+// One pass over the minibatch per net (actor, then critic).
 #pragma once
 #include <cooperative_groups.h>
 #include "update.cuh"
