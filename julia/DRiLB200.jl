@@ -294,4 +294,41 @@ function DRiL.train!(agent::Agent, env::CudaBatchedEnv, alg::PPO{T}, max_steps::
     return learn_stats, to
 end
 
+# ---- kernel-path switches and data-parallel setup (include/dril_b200.h) --------------------------------------------
+"`set_option(\"tc\" | \"fused_tail\" | \"tc_rollout\", 0/1)`: process-wide kernel-path switches (all default on)."
+set_option(key::AbstractString, value::Integer) =
+    check(ccall((:dril_set_option, LIB), Int32, (Cstring, Int32), key, value))
+
+"`:tensor` when the update of this policy runs the tcgen05 (3xTF32) loss/grad kernel, else `:fp32`."
+function update_path(p::DevicePolicy)
+    out = Ref{Int32}(0)
+    check(ccall((:dril_policy_update_path, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}), p.h, out))
+    return out[] == 1 ? :tensor : :fp32
+end
+
+"""
+    comm_init!(ctx, rank, nranks, unique_id; exchange_handles)
+
+One process (or task) per GPU.  `unique_id` is the 128-byte id of `comm_unique_id()` created on rank 0 and broadcast by
+the host program (MPI.jl, a file, sockets).  When `exchange_handles(my_handle::Vector{UInt8})::Vector{Vector{UInt8}}`
+is given (an all-gather of the 64-byte CUDA IPC handles in rank order) the gradient / moment exchanges run over NVLink
+peer memory inside the update kernel instead of NCCL.  Envs are sharded by `gid_offset = rank * n_envs`.
+"""
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:dril_comm_unique_id, LIB), Int32, (Ptr{UInt8},), id))
+    return id
+end
+function comm_init!(ctx::Context, rank::Integer, nranks::Integer, unique_id::Vector{UInt8}; exchange_handles = nothing,
+        n_params::Integer = 0)
+    check(ccall((:dril_comm_init, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), ctx.h, rank, nranks, unique_id))
+    if exchange_handles !== nothing
+        mine = Vector{UInt8}(undef, 64)
+        check(ccall((:dril_comm_p2p_export, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{UInt8}), ctx.h, n_params + 8, mine))
+        all = reduce(vcat, exchange_handles(mine))
+        check(ccall((:dril_comm_p2p_import, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), ctx.h, all))
+    end
+    return nothing
+end
+
 end # module
