@@ -314,12 +314,13 @@ def run_ours(args):
                  "note": note})
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_w,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (on-device env batches of the named shape, orthogonal random-init weights, seed 0)",
         "config": {"workload": w["name"], "epochs": EPOCHS, "minibatches_per_epoch": N_MINIBATCHES, "batch_size_per_gpu": batch,
                    "env_steps_per_step_per_gpu": steps_per_iter, "adam_steps_per_step": EPOCHS * N_MINIBATCHES,
                    "l2": "flushed: 256 MB memset on the stream before every timed step (inside the timed region)",
+                   "warmup_iterations_run": n_w,        # W requested, extended to >= 0.3 s of untimed work
                    "parallelism": f"dp{world} over envs, {comm}" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "dril_b200.train (train!): host parameters in, per-iteration learn_stats + final parameters out, wall clock"},
