@@ -696,13 +696,14 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
                 *reinterpret_cast<volatile unsigned long long*>(tl.pp.peer_cflag[r] + (size_t)tl.pp.rank * tl.pp.max_cta + blockIdx.x) = seq;
         }
         if (tid < tl.pp.nranks) {
-            const volatile unsigned long long* f = tl.pp.local_cflag + (size_t)tid * tl.pp.max_cta + blockIdx.x;
+            // acquire loads at system scope: the flag and the slices it guards were written by the peers' SMs over NVLink
+            const unsigned long long* f = const_cast<const unsigned long long*>(tl.pp.local_cflag) + (size_t)tid * tl.pp.max_cta + blockIdx.x;
             long long spins = 0;
-            while (*f < seq) {
-                __nanosleep(32);
-                if (++spins > (1ll << 24)) { atomicExch(tl.pp.err, 1); break; }
-            }
-            __threadfence_system();
+            unsigned long long seen;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+                if (seen < seq && ++spins > (1ll << 26)) { atomicExch(tl.pp.err, 1); break; }
+            } while (seen < seq);
         }
         __syncthreads();
         // sum of all ranks' slices in rank order (identical on every rank => bit-identical parameters)
