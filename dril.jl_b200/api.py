@@ -287,10 +287,8 @@ def load_policy_params_and_state(agent, path, suffix=".npz", restore_optimizer=F
 # ---- collection (buffers/rollout_buffer.jl:46-90) -----------------------------------------
 def collect_rollout(rollout_buffer, agent, alg, env, callbacks=None, forced_actions=None):
     """collect_rollout!(buffer, agent, alg, env) -> (fps, success): fused device rollout + GAE."""
-    if callbacks:
-        loc = dict(agent=agent, env=env, alg=alg, n_steps=rollout_buffer.n_steps, n_envs=rollout_buffer.n_envs)
-        if not all(c.on_step(loc) for c in callbacks):   # per-rollout granularity on the fused path
-            return 0.0, False
+    if not _on_step_hooks(callbacks, agent, env, alg, rollout_buffer.n_steps, rollout_buffer.n_envs):
+        return 0.0, False
     fa = None
     if forced_actions is not None:
         if rollout_buffer.discrete:
@@ -305,6 +303,25 @@ def collect_rollout(rollout_buffer, agent, alg, env, callbacks=None, forced_acti
 
 def _hook(callbacks, name, loc):
     return all(getattr(c, name)(loc) for c in callbacks) if callbacks else True
+
+
+def _on_step_hooks(callbacks, agent, env, alg, n_steps, n_envs):
+    """on_step of collect_trajectories (buffers/trajectory.jl:34-39): called before every env step i = 1..n_steps with
+    the locals of the collection loop; the first `false` aborts the collection (and train! returns nothing).  The
+    fused rollout cannot be interrupted, so all n_steps hooks of a rollout are evaluated BEFORE it is launched: the
+    step counter, the abort decision and `steps_taken(agent)` (rollout granularity, ppo.jl:173, pinned by
+    test/test_callbacks.jl:92-99) are those of the reference; the env has not advanced between the hooks of one rollout
+    (documented deviation).  Callbacks that do not override on_step cost nothing."""
+    active = [c for c in (callbacks or []) if type(c).on_step is not AbstractCallback.on_step]
+    if not active:
+        return True
+    loc = dict(agent=agent, env=env, alg=alg, n_steps=n_steps, n_envs=n_envs, callbacks=callbacks,
+               obs_space=env.observation_space(), act_space=env.action_space())
+    for i in range(1, n_steps + 1):
+        loc["i"] = i
+        if not all(c.on_step(loc) for c in active):
+            return False
+    return True
 
 
 LEARN_STATS_KEYS = ("entropy_losses", "policy_losses", "value_losses", "approx_kl_divs", "clip_fractions", "losses",
@@ -354,6 +371,8 @@ def train(agent, env, alg, max_steps, callbacks=None, sync_every_iteration=True)
     for i in range(1, iterations + 1):
         learning_rate = alg.learning_rate                   # Optimisers.adjust! each iteration (ppo.jl:155-157)
         if not _hook(callbacks, "on_rollout_start", dict(locals())):
+            return None
+        if not _on_step_hooks(callbacks, agent, env, alg, n_steps, n_envs):
             return None
         if pipelined:
             if i == 1:

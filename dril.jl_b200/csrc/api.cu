@@ -37,11 +37,14 @@ extern "C" int32_t dril_version(void) { return 100; }
 static int g_opt_tc = getenv("DRIL_TC") ? atoi(getenv("DRIL_TC")) : 1;
 static int g_opt_tc_rollout = getenv("DRIL_TC_ROLLOUT") ? atoi(getenv("DRIL_TC_ROLLOUT")) : 1;   // tensor-core rollout (CartPole, [64,64])
 static int g_opt_tail = getenv("DRIL_TAIL") ? atoi(getenv("DRIL_TAIL")) : 1;   // fused reduce/clip/Adam tail of the TC kernel
+// fp32 loss/grad kernel, wide nets: one net per pass with shared activation rows (fixed per policy at creation)
+static int g_opt_single_net = getenv("DRIL_SINGLE_NET") ? atoi(getenv("DRIL_SINGLE_NET")) : 1;
 extern "C" int32_t dril_set_option(const char* key, int32_t value) {
     DRIL_REQUIRE(key, "key is NULL");
     if (!strcmp(key, "tc")) { g_opt_tc = value; return DRIL_OK; }
     if (!strcmp(key, "fused_tail")) { g_opt_tail = value; return DRIL_OK; }
     if (!strcmp(key, "tc_rollout")) { g_opt_tc_rollout = value; return DRIL_OK; }
+    if (!strcmp(key, "single_net")) { g_opt_single_net = value; return DRIL_OK; }   // policies created afterwards
     dril_set_error("unknown option '%s'", key);
     return DRIL_ERR_INVALID;
 }
@@ -176,6 +179,7 @@ struct dril_policy {
     double *iter_acc = nullptr, *ev_acc = nullptr, *mbstats = nullptr, *adv_partial = nullptr;
     int* stop_flag = nullptr;
     int gpart_ctas = 0;
+    int plan_single = -1;      // single-net pass mode of the fp32 loss kernel, fixed when the policy is created
     int mbstats_cap = 0;
     uint64_t seed = 0;
     uint32_t step_index = 0;
@@ -561,7 +565,7 @@ extern "C" int32_t dril_buffer_upload(dril_buffer* b, int32_t field, const void*
 // policy
 // ---------------------------------------------------------------------------------------
 static inline int pad4(int x) { return (x + 3) & ~3; }
-struct LossLaunch { int M4; bool ws; size_t smem; int grid_cap; int splits; };
+struct LossLaunch { int M4; bool ws; size_t smem; int grid_cap; int splits; bool single; };
 static int32_t plan_loss(dril_policy* p, LossLaunch* out);
 
 extern "C" int32_t dril_policy_create(dril_ctx* c, int32_t obs_dim, int32_t n_hidden, const int32_t* hidden,
@@ -649,7 +653,7 @@ extern "C" int32_t dril_policy_create(dril_ctx* c, int32_t obs_dim, int32_t n_hi
     {   // gradient partial planes per parameter (must mirror the tile choice in ppo_loss_grad_kernel)
         LossLaunch ll;
         DRIL_TRY(plan_loss(p, &ll));
-        p->loss_M4 = ll.M4; p->loss_ws = ll.ws; p->loss_splits = ll.splits;
+        p->loss_M4 = ll.M4; p->loss_ws = ll.ws; p->loss_splits = ll.splits; p->plan_single = ll.single ? 1 : 0;
         std::vector<unsigned char> planes(np, 1);
         for (int net = 0; net < 2; ++net)
             for (int l = 0; l < pd.n_layers; ++l) {
@@ -1351,15 +1355,23 @@ static int32_t plan_loss(dril_policy* p, LossLaunch* out) {
     // widest tile (<= 128 samples, multiple of 16 so the 8x8 paths apply) that fits; weights in
     // shared memory when there is room for at least a 32-sample tile next to them
     int M4 = 128;
-    bool ws = true;
-    auto total = [&](int m4, bool w) { return loss_smem_layout(pd, m4, w).total; };
+    bool ws = true, single = false;
+    auto total = [&](int m4, bool w, bool sn = false) { return loss_smem_layout(pd, m4, w, sn).total; };
     while (M4 > 16 && total(M4, true) > DRIL_SMEM_MAX) M4 -= 16;
     if (total(M4, true) > DRIL_SMEM_MAX || M4 < 32) {
         ws = false; M4 = 128;
         while (M4 > 16 && total(M4, false) > DRIL_SMEM_MAX) M4 -= 16;
+        // wide nets (weights streamed from L2): when both nets' activations do not fit a 128-sample tile, process the
+        // nets in two passes with shared activation rows -> wider tile, weights read less often per sample, and
+        // thread-tile counts that divide the block evenly
+        if (M4 < 128 && (p->plan_single >= 0 ? p->plan_single : g_opt_single_net)) {
+            int Ms = 128;
+            while (Ms > 16 && total(Ms, false, true) > DRIL_SMEM_MAX) Ms -= 16;
+            if (Ms > M4 && total(Ms, false, true) <= DRIL_SMEM_MAX) { single = true; M4 = Ms; }
+        }
     }
-    if (total(M4, ws) > DRIL_SMEM_MAX) { dril_set_error("network too wide for the loss kernel's shared memory"); return DRIL_ERR_UNSUPPORTED; }
-    out->M4 = M4; out->ws = ws; out->smem = total(M4, ws);
+    if (total(M4, ws, single) > DRIL_SMEM_MAX) { dril_set_error("network too wide for the loss kernel's shared memory"); return DRIL_ERR_UNSUPPORTED; }
+    out->M4 = M4; out->ws = ws; out->single = single; out->smem = total(M4, ws, single);
     int splits = 1;
     while (splits < DRIL_GPLANES && (M4 / (splits * 2)) % 4 == 0 && M4 / (splits * 2) >= 4) splits *= 2;
     out->splits = splits;
@@ -1380,7 +1392,7 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
     memset(&a, 0, sizeof(a));
     a.pd = pd; a.buf = bd; a.pack = p->pack; a.flat = p->flat; a.mbstats = mbstats_dev; a.gpart = p->gpart;
     a.stop_flag = p->stop_flag; a.mb = mb; a.hp = hp; a.M4 = ll.M4; a.weights_smem = ll.ws;
-    a.half_stride = p->gpart_ctas; a.small_splits = ll.splits;
+    a.half_stride = p->gpart_ctas; a.small_splits = ll.splits; a.single_net = ll.single ? 1 : 0;
     const bool tc = g_opt_tc && tc_eligible(pd);
     long long tiles = (mb.count + (tc ? TC_M : ll.M4) - 1) / (tc ? TC_M : ll.M4);
     int grid = (int)std::max<long long>(1, std::min<long long>(tiles, tc ? std::min(c->sm_count, p->gpart_ctas) : ll.grid_cap));

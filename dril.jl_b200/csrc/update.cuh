@@ -74,15 +74,27 @@ struct LossSmem {
     size_t w, x, h[2][DRIL_MAX_LAYERS], dout[2], samp, dbl_bytes_off, total;
 };
 
-__host__ __device__ inline LossSmem loss_smem_layout(const PolicyDesc& pd, int M4, bool weights_smem) {
+// single_net: the nets are processed in two passes over the minibatch (actor, then critic) and share one set of
+// activation rows, so a wide network keeps a twice as wide sample tile (weights streamed from L2 are then read half
+// as often per sample).
+__host__ __device__ inline LossSmem loss_smem_layout(const PolicyDesc& pd, int M4, bool weights_smem, bool single_net = false) {
     LossSmem s;
     s.ld = M4 + 4;
     size_t o = 0;
     s.w = o; o += weights_smem ? (size_t)pd.pack_total : 0;
     s.x = o; o += (size_t)pd.obs_dim_p * s.ld;
-    for (int net = 0; net < 2; ++net)
-        for (int l = 0; l < pd.n_layers; ++l) { s.h[net][l] = o; o += (size_t)pd.L[net][l].Np * s.ld; }
-    for (int net = 0; net < 2; ++net) { s.dout[net] = o; o += (size_t)pd.L[net][pd.n_layers - 1].Np * s.ld; }
+    if (single_net) {
+        for (int l = 0; l < pd.n_layers; ++l) {
+            const int np = pd.L[0][l].Np > pd.L[1][l].Np ? pd.L[0][l].Np : pd.L[1][l].Np;
+            s.h[0][l] = s.h[1][l] = o; o += (size_t)np * s.ld;
+        }
+        const int npl = pd.L[0][pd.n_layers - 1].Np > pd.L[1][pd.n_layers - 1].Np ? pd.L[0][pd.n_layers - 1].Np : pd.L[1][pd.n_layers - 1].Np;
+        s.dout[0] = s.dout[1] = o; o += (size_t)npl * s.ld;
+    } else {
+        for (int net = 0; net < 2; ++net)
+            for (int l = 0; l < pd.n_layers; ++l) { s.h[net][l] = o; o += (size_t)pd.L[net][l].Np * s.ld; }
+        for (int net = 0; net < 2; ++net) { s.dout[net] = o; o += (size_t)pd.L[net][pd.n_layers - 1].Np * s.ld; }
+    }
     int arows = pd.act_kind == DRIL_ACT_CONTINUOUS ? 2 * pd.act_n : 1;   // actions (+ log_std grad contributions)
     s.samp = o; o += (size_t)(4 + arows) * s.ld;   // adv, ret, old_logp, old_val, actions...
     o = (o + 3) & ~(size_t)3;
@@ -102,6 +114,7 @@ struct LossArgs {
     Minibatch mb;
     UpdateHyper hp;
     int M4, weights_smem, half_stride;   // half_stride: CTAs per partial plane
+    int single_net;                      // 1: two passes (actor, critic) over the minibatch with shared activation rows
     int small_splits;                    // sample-range splits of the 4x4 dW tiles (planes 0..small_splits-1)
 };
 
@@ -266,7 +279,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
     const PolicyDesc& pd = a.pd;
     const BufDev& buf = a.buf;
     const int M4 = a.M4, D = pd.obs_dim, Dp = pd.obs_dim_p, NL = pd.n_layers;
-    const LossSmem S = loss_smem_layout(pd, M4, WS);
+    const LossSmem S = loss_smem_layout(pd, M4, WS, a.single_net != 0);
     const int ld = S.ld;
     const int tid = threadIdx.x;
     float* sX = smem + S.x;
@@ -304,9 +317,11 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
     double ls_acc = 0;                                                          // thread j < act_n: log_std gradient
     const long long n_tiles = (a.mb.count + M4 - 1) / M4;
     const bool m8 = (M4 & 7) == 0;
-    bool first = true;
     __syncthreads();
 
+    for (int pass = 0; pass < (a.single_net ? 2 : 1); ++pass) {
+    const int nmask = a.single_net ? (1 << pass) : 3;        // bit0 actor, bit1 critic: the nets this pass works on
+    bool first = true;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first = false) {
         const long long p0 = a.mb.start + tile * M4;
         const int nvalid = (int)min((long long)M4, a.mb.start + a.mb.count - p0);
@@ -333,7 +348,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
         for (int l = 0; l < NL; ++l) {
             const float* ia = l == 0 ? sX : smem + S.h[0][l - 1];
             const float* ic = l == 0 ? sX : smem + S.h[1][l - 1];
-            dense_layer_auto(pd, Wbase, l, ia, ic, smem + S.h[0][l], smem + S.h[1][l], M4, ld, 3);
+            dense_layer_auto(pd, Wbase, l, ia, ic, smem + S.h[0][l], smem + S.h[1][l], M4, ld, nmask);
             __syncthreads();
         }
         // ---- loss head: dL/dlogits (or dL/dmean), dL/dvalue ---------------------------------
@@ -343,13 +358,15 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
             const bool valid = tid < nvalid;
             const float* z = smem + S.h[0][NL - 1] + tid;
             const float adv = sAdv[tid];
-            float logp, ent;
+            float logp = 0.f, ent = 0.f;
             const int A = pd.act_n;
             const int Ap = pd.L[0][NL - 1].Np;
             float g_logp = 0.f;
             const float g_ent = valid ? -a.hp.ent_coef * invB : 0.f;
             float ratio = 1.f, s1 = 0.f, s2 = 0.f, log_ratio = 0.f, rc = 1.f;
-            if (pd.act_kind == DRIL_ACT_DISCRETE) {
+            if (!(nmask & 1)) {
+                // critic-only pass
+            } else if (pd.act_kind == DRIL_ACT_DISCRETE) {
                 int aidx = reinterpret_cast<const int*>(sActn)[tid] - pd.act_start;
                 aidx = aidx < 0 ? 0 : (aidx >= A ? A - 1 : aidx);
                 float m = z[0];
@@ -401,21 +418,23 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
                 }
             }
             // critic
-            const float v_raw = smem[S.h[1][NL - 1] + tid];
-            float v = v_raw;
-            bool v_pass = true;
-            if (a.hp.clip_range_vf >= 0.f) {
-                float dlt = v_raw - sOldV[tid];
-                v_pass = dlt >= -a.hp.clip_range_vf && dlt <= a.hp.clip_range_vf;
-                v = sOldV[tid] + fminf(fmaxf(dlt, -a.hp.clip_range_vf), a.hp.clip_range_vf);
+            if (nmask & 2) {
+                const float v_raw = smem[S.h[1][NL - 1] + tid];
+                float v = v_raw;
+                bool v_pass = true;
+                if (a.hp.clip_range_vf >= 0.f) {
+                    float dlt = v_raw - sOldV[tid];
+                    v_pass = dlt >= -a.hp.clip_range_vf && dlt <= a.hp.clip_range_vf;
+                    v = sOldV[tid] + fminf(fmaxf(dlt, -a.hp.clip_range_vf), a.hp.clip_range_vf);
+                }
+                const float verr = v - sRet[tid];
+                const float g_val = (valid && v_pass) ? a.hp.vf_coef * 2.0f * verr * invB : 0.f;
+                const int Cp = pd.L[1][NL - 1].Np;
+                for (int j = 0; j < Cp; ++j) gC[(size_t)j * ld + tid] = j == 0 ? g_val : 0.f;
+                if (valid) st_v += (double)(verr * verr);
             }
-            const float verr = v - sRet[tid];
-            const float g_val = (valid && v_pass) ? a.hp.vf_coef * 2.0f * verr * invB : 0.f;
-            const int Cp = pd.L[1][NL - 1].Np;
-            for (int j = 0; j < Cp; ++j) gC[(size_t)j * ld + tid] = j == 0 ? g_val : 0.f;
-            if (valid) {
+            if (valid && (nmask & 1)) {
                 st_p += (double)(-fminf(s1, s2));
-                st_v += (double)(verr * verr);
                 st_e += (double)ent;
                 st_clip += (ratio != rc) ? 1.0 : 0.0;
                 st_kl += (double)(expf(log_ratio) - 1.0f - log_ratio);
@@ -423,7 +442,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
             }
         }
         __syncthreads();
-        if (pd.act_kind == DRIL_ACT_CONTINUOUS && tid < pd.act_n) {
+        if ((nmask & 1) && pd.act_kind == DRIL_ACT_CONTINUOUS && tid < pd.act_n) {
             double s = 0;
             for (int e = 0; e < nvalid; ++e) s += (double)sActn[(size_t)(pd.act_n + tid) * ld + e];
             ls_acc += s;
@@ -439,9 +458,10 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
                 const bool a8 = m8 && (M4 & 15) == 0 && (La.Kp & 7) == 0 && (La.Np & 7) == 0;
                 const bool c8 = m8 && (M4 & 15) == 0 && (Lc.Kp & 7) == 0 && (Lc.Np & 7) == 0;
                 const int nsplit = a.small_splits;
-                const int ca = a8 ? (La.Kp >> 3) * (La.Np >> 3) * 2 : (La.Kp >> 2) * (La.Np >> 2) * nsplit;
-                const int cc = c8 ? (Lc.Kp >> 3) * (Lc.Np >> 3) * 2 : (Lc.Kp >> 2) * (Lc.Np >> 2) * nsplit;
-                const int cb = La.N + Lc.N;
+                const int ca = !(nmask & 1) ? 0 : (a8 ? (La.Kp >> 3) * (La.Np >> 3) * 2 : (La.Kp >> 2) * (La.Np >> 2) * nsplit);
+                const int cc = !(nmask & 2) ? 0 : (c8 ? (Lc.Kp >> 3) * (Lc.Np >> 3) * 2 : (Lc.Kp >> 2) * (Lc.Np >> 2) * nsplit);
+                const int nba = (nmask & 1) ? La.N : 0;
+                const int cb = nba + ((nmask & 2) ? Lc.N : 0);
                 for (int t = tid; t < ca + cc + cb; t += blockDim.x) {
                     if (t < ca + cc) {
                         const bool crit = t >= ca;
@@ -470,8 +490,8 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
                         }
                     } else {
                         int u = t - ca - cc;
-                        const bool crit = u >= La.N;
-                        if (crit) u -= La.N;
+                        const bool crit = u >= nba;
+                        if (crit) u -= nba;
                         const LayerDesc& Ld = crit ? Lc : La;
                         const float* dZ = (crit ? dZc : dZa) + (size_t)u * ld;
                         float s = 0.f;
@@ -490,8 +510,8 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
                 const bool a8 = m8 && (La.Kp & 7) == 0 && La.N >= 8;
                 const bool c8 = m8 && (Lc.Kp & 7) == 0 && Lc.N >= 8;
                 const int mt4 = M4 >> 2, mt8 = M4 >> 3;
-                const int ca = a8 ? (La.Kp >> 3) * mt8 : (La.Kp >> 2) * mt4;
-                const int cc = c8 ? (Lc.Kp >> 3) * mt8 : (Lc.Kp >> 2) * mt4;
+                const int ca = !(nmask & 1) ? 0 : (a8 ? (La.Kp >> 3) * mt8 : (La.Kp >> 2) * mt4);
+                const int cc = !(nmask & 2) ? 0 : (c8 ? (Lc.Kp >> 3) * mt8 : (Lc.Kp >> 2) * mt4);
                 for (int t = tid; t < ca + cc; t += blockDim.x) {
                     const bool crit = t >= ca;
                     const int u = crit ? t - ca : t;
@@ -509,6 +529,8 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
                 __syncthreads();
             }
         }
+    }
+    __syncthreads();       // the next pass re-stages the sample rows the last backward phase may still read
     }
     // ---- per-CTA tail: log_std gradient + statistic sums --------------------------------------
     if (pd.act_kind == DRIL_ACT_CONTINUOUS && tid < pd.act_n) gp[pd.pack_fwd + tid] = (float)ls_acc;

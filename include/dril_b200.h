@@ -125,7 +125,9 @@ int32_t dril_device_count(int32_t* count);
  * test_gpu_parity.py::test_kernel_paths_vs_oracle).  Unknown keys are an error.
  *   "tc"          tensor-core (tcgen05, 3xTF32) loss/grad kernel for hidden_dims = [64, 64], obs_dim <= 4, Discrete(<= 2)
  *   "fused_tail"  partial reduction + (peer-memory allreduce) + clip + KL stop + Adam inside that kernel (cooperative launch)
- *   "tc_rollout"  tensor-core rollout for CartPole with such a policy (actor-only step loop + batched critic pass) */
+ *   "tc_rollout"  tensor-core rollout for CartPole with such a policy (actor-only step loop + batched critic pass)
+ *   "single_net"  fp32 loss/grad kernel, networks too wide for a 128-sample tile of both nets: one net per pass over the
+ *                 minibatch with shared activation rows (applies to policies created afterwards) */
 int32_t dril_set_option(const char* key, int32_t value);
 
 /* ---- context ---------------------------------------------------------------------------- */

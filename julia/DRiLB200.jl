@@ -224,8 +224,23 @@ function DeviceRolloutBuffer(ctx::Context, env::CudaBatchedEnv, n_steps::Integer
 end
 Base.length(b::DeviceRolloutBuffer) = b.n_steps * b.n_envs
 
+"""
+on_step of collect_trajectories (src/buffers/trajectory.jl:34-39): one call per env step i = 1..n_steps; the first
+`false` aborts.  The fused rollout cannot be interrupted, so the n_steps hooks of a rollout run before it is launched
+(same step counter, abort decision and `steps_taken`, which moves once per rollout: test/test_callbacks.jl:92-99).
+"""
+function on_step_hooks(callbacks, agent, env, alg, n_steps)
+    isnothing(callbacks) && return true
+    n_envs = env.n_envs
+    for i in 1:n_steps
+        all(c -> DRiL.on_step(c, Base.@locals), callbacks) || return false
+    end
+    return true
+end
+
 "collect_rollout!(buffer, agent, alg, env) -> (fps, success)  (src/buffers/rollout_buffer.jl:46-90)"
 function DRiL.collect_rollout!(buf::DeviceRolloutBuffer, agent::Agent, alg::PPO, env::CudaBatchedEnv; callbacks = nothing)
+    on_step_hooks(callbacks, agent, env, alg, buf.n_steps) || return 0.0f0, false
     p = device_policy(agent, env.ctx)
     push_params!(p, agent)
     fps = Ref{Float32}(0)
@@ -262,6 +277,7 @@ function DRiL.train!(agent::Agent, env::CudaBatchedEnv, alg::PPO{T}, max_steps::
     for i in 1:iterations
         learning_rate = alg.learning_rate
         hook(DRiL.on_rollout_start, Base.@locals) || return nothing
+        on_step_hooks(callbacks, agent, env, alg, n_steps) || return nothing
         hyper = Ref(PPOHyper(alg))
         check(ccall((:dril_ppo_iteration_async, LIB), Int32,
             (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{PPOHyper}, Int32, Int64, UInt64, UInt64),

@@ -127,3 +127,42 @@ def test_iteration_explained_variance_matches_buffer(D):
     ev = 1.0 - np.var(v - r, ddof=1) / np.var(r, ddof=1)
     assert abs(out[0]["explained_variances"][0] - ev) < 1e-5
     assert abs(buf.explained_variance() - ev) < 1e-5
+
+
+def test_callbacks_early_stopping(D):
+    """test/test_callbacks.jl:56-100: a hook returning false stops training; steps_taken is 0 after an on_training_start /
+    on_rollout_start stop and exactly one rollout (512) when on_step stops at a threshold of 500."""
+    def setup():
+        env = D.CudaBatchedEnv("cartpole", 8, seed=0, monitor_window=100, normalize=D.NormalizeConfig(gamma=0.99))
+        layer = D.ActorCriticLayer(env.observation_space(), env.action_space())
+        alg = D.PPO(ent_coef=0.1, n_steps=64, batch_size=64, epochs=10)
+        return D.Agent(layer, alg, rng=np.random.default_rng(0)), env, alg
+
+    class StopAtStart(D.AbstractCallback):
+        def on_training_start(self, loc): return False
+
+    class StopAtRollout(D.AbstractCallback):
+        def on_rollout_start(self, loc): return False
+
+    class StopOnStep(D.AbstractCallback):
+        def __init__(self, threshold): self.threshold, self.calls, self.last_i = threshold, 0, 0
+
+        def on_step(self, loc):
+            self.calls += 1
+            self.last_i = loc["i"]
+            return D.steps_taken(loc["agent"]) < self.threshold
+
+    for cb in (StopAtStart(), StopAtRollout()):
+        agent, env, alg = setup()
+        assert D.train(agent, env, alg, 3000, callbacks=[cb]) is None
+        assert D.steps_taken(agent) == 0
+    agent, env, alg = setup()
+    cb = StopOnStep(500)
+    assert D.train(agent, env, alg, 3000, callbacks=[cb]) is None
+    assert D.steps_taken(agent) == 512
+    assert cb.calls == 64 + 1 and cb.last_i == 1          # 64 hooks of rollout 1, the first hook of rollout 2 stops
+    # collect_rollout!(...; callbacks) reports the failure like rollout_buffer.jl:53-57
+    buf = D.RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, 64, 8)
+    fps, ok = D.collect_rollout(buf, agent, alg, env, callbacks=[cb])
+    assert not ok
+    buf.close()
