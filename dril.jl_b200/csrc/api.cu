@@ -39,12 +39,15 @@ static int g_opt_tc_rollout = getenv("DRIL_TC_ROLLOUT") ? atoi(getenv("DRIL_TC_R
 static int g_opt_tail = getenv("DRIL_TAIL") ? atoi(getenv("DRIL_TAIL")) : 1;   // fused reduce/clip/Adam tail of the TC kernel
 // fp32 loss/grad kernel, wide nets: one net per pass with shared activation rows (fixed per policy at creation)
 static int g_opt_single_net = getenv("DRIL_SINGLE_NET") ? atoi(getenv("DRIL_SINGLE_NET")) : 1;
+// fp32 loss/grad kernel: layers with padded dims multiple of 16 on mma.sync 3xTF32 tiles (fixed per policy at creation)
+static int g_opt_mma = getenv("DRIL_MMA") ? atoi(getenv("DRIL_MMA")) : 1;
 extern "C" int32_t dril_set_option(const char* key, int32_t value) {
     DRIL_REQUIRE(key, "key is NULL");
     if (!strcmp(key, "tc")) { g_opt_tc = value; return DRIL_OK; }
     if (!strcmp(key, "fused_tail")) { g_opt_tail = value; return DRIL_OK; }
     if (!strcmp(key, "tc_rollout")) { g_opt_tc_rollout = value; return DRIL_OK; }
     if (!strcmp(key, "single_net")) { g_opt_single_net = value; return DRIL_OK; }   // policies created afterwards
+    if (!strcmp(key, "mma")) { g_opt_mma = value; return DRIL_OK; }                 // policies created afterwards
     dril_set_error("unknown option '%s'", key);
     return DRIL_ERR_INVALID;
 }
@@ -180,6 +183,7 @@ struct dril_policy {
     int* stop_flag = nullptr;
     int gpart_ctas = 0;
     int plan_single = -1;      // single-net pass mode of the fp32 loss kernel, fixed when the policy is created
+    int plan_mma = -1;         // mma.sync tiles for the wide layers of the fp32 loss kernel, fixed when the policy is created
     int mbstats_cap = 0;
     uint64_t seed = 0;
     uint32_t step_index = 0;
@@ -565,7 +569,7 @@ extern "C" int32_t dril_buffer_upload(dril_buffer* b, int32_t field, const void*
 // policy
 // ---------------------------------------------------------------------------------------
 static inline int pad4(int x) { return (x + 3) & ~3; }
-struct LossLaunch { int M4; bool ws; size_t smem; int grid_cap; int splits; bool single; };
+struct LossLaunch { int M4; bool ws; size_t smem; int grid_cap; int splits; bool single; bool mma; };
 static int32_t plan_loss(dril_policy* p, LossLaunch* out);
 
 extern "C" int32_t dril_policy_create(dril_ctx* c, int32_t obs_dim, int32_t n_hidden, const int32_t* hidden,
@@ -654,12 +658,14 @@ extern "C" int32_t dril_policy_create(dril_ctx* c, int32_t obs_dim, int32_t n_hi
         LossLaunch ll;
         DRIL_TRY(plan_loss(p, &ll));
         p->loss_M4 = ll.M4; p->loss_ws = ll.ws; p->loss_splits = ll.splits; p->plan_single = ll.single ? 1 : 0;
+        p->plan_mma = ll.mma ? 1 : 0;
         std::vector<unsigned char> planes(np, 1);
         for (int net = 0; net < 2; ++net)
             for (int l = 0; l < pd.n_layers; ++l) {
                 const LayerDesc& L = pd.L[net][l];
                 const bool t8 = (ll.M4 % 16) == 0 && (L.Kp % 8) == 0 && (L.Np % 8) == 0;
-                for (int i = 0; i < L.K * L.N; ++i) planes[L.w_off + i] = (unsigned char)(t8 ? 2 : ll.splits);
+                const bool mma = ll.mma && (L.Kp % 16) == 0 && (L.Np % 16) == 0 && L.Kp >= 16 && L.Np >= 16;   // mma_layer_ok
+                for (int i = 0; i < L.K * L.N; ++i) planes[L.w_off + i] = (unsigned char)(mma ? 1 : (t8 ? 2 : ll.splits));
             }
         DRIL_TRY(dmalloc(&p->f2planes, np));
         DRIL_CUDA(cudaMemcpy(p->f2planes, planes.data(), np, cudaMemcpyHostToDevice));
@@ -1372,6 +1378,7 @@ static int32_t plan_loss(dril_policy* p, LossLaunch* out) {
     }
     if (total(M4, ws, single) > DRIL_SMEM_MAX) { dril_set_error("network too wide for the loss kernel's shared memory"); return DRIL_ERR_UNSUPPORTED; }
     out->M4 = M4; out->ws = ws; out->single = single; out->smem = total(M4, ws, single);
+    out->mma = M4 == MMA_TILE_M && (p->plan_mma >= 0 ? p->plan_mma : g_opt_mma) != 0;
     int splits = 1;
     while (splits < DRIL_GPLANES && (M4 / (splits * 2)) % 4 == 0 && M4 / (splits * 2) >= 4) splits *= 2;
     out->splits = splits;
@@ -1393,6 +1400,7 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
     a.pd = pd; a.buf = bd; a.pack = p->pack; a.flat = p->flat; a.mbstats = mbstats_dev; a.gpart = p->gpart;
     a.stop_flag = p->stop_flag; a.mb = mb; a.hp = hp; a.M4 = ll.M4; a.weights_smem = ll.ws;
     a.half_stride = p->gpart_ctas; a.small_splits = ll.splits; a.single_net = ll.single ? 1 : 0;
+    a.use_mma = ll.mma ? 1 : 0;
     const bool tc = g_opt_tc && tc_eligible(pd);
     long long tiles = (mb.count + (tc ? TC_M : ll.M4) - 1) / (tc ? TC_M : ll.M4);
     int grid = (int)std::max<long long>(1, std::min<long long>(tiles, tc ? std::min(c->sm_count, p->gpart_ctas) : ll.grid_cap));

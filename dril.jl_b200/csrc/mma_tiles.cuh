@@ -1,0 +1,169 @@
+// Warp-level tensor-core tiles (mma.sync.m16n8k8 TF32, 3xTF32 split) for the wide layers of the general-shape
+// loss/grad kernel (update.cuh): hidden layers whose padded dims are multiples of 16 on a 128-sample tile.
+//
+// The tcgen05 kernel (update_tc.cuh) covers the reference's default [64,64] discrete policy; every other shape ran on
+// fp32 FMA tiles at ~31 % of the FMA pipe (40 MAC/clk/SM).  The legacy warp-level tensor path issues 512 TF32 MAC/clk/SM
+// on sm_100a (tools/mma_probe.cu), i.e. 170 MAC/clk/SM after the 3-way split that keeps fp32-level accuracy
+// (hi = x with 13 mantissa bits cleared, lo = x - hi; hi*hi + lo*hi + hi*lo, fp32 accumulation; relative error ~2^-21).
+//
+// Operand layouts are the ones the FMA tiles use, so the two kinds mix freely inside a layer loop:
+//   activations feature-major in shared memory  act[f * ld + m]   (m = sample 0..127, ld = 132)
+//   weights in the packed global layout          W[k * Np + n], Wt[n * Kp + k]   (read once per tile and CTA, L2)
+// Fragment coordinates (g = lane >> 2, t = lane & 3), PTX ISA m16n8k8 .tf32:
+//   A (16x8, row): a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)
+//   B (8x8,  col): b0 (k = t, n = g)       b1 (k = t+4, n = g)
+//   C (16x8):      c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+#pragma once
+#include "common.cuh"
+
+#define MMA_TILE_M 128    // samples per tile the MMA paths are written for
+
+__device__ __forceinline__ bool mma_layer_ok(int Kp, int Np) { return (Kp & 15) == 0 && (Np & 15) == 0 && Kp >= 16 && Np >= 16; }
+
+__device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_red_add_v2(float* addr, float x, float y) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(x), "f"(y) : "memory");
+}
+
+// out[r][m] = sum_c Wm[c * ldw + r] * In[c * ld + m]   for rows r in [r0, r0+16), samples m in [8*mb0, 8*(mb0+MB)),
+// contraction over c in [0, C) (C multiple of 8).  Wm global (or shared) with row stride ldw; In shared.
+//   EPI 0 (forward):   Out[r][m] = f(acc + bias[r])           f = tanh if apply_tanh
+//   EPI 1 (dH):        Out[r][m] = acc * (1 - Out[r][m]^2)     in place over the activation H
+template <int MB, int EPI>
+__device__ __forceinline__ void mma_rows_unit(const float* __restrict__ Wm, int ldw, int C, const float* __restrict__ In,
+                                              float* __restrict__ Out, int ld, int r0, int mb0, const float* __restrict__ bias,
+                                              bool apply_tanh) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float acc[MB][4];
+#pragma unroll
+    for (int i = 0; i < MB; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    // A fragment rows = output features r (from the weights), columns = contraction index
+    const float* wp = Wm + (size_t)t * ldw + r0 + g;
+    const float* ip = In + (size_t)t * ld + mb0 * 8 + g;
+    float w0 = wp[0], w1 = wp[8], w2 = wp[(size_t)4 * ldw], w3 = wp[(size_t)4 * ldw + 8];
+    for (int c0 = 0; c0 < C; c0 += 8) {
+        uint32_t ahi[4], alo[4];
+        mma_split(w0, ahi[0], alo[0]); mma_split(w1, ahi[1], alo[1]); mma_split(w2, ahi[2], alo[2]); mma_split(w3, ahi[3], alo[3]);
+        if (c0 + 8 < C) {          // prefetch the next weight fragment (L2 latency) under this step's MMAs
+            const float* wn = wp + (size_t)(c0 + 8) * ldw;
+            w0 = wn[0]; w1 = wn[8]; w2 = wn[(size_t)4 * ldw]; w3 = wn[(size_t)4 * ldw + 8];
+        }
+        const float* ic = ip + (size_t)c0 * ld;
+#pragma unroll
+        for (int i = 0; i < MB; ++i) {
+            uint32_t bh0, bl0, bh1, bl1;
+            mma_split(ic[i * 8], bh0, bl0);
+            mma_split(ic[(size_t)4 * ld + i * 8], bh1, bl1);
+            mma_tf32(acc[i], alo, bh0, bh1);
+            mma_tf32(acc[i], ahi, bl0, bl1);
+            mma_tf32(acc[i], ahi, bh0, bh1);
+        }
+    }
+    const int ra = r0 + g, rb = r0 + g + 8;
+    float ba = 0.f, bb = 0.f;
+    if (EPI == 0) { ba = bias[ra]; bb = bias[rb]; }
+#pragma unroll
+    for (int i = 0; i < MB; ++i) {
+        const int m = (mb0 + i) * 8 + 2 * t;
+        float2* pa = reinterpret_cast<float2*>(Out + (size_t)ra * ld + m);
+        float2* pb = reinterpret_cast<float2*>(Out + (size_t)rb * ld + m);
+        float2 va, vb;
+        if (EPI == 0) {
+            va = make_float2(acc[i][0] + ba, acc[i][1] + ba);
+            vb = make_float2(acc[i][2] + bb, acc[i][3] + bb);
+            if (apply_tanh) { va.x = fast_tanh(va.x); va.y = fast_tanh(va.y); vb.x = fast_tanh(vb.x); vb.y = fast_tanh(vb.y); }
+        } else {
+            const float2 ha = *pa, hb = *pb;
+            va = make_float2(acc[i][0] * (1.0f - ha.x * ha.x), acc[i][1] * (1.0f - ha.y * ha.y));
+            vb = make_float2(acc[i][2] * (1.0f - hb.x * hb.x), acc[i][3] * (1.0f - hb.y * hb.y));
+        }
+        *pa = va; *pb = vb;
+    }
+}
+
+// All (row block, sample chunk) units of one GEMM of this shape over the CTA's warps (blockDim.x / 32 warps).
+// R = number of output rows (multiple of 16).  Caller synchronises afterwards.
+template <int EPI>
+__device__ __forceinline__ void mma_rows_layer(const float* __restrict__ Wm, int ldw, int R, int C, const float* __restrict__ In,
+                                               float* __restrict__ Out, int ld, const float* __restrict__ bias, bool apply_tanh) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int rblocks = R >> 4;
+    // widest sample chunk (most reuse of the weight fragment) that still gives every warp a unit
+    if (rblocks % nwarps == 0) {
+        for (int u = warp; u < rblocks; u += nwarps) mma_rows_unit<16, EPI>(Wm, ldw, C, In, Out, ld, u << 4, 0, bias, apply_tanh);
+    } else if ((rblocks * 2) % nwarps == 0) {
+        for (int u = warp; u < rblocks * 2; u += nwarps) mma_rows_unit<8, EPI>(Wm, ldw, C, In, Out, ld, (u >> 1) << 4, (u & 1) * 8, bias, apply_tanh);
+    } else {
+        for (int u = warp; u < rblocks * 4; u += nwarps) mma_rows_unit<4, EPI>(Wm, ldw, C, In, Out, ld, (u >> 2) << 4, (u & 3) * 4, bias, apply_tanh);
+    }
+}
+
+// dW[k][n] (+)= sum_m Ain[k * ld + m] * dZ[n * ld + m] over the 128 samples of the tile, rows k in [k0, k0+16),
+// columns n in [8*nb0, 8*(nb0+NB)); written (first tile of the pass) or red-added into this CTA's packed partial.
+template <int NB>
+__device__ __forceinline__ void mma_dw_unit(const float* __restrict__ Ain, const float* __restrict__ dZ, int ld, int k0, int nb0,
+                                            float* __restrict__ gW, int Np, bool first) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float acc[NB][4];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    const float* ap = Ain + (size_t)(k0 + g) * ld + t;          // A (row k, col m): conflict-free (bank 4g + t)
+    const float* zp = dZ + (size_t)(nb0 * 8 + g) * ld + t;      // B (m, col n)
+#pragma unroll 2
+    for (int m0 = 0; m0 < MMA_TILE_M; m0 += 8) {
+        uint32_t ahi[4], alo[4];
+        mma_split(ap[m0], ahi[0], alo[0]);
+        mma_split(ap[(size_t)8 * ld + m0], ahi[1], alo[1]);
+        mma_split(ap[m0 + 4], ahi[2], alo[2]);
+        mma_split(ap[(size_t)8 * ld + m0 + 4], ahi[3], alo[3]);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            uint32_t bh0, bl0, bh1, bl1;
+            mma_split(zp[(size_t)i * 8 * ld + m0], bh0, bl0);
+            mma_split(zp[(size_t)i * 8 * ld + m0 + 4], bh1, bl1);
+            mma_tf32(acc[i], alo, bh0, bh1);
+            mma_tf32(acc[i], ahi, bl0, bl1);
+            mma_tf32(acc[i], ahi, bh0, bh1);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        const int n = (nb0 + i) * 8 + 2 * t;
+        float* pa = gW + (size_t)(k0 + g) * Np + n;
+        float* pb = gW + (size_t)(k0 + g + 8) * Np + n;
+        if (first) {
+            *reinterpret_cast<float2*>(pa) = make_float2(acc[i][0], acc[i][1]);
+            *reinterpret_cast<float2*>(pb) = make_float2(acc[i][2], acc[i][3]);
+        } else {
+            mma_red_add_v2(pa, acc[i][0], acc[i][1]);
+            mma_red_add_v2(pb, acc[i][2], acc[i][3]);
+        }
+    }
+}
+
+// dW of one layer (Kp x Np) over the CTA's warps.  Caller synchronises afterwards.
+__device__ __forceinline__ void mma_dw_layer(const float* __restrict__ Ain, const float* __restrict__ dZ, int ld, int Kp, int Np,
+                                             float* __restrict__ gW, bool first) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int kblocks = Kp >> 4, nblocks = Np >> 3;
+    if ((nblocks & 15) == 0 && (kblocks * (nblocks >> 4)) % nwarps == 0) {
+        const int per = nblocks >> 4;
+        for (int u = warp; u < kblocks * per; u += nwarps) mma_dw_unit<16>(Ain, dZ, ld, (u / per) << 4, (u % per) * 16, gW, Np, first);
+    } else if ((nblocks & 7) == 0 && (kblocks * (nblocks >> 3)) % nwarps == 0) {
+        const int per = nblocks >> 3;
+        for (int u = warp; u < kblocks * per; u += nwarps) mma_dw_unit<8>(Ain, dZ, ld, (u / per) << 4, (u % per) * 8, gW, Np, first);
+    } else if ((nblocks & 3) == 0 && (kblocks * (nblocks >> 2)) % nwarps == 0) {
+        const int per = nblocks >> 2;
+        for (int u = warp; u < kblocks * per; u += nwarps) mma_dw_unit<4>(Ain, dZ, ld, (u / per) << 4, (u % per) * 4, gW, Np, first);
+    } else {
+        const int per = nblocks >> 1;
+        for (int u = warp; u < kblocks * per; u += nwarps) mma_dw_unit<2>(Ain, dZ, ld, (u / per) << 4, (u % per) * 2, gW, Np, first);
+    }
+}

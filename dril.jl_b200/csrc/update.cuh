@@ -9,6 +9,7 @@
 // evaluated on the fly (no permutation array, no gather pass).
 #pragma once
 #include "mlp.cuh"
+#include "mma_tiles.cuh"
 
 struct UpdateHyper {
     float clip_range, clip_range_vf, ent_coef, vf_coef, max_grad_norm, target_kl;
@@ -115,6 +116,7 @@ struct LossArgs {
     UpdateHyper hp;
     int M4, weights_smem, half_stride;   // half_stride: CTAs per partial plane
     int single_net;                      // 1: two passes (actor, critic) over the minibatch with shared activation rows
+    int use_mma;                         // 1: layers with Kp, Np multiples of 16 run on mma.sync 3xTF32 tiles (needs M4 == 128)
     int small_splits;                    // sample-range splits of the 4x4 dW tiles (planes 0..small_splits-1)
 };
 
@@ -348,7 +350,16 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
         for (int l = 0; l < NL; ++l) {
             const float* ia = l == 0 ? sX : smem + S.h[0][l - 1];
             const float* ic = l == 0 ? sX : smem + S.h[1][l - 1];
-            dense_layer_auto(pd, Wbase, l, ia, ic, smem + S.h[0][l], smem + S.h[1][l], M4, ld, nmask);
+            int fmask = nmask;             // nets of this layer left to the FMA tiles
+            for (int net = 0; net < 2; ++net) {
+                const LayerDesc& Ld = pd.L[net][l];
+                if ((nmask >> net & 1) && a.use_mma && mma_layer_ok(Ld.Kp, Ld.Np)) {
+                    mma_rows_layer<0>(Wbase + Ld.pw_off, Ld.Np, Ld.Np, Ld.Kp, net ? ic : ia, smem + S.h[net][l], ld, Wbase + Ld.pb_off,
+                                      l < NL - 1);
+                    fmask &= ~(1 << net);
+                }
+            }
+            if (fmask) dense_layer_auto(pd, Wbase, l, ia, ic, smem + S.h[0][l], smem + S.h[1][l], M4, ld, fmask);
             __syncthreads();
         }
         // ---- loss head: dL/dlogits (or dL/dmean), dL/dvalue ---------------------------------
@@ -458,8 +469,11 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
                 const bool a8 = m8 && (M4 & 15) == 0 && (La.Kp & 7) == 0 && (La.Np & 7) == 0;
                 const bool c8 = m8 && (M4 & 15) == 0 && (Lc.Kp & 7) == 0 && (Lc.Np & 7) == 0;
                 const int nsplit = a.small_splits;
-                const int ca = !(nmask & 1) ? 0 : (a8 ? (La.Kp >> 3) * (La.Np >> 3) * 2 : (La.Kp >> 2) * (La.Np >> 2) * nsplit);
-                const int cc = !(nmask & 2) ? 0 : (c8 ? (Lc.Kp >> 3) * (Lc.Np >> 3) * 2 : (Lc.Kp >> 2) * (Lc.Np >> 2) * nsplit);
+                const bool amma = a.use_mma && mma_layer_ok(La.Kp, La.Np), cmma = a.use_mma && mma_layer_ok(Lc.Kp, Lc.Np);
+                if ((nmask & 1) && amma) mma_dw_layer(l == 0 ? sX : smem + S.h[0][l - 1], dZa, ld, La.Kp, La.Np, gp + La.pw_off, first);
+                if ((nmask & 2) && cmma) mma_dw_layer(l == 0 ? sX : smem + S.h[1][l - 1], dZc, ld, Lc.Kp, Lc.Np, gp + Lc.pw_off, first);
+                const int ca = (!(nmask & 1) || amma) ? 0 : (a8 ? (La.Kp >> 3) * (La.Np >> 3) * 2 : (La.Kp >> 2) * (La.Np >> 2) * nsplit);
+                const int cc = (!(nmask & 2) || cmma) ? 0 : (c8 ? (Lc.Kp >> 3) * (Lc.Np >> 3) * 2 : (Lc.Kp >> 2) * (Lc.Np >> 2) * nsplit);
                 const int nba = (nmask & 1) ? La.N : 0;
                 const int cb = nba + ((nmask & 2) ? Lc.N : 0);
                 for (int t = tid; t < ca + cc + cb; t += blockDim.x) {
@@ -510,8 +524,11 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
                 const bool a8 = m8 && (La.Kp & 7) == 0 && La.N >= 8;
                 const bool c8 = m8 && (Lc.Kp & 7) == 0 && Lc.N >= 8;
                 const int mt4 = M4 >> 2, mt8 = M4 >> 3;
-                const int ca = !(nmask & 1) ? 0 : (a8 ? (La.Kp >> 3) * mt8 : (La.Kp >> 2) * mt4);
-                const int cc = !(nmask & 2) ? 0 : (c8 ? (Lc.Kp >> 3) * mt8 : (Lc.Kp >> 2) * mt4);
+                const bool amma = a.use_mma && mma_layer_ok(La.Kp, La.Np), cmma = a.use_mma && mma_layer_ok(Lc.Kp, Lc.Np);
+                if ((nmask & 1) && amma) mma_rows_layer<1>(Wbase + La.pwt_off, La.Kp, La.Kp, La.Np, dZa, smem + S.h[0][l - 1], ld, nullptr, false);
+                if ((nmask & 2) && cmma) mma_rows_layer<1>(Wbase + Lc.pwt_off, Lc.Kp, Lc.Kp, Lc.Np, dZc, smem + S.h[1][l - 1], ld, nullptr, false);
+                const int ca = (!(nmask & 1) || amma) ? 0 : (a8 ? (La.Kp >> 3) * mt8 : (La.Kp >> 2) * mt4);
+                const int cc = (!(nmask & 2) || cmma) ? 0 : (c8 ? (Lc.Kp >> 3) * mt8 : (Lc.Kp >> 2) * mt4);
                 for (int t = tid; t < ca + cc; t += blockDim.x) {
                     const bool crit = t >= ca;
                     const int u = crit ? t - ca : t;

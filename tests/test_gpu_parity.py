@@ -607,27 +607,38 @@ def test_fused_rollout_edge_shapes(D, n, T, ms):
         buf.close()
 
 
-@pytest.mark.parametrize("single", [1, 0])
-@pytest.mark.parametrize("name", ["pendulum", "wide_discrete"])
-def test_wide_net_single_net_passes(D, name, single):
-    """Networks too wide for a 128-sample tile of both nets: the fp32 loss/grad kernel processes one net per pass with
-    shared activation rows (option "single_net", fixed per policy at creation); both modes meet north_star (c)."""
-    spec = SPECS["pendulum"]() if name == "pendulum" else OP.PolicySpec(10, [128, 96], "discrete", 5, act_start=0)
+WIDE = {
+    "pendulum": lambda: SPECS["pendulum"](),
+    "wide_discrete": lambda: OP.PolicySpec(10, [128, 96], "discrete", 5, act_start=0),
+    "mid_box": lambda: OP.PolicySpec(6, [64, 32, 16], "continuous", 2, act_low=[-1, -1], act_high=[1, 1]),
+    "cartpole_fp32": lambda: SPECS["cartpole"](),
+}
+
+
+@pytest.mark.parametrize("single,mma", [(1, 1), (1, 0), (0, 1), (0, 0)])
+@pytest.mark.parametrize("name", list(WIDE))
+def test_wide_net_single_net_passes(D, name, single, mma):
+    """General-shape loss/grad kernel: (a) networks too wide for a 128-sample tile of both nets are processed one net per
+    pass with shared activation rows (option "single_net"); (b) layers whose padded dims are multiples of 16 run on
+    mma.sync 3xTF32 tiles (option "mma").  Both are fixed per policy at creation; every combination meets north_star (c)."""
+    spec = WIDE[name]()
     rng = np.random.default_rng(11)
     flat = (OP.init_params(spec, seed=4) + rng.normal(size=spec.n_params()).astype(f32) * 0.05).astype(f32)
-    D.set_option("single_net", single)
+    D.set_option("single_net", single); D.set_option("mma", mma); D.set_option("tc", 0)
     try:
         p = _device_policy(D, spec, flat)
+        assert p.update_path() != "tensor"
+        for B in (77, 128, 1000):
+            mb = _minibatch(spec, flat, B, rng)
+            alg = D.PPO(ent_coef=0.01, clip_range_vf=0.3)
+            cfg = OO.PPOConfig(ent_coef=0.01, clip_range_vf=0.3)
+            loss, stats, g = p.loss_grad(*mb, alg.hyper())
+            eloss, estats, eg = OO.ppo_loss_and_grads(spec, flat, *mb, cfg)
+            assert abs(loss - eloss) <= 1e-4 * max(1.0, abs(eloss))
+            for k in estats:
+                assert abs(stats[k] - estats[k]) <= 1e-4 * max(1.0, abs(estats[k])), (k, stats[k], estats[k])
+            assert _relerr(g, eg) < 1e-4, _relerr(g, eg)
+            print(name, single, mma, B, "grad relerr", _relerr(g, eg))
+        p.close()
     finally:
-        D.set_option("single_net", 1)
-    for B in (77, 128, 1000):
-        mb = _minibatch(spec, flat, B, rng)
-        alg = D.PPO(ent_coef=0.01, clip_range_vf=0.3)
-        cfg = OO.PPOConfig(ent_coef=0.01, clip_range_vf=0.3)
-        loss, stats, g = p.loss_grad(*mb, alg.hyper())
-        eloss, estats, eg = OO.ppo_loss_and_grads(spec, flat, *mb, cfg)
-        assert abs(loss - eloss) <= 1e-4 * max(1.0, abs(eloss))
-        for k in estats:
-            assert abs(stats[k] - estats[k]) <= 1e-4 * max(1.0, abs(estats[k])), (k, stats[k], estats[k])
-        assert _relerr(g, eg) < 1e-4, _relerr(g, eg)
-    p.close()
+        D.set_option("single_net", 1); D.set_option("mma", 1); D.set_option("tc", 1)
