@@ -282,7 +282,8 @@ def run_ours(args):
     fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
     lg_path = agent.device.update_path()            # "tensor": tcgen05 3xTF32 kernel, "fp32": CUDA-core kernel
     hid_flops = 2 * sum(i * o for net in (0, 1) for (i, o) in layer.layer_dims(net)[1:-1])     # the square hidden GEMMs
-    lg_tensor_flops = 3 * (3 * hid_flops) * steps_per_iter * EPOCHS if lg_path == "tensor" else 0.0   # 3 GEMMs x 3 TF32 passes
+    lg_tensor_flops = 3 * (3 * hid_flops) * steps_per_iter * EPOCHS if lg_path in ("tensor", "mma") else 0.0   # 3 GEMMs x 3 TF32 passes
+    mma_tf32_peak = 148 * 512 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12    # mma.sync TF32 issue rate measured by tools/mma_probe.cu
     rooflines = {
         "rollout": {"bound": "hbm", "achieved": ro_bytes / (ro["ms_per_step"] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                     "fp32_tflops": ro_flops / (ro["ms_per_step"] * 1e-3) / 1e12, "share": ro.get("share")},
@@ -304,6 +305,13 @@ def run_ours(args):
                 "holds at ~2e-6); achieved = fp32-equivalent algorithmic FLOPs (fwd + 2x bwd) / time, peak = measured dense bf16 by "
                 "contract; tf32 peak is half of it and 3 tensor passes are issued per algorithmic FLOP (frac_of_tf32_peak_issued); "
                 "the kernel is bound by its CUDA-core phases (tanh, loss head, thin-layer gradient reductions), see DESIGN.md")
+    elif lg_path == "mma":
+        rooflines["loss_grad"]["frac_of_mma_sync_tf32_peak_issued"] = rooflines["loss_grad"]["tf32_issued_tflops"] / mma_tf32_peak
+        roof = dict(rooflines.get(dominant, rooflines["loss_grad"]))
+        note = ("general-shape loss_grad kernel: hidden GEMMs on warp-level tensor-core tiles (mma.sync m16n8k8 TF32, 3xTF32 split, "
+                "fp32-level accuracy), thin layers and loss head on CUDA cores; achieved = fp32-equivalent algorithmic FLOPs / time, "
+                "peak = measured dense bf16 (tcgen05 path) by contract; frac_of_mma_sync_tf32_peak_issued counts the 3 issued passes "
+                "against the 512 MAC/clk/SM the legacy tensor path sustains on sm_100a (profiles/r01_mma_sync_rates.txt)")
     else:
         note = ("fp32 CUDA-core kernels; frac is against the tensor peak by contract, frac_of_fp32_fma_peak is the pipe it actually "
                 "runs on")

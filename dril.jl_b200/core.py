@@ -295,10 +295,11 @@ class DevicePolicy:
         self.n_params = n.value
 
     def update_path(self):
-        """'tensor' when the update runs the tcgen05 (3xTF32) loss/grad kernel for this policy, else 'fp32'."""
+        """'tensor': the update runs the tcgen05 (3xTF32) loss/grad kernel for this policy; 'mma': the general-shape kernel
+        with its wide layers on mma.sync 3xTF32 tiles; 'fp32': the general-shape kernel on FMA tiles only."""
         o = L.c_i32(0)
         L.check(self.ctx.lib.dril_policy_update_path(self.h, C.byref(o)))
-        return "tensor" if o.value else "fp32"
+        return {1: "tensor", 2: "mma"}.get(o.value, "fp32")
 
     def set_params(self, flat):
         flat = L.f32(flat)

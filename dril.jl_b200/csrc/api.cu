@@ -703,10 +703,18 @@ extern "C" int32_t dril_policy_num_params(dril_policy* p, int64_t* n) {
     *n = p->pd.n_params;
     return DRIL_OK;
 }
-/* 1 when dril_ppo_update / dril_ppo_loss_grad run the tensor-core (tcgen05) loss/grad kernel for this policy, else 0 */
+/* 1 when dril_ppo_update / dril_ppo_loss_grad run the tcgen05 loss/grad kernel for this policy; 2 when they run the
+ * general-shape kernel with at least one layer on mma.sync 3xTF32 tiles; 0: general-shape kernel, fp32 FMA tiles only */
 extern "C" int32_t dril_policy_update_path(dril_policy* p, int32_t* out) {
     DRIL_REQUIRE(p && out, "NULL argument");
-    *out = (g_opt_tc && tc_eligible(p->pd)) ? 1 : 0;
+    *out = 0;
+    if (g_opt_tc && tc_eligible(p->pd)) { *out = 1; return DRIL_OK; }
+    if (p->plan_mma == 1)
+        for (int net = 0; net < 2; ++net)
+            for (int l = 0; l < p->pd.n_layers; ++l) {
+                const LayerDesc& L = p->pd.L[net][l];
+                if ((L.Kp % 16) == 0 && (L.Np % 16) == 0 && L.Kp >= 16 && L.Np >= 16) *out = 2;
+            }
     return DRIL_OK;
 }
 static int32_t repack(dril_policy* p) {

@@ -20,9 +20,10 @@
 
 __device__ __forceinline__ bool mma_layer_ok(int Kp, int Np) { return (Kp & 15) == 0 && (Np & 15) == 0 && Kp >= 16 && Np >= 16; }
 
+// not volatile: pure function of its operands, so the compiler may interleave independent accumulators
 __device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void mma_split(float x, uint32_t& hi, uint32_t& lo) {
     hi = __float_as_uint(x) & 0xFFFFE000u;
@@ -32,138 +33,189 @@ __device__ __forceinline__ void mma_red_add_v2(float* addr, float x, float y) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(x), "f"(y) : "memory");
 }
 
-// out[r][m] = sum_c Wm[c * ldw + r] * In[c * ld + m]   for rows r in [r0, r0+16), samples m in [8*mb0, 8*(mb0+MB)),
-// contraction over c in [0, C) (C multiple of 8).  Wm global (or shared) with row stride ldw; In shared.
+// out[r][m] = sum_c Wm[c * ldw + r] * In[c * ld + m]   for the RB row blocks r in [r0, r0 + 16 RB), samples m in
+// [8*mb0, 8*(mb0+MB)), contraction over c in [0, C) (C multiple of 8).  Wm global (or shared), row stride ldw; In shared.
+// A warp keeps RB x MB accumulator tiles: every In fragment is split once and used by RB row blocks, every weight
+// fragment by MB sample blocks; the three products of a split go to RB*2 different accumulators in turn so that
+// dependent MMAs are 2 RB issues apart.
 //   EPI 0 (forward):   Out[r][m] = f(acc + bias[r])           f = tanh if apply_tanh
 //   EPI 1 (dH):        Out[r][m] = acc * (1 - Out[r][m]^2)     in place over the activation H
-template <int MB, int EPI>
+template <int RB, int MB, int EPI>
 __device__ __forceinline__ void mma_rows_unit(const float* __restrict__ Wm, int ldw, int C, const float* __restrict__ In,
                                               float* __restrict__ Out, int ld, int r0, int mb0, const float* __restrict__ bias,
                                               bool apply_tanh) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    float acc[MB][4];
+    float acc[RB][MB][4];
 #pragma unroll
-    for (int i = 0; i < MB; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int i = 0; i < MB; ++i) { acc[r][i][0] = acc[r][i][1] = acc[r][i][2] = acc[r][i][3] = 0.f; }
     // A fragment rows = output features r (from the weights), columns = contraction index
     const float* wp = Wm + (size_t)t * ldw + r0 + g;
     const float* ip = In + (size_t)t * ld + mb0 * 8 + g;
-    float w0 = wp[0], w1 = wp[8], w2 = wp[(size_t)4 * ldw], w3 = wp[(size_t)4 * ldw + 8];
+    float w[RB][4];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) { w[r][0] = wp[r * 16]; w[r][1] = wp[r * 16 + 8]; w[r][2] = wp[(size_t)4 * ldw + r * 16]; w[r][3] = wp[(size_t)4 * ldw + r * 16 + 8]; }
     for (int c0 = 0; c0 < C; c0 += 8) {
-        uint32_t ahi[4], alo[4];
-        mma_split(w0, ahi[0], alo[0]); mma_split(w1, ahi[1], alo[1]); mma_split(w2, ahi[2], alo[2]); mma_split(w3, ahi[3], alo[3]);
-        if (c0 + 8 < C) {          // prefetch the next weight fragment (L2 latency) under this step's MMAs
+        uint32_t ahi[RB][4], alo[RB][4];
+#pragma unroll
+        for (int r = 0; r < RB; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mma_split(w[r][q], ahi[r][q], alo[r][q]);
+        if (c0 + 8 < C) {          // prefetch the next weight fragments (L2 latency) under this step's MMAs
             const float* wn = wp + (size_t)(c0 + 8) * ldw;
-            w0 = wn[0]; w1 = wn[8]; w2 = wn[(size_t)4 * ldw]; w3 = wn[(size_t)4 * ldw + 8];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) { w[r][0] = wn[r * 16]; w[r][1] = wn[r * 16 + 8]; w[r][2] = wn[(size_t)4 * ldw + r * 16]; w[r][3] = wn[(size_t)4 * ldw + r * 16 + 8]; }
         }
         const float* ic = ip + (size_t)c0 * ld;
 #pragma unroll
-        for (int i = 0; i < MB; ++i) {
-            uint32_t bh0, bl0, bh1, bl1;
-            mma_split(ic[i * 8], bh0, bl0);
-            mma_split(ic[(size_t)4 * ld + i * 8], bh1, bl1);
-            mma_tf32(acc[i], alo, bh0, bh1);
-            mma_tf32(acc[i], ahi, bl0, bl1);
-            mma_tf32(acc[i], ahi, bh0, bh1);
+        for (int i = 0; i < MB; i += 2) {
+            uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                mma_split(ic[(i + j) * 8], bh[j][0], bl[j][0]);
+                mma_split(ic[(size_t)4 * ld + (i + j) * 8], bh[j][1], bl[j][1]);
+            }
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) mma_tf32(acc[r][i + j], alo[r], bh[j][0], bh[j][1]);
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) mma_tf32(acc[r][i + j], ahi[r], bl[j][0], bl[j][1]);
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) mma_tf32(acc[r][i + j], ahi[r], bh[j][0], bh[j][1]);
         }
     }
-    const int ra = r0 + g, rb = r0 + g + 8;
-    float ba = 0.f, bb = 0.f;
-    if (EPI == 0) { ba = bias[ra]; bb = bias[rb]; }
 #pragma unroll
-    for (int i = 0; i < MB; ++i) {
-        const int m = (mb0 + i) * 8 + 2 * t;
-        float2* pa = reinterpret_cast<float2*>(Out + (size_t)ra * ld + m);
-        float2* pb = reinterpret_cast<float2*>(Out + (size_t)rb * ld + m);
-        float2 va, vb;
-        if (EPI == 0) {
-            va = make_float2(acc[i][0] + ba, acc[i][1] + ba);
-            vb = make_float2(acc[i][2] + bb, acc[i][3] + bb);
-            if (apply_tanh) { va.x = fast_tanh(va.x); va.y = fast_tanh(va.y); vb.x = fast_tanh(vb.x); vb.y = fast_tanh(vb.y); }
-        } else {
-            const float2 ha = *pa, hb = *pb;
-            va = make_float2(acc[i][0] * (1.0f - ha.x * ha.x), acc[i][1] * (1.0f - ha.y * ha.y));
-            vb = make_float2(acc[i][2] * (1.0f - hb.x * hb.x), acc[i][3] * (1.0f - hb.y * hb.y));
+    for (int r = 0; r < RB; ++r) {
+        const int ra = r0 + r * 16 + g, rb = ra + 8;
+        float ba = 0.f, bb = 0.f;
+        if (EPI == 0) { ba = bias[ra]; bb = bias[rb]; }
+#pragma unroll
+        for (int i = 0; i < MB; ++i) {
+            const int m = (mb0 + i) * 8 + 2 * t;
+            float2* pa = reinterpret_cast<float2*>(Out + (size_t)ra * ld + m);
+            float2* pb = reinterpret_cast<float2*>(Out + (size_t)rb * ld + m);
+            float2 va, vb;
+            if (EPI == 0) {
+                va = make_float2(acc[r][i][0] + ba, acc[r][i][1] + ba);
+                vb = make_float2(acc[r][i][2] + bb, acc[r][i][3] + bb);
+                if (apply_tanh) { va.x = fast_tanh(va.x); va.y = fast_tanh(va.y); vb.x = fast_tanh(vb.x); vb.y = fast_tanh(vb.y); }
+            } else {
+                const float2 ha = *pa, hb = *pb;
+                va = make_float2(acc[r][i][0] * (1.0f - ha.x * ha.x), acc[r][i][1] * (1.0f - ha.y * ha.y));
+                vb = make_float2(acc[r][i][2] * (1.0f - hb.x * hb.x), acc[r][i][3] * (1.0f - hb.y * hb.y));
+            }
+            *pa = va; *pb = vb;
         }
-        *pa = va; *pb = vb;
     }
 }
 
-// All (row block, sample chunk) units of one GEMM of this shape over the CTA's warps (blockDim.x / 32 warps).
-// R = number of output rows (multiple of 16).  Caller synchronises afterwards.
+// All (row-block group, sample chunk) units of one GEMM of this shape over the CTA's warps.  R = number of output rows
+// (multiple of 16).  Caller synchronises afterwards.
 template <int EPI>
 __device__ __forceinline__ void mma_rows_layer(const float* __restrict__ Wm, int ldw, int R, int C, const float* __restrict__ In,
                                                float* __restrict__ Out, int ld, const float* __restrict__ bias, bool apply_tanh) {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int rblocks = R >> 4;
-    // widest sample chunk (most reuse of the weight fragment) that still gives every warp a unit
-    if (rblocks % nwarps == 0) {
-        for (int u = warp; u < rblocks; u += nwarps) mma_rows_unit<16, EPI>(Wm, ldw, C, In, Out, ld, u << 4, 0, bias, apply_tanh);
-    } else if ((rblocks * 2) % nwarps == 0) {
-        for (int u = warp; u < rblocks * 2; u += nwarps) mma_rows_unit<8, EPI>(Wm, ldw, C, In, Out, ld, (u >> 1) << 4, (u & 1) * 8, bias, apply_tanh);
-    } else {
-        for (int u = warp; u < rblocks * 4; u += nwarps) mma_rows_unit<4, EPI>(Wm, ldw, C, In, Out, ld, (u >> 2) << 4, (u & 3) * 4, bias, apply_tanh);
+    // two row blocks per warp where the row count allows; the widest sample chunk that still gives every warp a unit
+    if ((rblocks & 1) == 0 && rblocks % nwarps == 0) {                 // RB 2 x MB 8: rblocks units
+        for (int u = warp; u < rblocks; u += nwarps)
+            mma_rows_unit<2, 8, EPI>(Wm, ldw, C, In, Out, ld, (u >> 1) << 5, (u & 1) * 8, bias, apply_tanh);
+    } else if ((rblocks & 1) == 0 && (rblocks * 2) % nwarps == 0) {    // RB 2 x MB 4: 2 rblocks units
+        for (int u = warp; u < rblocks * 2; u += nwarps)
+            mma_rows_unit<2, 4, EPI>(Wm, ldw, C, In, Out, ld, (u >> 2) << 5, (u & 3) * 4, bias, apply_tanh);
+    } else if ((rblocks & 1) == 0) {                                    // RB 2 x MB 2: 4 rblocks units
+        for (int u = warp; u < rblocks * 4; u += nwarps)
+            mma_rows_unit<2, 2, EPI>(Wm, ldw, C, In, Out, ld, (u >> 3) << 5, (u & 7) * 2, bias, apply_tanh);
+    } else {                                                            // odd number of row blocks: RB 1 x MB 4
+        for (int u = warp; u < rblocks * 4; u += nwarps)
+            mma_rows_unit<1, 4, EPI>(Wm, ldw, C, In, Out, ld, (u >> 2) << 4, (u & 3) * 4, bias, apply_tanh);
     }
 }
 
-// dW[k][n] (+)= sum_m Ain[k * ld + m] * dZ[n * ld + m] over the 128 samples of the tile, rows k in [k0, k0+16),
-// columns n in [8*nb0, 8*(nb0+NB)); written (first tile of the pass) or red-added into this CTA's packed partial.
-template <int NB>
+// dW[k][n] (+)= sum_m Ain[k * ld + m] * dZ[n * ld + m] over the 128 samples of the tile, the KB row blocks k in
+// [k0, k0 + 16 KB), columns n in [8*nb0, 8*(nb0+NB)); written (first tile of the pass) or red-added into this CTA's
+// packed partial.  Same accumulator interleaving as mma_rows_unit.
+template <int KB, int NB>
 __device__ __forceinline__ void mma_dw_unit(const float* __restrict__ Ain, const float* __restrict__ dZ, int ld, int k0, int nb0,
                                             float* __restrict__ gW, int Np, bool first) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    float acc[NB][4];
+    float acc[KB][NB][4];
 #pragma unroll
-    for (int i = 0; i < NB; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    for (int r = 0; r < KB; ++r)
+#pragma unroll
+        for (int i = 0; i < NB; ++i) { acc[r][i][0] = acc[r][i][1] = acc[r][i][2] = acc[r][i][3] = 0.f; }
     const float* ap = Ain + (size_t)(k0 + g) * ld + t;          // A (row k, col m): conflict-free (bank 4g + t)
     const float* zp = dZ + (size_t)(nb0 * 8 + g) * ld + t;      // B (m, col n)
-#pragma unroll 2
     for (int m0 = 0; m0 < MMA_TILE_M; m0 += 8) {
-        uint32_t ahi[4], alo[4];
-        mma_split(ap[m0], ahi[0], alo[0]);
-        mma_split(ap[(size_t)8 * ld + m0], ahi[1], alo[1]);
-        mma_split(ap[m0 + 4], ahi[2], alo[2]);
-        mma_split(ap[(size_t)8 * ld + m0 + 4], ahi[3], alo[3]);
+        uint32_t ahi[KB][4], alo[KB][4];
+#pragma unroll
+        for (int r = 0; r < KB; ++r) {
+            mma_split(ap[(size_t)(r * 16) * ld + m0], ahi[r][0], alo[r][0]);
+            mma_split(ap[(size_t)(r * 16 + 8) * ld + m0], ahi[r][1], alo[r][1]);
+            mma_split(ap[(size_t)(r * 16) * ld + m0 + 4], ahi[r][2], alo[r][2]);
+            mma_split(ap[(size_t)(r * 16 + 8) * ld + m0 + 4], ahi[r][3], alo[r][3]);
+        }
+#pragma unroll
+        for (int i = 0; i < NB; i += 2) {
+            uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                mma_split(zp[(size_t)(i + j) * 8 * ld + m0], bh[j][0], bl[j][0]);
+                mma_split(zp[(size_t)(i + j) * 8 * ld + m0 + 4], bh[j][1], bl[j][1]);
+            }
+#pragma unroll
+            for (int r = 0; r < KB; ++r)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) mma_tf32(acc[r][i + j], alo[r], bh[j][0], bh[j][1]);
+#pragma unroll
+            for (int r = 0; r < KB; ++r)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) mma_tf32(acc[r][i + j], ahi[r], bl[j][0], bl[j][1]);
+#pragma unroll
+            for (int r = 0; r < KB; ++r)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) mma_tf32(acc[r][i + j], ahi[r], bh[j][0], bh[j][1]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < KB; ++r)
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            uint32_t bh0, bl0, bh1, bl1;
-            mma_split(zp[(size_t)i * 8 * ld + m0], bh0, bl0);
-            mma_split(zp[(size_t)i * 8 * ld + m0 + 4], bh1, bl1);
-            mma_tf32(acc[i], alo, bh0, bh1);
-            mma_tf32(acc[i], ahi, bl0, bl1);
-            mma_tf32(acc[i], ahi, bh0, bh1);
+            const int n = (nb0 + i) * 8 + 2 * t;
+            float* pa = gW + (size_t)(k0 + r * 16 + g) * Np + n;
+            float* pb = gW + (size_t)(k0 + r * 16 + g + 8) * Np + n;
+            if (first) {
+                *reinterpret_cast<float2*>(pa) = make_float2(acc[r][i][0], acc[r][i][1]);
+                *reinterpret_cast<float2*>(pb) = make_float2(acc[r][i][2], acc[r][i][3]);
+            } else {
+                mma_red_add_v2(pa, acc[r][i][0], acc[r][i][1]);
+                mma_red_add_v2(pb, acc[r][i][2], acc[r][i][3]);
+            }
         }
-    }
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        const int n = (nb0 + i) * 8 + 2 * t;
-        float* pa = gW + (size_t)(k0 + g) * Np + n;
-        float* pb = gW + (size_t)(k0 + g + 8) * Np + n;
-        if (first) {
-            *reinterpret_cast<float2*>(pa) = make_float2(acc[i][0], acc[i][1]);
-            *reinterpret_cast<float2*>(pb) = make_float2(acc[i][2], acc[i][3]);
-        } else {
-            mma_red_add_v2(pa, acc[i][0], acc[i][1]);
-            mma_red_add_v2(pb, acc[i][2], acc[i][3]);
-        }
-    }
 }
 
-// dW of one layer (Kp x Np) over the CTA's warps.  Caller synchronises afterwards.
+// dW of one layer (Kp x Np, both multiples of 16) over the CTA's warps.  Caller synchronises afterwards.
 __device__ __forceinline__ void mma_dw_layer(const float* __restrict__ Ain, const float* __restrict__ dZ, int ld, int Kp, int Np,
                                              float* __restrict__ gW, bool first) {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int kblocks = Kp >> 4, nblocks = Np >> 3;
-    if ((nblocks & 15) == 0 && (kblocks * (nblocks >> 4)) % nwarps == 0) {
-        const int per = nblocks >> 4;
-        for (int u = warp; u < kblocks * per; u += nwarps) mma_dw_unit<16>(Ain, dZ, ld, (u / per) << 4, (u % per) * 16, gW, Np, first);
-    } else if ((nblocks & 7) == 0 && (kblocks * (nblocks >> 3)) % nwarps == 0) {
+    const int kblocks = Kp >> 4, nblocks = Np >> 3;      // nblocks is even
+    if ((kblocks & 1) == 0 && (nblocks & 7) == 0 && ((kblocks >> 1) * (nblocks >> 3)) % nwarps == 0) {          // KB 2 x NB 8
         const int per = nblocks >> 3;
-        for (int u = warp; u < kblocks * per; u += nwarps) mma_dw_unit<8>(Ain, dZ, ld, (u / per) << 4, (u % per) * 8, gW, Np, first);
-    } else if ((nblocks & 3) == 0 && (kblocks * (nblocks >> 2)) % nwarps == 0) {
+        for (int u = warp; u < (kblocks >> 1) * per; u += nwarps) mma_dw_unit<2, 8>(Ain, dZ, ld, (u / per) << 5, (u % per) * 8, gW, Np, first);
+    } else if ((kblocks & 1) == 0 && (nblocks & 3) == 0 && ((kblocks >> 1) * (nblocks >> 2)) % nwarps == 0) {   // KB 2 x NB 4
         const int per = nblocks >> 2;
-        for (int u = warp; u < kblocks * per; u += nwarps) mma_dw_unit<4>(Ain, dZ, ld, (u / per) << 4, (u % per) * 4, gW, Np, first);
-    } else {
+        for (int u = warp; u < (kblocks >> 1) * per; u += nwarps) mma_dw_unit<2, 4>(Ain, dZ, ld, (u / per) << 5, (u % per) * 4, gW, Np, first);
+    } else if ((kblocks & 1) == 0) {                                                                            // KB 2 x NB 2
         const int per = nblocks >> 1;
-        for (int u = warp; u < kblocks * per; u += nwarps) mma_dw_unit<2>(Ain, dZ, ld, (u / per) << 4, (u % per) * 2, gW, Np, first);
+        for (int u = warp; u < (kblocks >> 1) * per; u += nwarps) mma_dw_unit<2, 2>(Ain, dZ, ld, (u / per) << 5, (u % per) * 2, gW, Np, first);
+    } else {                                                                                                    // KB 1 x NB 2
+        const int per = nblocks >> 1;
+        for (int u = warp; u < kblocks * per; u += nwarps) mma_dw_unit<1, 2>(Ain, dZ, ld, (u / per) << 4, (u % per) * 2, gW, Np, first);
     }
 }

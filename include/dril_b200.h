@@ -206,8 +206,10 @@ int32_t dril_policy_create(dril_ctx* ctx, int32_t obs_dim, int32_t n_hidden, con
 int32_t dril_policy_destroy(dril_policy* p);
 int32_t dril_policy_num_params(dril_policy* p, int64_t* n);
 /* which loss/grad kernel the update uses for this policy: 1 = tensor cores (tcgen05, 3xTF32; hidden_dims = [64, 64],
- * obs_dim <= 4, Discrete(n <= 2), option "tc" on), 0 = fp32 CUDA cores.  Both replace the same reference code
- * (src/algorithms/ppo.jl:188-254 loss functor + Zygote pullback) and meet the same 1e-4 parity bound. */
+ * obs_dim <= 4, Discrete(n <= 2), option "tc" on), 2 = general-shape kernel with the layers whose padded dims are
+ * multiples of 16 on warp-level tensor-core tiles (mma.sync TF32, 3xTF32; option "mma"), 0 = general-shape kernel on
+ * fp32 FMA tiles only.  All replace the same reference code (src/algorithms/ppo.jl:188-254 loss functor + Zygote
+ * pullback) and meet the same 1e-4 parity bound. */
 int32_t dril_policy_update_path(dril_policy* p, int32_t* out);
 /* flat fp32 vector in ComponentVector(ps) order: actor_head layers (weight (out,in) column-major,
  * bias), critic_head layers, log_std (layers/layer_lux.jl:4-52) */

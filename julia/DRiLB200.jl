@@ -311,15 +311,16 @@ function DRiL.train!(agent::Agent, env::CudaBatchedEnv, alg::PPO{T}, max_steps::
 end
 
 # ---- kernel-path switches and data-parallel setup (include/dril_b200.h) --------------------------------------------
-"`set_option(\"tc\" | \"fused_tail\" | \"tc_rollout\", 0/1)`: process-wide kernel-path switches (all default on)."
+"`set_option(\"tc\" | \"fused_tail\" | \"tc_rollout\" | \"single_net\" | \"mma\", 0/1)`: process-wide kernel-path switches (all default on;\nthe last two apply to policies created afterwards)."
 set_option(key::AbstractString, value::Integer) =
     check(ccall((:dril_set_option, LIB), Int32, (Cstring, Int32), key, value))
 
-"`:tensor` when the update of this policy runs the tcgen05 (3xTF32) loss/grad kernel, else `:fp32`."
+"`:tensor`: the update of this policy runs the tcgen05 (3xTF32) loss/grad kernel; `:mma`: the general-shape kernel with its
+wide layers on mma.sync 3xTF32 tiles; `:fp32`: the general-shape kernel on FMA tiles only."
 function update_path(p::DevicePolicy)
     out = Ref{Int32}(0)
     check(ccall((:dril_policy_update_path, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}), p.h, out))
-    return out[] == 1 ? :tensor : :fp32
+    return out[] == 1 ? :tensor : (out[] == 2 ? :mma : :fp32)
 end
 
 """

@@ -506,7 +506,7 @@ def test_kernel_paths_vs_oracle(D, tc, tail, tc_rollout):
         alg = D.PPO(n_steps=T, batch_size=500, epochs=2, ent_coef=0.01)
         agent = D.Agent(layer, alg, rng=np.random.default_rng(0))
         agent.set_parameters(flat)
-        assert agent.device.update_path() == ("tensor" if tc else "fp32")
+        assert agent.device.update_path() == ("tensor" if tc else "mma")    # [64,64] with "tc" off: mma.sync tiles
         buf = D.RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, T, n)
         D.collect_rollout(buf, agent, alg, env, forced_actions=forced)
         exp = OO.collect_rollout_timemajor(oenv, spec, flat, T, forced_actions=forced)
