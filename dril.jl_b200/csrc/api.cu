@@ -569,7 +569,7 @@ extern "C" int32_t dril_buffer_upload(dril_buffer* b, int32_t field, const void*
 // policy
 // ---------------------------------------------------------------------------------------
 static inline int pad4(int x) { return (x + 3) & ~3; }
-struct LossLaunch { int M4; bool ws; size_t smem; int grid_cap; int splits; bool single; bool mma; };
+struct LossLaunch { int M4; bool ws; size_t smem; int grid_cap; int splits; bool single; bool mma; bool thin; };
 static int32_t plan_loss(dril_policy* p, LossLaunch* out);
 
 extern "C" int32_t dril_policy_create(dril_ctx* c, int32_t obs_dim, int32_t n_hidden, const int32_t* hidden,
@@ -1370,7 +1370,7 @@ static int32_t plan_loss(dril_policy* p, LossLaunch* out) {
     // shared memory when there is room for at least a 32-sample tile next to them
     int M4 = 128;
     bool ws = true, single = false;
-    auto total = [&](int m4, bool w, bool sn = false) { return loss_smem_layout(pd, m4, w, sn).total; };
+    auto total = [&](int m4, bool w, bool sn = false, bool thin = false) { return loss_smem_layout(pd, m4, w, sn, thin).total; };
     while (M4 > 16 && total(M4, true) > DRIL_SMEM_MAX) M4 -= 16;
     if (total(M4, true) > DRIL_SMEM_MAX || M4 < 32) {
         ws = false; M4 = 128;
@@ -1387,6 +1387,10 @@ static int32_t plan_loss(dril_policy* p, LossLaunch* out) {
     if (total(M4, ws, single) > DRIL_SMEM_MAX) { dril_set_error("network too wide for the loss kernel's shared memory"); return DRIL_ERR_UNSUPPORTED; }
     out->M4 = M4; out->ws = ws; out->single = single; out->smem = total(M4, ws, single);
     out->mma = M4 == MMA_TILE_M && (p->plan_mma >= 0 ? p->plan_mma : g_opt_mma) != 0;
+    // MMA layers stream their weights from L2; the remaining (thin) layers' weights are staged in shared memory if they fit
+    out->thin = out->mma && !ws && loss_thin_floats(pd) > 0 && loss_thin_floats(pd) < pd.pack_total / 2 &&
+                total(M4, ws, single, true) <= DRIL_SMEM_MAX;
+    if (out->thin) out->smem = total(M4, ws, single, true);
     int splits = 1;
     while (splits < DRIL_GPLANES && (M4 / (splits * 2)) % 4 == 0 && M4 / (splits * 2) >= 4) splits *= 2;
     out->splits = splits;
@@ -1408,7 +1412,7 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
     a.pd = pd; a.buf = bd; a.pack = p->pack; a.flat = p->flat; a.mbstats = mbstats_dev; a.gpart = p->gpart;
     a.stop_flag = p->stop_flag; a.mb = mb; a.hp = hp; a.M4 = ll.M4; a.weights_smem = ll.ws;
     a.half_stride = p->gpart_ctas; a.small_splits = ll.splits; a.single_net = ll.single ? 1 : 0;
-    a.use_mma = ll.mma ? 1 : 0;
+    a.use_mma = ll.mma ? 1 : 0; a.stage_thin = ll.thin ? 1 : 0;
     const bool tc = g_opt_tc && tc_eligible(pd);
     long long tiles = (mb.count + (tc ? TC_M : ll.M4) - 1) / (tc ? TC_M : ll.M4);
     int grid = (int)std::max<long long>(1, std::min<long long>(tiles, tc ? std::min(c->sm_count, p->gpart_ctas) : ll.grid_cap));

@@ -72,13 +72,36 @@ __global__ void adv_stats_finalize_kernel(const double* __restrict__ partial, in
 // gradient partial in global memory (L2-resident read-modify-write by the owning thread).
 struct LossSmem {
     int ld;
-    size_t w, x, h[2][DRIL_MAX_LAYERS], dout[2], samp, dbl_bytes_off, total;
+    size_t w, x, h[2][DRIL_MAX_LAYERS], dout[2], samp, thin, dbl_bytes_off, total;
 };
+
+// Layers that stay on FMA tiles while the wide ones run on MMA tiles with weights streamed from L2 ("thin" layers: the
+// input layer, K = obs_dim, and the output layer, N = n_actions | 1): their W | bias and Wt blocks are staged in shared
+// memory, compacted in (net, layer) order, so that the few threads working on them do not wait for L2 on every k step.
+__host__ __device__ inline bool loss_layer_mma(const LayerDesc& L) { return (L.Kp & 15) == 0 && (L.Np & 15) == 0 && L.Kp >= 16 && L.Np >= 16; }
+__host__ __device__ inline int loss_thin_floats(const PolicyDesc& pd) {
+    int n = 0;
+    for (int net = 0; net < 2; ++net)
+        for (int l = 0; l < pd.n_layers; ++l)
+            if (!loss_layer_mma(pd.L[net][l])) n += 2 * pd.L[net][l].Kp * pd.L[net][l].Np + pd.L[net][l].Np;
+    return n;
+}
+// offset (floats) of the [W | bias] block of a thin layer inside the staged region; its Wt block follows directly
+__host__ __device__ inline int loss_thin_offset(const PolicyDesc& pd, int net, int l) {
+    int n = 0;
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < pd.n_layers; ++b) {
+            if (a == net && b == l) return n;
+            if (!loss_layer_mma(pd.L[a][b])) n += 2 * pd.L[a][b].Kp * pd.L[a][b].Np + pd.L[a][b].Np;
+        }
+    return n;
+}
 
 // single_net: the nets are processed in two passes over the minibatch (actor, then critic) and share one set of
 // activation rows, so a wide network keeps a twice as wide sample tile (weights streamed from L2 are then read half
 // as often per sample).
-__host__ __device__ inline LossSmem loss_smem_layout(const PolicyDesc& pd, int M4, bool weights_smem, bool single_net = false) {
+__host__ __device__ inline LossSmem loss_smem_layout(const PolicyDesc& pd, int M4, bool weights_smem, bool single_net = false,
+                                                     bool stage_thin = false) {
     LossSmem s;
     s.ld = M4 + 4;
     size_t o = 0;
@@ -99,6 +122,8 @@ __host__ __device__ inline LossSmem loss_smem_layout(const PolicyDesc& pd, int M
     int arows = pd.act_kind == DRIL_ACT_CONTINUOUS ? 2 * pd.act_n : 1;   // actions (+ log_std grad contributions)
     s.samp = o; o += (size_t)(4 + arows) * s.ld;   // adv, ret, old_logp, old_val, actions...
     o = (o + 3) & ~(size_t)3;
+    s.thin = o; o += stage_thin ? (size_t)loss_thin_floats(pd) : 0;
+    o = (o + 3) & ~(size_t)3;
     s.dbl_bytes_off = o * sizeof(float);
     s.total = s.dbl_bytes_off + 40 * sizeof(double);
     return s;
@@ -117,6 +142,7 @@ struct LossArgs {
     int M4, weights_smem, half_stride;   // half_stride: CTAs per partial plane
     int single_net;                      // 1: two passes (actor, critic) over the minibatch with shared activation rows
     int use_mma;                         // 1: layers with Kp, Np multiples of 16 run on mma.sync 3xTF32 tiles (needs M4 == 128)
+    int stage_thin;                      // 1: the other layers' weights are staged in shared memory (weights_smem == 0 only)
     int small_splits;                    // sample-range splits of the 4x4 dW tiles (planes 0..small_splits-1)
 };
 
@@ -281,7 +307,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
     const PolicyDesc& pd = a.pd;
     const BufDev& buf = a.buf;
     const int M4 = a.M4, D = pd.obs_dim, Dp = pd.obs_dim_p, NL = pd.n_layers;
-    const LossSmem S = loss_smem_layout(pd, M4, WS, a.single_net != 0);
+    const LossSmem S = loss_smem_layout(pd, M4, WS, a.single_net != 0, !WS && a.stage_thin);
     const int ld = S.ld;
     const int tid = threadIdx.x;
     float* sX = smem + S.x;
@@ -303,6 +329,19 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
         const float4* src = reinterpret_cast<const float4*>(a.pack);
         float4* dst = reinterpret_cast<float4*>(smem);
         for (int i = tid; i < pd.pack_total / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    const bool thin = !WS && a.stage_thin;
+    float* sThin = smem + S.thin;
+    if (thin) {
+        for (int net = 0; net < 2; ++net)
+            for (int l = 0; l < NL; ++l) {
+                const LayerDesc& Ld = pd.L[net][l];
+                if (loss_layer_mma(Ld)) continue;
+                float* dst = sThin + loss_thin_offset(pd, net, l);
+                const int nf = Ld.Kp * Ld.Np + Ld.Np, nt = Ld.Kp * Ld.Np;
+                for (int i = tid; i < nf; i += blockDim.x) dst[i] = a.pack[Ld.pw_off + i];
+                for (int i = tid; i < nt; i += blockDim.x) dst[nf + i] = a.pack[Ld.pwt_off + i];
+            }
     }
     // advantage normalisation constants of this (global) minibatch
     float adv_mean = 0.f, adv_den = 1.f;
@@ -359,7 +398,14 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
                     fmask &= ~(1 << net);
                 }
             }
-            if (fmask) dense_layer_auto(pd, Wbase, l, ia, ic, smem + S.h[0][l], smem + S.h[1][l], M4, ld, fmask);
+            if (fmask && thin) {           // staged copies: one call per net with the base shifted to the staged [W | bias] block
+                for (int net = 0; net < 2; ++net)
+                    if (fmask >> net & 1)
+                        dense_layer_auto(pd, sThin + loss_thin_offset(pd, net, l) - pd.L[net][l].pw_off, l, ia, ic, smem + S.h[0][l],
+                                         smem + S.h[1][l], M4, ld, 1 << net);
+            } else if (fmask) {
+                dense_layer_auto(pd, Wbase, l, ia, ic, smem + S.h[0][l], smem + S.h[1][l], M4, ld, fmask);
+            }
             __syncthreads();
         }
         // ---- loss head: dL/dlogits (or dL/dmean), dL/dvalue ---------------------------------
@@ -529,18 +575,22 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
                 if ((nmask & 2) && cmma) mma_rows_layer<1>(Wbase + Lc.pwt_off, Lc.Kp, Lc.Kp, Lc.Np, dZc, smem + S.h[1][l - 1], ld, nullptr, false);
                 const int ca = (!(nmask & 1) || amma) ? 0 : (a8 ? (La.Kp >> 3) * mt8 : (La.Kp >> 2) * mt4);
                 const int cc = (!(nmask & 2) || cmma) ? 0 : (c8 ? (Lc.Kp >> 3) * mt8 : (Lc.Kp >> 2) * mt4);
+                // staged Wt blocks of this layer (only read when the layer is not on MMA tiles)
+                const float* sWtA = sThin + loss_thin_offset(pd, 0, l) + La.Kp * La.Np + La.Np;
+                const float* sWtC = sThin + loss_thin_offset(pd, 1, l) + Lc.Kp * Lc.Np + Lc.Np;
                 for (int t = tid; t < ca + cc; t += blockDim.x) {
                     const bool crit = t >= ca;
                     const int u = crit ? t - ca : t;
                     const LayerDesc& Ld = crit ? Lc : La;
                     const float* dZ = crit ? dZc : dZa;
                     float* H = smem + S.h[crit][l - 1];
+                    const float* Wt = thin ? (crit ? sWtC : sWtA) : Wbase + Ld.pwt_off;
                     if (crit ? c8 : a8) {
                         const int kt = u / mt8, m = u - kt * mt8;
-                        dense_tile_dh8(Wbase + Ld.pwt_off, Ld.N, Ld.Kp, dZ, H, ld, kt, m, Ld.Kp >> 1, M4 >> 1);
+                        dense_tile_dh8(Wt, Ld.N, Ld.Kp, dZ, H, ld, kt, m, Ld.Kp >> 1, M4 >> 1);
                     } else {
                         const int kt = u / mt4, m = u - kt * mt4;
-                        dense_tile_dh(Wbase + Ld.pwt_off, Ld.N, Ld.Kp, dZ, H, ld, kt << 2, m << 2);
+                        dense_tile_dh(Wt, Ld.N, Ld.Kp, dZ, H, ld, kt << 2, m << 2);
                     }
                 }
                 __syncthreads();
