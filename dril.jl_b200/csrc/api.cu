@@ -1079,6 +1079,17 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
     if (total(M4, ws) > DRIL_SMEM_MAX) { dril_set_error("network too wide for the rollout kernel's shared memory"); return DRIL_ERR_UNSUPPORTED; }
     // weights that leave no room for a reasonable tile are streamed from L2 instead
     if (ws && M4 < 32 && N >= 32ll * c->sm_count && total(64, false) <= DRIL_SMEM_MAX) { ws = false; M4 = 64; }
+    // wide nets whose weights stream from L2 anyway: 64-env tiles with the wide layers on mma.sync 3xTF32 tiles
+    // (mma_tiles.cuh) once there are enough envs to give every SM such a tile
+    if (has_policy && !ws && g_opt_mma && N >= 64ll * c->sm_count && total(64, false) <= DRIL_SMEM_MAX) {
+        bool any = false;
+        for (int net = 0; net < 2; ++net)
+            for (int l = 0; l < a.pd.n_layers; ++l) {
+                const LayerDesc& L = a.pd.L[net][l];
+                any = any || ((L.Kp % 16) == 0 && (L.Np % 16) == 0 && L.Kp >= 16 && L.Np >= 16);
+            }
+        if (any) { M4 = 64; flags |= RO_MMA; }
+    }
     if (ws) flags |= RO_WEIGHTS_SMEM;
     a.M4 = M4; a.flags = flags;
     a.n_tiles = (int)((N + M4 - 1) / M4);

@@ -10,6 +10,7 @@
 // processed together: one pass over the thread-tiles of both nets per layer.
 #pragma once
 #include "common.cuh"
+#include "mma_tiles.cuh"
 
 // C[n0..n0+3][m0..m0+3] = f( sum_k W[k][n0..] * A[k][m0..] + b[n0..] )
 __device__ __forceinline__ void dense_tile_fwd(const float* __restrict__ W, const float* __restrict__ bias,
@@ -149,14 +150,27 @@ __device__ __forceinline__ void dense_layer(const PolicyDesc& pd, const float* _
 // Whole forward of the selected nets; ping-pong buffers act[net][2][max_np*ld]; returns the
 // parity index of the buffer holding the final layer output. X is the shared input.
 // Contains a __syncthreads after every layer (so outputs are visible on return).
+// use_mma (tile width multiple of 16): layers whose padded dims are multiples of 16 run on the warp-level tensor-core
+// tiles of mma_tiles.cuh (3xTF32), the others on the FMA tiles.
 __device__ __forceinline__ int mlp_forward_pingpong(const PolicyDesc& pd, const float* __restrict__ Wbase,
                                                     const float* X, float* act_a, float* act_c, int M4, int ld,
-                                                    int net_mask) {
+                                                    int net_mask, bool use_mma = false) {
     const size_t bufsz = (size_t)pd.max_np * ld;
     for (int l = 0; l < pd.n_layers; ++l) {
         const float* ia = l == 0 ? X : act_a + ((l - 1) & 1) * bufsz;
         const float* ic = l == 0 ? X : act_c + ((l - 1) & 1) * bufsz;
-        dense_layer(pd, Wbase, l, ia, ic, act_a + (l & 1) * bufsz, act_c + (l & 1) * bufsz, M4, ld, net_mask);
+        int fmask = net_mask;
+        if (use_mma) {
+            for (int net = 0; net < 2; ++net) {
+                const LayerDesc& Ld = pd.L[net][l];
+                if ((net_mask >> net & 1) && mma_layer_ok(Ld.Kp, Ld.Np)) {
+                    mma_rows_layer<0>(Wbase + Ld.pw_off, Ld.Np, Ld.Np, Ld.Kp, net ? ic : ia, (net ? act_c : act_a) + (l & 1) * bufsz, ld,
+                                      Wbase + Ld.pb_off, l < pd.n_layers - 1, M4 >> 3);
+                    fmask &= ~(1 << net);
+                }
+            }
+        }
+        if (fmask) dense_layer(pd, Wbase, l, ia, ic, act_a + (l & 1) * bufsz, act_c + (l & 1) * bufsz, M4, ld, fmask);
         __syncthreads();
     }
     return (pd.n_layers - 1) & 1;

@@ -116,26 +116,37 @@ __device__ __forceinline__ void mma_rows_unit(const float* __restrict__ Wm, int 
 }
 
 // All (row-block group, sample chunk) units of one GEMM of this shape over the CTA's warps.  R = number of output rows
-// (multiple of 16).  Caller synchronises afterwards.
+// (multiple of 16), mblocks = sample blocks of 8 in the tile (even: tile width multiple of 16; 16 for the loss kernel's
+// 128-sample tiles, less in the rollout).  Caller synchronises afterwards.
+template <int RB, int MB, int EPI>
+__device__ __forceinline__ void mma_rows_units(const float* __restrict__ Wm, int ldw, int R, int C, const float* __restrict__ In,
+                                               float* __restrict__ Out, int ld, const float* __restrict__ bias, bool apply_tanh,
+                                               int mblocks) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int chunks = mblocks / MB, units = (R / (16 * RB)) * chunks;
+    for (int u = warp; u < units; u += nwarps)
+        mma_rows_unit<RB, MB, EPI>(Wm, ldw, C, In, Out, ld, (u / chunks) * 16 * RB, (u % chunks) * MB, bias, apply_tanh);
+}
 template <int EPI>
 __device__ __forceinline__ void mma_rows_layer(const float* __restrict__ Wm, int ldw, int R, int C, const float* __restrict__ In,
-                                               float* __restrict__ Out, int ld, const float* __restrict__ bias, bool apply_tanh) {
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+                                               float* __restrict__ Out, int ld, const float* __restrict__ bias, bool apply_tanh,
+                                               int mblocks = MMA_TILE_M / 8) {
+    const int nwarps = blockDim.x >> 5;
     const int rblocks = R >> 4;
-    // two row blocks per warp where the row count allows; the widest sample chunk that still gives every warp a unit
-    if ((rblocks & 1) == 0 && rblocks % nwarps == 0) {                 // RB 2 x MB 8: rblocks units
-        for (int u = warp; u < rblocks; u += nwarps)
-            mma_rows_unit<2, 8, EPI>(Wm, ldw, C, In, Out, ld, (u >> 1) << 5, (u & 1) * 8, bias, apply_tanh);
-    } else if ((rblocks & 1) == 0 && (rblocks * 2) % nwarps == 0) {    // RB 2 x MB 4: 2 rblocks units
-        for (int u = warp; u < rblocks * 2; u += nwarps)
-            mma_rows_unit<2, 4, EPI>(Wm, ldw, C, In, Out, ld, (u >> 2) << 5, (u & 3) * 4, bias, apply_tanh);
-    } else if ((rblocks & 1) == 0) {                                    // RB 2 x MB 2: 4 rblocks units
-        for (int u = warp; u < rblocks * 4; u += nwarps)
-            mma_rows_unit<2, 2, EPI>(Wm, ldw, C, In, Out, ld, (u >> 3) << 5, (u & 7) * 2, bias, apply_tanh);
-    } else {                                                            // odd number of row blocks: RB 1 x MB 4
-        for (int u = warp; u < rblocks * 4; u += nwarps)
-            mma_rows_unit<1, 4, EPI>(Wm, ldw, C, In, Out, ld, (u >> 2) << 4, (u & 3) * 4, bias, apply_tanh);
-    }
+    const bool r2 = (rblocks & 1) == 0;
+    // largest accumulator tile (most operand reuse) whose unit count divides over the warps; two row blocks preferred
+    if (r2 && (mblocks & 7) == 0 && ((rblocks >> 1) * (mblocks >> 3)) % nwarps == 0)
+        mma_rows_units<2, 8, EPI>(Wm, ldw, R, C, In, Out, ld, bias, apply_tanh, mblocks);
+    else if ((mblocks & 7) == 0 && (rblocks * (mblocks >> 3)) % nwarps == 0)
+        mma_rows_units<1, 8, EPI>(Wm, ldw, R, C, In, Out, ld, bias, apply_tanh, mblocks);
+    else if (r2 && (mblocks & 3) == 0 && ((rblocks >> 1) * (mblocks >> 2)) % nwarps == 0)
+        mma_rows_units<2, 4, EPI>(Wm, ldw, R, C, In, Out, ld, bias, apply_tanh, mblocks);
+    else if ((mblocks & 3) == 0 && (rblocks * (mblocks >> 2)) % nwarps == 0)
+        mma_rows_units<1, 4, EPI>(Wm, ldw, R, C, In, Out, ld, bias, apply_tanh, mblocks);
+    else if (r2)
+        mma_rows_units<2, 2, EPI>(Wm, ldw, R, C, In, Out, ld, bias, apply_tanh, mblocks);
+    else
+        mma_rows_units<1, 2, EPI>(Wm, ldw, R, C, In, Out, ld, bias, apply_tanh, mblocks);
 }
 
 // dW[k][n] (+)= sum_m Ain[k * ld + m] * dZ[n * ld + m] over the 128 samples of the tile, the KB row blocks k in

@@ -29,7 +29,8 @@ enum {
     RO_WEIGHTS_SMEM = 8,
     RO_GRID_SYNC = 16,        // training normaliser: cooperative launch + grid barrier per step
     RO_WRITE_OBS_OUT = 32,    // compat observe: write normalised obs to obs_out
-    RO_TILES_8X8 = 64         // throughput mode (many envs per SM): 8x8 register tiles in the hidden layers
+    RO_TILES_8X8 = 64,        // throughput mode (many envs per SM): 8x8 register tiles in the hidden layers
+    RO_MMA = 128              // general kernel, tile width multiple of 16: wide layers on mma.sync 3xTF32 tiles
 };
 
 struct RolloutArgs {
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
     const PolicyDesc& pd = a.pd;
     const bool has_policy = a.flags & RO_HAS_POLICY;
     const bool grid_sync = a.flags & RO_GRID_SYNC;
+    const bool use_mma = (a.flags & RO_MMA) != 0;
     const int D = env.obs_dim, Dp = (D + 3) & ~3;
     const int M4 = a.M4;
     const long long N = env.n_envs;
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
                     buf.obs[(row + n0) * D + i] = sX[(size_t)d * ld + e];
                 }
                 // actor + critic forward
-                fin = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, 3);
+                fin = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, 3, use_mma);
             }
             // sample / replay action, log-prob, value; hand the env-space action to the step
             int a_disc = 0;
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
                 }
                 __syncthreads();
                 if (has_policy) {                               // V(terminal_obs), trajectory.jl:57-61
-                    int f = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, 2);
+                    int f = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, 2, use_mma);
                     if (mine && trunc) buf.boot[row + n] = sActC[(size_t)f * pd.max_np * ld + tid];
                     __syncthreads();
                 }
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
             int nvalid = (int)min((long long)M4, N - n0);
             tile_raw_obs(n0, nvalid);
             tile_normalize(sMean, sVar, nvalid);
-            int f = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, 2);
+            int f = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, 2, use_mma);
             if (tid < nvalid) buf.last_values[n0 + tid] = sActC[(size_t)f * pd.max_np * ld + tid];
             __syncthreads();
         }

@@ -225,7 +225,8 @@ def _mk(D, kind, n, seed, ms, monitor, norm):
 @pytest.mark.parametrize("kind,n,T,ms,monitor,norm", [
     ("cartpole", 64, 16, 500, True, False), ("cartpole", 333, 64, 20, True, False), ("cartpole", 4096, 32, 25, False, False),
     ("pendulum", 100, 40, 15, True, True), ("pendulum", 1000, 24, 10, True, True), ("cartpole", 200, 48, 18, True, True),
-    ("pendulum", 50, 30, 12, False, False)])
+    ("pendulum", 50, 30, 12, False, False),
+    ("pendulum", 10240, 5, 3, True, True)])     # >= 64 envs per SM with a wide net: 64-env tiles, wide layers on mma.sync tiles
 def test_fused_rollout_replay(D, kind, n, T, ms, monitor, norm):
     env, oenv, spec = _mk(D, kind, n, 9, ms, monitor, norm)
     rng = np.random.default_rng(4)
