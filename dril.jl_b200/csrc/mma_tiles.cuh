@@ -6,6 +6,10 @@
 // on sm_100a (tools/mma_probe.cu), i.e. 170 MAC/clk/SM after the 3-way split that keeps fp32-level accuracy
 // (hi = x with 13 mantissa bits cleared, lo = x - hi; hi*hi + lo*hi + hi*lo, fp32 accumulation; relative error ~2^-21).
 //
+// The tensor core reads only the upper 19 bits of a TF32 operand, so only `lo` costs instructions: ptxas drops the mask of
+// every `hi` that feeds nothing but an mma (seen in the SASS: HMMA.1688.F32.TF32 takes the raw LDS result for the hi*hi and
+// lo*hi products), leaving one LOP3 + one FADD per operand element.
+//
 // Operand layouts are the ones the FMA tiles use, so the two kinds mix freely inside a layer loop:
 //   activations feature-major in shared memory  act[f * ld + m]   (m = sample 0..127, ld = 132)
 //   weights in the packed global layout          W[k * Np + n], Wt[n * Kp + k]   (read once per tile and CTA, L2)

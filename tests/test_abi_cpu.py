@@ -45,6 +45,16 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.IterStats) == 104
 
 
+def test_kernel_path_options(lib):
+    """dril_set_option needs no device: every documented switch is accepted, unknown keys are an error with a message."""
+    import dril_b200
+    for key in ("tc", "fused_tail", "tc_rollout", "single_net", "mma"):
+        dril_b200.set_option(key, 1)
+    with pytest.raises(dril_b200.DrilError):
+        dril_b200.set_option("no_such_switch", 1)
+    assert lib.dril_last_error()
+
+
 def test_no_cpu_fallback(lib):
     import torch
     import dril_b200
