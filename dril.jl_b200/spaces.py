@@ -23,6 +23,13 @@ class Box:
         x = np.asarray(x)
         return x.shape == self.shape and (x >= self.low).all() and (x <= self.high).all()
 
+    def sample(self, rng=None, n=None):
+        """rand([rng,] space[, n]) — src/spaces.jl:60-106: uniform in [low, high] per dimension, Float32; with n a list of n
+        samples (Julia returns a Vector of Vectors)."""
+        rng = rng if rng is not None else np.random.default_rng()
+        one = lambda: (self.low + rng.random(self.shape, dtype=np.float32) * (self.high - self.low)).astype(np.float32)
+        return one() if n is None else [one() for _ in range(n)]
+
     def __repr__(self):
         return f"Box(shape={self.shape})"
 
@@ -41,7 +48,14 @@ class Discrete:
         return isinstance(o, Discrete) and self.n == o.n and self.start == o.start
 
     def __contains__(self, x):
-        return isinstance(x, (int, np.integer)) and self.start <= x <= self.start + self.n - 1
+        return isinstance(x, (int, np.integer)) and not isinstance(x, (bool, np.bool_)) and self.start <= x <= self.start + self.n - 1
+
+    def sample(self, rng=None, n=None):
+        """rand([rng,] space[, n]) — src/spaces.jl:190-227: integers start .. start+n-1."""
+        rng = rng if rng is not None else np.random.default_rng()
+        if n is None:
+            return int(rng.integers(self.start, self.start + self.n))
+        return [int(v) for v in rng.integers(self.start, self.start + self.n, size=n)]
 
     def __repr__(self):
         return f"Discrete({self.n}, {self.start})"
