@@ -70,6 +70,12 @@ __global__ void adv_stats_finalize_kernel(const double* __restrict__ partial, in
 // Phases per tile: gather | L forward layers | loss head | for l = L-1..0: {dW_l, db_l} then
 // {dZ_{l-1} = (dZ_l W_l^T) .* (1 - H_{l-1}^2) in place}.  dW partial sums go to this CTA's packed
 // gradient partial in global memory (L2-resident read-modify-write by the owning thread).
+// Variants chosen per policy by plan_loss (api.cu):
+//   weights_smem  all packed weights staged in shared memory (small nets), else streamed from L2;
+//   single_net    wide nets: two passes over the minibatch (actor, then critic) sharing one set of H rows -> 128-sample tile;
+//   use_mma       layers with Kp, Np multiples of 16 run forward / dH / dW on the warp-level tensor-core tiles of
+//                 mma_tiles.cuh (3xTF32) instead of the FMA tiles; dW then goes to plane 0 only;
+//   stage_thin    with use_mma and streamed weights: the remaining layers' weights staged in shared memory.
 struct LossSmem {
     int ld;
     size_t w, x, h[2][DRIL_MAX_LAYERS], dout[2], samp, thin, dbl_bytes_off, total;
