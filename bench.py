@@ -318,6 +318,11 @@ def run_ours(args):
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of workload C2
     # (profiles/r01_lossgrad_tc_final_summary.txt, profiles/r01_rollout_tc_final_summary.txt); null for other workloads
     traffic_c2 = {"loss_grad": 14.16e6 + 0.06e6, "rollout": 192.3e3} if (args.workload == "c2" and lg_path == "tensor") else {}
+    if args.workload == "c3" and lg_path == "mma":
+        # profiles/r01_lossgrad_mma_summary.txt: 137.7 MB read + 32.0 MB written per launch.  The reads are the 32-byte
+        # sectors of the Feistel-order gather (4-byte fields of 524 288 scattered rows, two passes), 11x the algorithmic
+        # bytes but 43 GB/s, far from a limit; the writes are the red.add traffic of the dW partials
+        traffic_c2 = {"loss_grad": 137.66e6 + 32.02e6}
     roof.update({"kernel": dominant, "traffic": traffic_c2.get(dominant), "peak_source": pk["source"] + (" sustained bf16" if roof["bound"] == "tensor" else " copy"),
                  "note": note})
 
