@@ -1397,7 +1397,7 @@ static int32_t plan_loss(dril_policy* p, LossLaunch* out) {
     }
     if (total(M4, ws, single) > DRIL_SMEM_MAX) { dril_set_error("network too wide for the loss kernel's shared memory"); return DRIL_ERR_UNSUPPORTED; }
     out->M4 = M4; out->ws = ws; out->single = single; out->smem = total(M4, ws, single);
-    out->mma = M4 == MMA_TILE_M && (p->plan_mma >= 0 ? p->plan_mma : g_opt_mma) != 0;
+    out->mma = (M4 % 16) == 0 && M4 >= 32 && (p->plan_mma >= 0 ? p->plan_mma : g_opt_mma) != 0;
     // MMA layers stream their weights from L2; the remaining (thin) layers' weights are staged in shared memory if they fit
     out->thin = out->mma && !ws && loss_thin_floats(pd) > 0 && loss_thin_floats(pd) < pd.pack_total / 2 &&
                 total(M4, ws, single, true) <= DRIL_SMEM_MAX;

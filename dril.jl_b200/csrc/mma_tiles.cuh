@@ -20,7 +20,7 @@
 #pragma once
 #include "common.cuh"
 
-#define MMA_TILE_M 128    // samples per tile the MMA paths are written for
+#define MMA_TILE_M 128    // samples per tile of the loss kernel when shared memory allows (any multiple of 16 works)
 
 __device__ __forceinline__ bool mma_layer_ok(int Kp, int Np) { return (Kp & 15) == 0 && (Np & 15) == 0 && Kp >= 16 && Np >= 16; }
 
@@ -153,12 +153,12 @@ __device__ __forceinline__ void mma_rows_layer(const float* __restrict__ Wm, int
         mma_rows_units<1, 2, EPI>(Wm, ldw, R, C, In, Out, ld, bias, apply_tanh, mblocks);
 }
 
-// dW[k][n] (+)= sum_m Ain[k * ld + m] * dZ[n * ld + m] over the 128 samples of the tile, the KB row blocks k in
+// dW[k][n] (+)= sum_m Ain[k * ld + m] * dZ[n * ld + m] over the M samples of the tile (multiple of 8), the KB row blocks k in
 // [k0, k0 + 16 KB), columns n in [8*nb0, 8*(nb0+NB)); written (first tile of the pass) or red-added into this CTA's
 // packed partial.  Same accumulator interleaving as mma_rows_unit.
 template <int KB, int NB>
 __device__ __forceinline__ void mma_dw_unit(const float* __restrict__ Ain, const float* __restrict__ dZ, int ld, int k0, int nb0,
-                                            float* __restrict__ gW, int Np, bool first) {
+                                            float* __restrict__ gW, int Np, bool first, int M) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     float acc[KB][NB][4];
 #pragma unroll
@@ -167,7 +167,7 @@ __device__ __forceinline__ void mma_dw_unit(const float* __restrict__ Ain, const
         for (int i = 0; i < NB; ++i) { acc[r][i][0] = acc[r][i][1] = acc[r][i][2] = acc[r][i][3] = 0.f; }
     const float* ap = Ain + (size_t)(k0 + g) * ld + t;          // A (row k, col m): conflict-free (bank 4g + t)
     const float* zp = dZ + (size_t)(nb0 * 8 + g) * ld + t;      // B (m, col n)
-    for (int m0 = 0; m0 < MMA_TILE_M; m0 += 8) {
+    for (int m0 = 0; m0 < M; m0 += 8) {
         uint32_t ahi[KB][4], alo[KB][4];
 #pragma unroll
         for (int r = 0; r < KB; ++r) {
@@ -217,20 +217,20 @@ __device__ __forceinline__ void mma_dw_unit(const float* __restrict__ Ain, const
 
 // dW of one layer (Kp x Np, both multiples of 16) over the CTA's warps.  Caller synchronises afterwards.
 __device__ __forceinline__ void mma_dw_layer(const float* __restrict__ Ain, const float* __restrict__ dZ, int ld, int Kp, int Np,
-                                             float* __restrict__ gW, bool first) {
+                                             float* __restrict__ gW, bool first, int M = MMA_TILE_M) {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int kblocks = Kp >> 4, nblocks = Np >> 3;      // nblocks is even
     if ((kblocks & 1) == 0 && (nblocks & 7) == 0 && ((kblocks >> 1) * (nblocks >> 3)) % nwarps == 0) {          // KB 2 x NB 8
         const int per = nblocks >> 3;
-        for (int u = warp; u < (kblocks >> 1) * per; u += nwarps) mma_dw_unit<2, 8>(Ain, dZ, ld, (u / per) << 5, (u % per) * 8, gW, Np, first);
+        for (int u = warp; u < (kblocks >> 1) * per; u += nwarps) mma_dw_unit<2, 8>(Ain, dZ, ld, (u / per) << 5, (u % per) * 8, gW, Np, first, M);
     } else if ((kblocks & 1) == 0 && (nblocks & 3) == 0 && ((kblocks >> 1) * (nblocks >> 2)) % nwarps == 0) {   // KB 2 x NB 4
         const int per = nblocks >> 2;
-        for (int u = warp; u < (kblocks >> 1) * per; u += nwarps) mma_dw_unit<2, 4>(Ain, dZ, ld, (u / per) << 5, (u % per) * 4, gW, Np, first);
+        for (int u = warp; u < (kblocks >> 1) * per; u += nwarps) mma_dw_unit<2, 4>(Ain, dZ, ld, (u / per) << 5, (u % per) * 4, gW, Np, first, M);
     } else if ((kblocks & 1) == 0) {                                                                            // KB 2 x NB 2
         const int per = nblocks >> 1;
-        for (int u = warp; u < (kblocks >> 1) * per; u += nwarps) mma_dw_unit<2, 2>(Ain, dZ, ld, (u / per) << 5, (u % per) * 2, gW, Np, first);
+        for (int u = warp; u < (kblocks >> 1) * per; u += nwarps) mma_dw_unit<2, 2>(Ain, dZ, ld, (u / per) << 5, (u % per) * 2, gW, Np, first, M);
     } else {                                                                                                    // KB 1 x NB 2
         const int per = nblocks >> 1;
-        for (int u = warp; u < kblocks * per; u += nwarps) mma_dw_unit<1, 2>(Ain, dZ, ld, (u / per) << 4, (u % per) * 2, gW, Np, first);
+        for (int u = warp; u < kblocks * per; u += nwarps) mma_dw_unit<1, 2>(Ain, dZ, ld, (u / per) << 4, (u % per) * 2, gW, Np, first, M);
     }
 }

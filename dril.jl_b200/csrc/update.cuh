@@ -73,7 +73,7 @@ __global__ void adv_stats_finalize_kernel(const double* __restrict__ partial, in
 // Variants chosen per policy by plan_loss (api.cu):
 //   weights_smem  all packed weights staged in shared memory (small nets), else streamed from L2;
 //   single_net    wide nets: two passes over the minibatch (actor, then critic) sharing one set of H rows -> 128-sample tile;
-//   use_mma       layers with Kp, Np multiples of 16 run forward / dH / dW on the warp-level tensor-core tiles of
+//   use_mma       (tile width multiple of 16) layers with Kp, Np multiples of 16 run forward / dH / dW on the tensor-core tiles of
 //                 mma_tiles.cuh (3xTF32) instead of the FMA tiles; dW then goes to plane 0 only;
 //   stage_thin    with use_mma and streamed weights: the remaining layers' weights staged in shared memory.
 struct LossSmem {
@@ -147,7 +147,7 @@ struct LossArgs {
     UpdateHyper hp;
     int M4, weights_smem, half_stride;   // half_stride: CTAs per partial plane
     int single_net;                      // 1: two passes (actor, critic) over the minibatch with shared activation rows
-    int use_mma;                         // 1: layers with Kp, Np multiples of 16 run on mma.sync 3xTF32 tiles (needs M4 == 128)
+    int use_mma;                         // 1: layers with Kp, Np multiples of 16 run on mma.sync 3xTF32 tiles (needs M4 % 16 == 0)
     int stage_thin;                      // 1: the other layers' weights are staged in shared memory (weights_smem == 0 only)
     int small_splits;                    // sample-range splits of the 4x4 dW tiles (planes 0..small_splits-1)
 };
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
                 const LayerDesc& Ld = pd.L[net][l];
                 if ((nmask >> net & 1) && a.use_mma && mma_layer_ok(Ld.Kp, Ld.Np)) {
                     mma_rows_layer<0>(Wbase + Ld.pw_off, Ld.Np, Ld.Np, Ld.Kp, net ? ic : ia, smem + S.h[net][l], ld, Wbase + Ld.pb_off,
-                                      l < NL - 1);
+                                      l < NL - 1, M4 >> 3);
                     fmask &= ~(1 << net);
                 }
             }
@@ -522,8 +522,8 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
                 const bool c8 = m8 && (M4 & 15) == 0 && (Lc.Kp & 7) == 0 && (Lc.Np & 7) == 0;
                 const int nsplit = a.small_splits;
                 const bool amma = a.use_mma && mma_layer_ok(La.Kp, La.Np), cmma = a.use_mma && mma_layer_ok(Lc.Kp, Lc.Np);
-                if ((nmask & 1) && amma) mma_dw_layer(l == 0 ? sX : smem + S.h[0][l - 1], dZa, ld, La.Kp, La.Np, gp + La.pw_off, first);
-                if ((nmask & 2) && cmma) mma_dw_layer(l == 0 ? sX : smem + S.h[1][l - 1], dZc, ld, Lc.Kp, Lc.Np, gp + Lc.pw_off, first);
+                if ((nmask & 1) && amma) mma_dw_layer(l == 0 ? sX : smem + S.h[0][l - 1], dZa, ld, La.Kp, La.Np, gp + La.pw_off, first, M4);
+                if ((nmask & 2) && cmma) mma_dw_layer(l == 0 ? sX : smem + S.h[1][l - 1], dZc, ld, Lc.Kp, Lc.Np, gp + Lc.pw_off, first, M4);
                 const int ca = (!(nmask & 1) || amma) ? 0 : (a8 ? (La.Kp >> 3) * (La.Np >> 3) * 2 : (La.Kp >> 2) * (La.Np >> 2) * nsplit);
                 const int cc = (!(nmask & 2) || cmma) ? 0 : (c8 ? (Lc.Kp >> 3) * (Lc.Np >> 3) * 2 : (Lc.Kp >> 2) * (Lc.Np >> 2) * nsplit);
                 const int nba = (nmask & 1) ? La.N : 0;
@@ -577,8 +577,8 @@ __global__ void __launch_bounds__(DRIL_THREADS) ppo_loss_grad_kernel(const __gri
                 const bool c8 = m8 && (Lc.Kp & 7) == 0 && Lc.N >= 8;
                 const int mt4 = M4 >> 2, mt8 = M4 >> 3;
                 const bool amma = a.use_mma && mma_layer_ok(La.Kp, La.Np), cmma = a.use_mma && mma_layer_ok(Lc.Kp, Lc.Np);
-                if ((nmask & 1) && amma) mma_rows_layer<1>(Wbase + La.pwt_off, La.Kp, La.Kp, La.Np, dZa, smem + S.h[0][l - 1], ld, nullptr, false);
-                if ((nmask & 2) && cmma) mma_rows_layer<1>(Wbase + Lc.pwt_off, Lc.Kp, Lc.Kp, Lc.Np, dZc, smem + S.h[1][l - 1], ld, nullptr, false);
+                if ((nmask & 1) && amma) mma_rows_layer<1>(Wbase + La.pwt_off, La.Kp, La.Kp, La.Np, dZa, smem + S.h[0][l - 1], ld, nullptr, false, M4 >> 3);
+                if ((nmask & 2) && cmma) mma_rows_layer<1>(Wbase + Lc.pwt_off, Lc.Kp, Lc.Kp, Lc.Np, dZc, smem + S.h[1][l - 1], ld, nullptr, false, M4 >> 3);
                 const int ca = (!(nmask & 1) || amma) ? 0 : (a8 ? (La.Kp >> 3) * mt8 : (La.Kp >> 2) * mt4);
                 const int cc = (!(nmask & 2) || cmma) ? 0 : (c8 ? (Lc.Kp >> 3) * mt8 : (Lc.Kp >> 2) * mt4);
                 // staged Wt blocks of this layer (only read when the layer is not on MMA tiles)

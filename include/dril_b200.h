@@ -128,7 +128,7 @@ int32_t dril_device_count(int32_t* count);
  *   "tc_rollout"  tensor-core rollout for CartPole with such a policy (actor-only step loop + batched critic pass)
  *   "single_net"  fp32 loss/grad kernel, networks too wide for a 128-sample tile of both nets: one net per pass over the
  *                 minibatch with shared activation rows (applies to policies created afterwards)
- *   "mma"         fp32 loss/grad kernel, 128-sample tiles: layers whose padded dims are multiples of 16 run on warp-level
+ *   "mma"         fp32 loss/grad kernel, sample tiles of a multiple of 16: layers whose padded dims are multiples of 16 run on warp-level
  *                 tensor-core tiles (mma.sync TF32, 3xTF32 split) instead of FMA tiles (policies created afterwards) */
 int32_t dril_set_option(const char* key, int32_t value);
 

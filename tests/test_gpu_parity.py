@@ -613,7 +613,8 @@ WIDE = {
     "wide_discrete": lambda: OP.PolicySpec(10, [128, 96], "discrete", 5, act_start=0),
     "mid_box": lambda: OP.PolicySpec(6, [64, 32, 16], "continuous", 2, act_low=[-1, -1], act_high=[1, 1]),
     "cartpole_fp32": lambda: SPECS["cartpole"](),
-    # activations of one net leave room for less than 128 samples: single-net passes on FMA tiles, no MMA tiles
+    # activations of one net leave room for less than 128 samples: single-net passes with a 96-sample tile (MMA tiles with
+    # 12 sample blocks); without single_net a 48-sample tile of both nets
     "very_wide": lambda: OP.PolicySpec(8, [256, 256], "continuous", 2, act_low=[-1, -1], act_high=[1, 1]),
 }
 
