@@ -1,5 +1,6 @@
 // Warp-level tensor-core tiles (mma.sync.m16n8k8 TF32, 3xTF32 split) for the wide layers of the general-shape
-// loss/grad kernel (update.cuh): hidden layers whose padded dims are multiples of 16 on a 128-sample tile.
+// loss/grad kernel (update.cuh) and the general rollout kernel (rollout.cuh): hidden layers whose padded dims are multiples
+// of 16, on sample tiles whose width is a multiple of 16 (128 in the update when shared memory allows, 64 in the rollout).
 //
 // The tcgen05 kernel (update_tc.cuh) covers the reference's default [64,64] discrete policy; every other shape ran on
 // fp32 FMA tiles at ~31 % of the FMA pipe (40 MAC/clk/SM).  The legacy warp-level tensor path issues 512 TF32 MAC/clk/SM
@@ -11,7 +12,7 @@
 // lo*hi products), leaving one LOP3 + one FADD per operand element.
 //
 // Operand layouts are the ones the FMA tiles use, so the two kinds mix freely inside a layer loop:
-//   activations feature-major in shared memory  act[f * ld + m]   (m = sample 0..127, ld = 132)
+//   activations feature-major in shared memory  act[f * ld + m]   (m = sample in the tile, ld = tile width + 4)
 //   weights in the packed global layout          W[k * Np + n], Wt[n * Kp + k]   (read once per tile and CTA, L2)
 // Fragment coordinates (g = lane >> 2, t = lane & 3), PTX ISA m16n8k8 .tf32:
 //   A (16x8, row): a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)
