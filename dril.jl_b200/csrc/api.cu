@@ -664,7 +664,7 @@ extern "C" int32_t dril_policy_create(dril_ctx* c, int32_t obs_dim, int32_t n_hi
             for (int l = 0; l < pd.n_layers; ++l) {
                 const LayerDesc& L = pd.L[net][l];
                 const bool t8 = (ll.M4 % 16) == 0 && (L.Kp % 8) == 0 && (L.Np % 8) == 0;
-                const bool mma = ll.mma && (L.Kp % 16) == 0 && (L.Np % 16) == 0 && L.Kp >= 16 && L.Np >= 16;   // mma_layer_ok
+                const bool mma = ll.mma && mma_layer_ok(L.Kp, L.Np);
                 for (int i = 0; i < L.K * L.N; ++i) planes[L.w_off + i] = (unsigned char)(mma ? 1 : (t8 ? 2 : ll.splits));
             }
         DRIL_TRY(dmalloc(&p->f2planes, np));
@@ -713,7 +713,7 @@ extern "C" int32_t dril_policy_update_path(dril_policy* p, int32_t* out) {
         for (int net = 0; net < 2; ++net)
             for (int l = 0; l < p->pd.n_layers; ++l) {
                 const LayerDesc& L = p->pd.L[net][l];
-                if ((L.Kp % 16) == 0 && (L.Np % 16) == 0 && L.Kp >= 16 && L.Np >= 16) *out = 2;
+                if (mma_layer_ok(L.Kp, L.Np)) *out = 2;
             }
     return DRIL_OK;
 }
@@ -1086,7 +1086,7 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
         for (int net = 0; net < 2; ++net)
             for (int l = 0; l < a.pd.n_layers; ++l) {
                 const LayerDesc& L = a.pd.L[net][l];
-                any = any || ((L.Kp % 16) == 0 && (L.Np % 16) == 0 && L.Kp >= 16 && L.Np >= 16);
+                any = any || mma_layer_ok(L.Kp, L.Np);
             }
         if (any) { M4 = 64; flags |= RO_MMA; }
     }

@@ -23,7 +23,8 @@
 
 #define MMA_TILE_M 128    // samples per tile of the loss kernel when shared memory allows (any multiple of 16 works)
 
-__device__ __forceinline__ bool mma_layer_ok(int Kp, int Np) { return (Kp & 15) == 0 && (Np & 15) == 0 && Kp >= 16 && Np >= 16; }
+// a layer (padded dims Kp x Np) runs on these tiles; the one predicate host planning (api.cu) and the kernels share
+__host__ __device__ inline bool mma_layer_ok(int Kp, int Np) { return (Kp & 15) == 0 && (Np & 15) == 0 && Kp >= 16 && Np >= 16; }
 
 // not volatile: pure function of its operands, so the compiler may interleave independent accumulators
 __device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {

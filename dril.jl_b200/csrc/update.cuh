@@ -84,7 +84,7 @@ struct LossSmem {
 // Layers that stay on FMA tiles while the wide ones run on MMA tiles with weights streamed from L2 ("thin" layers: the
 // input layer, K = obs_dim, and the output layer, N = n_actions | 1): their W | bias and Wt blocks are staged in shared
 // memory, compacted in (net, layer) order, so that the few threads working on them do not wait for L2 on every k step.
-__host__ __device__ inline bool loss_layer_mma(const LayerDesc& L) { return (L.Kp & 15) == 0 && (L.Np & 15) == 0 && L.Kp >= 16 && L.Np >= 16; }
+__host__ __device__ inline bool loss_layer_mma(const LayerDesc& L) { return mma_layer_ok(L.Kp, L.Np); }
 __host__ __device__ inline int loss_thin_floats(const PolicyDesc& pd) {
     int n = 0;
     for (int net = 0; net < 2; ++net)
