@@ -501,6 +501,8 @@ __device__ __forceinline__ void tc_pass(const LossArgs& a, unsigned char* sm, ui
             tc_commit(bar3);
         }
         TC_MARK(9);
+        // ---- the next tile of this group (j = 2 (it + 1) + g) is gathered while G2 / G3 run ---------------------------
+        if (it + 1 < n_own) cur = tc_gather<NOUT, ACTOR>(a, (long long)blockIdx.x + (long long)(2 * (it + 1) + g) * gridDim.x, m);
         tc_wait(bar2, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         TC_MARK(10);

@@ -646,3 +646,61 @@ def test_wide_net_single_net_passes(D, name, single, mma):
         p.close()
     finally:
         D.set_option("single_net", 1); D.set_option("mma", 1); D.set_option("tc", 1)
+
+
+# ------------------------------------------------------------------------------------------
+# many tiles per CTA: the tile loops of the loss/grad kernels (more tiles than SMs) against the oracle
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,B", [("cartpole", 148 * 128 * 4 + 77), ("cartpole", 148 * 64 * 3 + 5), ("pendulum", 148 * 128 * 2 + 33)])
+def test_ppo_loss_and_gradients_many_tiles(D, name, B):
+    """B large enough that every CTA (and each of its warp groups) processes several sample tiles; the small-B cases of
+    test_ppo_loss_and_gradients never leave the first tile of a CTA."""
+    spec = SPECS[name]()
+    rng = np.random.default_rng(7)
+    flat = (OP.init_params(spec, seed=3) + rng.normal(size=spec.n_params()).astype(f32) * 0.05).astype(f32)
+    p = _device_policy(D, spec, flat)
+    mb = _minibatch(spec, flat, B, rng)
+    alg = D.PPO(ent_coef=0.01)
+    cfg = OO.PPOConfig(ent_coef=0.01)
+    loss, stats, g = p.loss_grad(*mb, alg.hyper())
+    eloss, estats, eg = OO.ppo_loss_and_grads(spec, flat, *mb, cfg)
+    assert abs(loss - eloss) <= 1e-4 * max(1.0, abs(eloss))
+    for k in estats:
+        assert abs(stats[k] - estats[k]) <= 1e-4 * max(1.0, abs(estats[k])), (k, stats[k], estats[k])
+    assert _relerr(g, eg) < 1e-4, _relerr(g, eg)
+    p.close()
+
+
+@pytest.mark.parametrize("tc", [1, 0])
+def test_c2_shape_update_vs_oracle(D, tc):
+    """BASELINE config C2 at full size (4096 envs x 128 steps, 4 minibatches of 131 072 shuffled samples, 7 tiles per CTA):
+    one epoch of the update on the device buffer against the oracle on the same buffer and the same Feistel minibatches."""
+    D.set_option("tc", tc)
+    try:
+        n, T = 4096, 128
+        env, oenv, spec = _mk(D, "cartpole", n, 5, 500, False, False)
+        flat = OP.init_params(spec, seed=2)
+        layer = D.ActorCriticLayer(env.observation_space(), env.action_space(), hidden_dims=spec.hidden)
+        alg = D.PPO(n_steps=T, batch_size=T * n // 4, epochs=1, ent_coef=0.01)
+        agent = D.Agent(layer, alg, rng=np.random.default_rng(0))
+        agent.set_parameters(flat)
+        buf = D.RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, T, n)
+        D.collect_rollout(buf, agent, alg, env)
+        ob = {k: buf.download(k) for k in ("obs", "actions", "rewards", "values", "logprobs", "advantages", "returns")}
+        import ctypes as C
+        from dril_b200 import _lib as L
+        st = D.IterStats()
+        h = alg.hyper()
+        L.check(agent.ctx.lib.dril_ppo_update(agent.device.h, buf.h, C.byref(h), alg.epochs, alg.batch_size, 41, 2, C.byref(st)))
+        cfg = OO.PPOConfig(n_steps=T, batch_size=T * n // 4, epochs=1, ent_coef=0.01)
+        opt = OO.Adam(flat.size, lr=cfg.learning_rate)
+        new_flat, means, _ = OO.ppo_update(spec, flat, opt, ob, cfg, shuffle_seed=41, epoch_counter0=2)
+        got = agent.device.get_params()
+        assert st.n_minibatch_steps == 4
+        assert _relerr(got - flat, new_flat - flat) < 2e-3, _relerr(got - flat, new_flat - flat)
+        np.testing.assert_allclose(got, new_flat, rtol=1e-4, atol=2e-6)
+        for k in ("policy_loss", "value_loss", "entropy_loss", "approx_kl_div", "clip_fraction", "loss", "grad_norm"):
+            assert abs(getattr(st, k) - means[k]) <= 2e-4 * max(1.0, abs(means[k])), (k, getattr(st, k), means[k])
+        buf.close()
+    finally:
+        D.set_option("tc", 1)
