@@ -106,7 +106,7 @@ SPECIAL_RESTYPE = {"dril_last_error": C.c_char_p, "dril_version": c_i32}
 BUF_FIELDS = dict(obs=0, actions=1, rewards=2, values=3, logprobs=4, advantages=5, returns=6, flags=7, boot=8,
                   last_values=9, episode_r=10, episode_l=11)
 KERNEL_KINDS = ["rollout", "gae", "adv_stats", "loss_grad", "grad_reduce", "adam", "explained_var", "monitor",
-                "env", "policy", "allreduce"]
+                "env", "policy", "allreduce", "permute"]
 
 _lib = None
 

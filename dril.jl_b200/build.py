@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdril_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "env.cuh", "mlp.cuh", "mma_tiles.cuh", "rollout.cuh", "rollout_tc.cuh", "gae.cuh", "update.cuh", "update_tc.cuh",
+HEADERS = ["common.cuh", "env.cuh", "mlp.cuh", "mma_tiles.cuh", "rollout.cuh", "rollout_tc.cuh", "gae.cuh", "update.cuh", "update_tc.cuh", "update_ft.cuh",
            os.path.join("..", "..", "include", "dril_b200.h")]
 
 

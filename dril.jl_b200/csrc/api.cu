@@ -13,6 +13,7 @@
 #include "rollout.cuh"
 #include "update.cuh"
 #include "update_tc.cuh"
+#include "update_ft.cuh"
 #include "rollout_tc.cuh"
 
 #define DRIL_SMEM_MAX 232448  // 227 KB opt-in per CTA on sm_100
@@ -35,6 +36,8 @@ extern "C" int32_t dril_version(void) { return 100; }
 // options
 // ---------------------------------------------------------------------------------------
 static int g_opt_tc = getenv("DRIL_TC") ? atoi(getenv("DRIL_TC")) : 1;
+// features-on-lanes tcgen05 loss/grad kernel (update_ft.cuh) instead of the samples-on-lanes one (update_tc.cuh)
+static int g_opt_ft = getenv("DRIL_FT") ? atoi(getenv("DRIL_FT")) : 1;
 static int g_opt_tc_rollout = getenv("DRIL_TC_ROLLOUT") ? atoi(getenv("DRIL_TC_ROLLOUT")) : 1;   // tensor-core rollout (CartPole, [64,64])
 static int g_opt_tail = getenv("DRIL_TAIL") ? atoi(getenv("DRIL_TAIL")) : 1;   // fused reduce/clip/Adam tail of the TC kernel
 // fp32 loss/grad kernel, wide nets: one net per pass with shared activation rows (fixed per policy at creation)
@@ -44,6 +47,7 @@ static int g_opt_mma = getenv("DRIL_MMA") ? atoi(getenv("DRIL_MMA")) : 1;
 extern "C" int32_t dril_set_option(const char* key, int32_t value) {
     DRIL_REQUIRE(key, "key is NULL");
     if (!strcmp(key, "tc")) { g_opt_tc = value; return DRIL_OK; }
+    if (!strcmp(key, "ft")) { g_opt_ft = value; return DRIL_OK; }
     if (!strcmp(key, "fused_tail")) { g_opt_tail = value; return DRIL_OK; }
     if (!strcmp(key, "tc_rollout")) { g_opt_tc_rollout = value; return DRIL_OK; }
     if (!strcmp(key, "single_net")) { g_opt_single_net = value; return DRIL_OK; }   // policies created afterwards
@@ -206,6 +210,11 @@ struct dril_policy {
     // scratch for the host-pointer entry points
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // update_ft.cuh: the current epoch's samples as shuffled tile records
+    unsigned char* ft_tiles = nullptr;
+    size_t ft_tiles_bytes = 0;
+    int ft_tiles_per_mb = 0;
+    long long ft_batch = 1;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -287,6 +296,8 @@ extern "C" int32_t dril_ctx_create(int32_t device, uint64_t seed, dril_ctx** out
     DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
     DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX));
     DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_ft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
+    DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_ft_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
     DRIL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM_BYTES));
     *out = c;
     return DRIL_OK;
@@ -687,7 +698,7 @@ extern "C" int32_t dril_policy_destroy(dril_policy* p) {
     cudaStreamSynchronize(p->ctx->stream);
     void* ps[] = {p->flat, p->pack, p->m, p->v, p->g, p->gpart, p->flat2pack, p->flat2packT, p->flat2g, p->step,
                   p->iter_acc, p->ev_acc, p->mbstats, p->adv_partial, p->stop_flag, p->scratch, p->f2planes, p->f2planes_one, p->sq_part,
-                  p->ticket};
+                  p->ticket, p->ft_tiles};
     for (void* q : ps) if (q) cudaFree(q);
     for (int i = 0; i < 3; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
     for (auto& sl : p->slots) {
@@ -1413,6 +1424,28 @@ static int32_t plan_loss(dril_policy* p, LossLaunch* out) {
     return DRIL_OK;
 }
 
+// update_ft.cuh path: the samples of one epoch (all its minibatches) as shuffled, contiguous tile records
+static bool ft_active(const dril_policy* p) { return g_opt_tc && g_opt_ft && tc_eligible(p->pd); }
+static int32_t ft_stage_epoch(dril_policy* p, const BufDev& bd, const FeistelKey& fk, long long n_total, long long batch_size, int identity) {
+    dril_ctx* c = p->ctx;
+    const int n_mb = (int)((n_total + batch_size - 1) / batch_size);
+    const int tpm = (int)((std::min<long long>(batch_size, n_total) + FT_TS - 1) / FT_TS);
+    const size_t bytes = (size_t)n_mb * tpm * FT_TILE_BYTES;
+    if (p->ft_tiles_bytes < bytes) {
+        if (p->ft_tiles) { DRIL_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(p->ft_tiles); }
+        p->ft_tiles = nullptr; p->ft_tiles_bytes = 0;
+        DRIL_CUDA(cudaMalloc((void**)&p->ft_tiles, bytes));
+        p->ft_tiles_bytes = bytes;
+    }
+    p->ft_tiles_per_mb = tpm; p->ft_batch = batch_size;
+    const long long slots = (long long)n_mb * tpm * FT_TS;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((slots + 255) / 256, (long long)c->sm_count * 8));
+    Span sp(c, DRIL_K_PERMUTE);
+    ft_permute_kernel<<<grid, 256, 0, c->stream>>>(bd, fk, n_total, batch_size, n_mb, tpm, identity, p->pd.act_start, p->pd.act_n, p->ft_tiles);
+    DRIL_CUDA(cudaGetLastError());
+    return DRIL_OK;
+}
+
 // one minibatch: loss/grad kernel -> reduce -> (allreduce) -> clip + Adam
 static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch& mb, const double* mbstats_dev,
                               const UpdateHyper& hp, const LossLaunch& ll, bool apply, int apply_stats) {
@@ -1425,7 +1458,9 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
     a.half_stride = p->gpart_ctas; a.small_splits = ll.splits; a.single_net = ll.single ? 1 : 0;
     a.use_mma = ll.mma ? 1 : 0; a.stage_thin = ll.thin ? 1 : 0;
     const bool tc = g_opt_tc && tc_eligible(pd);
-    long long tiles = (mb.count + (tc ? TC_M : ll.M4) - 1) / (tc ? TC_M : ll.M4);
+    const bool ft = tc && g_opt_ft;
+    const int tile_m = ft ? FT_TS : (tc ? TC_M : ll.M4);
+    long long tiles = (mb.count + tile_m - 1) / tile_m;
     int grid = (int)std::max<long long>(1, std::min<long long>(tiles, tc ? std::min(c->sm_count, p->gpart_ctas) : ll.grid_cap));
     const unsigned char* planes_dev = tc ? p->f2planes_one : p->f2planes;
     AdamArgs aa;
@@ -1447,7 +1482,16 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
             tl.flat2g = p->flat2g; tl.f2planes = planes_dev; tl.stats_off = pd.pack_fwd + pd.act_n; tl.sq_part = p->sq_part;
             tl.adam = aa;
             if (p2p) tl.pp = c->p2p;
-            if (tail) {
+            if (ft) {
+                // tile records of this minibatch: written by ft_stage_epoch before the epoch's first step
+                FtArgs fa;
+                fa.tiles = p->ft_tiles;
+                fa.tile0 = (mb.start / std::max<long long>(1, p->ft_batch)) * p->ft_tiles_per_mb;
+                const void* fn = pd.act_n == 1 ? (const void*)ppo_loss_grad_ft_kernel<1> : (const void*)ppo_loss_grad_ft_kernel<2>;
+                void* args[] = {(void*)&a, (void*)&tl, (void*)&fa};
+                if (tail) DRIL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FT_THREADS), args, FT_SMEM_BYTES, c->stream));
+                else DRIL_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(FT_THREADS), args, FT_SMEM_BYTES, c->stream));
+            } else if (tail) {
                 void* args[] = {(void*)&a, (void*)&tl};
                 DRIL_CUDA(cudaLaunchCooperativeKernel((const void*)ppo_loss_grad_tc_kernel, dim3(grid), dim3(TC_THREADS), args,
                                                       TC_SMEM_BYTES, c->stream));
@@ -1535,6 +1579,7 @@ static int32_t update_async(dril_policy* p, dril_buffer* b, const dril_ppo_hyper
             n_extra = 0;
         }
         for (int e = 0; e < ne; ++e) {
+            if (ft_active(p)) DRIL_TRY(ft_stage_epoch(p, b->d, fks.k[e], n_total, batch_size, 0));
             for (int i = 0; i < n_mb; ++i) {
                 Minibatch mb;
                 mb.n_total = n_total; mb.start = (long long)i * batch_size;
@@ -1763,6 +1808,7 @@ extern "C" int32_t dril_ppo_loss_grad(dril_policy* p, const float* obs, const vo
         c->launches += 2;
         Minibatch mb;
         mb.n_total = B; mb.start = 0; mb.count = B; mb.global_count = (double)B; mb.fk = fk; mb.identity = 1;
+        if (ft_active(p) && (st = ft_stage_epoch(p, b->d, fk, B, B, 1))) break;
         if ((st = minibatch_step(p, b->d, mb, p->mbstats, hp, ll, false, 0))) break;
         std::vector<float> g((size_t)pd.n_params + 6);
         cudaMemcpyAsync(g.data(), p->g, g.size() * 4, cudaMemcpyDeviceToHost, c->stream);

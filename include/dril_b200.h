@@ -114,7 +114,7 @@ enum {
 enum {
     DRIL_K_ROLLOUT = 0, DRIL_K_GAE = 1, DRIL_K_ADV_STATS = 2, DRIL_K_LOSS_GRAD = 3,
     DRIL_K_GRAD_REDUCE = 4, DRIL_K_ADAM = 5, DRIL_K_EXPLAINED_VAR = 6, DRIL_K_MONITOR = 7,
-    DRIL_K_ENV = 8, DRIL_K_POLICY = 9, DRIL_K_ALLREDUCE = 10, DRIL_K_COUNT = 11
+    DRIL_K_ENV = 8, DRIL_K_POLICY = 9, DRIL_K_ALLREDUCE = 10, DRIL_K_PERMUTE = 11, DRIL_K_COUNT = 12
 };
 
 const char* dril_last_error(void);

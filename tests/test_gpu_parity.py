@@ -671,11 +671,12 @@ def test_ppo_loss_and_gradients_many_tiles(D, name, B):
     p.close()
 
 
-@pytest.mark.parametrize("tc", [1, 0])
-def test_c2_shape_update_vs_oracle(D, tc):
+@pytest.mark.parametrize("tc,ft", [(1, 1), (1, 0), (0, 0)])
+def test_c2_shape_update_vs_oracle(D, tc, ft):
     """BASELINE config C2 at full size (4096 envs x 128 steps, 4 minibatches of 131 072 shuffled samples, 7 tiles per CTA):
     one epoch of the update on the device buffer against the oracle on the same buffer and the same Feistel minibatches."""
     D.set_option("tc", tc)
+    D.set_option("ft", ft)
     try:
         n, T = 4096, 128
         env, oenv, spec = _mk(D, "cartpole", n, 5, 500, False, False)
@@ -704,3 +705,38 @@ def test_c2_shape_update_vs_oracle(D, tc):
         buf.close()
     finally:
         D.set_option("tc", 1)
+        D.set_option("ft", 1)
+
+
+@pytest.mark.parametrize("ft", [1, 0])
+@pytest.mark.parametrize("B", [1, 63, 64, 65, 1000, 148 * 64 * 2 + 31])
+def test_tcgen05_kernels_vs_oracle(D, ft, B):
+    """Both tcgen05 loss/grad kernels for the default [64,64] layer (features-on-lanes fp16 hi/lo, option "ft" = 1, and
+    samples-on-lanes 3xTF32, "ft" = 0) on ragged tile counts, with large and tiny advantage / return scales (the fp16
+    kernel rescales its deltas per tile) and with one action (Discrete(1): zero actor gradient)."""
+    D.set_option("ft", ft)
+    try:
+        for name, scale in (("cartpole", 1.0), ("cartpole", 3e4), ("cartpole", 1e-6), ("one_action", 1.0)):
+            spec = SPECS["cartpole"]() if name == "cartpole" else OP.PolicySpec(3, [64, 64], "discrete", 1, act_start=0)
+            rng = np.random.default_rng(B + int(ft))
+            flat = (OP.init_params(spec, seed=3) + rng.normal(size=spec.n_params()).astype(f32) * 0.05).astype(f32)
+            p = _device_policy(D, spec, flat)
+            assert p.update_path() == "tensor"
+            obs, actions, adv, ret, old_lp, old_v = _minibatch(spec, flat, B, rng)
+            ret = (ret * scale).astype(f32)
+            old_v = (old_v * scale).astype(f32)
+            for alg in (D.PPO(ent_coef=0.01), D.PPO(ent_coef=0.0, clip_range_vf=0.2 * scale, normalize_advantage=False, vf_coef=0.7)):
+                cfg = OO.PPOConfig(ent_coef=alg.ent_coef, clip_range_vf=alg.clip_range_vf, normalize_advantage=alg.normalize_advantage,
+                                   vf_coef=alg.vf_coef)
+                a_in = adv if alg.normalize_advantage or B == 1 else (adv * scale).astype(f32)
+                if B == 1 and alg.normalize_advantage:
+                    continue                      # std of one sample is NaN in the reference as well
+                loss, stats, g = p.loss_grad(obs, actions, a_in, ret, old_lp, old_v, alg.hyper())
+                eloss, estats, eg = OO.ppo_loss_and_grads(spec, flat, obs, actions, a_in, ret, old_lp, old_v, cfg)
+                assert abs(loss - eloss) <= 1e-4 * max(1.0, abs(eloss)), (name, scale, loss, eloss)
+                for k in estats:
+                    assert abs(stats[k] - estats[k]) <= 1e-4 * max(1.0, abs(estats[k])), (k, stats[k], estats[k])
+                assert _relerr(g, eg) < 1e-4, (name, scale, _relerr(g, eg))
+            p.close()
+    finally:
+        D.set_option("ft", 1)
