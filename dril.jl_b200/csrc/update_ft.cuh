@@ -35,7 +35,8 @@
 #define FT_COL_D 0            // G1 output -> H1 stash -> G2 output
 #define FT_COL_D3 64          // G3 output (dW1 of this tile)
 #define FT_COL_G0 128         // stash of 1 - H0^2
-#define FT_COL_GROUP 192
+#define FT_COL_D0 192         // G0 output: H0pre of the group's NEXT tile
+#define FT_COL_GROUP 256
 #define FT_TMEM_COLS 512
 #define FT_TILE_FLOATS 576
 #define FT_TILE_BYTES (FT_TILE_FLOATS * 4)
@@ -49,11 +50,14 @@
 #define FT_G_PART (FT_G_IN + 2 * FT_TILE_BYTES)      // [4 feature quarters][64 samples] float4 partial outputs
 #define FT_G_DOUT (FT_G_PART + 4 * 64 * 16)          // [net][64 samples] float2 dL/dout
 #define FT_G_MAX (FT_G_DOUT + 2 * 64 * 8)            // [net][sample half] max |dL/dout|
-#define FT_GROUP_BYTES (76 * 1024)
+#define FT_G_XIMG (((FT_G_MAX + 64) + 127) / 128 * 128)   // [hi, lo] images of [x; 1; 0..] (16 rows x 64 samples) of the NEXT tile
+#define FT_XIMG 2048
+#define FT_GROUP_BYTES (80 * 1024)
 #define FT_OFF_SMALL (FT_OFF_GROUP + 2 * FT_GROUP_BYTES)
 #define FT_SMALL_BYTES 1024
-#define FT_SMEM_BYTES (FT_OFF_SMALL + FT_SMALL_BYTES + 1024)
-static_assert(FT_G_MAX + 64 <= FT_GROUP_BYTES, "group region too small");
+#define FT_OFF_W0A (FT_OFF_SMALL + FT_SMALL_BYTES)   // [net][hi, lo] images of C2 * [W0; b0; 0..]^T (64 rows x 16)
+#define FT_SMEM_BYTES (FT_OFF_W0A + 4 * FT_XIMG + 1024)
+static_assert(FT_G_XIMG + 2 * FT_XIMG <= FT_GROUP_BYTES, "group region too small");
 #define FT_C2 2.8853900817779268f                    // 2 log2(e): tanh(x) = 1 - 2 / (1 + 2^(C2 x)); folded into W0, b0, W1, b1
 
 // tile record (floats): x [64][4] | advantage [64] | old log-prob [64] | action index [64] (int) | return [64] | old value [64]
@@ -62,6 +66,13 @@ static_assert(FT_G_MAX + 64 <= FT_GROUP_BYTES, "group region too small");
 #define FT_R_ACT 384
 #define FT_R_RET 448
 #define FT_R_OVAL 512
+
+// -DTC_TRACE: phase timestamps of CTA 0 (thread 0 of each group): g_tc_trace[group][tile slot][point]
+#ifdef TC_TRACE
+#define FT_MARK(pt) do { if (t == 0 && blockIdx.x == 0) g_tc_trace[g][it & 31][pt] = clock64(); } while (0)
+#else
+#define FT_MARK(pt) do { } while (0)
+#endif
 
 struct FtArgs {
     const unsigned char* tiles;    // records of this epoch, [minibatch][tiles_per_mb]
@@ -147,21 +158,31 @@ template <int NOUT>
 __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const __grid_constant__ LossArgs a, const __grid_constant__ TailArgs tl,
                                                                          const __grid_constant__ FtArgs fa) {
     extern __shared__ __align__(1024) unsigned char ft_smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2][5];       // per group: tile record 0 / 1, G1, G2, G3
+    __shared__ __align__(8) uint64_t bars[2][6];       // per group: tile record 0 / 1, G1, G2, G3, G0
+    __shared__ __align__(8) uint64_t bar_stagger;       // group 1 starts when group 0 issues its first G2 / G3
     __shared__ uint32_t tmem_base_s;
     __shared__ double scratch[32];
     __shared__ float s_f2[2];
-    __shared__ float s_b2[2][2][4];                    // [group][sample half][actor 0, actor 1, critic]
+    __shared__ float s_head[8][8];                     // [(group, sample half, q)][bias sums 0..1, statistic sums 0..5] of the head warps
     if (*a.stop_flag) return;
     const PolicyDesc& pd = a.pd;
     const int tid = threadIdx.x;
+#ifdef TC_TRACE
+    const int trace_slot = tl.mode ? (int)(*tl.adam.step & 15) : 0;
+    if (tid == 0 && blockIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        g_tc_trace[0][28][trace_slot] = (long long)gt;
+        g_tc_trace[0][30][0] = clock64();
+    }
+#endif
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler
     const int lane = tid & 31;
     const int g = warp >> 3, q = warp & 3, sh = (warp >> 2) & 1, t = tid & 255;
     const int net = lane >> 4, f = 16 * q + (lane & 15);             // feature role: TMEM lane 32 q + lane
     const int m0 = 32 * sh;                                          // this thread's samples of the tile: m0 .. m0 + 31
     const int ms = m0 + lane;                                        // sample role (output layer, loss head)
-    const bool issuer = (warp & 7) == 0;
+    const bool issuer = (warp & 7) == 0;                             // one elected lane of this warp issues the group's MMAs
     const uint32_t raw = tc_smem_u32(ft_smem_raw);
     const uint32_t sm_base = (raw + 1023u) & ~1023u;
     unsigned char* sm = ft_smem_raw + (sm_base - raw);
@@ -181,6 +202,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
     uint64_t* bar1 = &bars[g][2];
     uint64_t* bar2 = &bars[g][3];
     uint64_t* bar3 = &bars[g][4];
+    uint64_t* bar0 = &bars[g][5];
+    __half* sXimg = reinterpret_cast<__half*>(smg + FT_G_XIMG);
     const LayerDesc& L0 = pd.L[net][0];
     const LayerDesc& L1 = pd.L[net][1];
     const LayerDesc& L2 = pd.L[net][2];
@@ -192,28 +215,51 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
     }
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 10; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[0][0] + i)));
+        for (int i = 0; i < 12; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[0][0] + i)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bar_stagger)));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
-    for (int i = tid; i < 2 * 64 * 64; i += FT_THREADS) {
-        const int wn = i >> 12, k = (i >> 6) & 63, n = i & 63;
-        float w = a.pack[pd.L[wn][1].pw_off + k * 64 + n] * FT_C2;
-        w = fminf(fmaxf(w, -65504.f), 65504.f);
-        const __half hi = __float2half_rn(w);
-        const __half lo = __float2half_rn(w - __half2float(hi));
-        const int idx = ((n >> 3) * 8 + (k >> 3)) * 64 + (n & 7) * 8 + (k & 7);
-        reinterpret_cast<__half*>(sm + FT_OFF_W + (wn * 2) * FT_IMG)[idx] = hi;
-        reinterpret_cast<__half*>(sm + FT_OFF_W + (wn * 2 + 1) * FT_IMG)[idx] = lo;
+    {
+        // 16 elements per thread, loads issued together (one L2 round trip)
+        float wv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int i = tid + j * FT_THREADS, wn = i >> 12, kn = i & 4095;
+            wv[j] = a.pack[pd.L[wn][1].pw_off + kn];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int i = tid + j * FT_THREADS, wn = i >> 12, k = (i >> 6) & 63, n = i & 63;
+            float w = wv[j] * FT_C2;
+            w = fminf(fmaxf(w, -65504.f), 65504.f);
+            const __half hi = __float2half_rn(w);
+            const __half lo = __float2half_rn(w - __half2float(hi));
+            const int idx = ((n >> 3) * 8 + (k >> 3)) * 64 + (n & 7) * 8 + (k & 7);
+            reinterpret_cast<__half*>(sm + FT_OFF_W + (wn * 2) * FT_IMG)[idx] = hi;
+            reinterpret_cast<__half*>(sm + FT_OFF_W + (wn * 2 + 1) * FT_IMG)[idx] = lo;
+        }
     }
     if (tid < 64) {
         sW2a[tid] = make_float2(a.pack[pd.L[0][2].pw_off + tid * 4], NOUT > 1 ? a.pack[pd.L[0][2].pw_off + tid * 4 + 1] : 0.f);
         sW2c[tid] = a.pack[pd.L[1][2].pw_off + tid * 4];
     }
     if (tid < 4) sb2[tid] = tid < 2 ? (tid < NOUT ? a.pack[pd.L[0][2].pb_off + tid] : 0.f) : (tid == 2 ? a.pack[pd.L[1][2].pb_off] : 0.f);
-    float w0s[4];
-#pragma unroll
-    for (int d = 0; d < 4; ++d) w0s[d] = a.pack[L0.pw_off + d * 64 + f] * FT_C2;
-    const float b0s = a.pack[L0.pb_off + f] * FT_C2;
+    // layer 0 runs on the tensor cores as well: A = C2 * [W0; b0; 0]^T (64 x 16), B = [x; 1; 0] (16 x 64 samples)
+    for (int i = tid; i < 2 * 64 * 16; i += FT_THREADS) {
+        const int wn = i >> 10, k = (i >> 4) & 63, d = i & 15;
+        const LayerDesc& W0 = pd.L[wn][0];
+        float w = d < 4 ? a.pack[W0.pw_off + d * 64 + k] : (d == 4 ? a.pack[W0.pb_off + k] : 0.f);
+        w = fminf(fmaxf(w * FT_C2, -65504.f), 65504.f);
+        const __half hi = __float2half_rn(w);
+        const __half lo = __float2half_rn(w - __half2float(hi));
+        const int idx = ((k >> 3) * 2 + (d >> 3)) * 64 + (k & 7) * 8 + (d & 7);
+        reinterpret_cast<__half*>(sm + FT_OFF_W0A + (wn * 2) * FT_XIMG)[idx] = hi;
+        reinterpret_cast<__half*>(sm + FT_OFF_W0A + (wn * 2 + 1) * FT_XIMG)[idx] = lo;
+    }
+    for (int i = t; i < 2 * 1024; i += 256) {                        // x images: rows 5..15 stay zero, row 4 of the hi image is 1 (bias)
+        const int r = (i & 1023) >> 3 & 7, hl = i >> 10;            // element index within an image: [d / 8][m / 8][d % 8][m % 8]
+        sXimg[i] = __float2half_rn((hl == 0 && r == 4 && (i & 1023) < 512) ? 1.0f : 0.f);
+    }
     const float b1s = a.pack[L1.pb_off + f] * FT_C2;
     const float w2_0 = a.pack[L2.pw_off + f * 4];
     const float w2_1 = (net == 0 && NOUT > 1) ? a.pack[L2.pw_off + f * 4 + 1] : 0.f;
@@ -228,6 +274,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+#ifdef TC_TRACE
+    if (tid == 0 && blockIdx.x == 0) g_tc_trace[0][30][1] = clock64();
+#endif
     const float w2bound = fmaxf(fmaxf(sWmax[net], sWmax[2 + net]), fmaxf(sWmax[4 + net], sWmax[6 + net]));
     const uint32_t gcol = tb + (uint32_t)g * FT_COL_GROUP;
     const uint32_t my = gcol + ((uint32_t)(q * 32) << 16);            // this warp's lane quadrant, this group's columns
@@ -267,34 +316,76 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
 
     const uint32_t idesc_g1 = ft_idesc(64, 64, 0, 1), idesc_g2 = ft_idesc(64, 64, 1, 1), idesc_g3 = ft_idesc(64, 64, 0, 0);
     const uint32_t imgP = smg_base + FT_G_P, imgQ = smg_base + FT_G_Q, imgW = sm_base + FT_OFF_W;
+    const uint32_t imgX = smg_base + FT_G_XIMG, imgW0 = sm_base + FT_OFF_W0A;
+    // x of tile `it` of this group -> fp16 hi / lo rows 0..3 of the x images (thread <-> (sample, component))
+    auto build_x = [&](int it) {
+        const float* r = reinterpret_cast<const float*>(smg + FT_G_IN + (it & 1) * FT_TILE_BYTES);
+        const int m = t & 63, d = t >> 6;
+        const float x = fminf(fmaxf(r[m * 4 + d], -65504.f), 65504.f);
+        const __half hi = __float2half_rn(x);
+        const int idx = (m >> 3) * 64 + d * 8 + (m & 7);
+        sXimg[idx] = hi;
+        sXimg[1024 + idx] = __float2half_rn(x - __half2float(hi));
+    };
+    // G0: H0pre = C2 (W0^T x + b0) of the tile whose x images were just built (one K = 16 step, 3 products, both nets)
+    auto issue_g0 = [&]() {
+#pragma unroll
+        for (int wn = 0; wn < 2; ++wn)
+#pragma unroll
+            for (int ps = 0; ps < 3; ++ps)
+                ft_mma(gcol + FT_COL_D0 + ((uint32_t)wn << 20), tc_desc(imgW0 + (wn * 2 + (ps == 1 ? 1 : 0)) * FT_XIMG, 128, 256, 0),
+                       tc_desc(imgX + (ps == 2 ? 1 : 0) * FT_XIMG, 1024, 128, 0), idesc_g1, ps ? 1u : 0u);
+        tc_commit(bar0);
+    };
+    if (n_own > 0) {
+        tc_wait(barL, 0u);
+        build_x(0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        tc_group_sync(g);
+        if (issuer && tc_elect_one()) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            issue_g0();
+        }
+    }
     unsigned char* pP = smg + FT_G_P + (net * 2) * FT_IMG;           // this thread's net: hi image, lo image = + FT_IMG
     unsigned char* pQ = smg + FT_G_Q + (net * 2) * FT_IMG;
 
+    // the groups would otherwise run in lock-step (same phases at the same time, tensor pipe and issue slots idle in turn)
+    if (g == 1 && n_own > 0) tc_wait(&bar_stagger, 0u);
     for (int it = 0; it < n_own; ++it) {
         const uint32_t ph = (uint32_t)it & 1u;
         const float* rec = reinterpret_cast<const float*>(smg + FT_G_IN + (it & 1) * FT_TILE_BYTES);
         const float4* Xs = reinterpret_cast<const float4*>(rec);
+        FT_MARK(0);
         if (t == 0 && it + 1 < n_own) load_tile(it + 1);              // the other record buffer was released by the barrier that ended tile it - 1
-        tc_wait(barL + (it & 1), ((uint32_t)it >> 1) & 1u);
-        // ---- A: H0 = tanh(W0^T x + b0) for (net, f) over 32 samples -> H0 images; 1 - H0^2 -> TMEM stash --------------------
+        tc_wait(bar0, ph);                                            // H0pre of this tile (issued during the previous tile / before the loop)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        FT_MARK(1);
+        // ---- A: H0 = tanh(H0pre) for (net, f) over 32 samples -> H0 images; 1 - H0^2 -> TMEM stash ----------------------------
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float h[8], gd[8];
+        for (int hh = 0; hh < 2; ++hh) {
+            float pre[16];
+            ft_ld16(my + FT_COL_D0 + m0 + 16 * hh, pre);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 x = Xs[m0 + 8 * c + j];
-                const float pre = fmaf(x.w, w0s[3], fmaf(x.z, w0s[2], fmaf(x.y, w0s[1], fmaf(x.x, w0s[0], b0s))));
-                h[j] = ft_tanh_scaled(pre);
-                gd[j] = fmaf(-h[j], h[j], 1.0f);
+            for (int c = 0; c < 2; ++c) {
+                float h[8], gd[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    h[j] = ft_tanh_scaled(pre[8 * c + j]);
+                    gd[j] = fmaf(-h[j], h[j], 1.0f);
+                }
+                uint4 vh, vl;
+                ft_split2(h[0], h[1], vh.x, vl.x); ft_split2(h[2], h[3], vh.y, vl.y);
+                ft_split2(h[4], h[5], vh.z, vl.z); ft_split2(h[6], h[7], vh.w, vl.w);
+                const uint32_t off = ft_row_off(f, m0 + 16 * hh + 8 * c);
+                *reinterpret_cast<uint4*>(pP + off) = vh;
+                *reinterpret_cast<uint4*>(pP + FT_IMG + off) = vl;
+                tc_st8(my + FT_COL_G0 + m0 + 16 * hh + 8 * c, gd);
             }
-            uint4 vh, vl;
-            ft_split2(h[0], h[1], vh.x, vl.x); ft_split2(h[2], h[3], vh.y, vl.y);
-            ft_split2(h[4], h[5], vh.z, vl.z); ft_split2(h[6], h[7], vh.w, vl.w);
-            const uint32_t off = ft_row_off(f, m0 + 8 * c);
-            *reinterpret_cast<uint4*>(pP + off) = vh;
-            *reinterpret_cast<uint4*>(pP + FT_IMG + off) = vl;
-            tc_st8(my + FT_COL_G0 + m0 + 8 * c, gd);
         }
+        FT_MARK(2);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -315,8 +406,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
                 }
             tc_commit(bar1);
         }
+        FT_MARK(3);
         tc_wait(bar1, ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        FT_MARK(4);
         // ---- B1: H1 = tanh(H1pre + b1) -> fp32 tile for the output layer + TMEM stash -------------------------------------
         {
             float h1[32];
@@ -329,7 +422,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
             ft_st32(my + FT_COL_D + m0, h1);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
+        FT_MARK(5);
         tc_group_sync(g);
+        FT_MARK(6);
         // ---- output layer partials: thread <-> (sample ms, feature quarter q) ---------------------------------------------------
         {
             float pa0 = 0.f, pa1 = 0.f, pc = 0.f;
@@ -345,7 +440,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
             }
             sPart[q * 64 + ms] = make_float4(pa0, pa1, pc, 0.f);
         }
+        FT_MARK(7);
         tc_group_sync(g);
+        FT_MARK(8);
         // ---- loss head: warps with q == 0 the actor's, q == 1 the critic's, one thread per sample --------------------------------
         if (q < 2) {
             const float4 p0 = sPart[ms], p1 = sPart[64 + ms], p2 = sPart[128 + ms], p3 = sPart[192 + ms];
@@ -360,20 +457,22 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
                 if (valid && a.hp.normalize_advantage) adv = (adv - adv_mean) / adv_den;
                 const float olp = rec[FT_R_OLP + ms];
                 const int aidx = reinterpret_cast<const int*>(rec)[FT_R_ACT + ms];
+                // softmax -> log -> entropy exactly as categorical.jl:29-52 (log of the softmax); the exponential of the maximal
+                // logit is exp(0) = 1 and log p[a] is one of the log p[j], so NOUT - 1 expf and NOUT logf are evaluated
+                int jmax = 0;
                 float mx = out[0];
 #pragma unroll
-                for (int j = 1; j < NOUT; ++j) mx = fmaxf(mx, out[j]);
+                for (int j = 1; j < NOUT; ++j) if (out[j] > mx) { mx = out[j]; jmax = j; }
                 float ex[NOUT], s = 0.f;
 #pragma unroll
-                for (int j = 0; j < NOUT; ++j) { ex[j] = expf(out[j] - mx); s += ex[j]; }
-                float pj[NOUT], lpj[NOUT], hsum = 0.f, p_a = 0.f;
+                for (int j = 0; j < NOUT; ++j) { ex[j] = j == jmax ? 1.0f : expf(out[j] - mx); s += ex[j]; }
+                float pj[NOUT], lpj[NOUT], hsum = 0.f, logp = 0.f;
 #pragma unroll
                 for (int j = 0; j < NOUT; ++j) {
                     pj[j] = ex[j] / s; lpj[j] = logf(pj[j]); hsum += pj[j] * lpj[j];
-                    if (j == aidx) p_a = pj[j];
+                    if (j == aidx) logp = lpj[j];
                 }
                 const float ent = -hsum;
-                const float logp = logf(p_a);
                 const float log_ratio = logp - olp;
                 const float ratio = expf(log_ratio);
                 const float rc = fminf(fmaxf(ratio, 1.0f - a.hp.clip_range), 1.0f + a.hp.clip_range);
@@ -386,7 +485,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
                     stats[0] += -fminf(s1, s2);
                     stats[2] += ent;
                     stats[3] += (ratio != rc) ? 1.0f : 0.0f;
-                    stats[4] += expf(log_ratio) - 1.0f - log_ratio;
+                    stats[4] += ratio - 1.0f - log_ratio;
                     stats[5] += ratio;
                 }
                 accb2_0 += dout[0];
@@ -415,7 +514,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
             for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
             if (lane == 0) sMax[q * 2 + sh] = dmax;
         }
+        FT_MARK(9);
         tc_group_sync(g);
+        FT_MARK(10);
         // ---- B2: dZ1 = (W2 dout) .* (1 - H1^2), scaled by the tile's power of two -> dZ1 images; db1, dW2 sums -------------------
         float invS;
         {
@@ -453,10 +554,16 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
                 *reinterpret_cast<uint4*>(pQ + FT_IMG + off) = vl;
             }
         }
+        if (it + 1 < n_own) {                                         // x images of the next tile (its record arrived long ago)
+            tc_wait(barL + ((it + 1) & 1), ((uint32_t)(it + 1) >> 1) & 1u);
+            build_x(it + 1);
+        }
+        FT_MARK(11);
+        if (g == 0 && it == 0 && t == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&bar_stagger)) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         tc_group_sync(g);
-        // ---- G2: dH0 = W1 dZ1 (over the H1 stash), G3: dW1 = H0 dZ1^T ----------------------------------------------------------
+        // ---- G2: dH0 = W1 dZ1 (over the H1 stash), G3: dW1 = H0 dZ1^T, G0 of the next tile ---------------------------------------
         if (issuer && tc_elect_one()) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -483,9 +590,12 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
                                idesc_g3, (ps | kk) ? 1u : 0u);
                 }
             tc_commit(bar3);
+            if (it + 1 < n_own) issue_g0();
         }
+        FT_MARK(12);
         tc_wait(bar2, ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        FT_MARK(13);
         // ---- C: dZ0 = dH0 .* (1 - H0^2); db0 and dW0 sums over this thread's 32 samples ----------------------------------------
         {
             float sb = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -508,7 +618,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
             accW0_0 = fmaf(s0, cz, accW0_0); accW0_1 = fmaf(s1, cz, accW0_1); accW0_2 = fmaf(s2, cz, accW0_2); accW0_3 = fmaf(s3, cz, accW0_3);
         }
         // ---- flush this tile's dW1 (scaled by S) into the register accumulators ----------------------------------------------
+        FT_MARK(14);
         tc_wait(bar3, ph);
+        FT_MARK(15);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {
             float d3[32];
@@ -521,7 +633,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
     }
 
     // ---- end of the minibatch: combine sample halves and groups, write this CTA's partial plane -------------------------------
+#ifdef TC_TRACE
+    if ((tid & 255) == 0 && blockIdx.x == 0) g_tc_trace[0][30][4 + g] = clock64();
+#endif
     __syncthreads();
+#ifdef TC_TRACE
+    if (tid == 0 && blockIdx.x == 0) g_tc_trace[0][30][2] = clock64();
+#endif
     float* gp = a.gpart + (size_t)blockIdx.x * pd.gpack;
     float* sDW = reinterpret_cast<float*>(sm + FT_OFF_GROUP + FT_G_P);              // [net][64][64] (group 0's image region)
     float* sRed = reinterpret_cast<float*>(sm + FT_OFF_GROUP + FT_G_Q);             // [4 slots][8 sums][128]
@@ -535,10 +653,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
         r[0] = accW0_0; r[128] = accW0_1; r[256] = accW0_2; r[384] = accW0_3; r[512] = accb0; r[640] = accb1; r[768] = accW2_0; r[896] = accW2_1;
     }
     if (q < 2) {
-        const float b0v = warp_sum(accb2_0), b1v = warp_sum(accb2_1);
+        // head warps: output-layer bias gradients and the six statistic sums (warp sums, then 8 warp slots in fixed order)
+        float hv[8] = {accb2_0, accb2_1, stats[0], stats[1], stats[2], stats[3], stats[4], stats[5]};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hv[i] = warp_sum(hv[i]);
         if (lane == 0) {
-            if (q == 0) { s_b2[g][sh][0] = b0v; s_b2[g][sh][1] = b1v; }
-            else s_b2[g][sh][2] = b0v;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s_head[(g * 2 + sh) * 2 + q][i] = hv[i];
         }
     }
     __syncthreads();
@@ -562,18 +683,33 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
         else if (qn == 5) gp[R1.pb_off + rf] = s;
         else if (qn == 6 || (rn == 0 && NOUT > 1)) gp[R2.pw_off + rf * 4 + (qn - 6)] = s;
     }
-    if (tid < 3) {
-        const float s = (s_b2[0][0][tid] + s_b2[0][1][tid]) + (s_b2[1][0][tid] + s_b2[1][1][tid]);
-        if (tid < 2) { if (tid < NOUT) gp[pd.L[0][2].pb_off + tid] = s; }
-        else gp[pd.L[1][2].pb_off] = s;
-    }
+    if (tid < 16) {
+        // slot = (group, sample half, q): q = 0 actor head warps, q = 1 critic head warps
+        const int i = tid & 7, hq = tid >> 3;
+        double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const double s = block_sum((double)stats[i], scratch);
-        if (tid == 0) gp[pd.pack_fwd + pd.act_n + i] = (float)s;
+        for (int sl = 0; sl < 4; ++sl) s += (double)s_head[sl * 2 + hq][i];
+        if (hq == 0) {
+            if (i < 2) { if (i < NOUT) gp[pd.L[0][2].pb_off + i] = (float)s; }
+            else if (i != 3) gp[pd.pack_fwd + pd.act_n + (i - 2)] = (float)s;          // policy loss, entropy, clip fraction, kl, ratio
+        } else {
+            if (i == 0) gp[pd.L[1][2].pb_off] = (float)s;
+            else if (i == 3) gp[pd.pack_fwd + pd.act_n + 1] = (float)s;                 // value loss
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(FT_TMEM_COLS));
+#ifdef TC_TRACE
+    if (tid == 0 && blockIdx.x == 0) g_tc_trace[0][30][3] = clock64();
+#endif
     if (tl.mode) tc_fused_tail(a, tl, reinterpret_cast<float*>(sm + FT_OFF_GROUP + FT_G_P), scratch, s_f2);
+#ifdef TC_TRACE
+    if (tid == 0 && blockIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        g_tc_trace[0][29][trace_slot] = (long long)gt;
+        g_tc_trace[0][30][6] = clock64();
+    }
+#endif
 }

@@ -633,6 +633,15 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
     const int p_lo = min(n, (int)blockIdx.x * per), p_hi = min(n, p_lo + per);
     const int gpack = a.pd.gpack;
     TAIL_MARK(0);
+    // the packed index / plane count of this thread's first parameter do not depend on the other CTAs: fetched before the barrier
+    int idx_first = 0, planes_first = 1;
+    {
+        const int p = p_lo + (tid & 63);
+        if (p < p_hi) {
+            idx_first = p < ad.n_params ? tl.flat2g[p] : tl.stats_off + (p - ad.n_params);
+            planes_first = p < ad.n_params ? tl.f2planes[p] : 1;
+        }
+    }
     __threadfence();
     grid.sync();                                             // every CTA's partial planes are visible
     TAIL_MARK(1);
@@ -645,8 +654,8 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
         const int lp = tid & 63, grp = tid >> 6, p = base + lp;
         float part = 0.f;
         if (p < p_hi) {
-            const int idx = p < ad.n_params ? tl.flat2g[p] : tl.stats_off + (p - ad.n_params);
-            const int planes = p < ad.n_params ? tl.f2planes[p] : 1;
+            const int idx = base == p_lo ? idx_first : (p < ad.n_params ? tl.flat2g[p] : tl.stats_off + (p - ad.n_params));
+            const int planes = base == p_lo ? planes_first : (p < ad.n_params ? tl.f2planes[p] : 1);
             // all loads of this thread's share (every 8th CTA of up to 2 planes) are issued before the first add: one L2
             // round trip instead of one per batch of 8
             TAIL_MARK(5);
