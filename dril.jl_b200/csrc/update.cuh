@@ -644,14 +644,19 @@ __device__ __forceinline__ int adam_stop(const AdamArgs& a) {
 }
 // The per-iteration accumulators (learn_stats sums, applied-step count, running beta^t, step counter, stop flag):
 // threads 0..15 of ONE CTA, independent global round trips.  s_f[0..1] receive the Adam bias corrections 1 - beta^t.
+// `old` = iter_acc[tid] and invB = 1 / global_count may be fetched / computed by the caller ahead of time (they do not depend on
+// the reduced gradient): the fused tail does so before its second grid barrier.
+__device__ __forceinline__ void adam_accumulate_pre(const AdamArgs& a, float norm, int stop, int tid, float* s_f, double old, float invB);
 __device__ __forceinline__ void adam_accumulate(const AdamArgs& a, float norm, int stop, int tid, float* s_f) {
+    if (tid >= 16) return;
+    adam_accumulate_pre(a, norm, stop, tid, s_f, a.iter_acc[tid], (float)(1.0 / a.global_count));
+}
+__device__ __forceinline__ void adam_accumulate_pre(const AdamArgs& a, float norm, int stop, int tid, float* s_f, double old, float invB) {
     if (tid >= 16) return;
     // all loads first and unconditionally (one round trip): the per-thread cases below are pure arithmetic, so the
     // divergent switch does not serialise a global load per case
     const float* st = a.g + a.n_params;
-    const float st0 = st[0], st1 = st[1], st2 = st[2], st3 = st[3], st4 = st[4], st5 = st[5];
-    const double old = a.iter_acc[tid];
-    const float invB = (float)(1.0 / a.global_count);
+    const float st0 = __ldcg(st), st1 = __ldcg(st + 1), st2 = __ldcg(st + 2), st3 = __ldcg(st + 3), st4 = __ldcg(st + 4), st5 = __ldcg(st + 5);
     if (a.apply_stats) {
         const float p_loss = st0 * invB, v_loss = st1 * invB, ent = st2 * invB;
         const float ent_loss = -ent;

@@ -662,7 +662,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
             for (int i = 0; i < 8; ++i) s_head[(g * 2 + sh) * 2 + q][i] = hv[i];
         }
     }
+#ifdef TC_TRACE
+    if (tid == 0 && blockIdx.x == 0) g_tc_trace[0][30][7] = clock64();
+#endif
     __syncthreads();
+#ifdef TC_TRACE
+    if (tid == 0 && blockIdx.x == 0) g_tc_trace[0][30][8] = clock64();
+#endif
     if (g == 0) {
         const float* d = sDW + (net * 64 + f) * 64 + m0;
         float* gw = gp + L1.pw_off + f * 64 + m0;
@@ -697,8 +703,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
             else if (i == 3) gp[pd.pack_fwd + pd.act_n + 1] = (float)s;                 // value loss
         }
     }
+#ifdef TC_TRACE
+    if (tid == 0 && blockIdx.x == 0) g_tc_trace[0][30][9] = clock64();
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+#ifdef TC_TRACE
+    if (tid == 0 && blockIdx.x == 0) g_tc_trace[0][30][10] = clock64();
+#endif
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(FT_TMEM_COLS));
 #ifdef TC_TRACE
     if (tid == 0 && blockIdx.x == 0) g_tc_trace[0][30][3] = clock64();

@@ -733,6 +733,10 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
     float m_own = 0.f, v_own = 0.f, w_own = 0.f;
     int ip_own = -1, it_own = -1;
     if (own) { m_own = ad.m[p_own]; v_own = ad.v[p_own]; w_own = ad.flat[p_own]; ip_own = ad.flat2pack[p_own]; it_own = ad.flat2packT[p_own]; }
+    // CTA 0's statistic accumulators do not depend on the other CTAs either
+    double acc_old = 0.0;
+    float acc_invB = 0.f;
+    if (blockIdx.x == 0 && tid < 16) { acc_old = ad.iter_acc[tid]; acc_invB = (float)(1.0 / ad.global_count); }
     sq = block_sum(sq, scratch);
     if (tid == 0) tl.sq_part[blockIdx.x] = sq;
     __threadfence();
@@ -745,7 +749,7 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
     const float norm = (float)sqrt(q);
     const int stop = adam_stop(ad);
     TAIL_MARK(9);
-    if (blockIdx.x == 0) adam_accumulate(ad, norm, stop, tid, s_f);
+    if (blockIdx.x == 0) adam_accumulate_pre(ad, norm, stop, tid, s_f, acc_old, acc_invB);
     TAIL_MARK(10);
     if (tl.mode == 2 && blockIdx.x == 0 && tid == 32) *tl.pp.local_seq = seq;       // every CTA read the old value before the barrier
     if (stop) return;

@@ -44,6 +44,10 @@ print("tail (CTA 0): wait for all CTAs + barrier 1 = %d, slice reduction = %d, b
 k = tr[0, 30]
 print("kernel (CTA 0, cycles): prologue %d | loop until g0 done %d, g1 done %d | sync %d | end-of-pass reductions %d | tail %d | total %d" %
       (k[1] - k[0], k[4] - k[1], k[5] - k[1], k[2] - max(k[4], k[5]), k[3] - k[2], k[6] - k[3], k[6] - k[0]))
+print("end of pass: smem writes + warp sums %d | sync %d | global writes %d | sync %d | dealloc %d" % (k[7] - k[2], k[8] - k[7], k[9] - k[8], k[10] - k[9], k[3] - k[10]))
+tl = tr[1, 31, :11]
+print("  tail reduction: index loads %d, partial loads + sums %d, smem exchange %d, rest %d | after barrier 2: sq sum %d, stop flag %d, accumulators %d, Adam %d" %
+      (tl[5] - tl[1], tl[6] - tl[5], tl[7] - tl[6], tl[2] - tl[7], tl[8] - tl[3], tl[9] - tl[8], tl[10] - tl[9], tl[4] - tl[10]))
 st, en = tr[0, 28], tr[0, 29]
 order = np.argsort(st)
 prev = None
