@@ -10,5 +10,5 @@ from .api import (AbstractCallback, AbstractTrainingLogger, ActorCriticLayer, Ag
                   ContinuousActorCriticLayer, DictLogger, DiscreteActorCriticLayer, MonitorWrapperEnv,
                   MultiThreadedParallelEnv, NeuralPolicy, NormalizeWrapperEnv, NormWrapperPolicy, NoTrainingLogger, PPO,
                   collect_rollout, evaluate_agent, extract_policy, get_action_and_values, get_hparams,
-                  load_policy_params_and_state, predict_actions, predict_values, save_policy_params_and_state,
-                  steps_taken, to_env, train)
+                  load_normalization_stats, load_policy_params_and_state, predict_actions, predict_values,
+                  save_normalization_stats, save_policy_params_and_state, steps_taken, sync_normalization_stats, to_env, train)

@@ -92,6 +92,9 @@ PROTOTYPES = {
     "dril_buffer_upload": [P, c_i32, P, c_i64],
     "dril_buffer_field_bytes": [P, c_i32, C.POINTER(c_i64)],
     "dril_rollout_collect": [P, P, P, P, C.POINTER(c_f32)],
+    "dril_rollout_collect_steps": [P, P, P, c_i64, c_i64, c_i32, P],
+    "dril_evaluate": [P, P, c_i64, c_i32, c_i32, P, P, C.POINTER(c_i64), C.POINTER(c_i64)],
+    "dril_env_zero_returns": [P],
     "dril_gae": [P, c_f32, c_f32],
     "dril_gae_raw": [P, P, P, P, P, P, P, c_i64, c_i64, c_f32, c_f32, P, P],
     "dril_ppo_loss_grad": [P, P, P, P, P, P, P, c_i64, C.POINTER(PPOHyper), C.POINTER(c_f32), P, P],

@@ -25,7 +25,8 @@ BroadcastedParallelEnv = MultiThreadedParallelEnv
 def _rewrap(env, **over):
     args = dict(kind=env.kind, n_envs=env.n_envs, max_steps=env.max_steps, obs_dim=env.obs_dim,
                 act_start=env.act_start, ctx=env.ctx, monitor_window=env.monitor_window,
-                normalize=env.normalize, gid_offset=env.gid_offset)
+                normalize=env.normalize, gid_offset=env.gid_offset,
+                obs_shape=env.obs_shape if len(env.obs_shape) > 1 else None)
     args.update(over)
     kind, n = args.pop("kind"), args.pop("n_envs")
     st, steps = env.get_state()
@@ -286,17 +287,34 @@ def load_policy_params_and_state(agent, path, suffix=".npz", restore_optimizer=F
 
 # ---- collection (buffers/rollout_buffer.jl:46-90) -----------------------------------------
 def collect_rollout(rollout_buffer, agent, alg, env, callbacks=None, forced_actions=None):
-    """collect_rollout!(buffer, agent, alg, env) -> (fps, success): fused device rollout + GAE."""
-    if not _on_step_hooks(callbacks, agent, env, alg, rollout_buffer.n_steps, rollout_buffer.n_envs):
-        return 0.0, False
+    """collect_rollout!(buffer, agent, alg, env) -> (fps, success): fused device rollout + GAE.
+    When a callback overrides on_step the rollout runs in chunks of one step (dril_rollout_collect_steps) so that the
+    hook of step i sees the env after i - 1 steps and a `false` stops the collection there (trajectory.jl:34-39)."""
     fa = None
     if forced_actions is not None:
         if rollout_buffer.discrete:
             fa = np.ascontiguousarray(np.asarray(forced_actions).reshape(len(rollout_buffer)), dtype=np.int64)
         else:
             fa = L.f32(np.asarray(forced_actions).reshape(len(rollout_buffer), rollout_buffer.act_dim))
+    lib = agent.ctx.lib
+    active = _on_step_callbacks(callbacks)
+    if active:
+        n_steps, n_envs = rollout_buffer.n_steps, rollout_buffer.n_envs
+        loc = dict(agent=agent, env=env, alg=alg, n_steps=n_steps, n_envs=n_envs, callbacks=callbacks,
+                   roll_buffer=rollout_buffer, obs_space=env.observation_space(), act_space=env.action_space())
+        t0 = time.time()
+        L.check(lib.dril_rollout_collect_steps(env.h, agent.device.h, rollout_buffer.h, 0, 0, 1, None))   # new_obs = observe(env), :32
+        for i in range(1, n_steps + 1):
+            loc["i"] = i
+            if not all(c.on_step(loc) for c in active):
+                return 0.0, False
+            chunk = None if fa is None else np.ascontiguousarray(fa[(i - 1) * n_envs:i * n_envs])
+            L.check(lib.dril_rollout_collect_steps(env.h, agent.device.h, rollout_buffer.h, i - 1, 1, 0, L.ptr(chunk)))
+        fps = n_steps * n_envs / max(time.time() - t0, 1e-12)
+        rollout_buffer.compute_advantages(alg.gamma, alg.gae_lambda)
+        return fps, True
     fps = L.c_f32(0)
-    L.check(agent.ctx.lib.dril_rollout_collect(env.h, agent.device.h, rollout_buffer.h, L.ptr(fa), C.byref(fps)))
+    L.check(lib.dril_rollout_collect(env.h, agent.device.h, rollout_buffer.h, L.ptr(fa), C.byref(fps)))
     rollout_buffer.compute_advantages(alg.gamma, alg.gae_lambda)
     return fps.value, True
 
@@ -305,23 +323,9 @@ def _hook(callbacks, name, loc):
     return all(getattr(c, name)(loc) for c in callbacks) if callbacks else True
 
 
-def _on_step_hooks(callbacks, agent, env, alg, n_steps, n_envs):
-    """on_step of collect_trajectories (buffers/trajectory.jl:34-39): called before every env step i = 1..n_steps with
-    the locals of the collection loop; the first `false` aborts the collection (and train! returns nothing).  The
-    fused rollout cannot be interrupted, so all n_steps hooks of a rollout are evaluated BEFORE it is launched: the
-    step counter, the abort decision and `steps_taken(agent)` (rollout granularity, ppo.jl:173, pinned by
-    test/test_callbacks.jl:92-99) are those of the reference; the env has not advanced between the hooks of one rollout
-    (documented deviation).  Callbacks that do not override on_step cost nothing."""
-    active = [c for c in (callbacks or []) if type(c).on_step is not AbstractCallback.on_step]
-    if not active:
-        return True
-    loc = dict(agent=agent, env=env, alg=alg, n_steps=n_steps, n_envs=n_envs, callbacks=callbacks,
-               obs_space=env.observation_space(), act_space=env.action_space())
-    for i in range(1, n_steps + 1):
-        loc["i"] = i
-        if not all(c.on_step(loc) for c in active):
-            return False
-    return True
+def _on_step_callbacks(callbacks):
+    """Callbacks that override on_step (buffers/trajectory.jl:34-39); the others cost nothing and keep the fused rollout."""
+    return [c for c in (callbacks or []) if type(c).on_step is not AbstractCallback.on_step]
 
 
 LEARN_STATS_KEYS = ("entropy_losses", "policy_losses", "value_losses", "approx_kl_divs", "clip_fractions", "losses",
@@ -368,55 +372,86 @@ def train(agent, env, alg, max_steps, callbacks=None, sync_every_iteration=True)
                                              alg.batch_size, agent.shuffle_seed, agent.epoch_counter))
         agent.epoch_counter += alg.epochs
 
-    for i in range(1, iterations + 1):
-        learning_rate = alg.learning_rate                   # Optimisers.adjust! each iteration (ppo.jl:155-157)
-        if not _hook(callbacks, "on_rollout_start", dict(locals())):
-            return None
-        if not _on_step_hooks(callbacks, agent, env, alg, n_steps, n_envs):
-            return None
-        if pipelined:
-            if i == 1:
-                enqueue()
-            if i < iterations:
-                enqueue()
-        else:
-            enqueue()
+    def drain():
         st = L.IterStats()
-        L.check(lib.dril_iteration_result(agent.device.h, C.byref(st)))
-        fps = n_steps * n_envs / max(st.rollout_ms * 1e-3, 1e-12)
-        total_fps.append(fps)
-        agent.stats.steps_taken += n_steps * n_envs         # add_step! (ppo.jl:173)
-        agent.stats.gradient_updates += st.n_minibatch_steps
-        agent.logger.increment_step(n_steps * n_envs)
-        agent.logger.log_scalar("env/fps", fps)
-        if st.episodes_in_window > 0:                       # log_stats(env, logger), monitorWrapperEnv.jl:64-70
-            agent.logger.log_scalar("env/ep_rew_mean", st.ep_rew_mean)
-            agent.logger.log_scalar("env/ep_len_mean", st.ep_len_mean)
-        if not _hook(callbacks, "on_rollout_end", dict(locals())):
-            return None
-        learn["learning_rates"].append(learning_rate)
-        learn["explained_variances"].append(st.explained_variance)
-        learn["entropy_losses"].append(st.entropy_loss)
-        learn["policy_losses"].append(st.policy_loss)
-        learn["value_losses"].append(st.value_loss)
-        learn["approx_kl_divs"].append(st.approx_kl_div)
-        learn["clip_fractions"].append(st.clip_fraction)
-        learn["losses"].append(st.loss)
-        learn["grad_norms"].append(st.grad_norm)
-        to["collect_rollout_ms"] += st.rollout_ms
-        to["update_ms"] += st.update_ms
-        lg = agent.logger
-        lg.log_scalar("train/entropy_loss", st.entropy_loss)
-        lg.log_scalar("train/explained_variance", st.explained_variance)
-        lg.log_scalar("train/policy_loss", st.policy_loss)
-        lg.log_scalar("train/value_loss", st.value_loss)
-        lg.log_scalar("train/approx_kl_div", st.approx_kl_div)
-        lg.log_scalar("train/clip_fraction", st.clip_fraction)
-        lg.log_scalar("train/loss", st.loss)
-        lg.log_scalar("train/grad_norm", st.grad_norm)
-        lg.log_scalar("train/learning_rate", learning_rate)
-    params = agent.sync_from_device()                       # copy updated parameters back
-    if not agent.layer.discrete:
+        while lib.dril_iteration_result(agent.device.h, C.byref(st)) == 0:
+            pass
+
+    completed = False
+    try:
+        for i in range(1, iterations + 1):
+            learning_rate = alg.learning_rate                   # Optimisers.adjust! each iteration (ppo.jl:155-157)
+            if not _hook(callbacks, "on_rollout_start", dict(locals())):
+                return None
+            st = L.IterStats()
+            if pipelined:
+                if i == 1:
+                    enqueue()
+                if i < iterations:
+                    enqueue()
+                L.check(lib.dril_iteration_result(agent.device.h, C.byref(st)))
+                fps = n_steps * n_envs / max(st.rollout_ms * 1e-3, 1e-12)
+            else:
+                # with callbacks the iteration is split like the reference's (ppo.jl:160-186): collect_rollout! (on_step
+                # hooks inside), bookkeeping, on_rollout_end, and only then the update, so that a hook returning false skips
+                # the update and every hook sees the parameters the rollout was collected with
+                fps, ok = collect_rollout(roll_buffer, agent, alg, env, callbacks=callbacks)
+                if not ok:
+                    return None
+                ms = env.monitor_stats() if env.is_monitored() else None
+            total_fps.append(fps)
+            agent.stats.steps_taken += n_steps * n_envs         # add_step! (ppo.jl:173)
+            agent.logger.increment_step(n_steps * n_envs)
+            agent.logger.log_scalar("env/fps", fps)
+            if pipelined:
+                if st.episodes_in_window > 0:                   # log_stats(env, logger), monitorWrapperEnv.jl:64-70
+                    agent.logger.log_scalar("env/ep_rew_mean", st.ep_rew_mean)
+                    agent.logger.log_scalar("env/ep_len_mean", st.ep_len_mean)
+            elif ms is not None and ms["n_in_window"] > 0:
+                agent.logger.log_scalar("env/ep_rew_mean", ms["ep_rew_mean"])
+                agent.logger.log_scalar("env/ep_len_mean", ms["ep_len_mean"])
+            if not _hook(callbacks, "on_rollout_end", dict(locals())):
+                return None
+            if not pipelined:
+                rollout_ms = n_steps * n_envs / max(fps, 1e-12) * 1e3
+                L.check(lib.dril_ppo_update(agent.device.h, roll_buffer.h, C.byref(alg.hyper()), alg.epochs, alg.batch_size,
+                                            agent.shuffle_seed, agent.epoch_counter, C.byref(st)))
+                agent.epoch_counter += alg.epochs
+                st.rollout_ms = rollout_ms
+            agent.stats.gradient_updates += st.n_minibatch_steps
+            learn["learning_rates"].append(learning_rate)
+            learn["explained_variances"].append(st.explained_variance)
+            learn["entropy_losses"].append(st.entropy_loss)
+            learn["policy_losses"].append(st.policy_loss)
+            learn["value_losses"].append(st.value_loss)
+            learn["approx_kl_divs"].append(st.approx_kl_div)
+            learn["clip_fractions"].append(st.clip_fraction)
+            learn["losses"].append(st.loss)
+            learn["grad_norms"].append(st.grad_norm)
+            to["collect_rollout_ms"] += st.rollout_ms
+            to["update_ms"] += st.update_ms
+            lg = agent.logger
+            lg.log_scalar("train/entropy_loss", st.entropy_loss)
+            lg.log_scalar("train/explained_variance", st.explained_variance)
+            lg.log_scalar("train/policy_loss", st.policy_loss)
+            lg.log_scalar("train/value_loss", st.value_loss)
+            lg.log_scalar("train/approx_kl_div", st.approx_kl_div)
+            lg.log_scalar("train/clip_fraction", st.clip_fraction)
+            lg.log_scalar("train/loss", st.loss)
+            lg.log_scalar("train/grad_norm", st.grad_norm)
+            lg.log_scalar("train/learning_rate", learning_rate)
+            if st.kl_stopped and agent.verbose:
+                print(f"Early stopping at iteration {i} due to reaching max kl")      # ppo.jl:236 @info
+            if not agent.layer.discrete and not pipelined:                          # ppo.jl:295-297, every iteration
+                lg.log_scalar("train/std", float(np.mean(np.exp(agent.device.get_params()[-agent.layer.act_n:]))))
+        completed = True
+    finally:
+        # an aborted train! keeps the parameters it updated in place (ppo.jl:179-186): whatever the exit path, unread pipelined
+        # results are drained and the host copy (the source of truth between calls) follows the device
+        if not completed:
+            drain()
+        params = agent.sync_from_device()                   # copy updated parameters back
+    if not agent.layer.discrete and pipelined:
         agent.logger.log_scalar("train/std", float(np.mean(np.exp(params[-agent.layer.act_n:]))))
     to["training_loop"] = time.time() - t_loop
     learn_stats = {k: np.asarray(v, dtype=np.float32) for k, v in learn.items()}
@@ -427,32 +462,49 @@ def train(agent, env, alg, max_steps, callbacks=None, sync_every_iteration=True)
 
 # ---- evaluation (src/evaluation.jl:54-143) -------------------------------------------------
 def evaluate_agent(agent, env, n_eval_episodes=10, deterministic=True, reward_threshold=None, return_stats=True,
-                   warn=True, rng=None):
+                   warn=True, rng=None, chunk_steps=None, on_device=True):
+    """evaluate_agent(agent, env; n_eval_episodes, deterministic, reward_threshold, return_stats) — src/evaluation.jl:54-143.
+    For a CudaBatchedEnv the episode loop runs on the device (dril_evaluate: fused policy + env steps in chunks, one
+    device -> host copy of the episode records per chunk); `on_device=False` keeps the step-by-step host loop over the
+    AbstractParallelEnv interface (observe / predict_actions / act!), which is what any other env type gets."""
     monitored = env.is_monitored()
-    episode_rewards, episode_lengths = [], []
-    n_envs = env.number_of_envs()
-    cur_r = np.zeros(n_envs, np.float32)
-    cur_l = np.zeros(n_envs, np.int64)
-    env.reset()
-    obs = env.observe()
-    while len(episode_rewards) < n_eval_episodes:
-        actions = predict_actions(agent, obs, deterministic=deterministic)
-        r, term, trunc, infos = env.act(actions)
-        cur_r += r
-        cur_l += 1
+    if not monitored and warn:
+        import warnings
+        warnings.warn("Evaluation environment is not wrapped with a Monitor wrapper. This may result in reporting modified "
+                      "episode lengths and rewards, if other wrappers happen to modify these.")
+    if on_device and isinstance(env, CudaBatchedEnv):
+        er = np.empty(n_eval_episodes, np.float32)
+        el = np.empty(n_eval_episodes, np.int64)
+        got, steps = L.c_i64(0), L.c_i64(0)
+        k = int(chunk_steps or max(1, min(64, env.max_steps)))
+        L.check(agent.ctx.lib.dril_evaluate(env.h, agent.device.h, int(n_eval_episodes), int(bool(deterministic)), k,
+                                            L.ptr(er), L.ptr(el), C.byref(got), C.byref(steps)))
+        assert got.value == n_eval_episodes
+    else:
+        episode_rewards, episode_lengths = [], []
+        n_envs = env.number_of_envs()
+        cur_r = np.zeros(n_envs, np.float32)
+        cur_l = np.zeros(n_envs, np.int64)
+        env.reset()
         obs = env.observe()
-        done = term | trunc
-        for i in range(n_envs):
-            if len(episode_rewards) < n_eval_episodes and done[i]:
-                if monitored and "episode" in infos[i]:
-                    episode_rewards.append(infos[i]["episode"]["r"])
-                    episode_lengths.append(infos[i]["episode"]["l"])
-                else:
-                    episode_rewards.append(float(cur_r[i]))
-                    episode_lengths.append(int(cur_l[i]))
-                cur_r[i] = 0
-                cur_l[i] = 0
-    er, el = np.asarray(episode_rewards, np.float32), np.asarray(episode_lengths)
+        while len(episode_rewards) < n_eval_episodes:
+            actions = predict_actions(agent, obs, deterministic=deterministic)
+            r, term, trunc, infos = env.act(actions)
+            cur_r += r
+            cur_l += 1
+            obs = env.observe()
+            done = term | trunc
+            for i in range(n_envs):
+                if len(episode_rewards) < n_eval_episodes and done[i]:
+                    if monitored and "episode" in infos[i]:
+                        episode_rewards.append(infos[i]["episode"]["r"])
+                        episode_lengths.append(infos[i]["episode"]["l"])
+                    else:
+                        episode_rewards.append(float(cur_r[i]))
+                        episode_lengths.append(int(cur_l[i]))
+                    cur_r[i] = 0
+                    cur_l[i] = 0
+        er, el = np.asarray(episode_rewards, np.float32), np.asarray(episode_lengths)
     mean_reward = float(er.mean())
     if reward_threshold is not None and mean_reward < reward_threshold:
         raise RuntimeError(f"Mean reward below threshold: {mean_reward:.2f} < {reward_threshold}")
@@ -460,6 +512,39 @@ def evaluate_agent(agent, env, n_eval_episodes=10, deterministic=True, reward_th
         sd = lambda x: float(np.std(x, ddof=1)) if len(x) > 1 else float("nan")
         return dict(mean_reward=mean_reward, std_reward=sd(er), mean_length=float(el.mean()), std_length=sd(el))
     return er, el
+
+
+# ---- normaliser statistics (environment_wrappers/normalizeWrapperEnv.jl:261-309) -----------
+_NORM_KEYS = ("obs_mean", "obs_var", "obs_count", "ret_mean", "ret_var", "ret_count")
+
+
+def save_normalization_stats(env, filepath):
+    """save_normalization_stats(env, filepath): the ten keys of normalizeWrapperEnv.jl:261-277 as an NPZ file (JLD2 on the
+    Julia side)."""
+    s = env.norm_stats()
+    cfg = env.normalize
+    path = filepath if filepath.endswith(".npz") else filepath + ".npz"
+    np.savez(path, obs_mean=s["obs_mean"], obs_var=s["obs_var"], obs_count=np.int64(s["obs_count"]),
+             ret_mean=np.float32(s["ret_mean"]), ret_var=np.float32(s["ret_var"]), ret_count=np.int64(s["ret_count"]),
+             clip_obs=np.float32(cfg.clip_obs), clip_reward=np.float32(cfg.clip_reward), gamma=np.float32(cfg.gamma),
+             epsilon=np.float32(cfg.epsilon))
+    return path
+
+
+def load_normalization_stats(env, filepath):
+    """load_normalization_stats!(env, filepath): running statistics only; clips / gamma / epsilon stay the env's own
+    (normalizeWrapperEnv.jl:279-297)."""
+    path = filepath if filepath.endswith(".npz") else filepath + ".npz"
+    d = np.load(path)
+    env.set_norm_stats({k: d[k] for k in _NORM_KEYS})
+    return env
+
+
+def sync_normalization_stats(eval_env, train_env):
+    """sync_normalization_stats!(eval_env, train_env): copy the running statistics and zero the eval env's discounted
+    returns; the env counts may differ (normalizeWrapperEnv.jl:299-309)."""
+    eval_env.set_norm_stats(train_env.norm_stats())
+    L.check(eval_env.ctx.lib.dril_env_zero_returns(eval_env.h))
 
 
 # ---- deployment (src/deployment/deployment_policy.jl:3-71) ---------------------------------

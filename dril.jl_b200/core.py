@@ -116,7 +116,7 @@ class CudaBatchedEnv:
     path used by evaluate_agent and callbacks; training uses the fused device rollout."""
 
     def __init__(self, kind, n_envs, max_steps=0, obs_dim=0, act_start=1, seed=None, ctx=None,
-                 monitor_window=0, normalize=None, gid_offset=0):
+                 monitor_window=0, normalize=None, gid_offset=0, obs_shape=None):
         self.kind = kind.lower()
         assert self.kind in ENV_KINDS, f"unknown env kind {kind}"
         self.ctx = ctx or Context.default()
@@ -132,10 +132,17 @@ class CudaBatchedEnv:
             hi = np.array([1, 1, 8], dtype=np.float32)
             self._obs_space, self._act_space = Box(-hi, hi), Box(np.array([-2.0], np.float32), np.array([2.0], np.float32))
         else:
+            # multi-dimensional Box observations (test/test_buffers.jl:280-314): the feature extractor of the layer is a
+            # parameter-free Flatten (layers/layer_helpers.jl:13-25), so the device works on prod(obs_shape) features and only
+            # the host-facing arrays carry the shape
+            if obs_shape is not None:
+                obs_dim = int(np.prod(obs_shape))
             assert obs_dim >= 1
             self.obs_dim, self.max_steps = int(obs_dim), max_steps or 500
-            self._obs_space = Box(-np.ones(obs_dim, np.float32), np.ones(obs_dim, np.float32))
+            shape = tuple(int(x) for x in obs_shape) if obs_shape is not None else (self.obs_dim,)
+            self._obs_space = Box(-np.ones(shape, np.float32), np.ones(shape, np.float32))
             self._act_space = Discrete(2, act_start)
+        self.obs_shape = tuple(self._obs_space.size())
         lib = self.ctx.lib
         h = L.P()
         cfg = normalize.c() if normalize is not None else None
@@ -170,7 +177,7 @@ class CudaBatchedEnv:
     def observe(self):
         out = np.empty((self.n_envs, self.obs_dim), dtype=np.float32)
         L.check(self.ctx.lib.dril_env_observe(self.h, L.ptr(out)))
-        return out
+        return out.reshape((self.n_envs,) + self.obs_shape)
 
     def act(self, actions):
         """act!(env, actions) -> rewards, terminateds, truncateds, infos (list of dicts)."""
@@ -192,7 +199,7 @@ class CudaBatchedEnv:
         for i in range(n):
             d = {}
             if self._trunc[i]:
-                d["terminal_observation"] = tobs[i].copy()
+                d["terminal_observation"] = tobs[i].reshape(self.obs_shape).copy()
             if self.monitor_window and (self._term[i] or self._trunc[i]):
                 d["episode"] = {"r": float(epr[i]), "l": int(epl[i])}
             infos.append(d)
@@ -398,6 +405,7 @@ class RolloutBuffer:
         self.ctx = ctx or Context.default()
         self.gae_lambda, self.gamma, self.n_steps, self.n_envs = float(gae_lambda), float(gamma), int(n_steps), int(n_envs)
         self.obs_dim = int(np.prod(observation_space.size()))
+        self.obs_shape = tuple(int(x) for x in observation_space.size())
         self.discrete = isinstance(action_space, Discrete)
         self.act_dim = 1 if self.discrete else int(np.prod(action_space.size()))
         h = L.P()
@@ -411,7 +419,7 @@ class RolloutBuffer:
     def _shape(self, field):
         T, N = self.n_steps, self.n_envs
         if field == "obs":
-            return (T, N, self.obs_dim)
+            return (T, N) + self.obs_shape
         if field == "actions":
             return (T, N, self.act_dim)
         if field == "last_values":

@@ -157,6 +157,7 @@ struct dril_buffer {
     int act_elems;  // per-sample action elements
     TcRolloutScratch tcs = {nullptr, nullptr, nullptr, nullptr, 0};   // tensor-core rollout: inputs of the batched critic pass
     void* tcs_slab = nullptr;
+    bool is_view = false;   // rows [t0, t0 + T) of another buffer (chunked collection): no tensor-core rollout scratch
 };
 
 struct dril_env {
@@ -1005,7 +1006,8 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
     const bool upd = d.normalize && d.training && (d.norm_obs || d.norm_reward);
     if (upd) flags |= RO_GRID_SYNC;
     const long long N = d.n_envs;
-    if (has_policy && g_opt_tc_rollout && !d.normalize && d.kind == DRIL_ENV_CARTPOLE && d.obs_dim == 4 && T > 0 && tc_eligible(a.pd) &&
+    const bool general_only = (base_flags & RO_DETERMINISTIC) != 0 || b->is_view;   // evaluation / chunked collection
+    if (has_policy && !general_only && g_opt_tc_rollout && !d.normalize && d.kind == DRIL_ENV_CARTPOLE && d.obs_dim == 4 && T > 0 && tc_eligible(a.pd) &&
         T == b->d.T) {
         // tensor-core path: actor-only step loop (64 envs per CTA) + one batched critic pass for values / bootstrap values
         if (!b->tcs_slab) {
@@ -1042,7 +1044,7 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
         return DRIL_OK;
     }
     static const int env_nofast = getenv("DRIL_ROLLOUT_NO_FAST") ? atoi(getenv("DRIL_ROLLOUT_NO_FAST")) : 0;
-    if (has_policy && !upd && !env_nofast && d.kind != DRIL_ENV_SYNTHETIC && a.pd.act_n <= RF_MAX_OUT - 1 && T > 0 &&
+    if (has_policy && !upd && !env_nofast && !(base_flags & RO_DETERMINISTIC) && d.kind != DRIL_ENV_SYNTHETIC && a.pd.act_n <= RF_MAX_OUT - 1 && T > 0 &&
         (a.pd.act_kind == DRIL_ACT_DISCRETE || a.pd.act_n == 1)) {
         // fast path: state in registers, one tile per CTA, K-split output layers
         static const int f_ctas = getenv("DRIL_FAST_CTAS_PER_SM") ? atoi(getenv("DRIL_FAST_CTAS_PER_SM")) : 2;
@@ -1319,6 +1321,139 @@ extern "C" int32_t dril_rollout_collect(dril_env* e, dril_policy* p, dril_buffer
     float ms = 0.f;
     DRIL_CUDA(cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]));
     if (fps_out) *fps_out = (float)((double)b->d.T * b->d.N / (ms * 1e-3));
+    return DRIL_OK;
+}
+
+
+// rows [t0, t0 + tc) of a buffer as a buffer of tc steps (pointers into the same slab; last_values shared)
+static dril_buffer buffer_view(dril_buffer* b, long long t0, long long tc) {
+    dril_buffer v = *b;
+    const long long N = b->d.N;
+    const size_t r0 = (size_t)t0 * N;
+    v.d.T = tc;
+    v.d.obs += r0 * b->d.obs_dim;
+    v.d.actions = (char*)b->d.actions + r0 * b->act_elems * 4;
+    v.d.rewards += r0; v.d.values += r0; v.d.logprobs += r0; v.d.advantages += r0; v.d.returns += r0; v.d.boot += r0;
+    v.d.episode_r += r0; v.d.episode_l += r0; v.d.flags += r0; v.d.done_count += t0;
+    v.is_view = true; v.tcs_slab = nullptr;
+    return v;
+}
+
+/* Steps [t_begin, t_begin + t_count) of a rollout into rows [t_begin, ...) of the buffer: collect_trajectories
+ * (buffers/trajectory.jl:22-78) run in chunks so that on_step callbacks (:34-39) see the advancing env and can stop the
+ * collection mid-rollout.  start != 0 begins a rollout: per-rollout counters zeroed and the observe() before the loop (:32),
+ * which precedes the first on_step hook, so it can be requested on its own with t_count = 0.  The bootstrap values of the
+ * last chunk are the rollout's.  Follow with dril_gae once t_begin + t_count == n_steps. */
+extern "C" int32_t dril_rollout_collect_steps(dril_env* e, dril_policy* p, dril_buffer* b, int64_t t_begin, int64_t t_count,
+                                              int32_t start, const void* forced_actions) {
+    DRIL_TRY(check_compat(e, p, b));
+    DRIL_REQUIRE(t_begin >= 0 && t_count >= 0 && t_begin + t_count <= b->d.T, "steps [%lld, %lld) outside the buffer's %lld steps",
+                 (long long)t_begin, (long long)(t_begin + t_count), b->d.T);
+    DRIL_REQUIRE(t_count >= 1 || start, "nothing to do");
+    dril_ctx* c = e->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    dril_buffer v = buffer_view(b, t_begin, std::max<int64_t>(t_count, 1));
+    void* forced_dev = nullptr;
+    if (forced_actions && t_count > 0) {
+        const size_t cnt = (size_t)t_count * b->d.N;
+        DRIL_TRY(ensure_scratch(p, cnt * b->act_elems * 4));
+        DRIL_TRY(stage_actions(c, b->d.act_kind, b->d.act_dim, forced_actions, cnt, p->scratch));
+        forced_dev = p->scratch;
+    }
+    if (start) {
+        DRIL_CUDA(cudaMemsetAsync(b->d.done_count, 0, (size_t)b->d.T * 4, c->stream));
+        DRIL_CUDA(cudaMemsetAsync(e->d.roll_sums, 0, 16, c->stream));
+        DRIL_CUDA(cudaMemsetAsync(e->d.roll_eps, 0, 8, c->stream));
+    }
+    const bool obs_stats = e->d.normalize && e->d.training && e->d.norm_obs;
+    if (t_count > 0 || (start && obs_stats))
+        DRIL_TRY(launch_rollout(e, t_count > 0 ? p : nullptr, &v, forced_dev, nullptr, (int)t_count, (start ? RO_INITIAL_OBSERVE : 0) | RO_FOLD_NEXT_OBSERVE));
+    p->step_index += (uint32_t)t_count;
+    if (t_count > 0 && t_begin + t_count == b->d.T) {
+        DRIL_TRY(launch_monitor_finalize(e, b));
+        unsigned long long eps = 0;
+        DRIL_CUDA(cudaMemcpyAsync(&eps, e->d.roll_eps, 8, cudaMemcpyDeviceToHost, c->stream));
+        DRIL_CUDA(cudaStreamSynchronize(c->stream));
+        e->total_episodes += (int64_t)eps;
+    } else {
+        DRIL_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return DRIL_OK;
+}
+
+/* evaluate_agent (src/evaluation.jl:54-143) with the episode loop on the device: reset!(env), then the policy (mode of the
+ * distribution when deterministic) steps all envs in chunks of `chunk_steps` fused steps; after every chunk ONE device -> host
+ * copy brings the chunk's done flags and episode records, and finished episodes are appended in the reference's order
+ * (step by step, env index within a step) until n_eval_episodes are collected.  Episode returns / lengths are the
+ * MonitorWrapperEnv records when the env is monitored (evaluation.jl:110-113), else the sums of the step rewards the
+ * outermost wrapper returned (:114-117).  The env is left where the last chunk ended (up to chunk_steps - 1 steps past the
+ * reference's stopping point). */
+extern "C" int32_t dril_evaluate(dril_env* e, dril_policy* p, int64_t n_eval_episodes, int32_t deterministic, int32_t chunk_steps,
+                                 float* episode_rewards, int64_t* episode_lengths, int64_t* n_collected, int64_t* env_steps) {
+    DRIL_REQUIRE(e && p && episode_rewards && episode_lengths, "NULL argument");
+    DRIL_REQUIRE(e->ctx == p->ctx, "env and policy must share a ctx");
+    DRIL_REQUIRE(n_eval_episodes >= 1 && chunk_steps >= 1, "n_eval_episodes and chunk_steps must be positive");
+    dril_ctx* c = e->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    const long long N = e->d.n_envs;
+    const int K = chunk_steps;
+    dril_buffer* b = nullptr;
+    DRIL_TRY(dril_buffer_create(c, K, N, e->d.obs_dim, p->pd.act_kind, p->pd.act_kind == DRIL_ACT_DISCRETE ? 1 : p->pd.act_n, &b));
+    int32_t st = check_compat(e, p, b);
+    std::vector<unsigned char> flags((size_t)K * N);
+    std::vector<float> er((size_t)K * N), rew((size_t)K * N);
+    std::vector<int> el((size_t)K * N);
+    std::vector<float> cur_r((size_t)N, 0.f);
+    std::vector<long long> cur_l((size_t)N, 0);
+    long long got = 0, steps = 0;
+    const bool mon = e->d.monitor != 0;
+    if (st == DRIL_OK) st = dril_env_reset(e);
+    for (long long chunk = 0; st == DRIL_OK && got < n_eval_episodes; ++chunk) {
+        if (chunk > 100000) { dril_set_error("dril_evaluate: no episode finished in %lld steps", steps); st = DRIL_ERR_INVALID; break; }
+        cudaMemsetAsync(b->d.done_count, 0, (size_t)K * 4, c->stream);
+        cudaMemsetAsync(e->d.roll_sums, 0, 16, c->stream);
+        cudaMemsetAsync(e->d.roll_eps, 0, 8, c->stream);
+        if ((st = launch_rollout(e, p, b, nullptr, nullptr, K, (chunk == 0 ? RO_INITIAL_OBSERVE : 0) | RO_FOLD_NEXT_OBSERVE |
+                                 (deterministic ? RO_DETERMINISTIC : 0)))) break;
+        p->step_index += (uint32_t)K;
+        if ((st = launch_monitor_finalize(e, b))) break;
+        unsigned long long eps = 0;
+        cudaMemcpyAsync(flags.data(), b->d.flags, flags.size(), cudaMemcpyDeviceToHost, c->stream);
+        if (mon) {
+            cudaMemcpyAsync(er.data(), b->d.episode_r, er.size() * 4, cudaMemcpyDeviceToHost, c->stream);
+            cudaMemcpyAsync(el.data(), b->d.episode_l, el.size() * 4, cudaMemcpyDeviceToHost, c->stream);
+        } else {
+            cudaMemcpyAsync(rew.data(), b->d.rewards, rew.size() * 4, cudaMemcpyDeviceToHost, c->stream);
+        }
+        cudaMemcpyAsync(&eps, e->d.roll_eps, 8, cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { dril_set_error("CUDA failure in dril_evaluate: %s", cudaGetErrorString(cudaGetLastError())); st = DRIL_ERR_CUDA; break; }
+        e->total_episodes += (int64_t)eps;
+        for (int t = 0; t < K && got < n_eval_episodes; ++t) {
+            steps += 1;
+            for (long long n = 0; n < N; ++n) {
+                const size_t i = (size_t)t * N + n;
+                if (!mon) { cur_r[n] += rew[i]; cur_l[n] += 1; }
+                if ((flags[i] & 3) && got < n_eval_episodes) {
+                    episode_rewards[got] = mon ? er[i] : cur_r[n];
+                    episode_lengths[got] = mon ? (int64_t)el[i] : (int64_t)cur_l[n];
+                    ++got;
+                    cur_r[n] = 0.f; cur_l[n] = 0;
+                }
+            }
+        }
+    }
+    dril_buffer_destroy(b);
+    if (n_collected) *n_collected = got;
+    if (env_steps) *env_steps = steps;
+    return st;
+}
+
+/* sync_normalization_stats! zeroes the discounted-return accumulators of the receiving env (normalizeWrapperEnv.jl:306) */
+extern "C" int32_t dril_env_zero_returns(dril_env* e) {
+    DRIL_REQUIRE(e, "NULL argument");
+    DRIL_CUDA(cudaSetDevice(e->ctx->device));
+    if (e->d.ret) DRIL_CUDA(cudaMemsetAsync(e->d.ret, 0, (size_t)e->d.n_envs * 4, e->ctx->stream));
+    DRIL_CUDA(cudaStreamSynchronize(e->ctx->stream));
     return DRIL_OK;
 }
 

@@ -30,7 +30,8 @@ enum {
     RO_GRID_SYNC = 16,        // training normaliser: cooperative launch + grid barrier per step
     RO_WRITE_OBS_OUT = 32,    // compat observe: write normalised obs to obs_out
     RO_TILES_8X8 = 64,        // throughput mode (many envs per SM): 8x8 register tiles in the hidden layers
-    RO_MMA = 128              // general kernel, tile width multiple of 16: wide layers on mma.sync 3xTF32 tiles
+    RO_MMA = 128,             // general kernel, tile width multiple of 16: wide layers on mma.sync 3xTF32 tiles
+    RO_DETERMINISTIC = 256    // general kernel: mode of the distribution instead of a sample (evaluate_agent, evaluation.jl:54-143)
 };
 
 struct RolloutArgs {
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
                         int mode = 0, forced_v = 0;
                         double u = 0.0;
                         if (a.forced) { mode = 2; forced_v = reinterpret_cast<const int*>(a.forced)[row + n]; }
+                        else if (a.flags & RO_DETERMINISTIC) mode = 1;
                         else {
                             uint32_t x[4];
                             philox4x32(gid, a.step0 + (uint32_t)t, 0u, DRIL_TAG_SAMPLE, a.pseed, x);
@@ -327,6 +329,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
                             float ls = a.flat[pd.log_std_off + j];
                             float act;
                             if (a.forced) act = reinterpret_cast<const float*>(a.forced)[(row + n) * A + j];
+                            else if (a.flags & RO_DETERMINISTIC) act = mean;            // mode(DiagGaussian) = mean (diagGaussian.jl:40-47)
                             else act = __fadd_rn(mean, __fmul_rn(expf(ls), sample_normal(gid, a.step0 + (uint32_t)t, j, a.pseed)));
                             float diff = act - mean;
                             dss += diff * diff * expf(-2.0f * ls);

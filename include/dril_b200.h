@@ -194,6 +194,8 @@ int32_t dril_env_set_norm_stats(dril_env* env, const float* obs_mean, const floa
 int32_t dril_env_set_training(dril_env* env, int32_t training);
 /* original (un-normalised) obs / rewards of the last observe/act (old_obs, old_rewards) */
 int32_t dril_env_get_original(dril_env* env, float* obs_out, float* rewards_out);
+/* the zeroing of `returns` in sync_normalization_stats! (normalizeWrapperEnv.jl:299-309) */
+int32_t dril_env_zero_returns(dril_env* env);
 /* log_stats(env): mean return / length over the last `monitor_window` episodes (monitorWrapperEnv.jl:64-70) */
 int32_t dril_env_monitor_stats(dril_env* env, float* ep_rew_mean, float* ep_len_mean,
                                int64_t* n_in_window, int64_t* total_episodes);
@@ -244,6 +246,19 @@ int32_t dril_buffer_field_bytes(dril_buffer* b, int32_t field, int64_t* bytes);
  * forced_actions (nullable): replay int64[T][N] | float[T][N][act_dim] instead of sampling. */
 int32_t dril_rollout_collect(dril_env* env, dril_policy* p, dril_buffer* buf,
                              const void* forced_actions, float* fps_out);
+/* Steps [t_begin, t_begin + t_count) of a rollout into the same rows of the buffer: collect_trajectories run in chunks
+ * so that on_step callbacks (buffers/trajectory.jl:34-39) see the advancing env and can stop the collection mid-rollout.
+ * start != 0 begins a rollout (per-rollout counters zeroed, the observe() of trajectory.jl:32, which precedes the first
+ * hook: t_count = 0 requests it alone); Monitor / Normalize state carries across chunks; the bootstrap values of the last
+ * chunk are the rollout's.  Follow with dril_gae after the last chunk. */
+int32_t dril_rollout_collect_steps(dril_env* env, dril_policy* p, dril_buffer* buf, int64_t t_begin, int64_t t_count,
+                                   int32_t start, const void* forced_actions);
+/* evaluate_agent (src/evaluation.jl:54-143) with the episode loop on the device: reset!(env), `chunk_steps` fused policy
+ * steps per launch (mode of the distribution when deterministic), one device -> host copy of the chunk's episode records
+ * per launch; episodes are appended in the reference's order (step, then env index) until n_eval_episodes are
+ * collected.  episode_rewards / episode_lengths: host arrays of n_eval_episodes elements. */
+int32_t dril_evaluate(dril_env* env, dril_policy* p, int64_t n_eval_episodes, int32_t deterministic, int32_t chunk_steps,
+                      float* episode_rewards, int64_t* episode_lengths, int64_t* n_collected, int64_t* env_steps);
 /* compute_advantages! + returns = adv + values (trajectory.jl:80-102, rollout_buffer.jl:83-87) */
 int32_t dril_gae(dril_buffer* buf, float gamma, float gae_lambda);
 /* raw-array parity entry: time-major host arrays [T][N]; boot[T][N], last_values[N] */
