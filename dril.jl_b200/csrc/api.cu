@@ -148,6 +148,7 @@ struct dril_ctx {
     bool p2p_enabled = false;
     void* l2_scratch = nullptr;
     size_t l2_bytes = 0;
+    std::vector<struct dril_policy*> policies;   // live policies of this ctx (their env back-pointers are cleared by dril_env_destroy)
 };
 
 struct dril_buffer {
@@ -170,6 +171,12 @@ struct dril_env {
     int max_blocks = 0;
     int64_t total_episodes = 0;
     PolicyDesc nopolicy;             // zeroed descriptor for policy-less launches
+    // data-parallel runs: per-rollout normaliser moments, the statistics every rank started the rollout with, and the small
+    // fp64 exchange buffer [explained-variance moments 4 | monitor sums 3 | normaliser moments 2 (D + 1) + 2]
+    double* roll_moments = nullptr;
+    double* xr = nullptr;
+    float* norm_snap = nullptr;
+    long long* norm_snap_cnt = nullptr;
 };
 
 struct dril_policy {
@@ -216,6 +223,8 @@ struct dril_policy {
     size_t ft_tiles_bytes = 0;
     int ft_tiles_per_mb = 0;
     long long ft_batch = 1;
+    // Adam betas of the most recent update (dril_ppo_hyper carries them per call); Optimisers.Adam defaults until then
+    double beta1 = 0.9, beta2 = 0.999;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -690,6 +699,7 @@ extern "C" int32_t dril_policy_create(dril_ctx* c, int32_t obs_dim, int32_t n_hi
         double ones[2] = {1.0, 1.0};
         DRIL_CUDA(cudaMemcpy(p->iter_acc + 12, ones, 16, cudaMemcpyHostToDevice));
     }
+    c->policies.push_back(p);
     *out = p;
     return DRIL_OK;
 }
@@ -697,6 +707,10 @@ extern "C" int32_t dril_policy_destroy(dril_policy* p) {
     if (!p) return DRIL_OK;
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
+    {
+        auto& v = p->ctx->policies;
+        v.erase(std::remove(v.begin(), v.end(), p), v.end());
+    }
     void* ps[] = {p->flat, p->pack, p->m, p->v, p->g, p->gpart, p->flat2pack, p->flat2packT, p->flat2g, p->step,
                   p->iter_acc, p->ev_acc, p->mbstats, p->adv_partial, p->stop_flag, p->scratch, p->f2planes, p->f2planes_one, p->sq_part,
                   p->ticket, p->ft_tiles};
@@ -773,7 +787,8 @@ extern "C" int32_t dril_policy_set_opt_state(dril_policy* p, const float* m, con
     DRIL_CUDA(cudaMemcpyAsync(p->m, m, n * 4, cudaMemcpyHostToDevice, p->ctx->stream));
     DRIL_CUDA(cudaMemcpyAsync(p->v, v, n * 4, cudaMemcpyHostToDevice, p->ctx->stream));
     DRIL_CUDA(cudaMemcpyAsync(p->step, &s, 8, cudaMemcpyHostToDevice, p->ctx->stream));
-    double pw[2] = {pow(0.9, (double)step), pow(0.999, (double)step)};   // Optimisers.Adam default betas (ppo.jl:64-66)
+    // running beta^t of the bias correction: the betas of the last update (Optimisers.Adam defaults (0.9, 0.999), ppo.jl:64-66, before one)
+    double pw[2] = {pow(p->beta1, (double)step), pow(p->beta2, (double)step)};
     DRIL_CUDA(cudaMemcpyAsync(p->iter_acc + 12, pw, 16, cudaMemcpyHostToDevice, p->ctx->stream));
     DRIL_CUDA(cudaStreamSynchronize(p->ctx->stream));
     return DRIL_OK;
@@ -930,6 +945,10 @@ extern "C" int32_t dril_env_create(dril_ctx* c, int32_t kind, int64_t n_envs, in
     DRIL_TRY(dmalloc(&d.ret, n)); DRIL_TRY(dmalloc(&d.obs_mean, (size_t)d.obs_dim)); DRIL_TRY(dmalloc(&d.obs_var, (size_t)d.obs_dim));
     DRIL_TRY(dmalloc(&d.ret_stats, 2)); DRIL_TRY(dmalloc(&d.counts, 2));
     DRIL_TRY(dmalloc(&d.partials, (size_t)2 * e->max_blocks * (2 * d.obs_dim + 2)));
+    DRIL_TRY(dmalloc(&e->roll_moments, (size_t)2 * (d.obs_dim + 1) + 2));     // handed to the kernels only in data-parallel runs
+    DRIL_TRY(dmalloc(&e->xr, (size_t)4 + 3 + 2 * (d.obs_dim + 1) + 2));
+    DRIL_TRY(dmalloc(&e->norm_snap, (size_t)2 * d.obs_dim + 2)); DRIL_TRY(dmalloc(&e->norm_snap_cnt, 2));
+    d.roll_moments = nullptr;
     DRIL_CUDA(cudaMemset(d.ret, 0, n * 4));
     {   // RunningMeanStd init: mean 0, var 1, count 0 (normalizeWrapperEnv.jl:13-15)
         std::vector<float> ones((size_t)d.obs_dim, 1.0f);
@@ -951,10 +970,15 @@ extern "C" int32_t dril_env_destroy(dril_env* e) {
     if (!e) return DRIL_OK;
     cudaSetDevice(e->ctx->device);
     cudaStreamSynchronize(e->ctx->stream);
+    // iterations still in flight keep a back-pointer to their env (episode bookkeeping in dril_iteration_result): cleared here
+    for (dril_policy* p : e->ctx->policies) {
+        if (p->last_env == e) p->last_env = nullptr;
+        for (auto& sl : p->slots) if (sl.env == e) sl.env = nullptr;
+    }
     EnvDev& d = e->d;
     void* ps[] = {d.state, d.steps, d.episode, d.life, d.tobs, d.old_obs, d.old_rewards, d.ep_ret, d.ep_len, d.roll_sums,
                   d.roll_eps, d.ret, d.obs_mean, d.obs_var, d.ret_stats, d.counts, d.partials, e->ring.ret, e->ring.len,
-                  e->ring.head, e->compat_actions, e->compat_obs};
+                  e->ring.head, e->compat_actions, e->compat_obs, e->roll_moments, e->xr, e->norm_snap, e->norm_snap_cnt};
     for (void* p : ps) if (p) cudaFree(p);
     dril_buffer_destroy(e->compat);
     delete e;
@@ -1289,11 +1313,47 @@ static int32_t check_compat(dril_env* e, dril_policy* p, dril_buffer* b) {
     return DRIL_OK;
 }
 
+// Data-parallel runs: every rank normalises its own env shard during a rollout; afterwards the ranks merge the
+// rollout's (count, mean, M2) over ALL shards into the statistics they started the rollout with (Chan merge of
+// normalizeWrapperEnv.jl:37-48), so every rollout begins with identical statistics on every rank, and the Monitor sums
+// (episode returns / lengths / count of the rollout) become global.
+static bool dp_norm_active(const dril_env* e) {
+    return e->ctx->nranks > 1 && e->d.normalize && e->d.training && (e->d.norm_obs || e->d.norm_reward);
+}
+static int dp_xr_count(const dril_env* e) { return 3 + 2 * (e->d.obs_dim + 1) + 2; }
+static int32_t dp_rollout_begin(dril_env* e) {
+    dril_ctx* c = e->ctx;
+    e->d.roll_moments = nullptr;
+    if (!dp_norm_active(e)) return DRIL_OK;
+    e->d.roll_moments = e->roll_moments;
+    norm_snapshot_kernel<<<1, 64, 0, c->stream>>>(e->d, e->norm_snap, e->norm_snap_cnt);
+    DRIL_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return DRIL_OK;
+}
+static int32_t dp_rollout_pack(dril_env* e) {
+    dril_ctx* c = e->ctx;
+    if (c->nranks == 1) return DRIL_OK;
+    norm_monitor_pack_kernel<<<1, 64, 0, c->stream>>>(e->d, e->xr + 4, e->norm_snap, e->norm_snap_cnt, 2 * (e->d.obs_dim + 1) + 2);
+    DRIL_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return DRIL_OK;
+}
+static int32_t dp_rollout_merge(dril_env* e) {
+    dril_ctx* c = e->ctx;
+    if (c->nranks == 1) return DRIL_OK;
+    norm_monitor_merge_kernel<<<1, 64, 0, c->stream>>>(e->d, e->xr + 4, e->norm_snap, e->norm_snap_cnt, dp_norm_active(e) ? 1 : 0);
+    DRIL_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return DRIL_OK;
+}
+
 static int32_t rollout_async(dril_env* e, dril_policy* p, dril_buffer* b, const void* forced_dev) {
     dril_ctx* c = e->ctx;
     DRIL_CUDA(cudaMemsetAsync(b->d.done_count, 0, (size_t)b->d.T * 4, c->stream));
     DRIL_CUDA(cudaMemsetAsync(e->d.roll_sums, 0, 16, c->stream));
     DRIL_CUDA(cudaMemsetAsync(e->d.roll_eps, 0, 8, c->stream));
+    DRIL_TRY(dp_rollout_begin(e));
     DRIL_TRY(launch_rollout(e, p, b, forced_dev, nullptr, (int)b->d.T, RO_INITIAL_OBSERVE | RO_FOLD_NEXT_OBSERVE));
     p->step_index += (uint32_t)b->d.T;
     return DRIL_OK;
@@ -1313,6 +1373,11 @@ extern "C" int32_t dril_rollout_collect(dril_env* e, dril_policy* p, dril_buffer
     DRIL_CUDA(cudaEventRecord(p->ev[0], c->stream));
     DRIL_TRY(rollout_async(e, p, b, forced_dev));
     DRIL_CUDA(cudaEventRecord(p->ev[1], c->stream));
+    if (c->nranks > 1) {
+        DRIL_TRY(dp_rollout_pack(e));
+        DRIL_TRY(allreduce_small(c, nullptr, 0, e->xr + 4, dp_xr_count(e)));
+        DRIL_TRY(dp_rollout_merge(e));
+    }
     DRIL_TRY(launch_monitor_finalize(e, b));
     unsigned long long eps = 0;
     DRIL_CUDA(cudaMemcpyAsync(&eps, e->d.roll_eps, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1687,6 +1752,7 @@ static int32_t update_async(dril_policy* p, dril_buffer* b, const dril_ppo_hyper
     DRIL_REQUIRE(epochs >= 0, "epochs must be non-negative");
     const int n_mb = (int)((n_total + batch_size - 1) / batch_size);
     const UpdateHyper hp = to_hyper(h);
+    p->beta1 = (double)h->adam_beta1; p->beta2 = (double)h->adam_beta2;
     LossLaunch ll;
     DRIL_TRY(plan_loss(p, &ll));
     const int bpm = (int)std::max<long long>(1, std::min<long long>(64, (std::min<long long>(batch_size, n_total) + 2047) / 2048));
@@ -1851,15 +1917,21 @@ extern "C" int32_t dril_ppo_iteration_async(dril_env* e, dril_policy* p, dril_bu
     p->last_env = e; p->last_buf = b; p->last_lr = h->learning_rate;
     DRIL_CUDA(cudaEventRecord(sl.ev[0], c->stream));
     DRIL_TRY(rollout_async(e, p, b, nullptr));
-    DRIL_CUDA(cudaMemsetAsync(p->ev_acc, 0, 32, c->stream));
-    DRIL_TRY(gae_async(c, b->d, h->gamma, h->gae_lambda, p->ev_acc));   // + explained-variance moments (ppo.jl:256)
+    // data-parallel: explained-variance moments, Monitor sums and the rollout's normaliser moments travel in ONE small fp64
+    // exchange together with the first batch of minibatch advantage moments
+    const bool dp = c->nranks > 1;
+    double* ev = dp ? e->xr : p->ev_acc;
+    DRIL_CUDA(cudaMemsetAsync(ev, 0, 32, c->stream));
+    DRIL_TRY(gae_async(c, b->d, h->gamma, h->gae_lambda, ev));   // + explained-variance moments (ppo.jl:256)
     DRIL_TRY(launch_monitor_finalize(e, b));
+    if (dp) DRIL_TRY(dp_rollout_pack(e));
     DRIL_CUDA(cudaEventRecord(sl.ev[1], c->stream));
-    DRIL_TRY(update_async(p, b, h, epochs, batch_size, shuffle_seed, epoch_counter, p->ev_acc, 4));
+    DRIL_TRY(update_async(p, b, h, epochs, batch_size, shuffle_seed, epoch_counter, ev, dp ? 4 + dp_xr_count(e) : 4));
+    if (dp) DRIL_TRY(dp_rollout_merge(e));
     DRIL_CUDA(cudaEventRecord(sl.ev[2], c->stream));
     {
         IterRecordSrc src;
-        src.acc = p->iter_acc; src.ev = p->ev_acc; src.roll_sums = e->d.roll_sums; src.roll_eps = e->d.roll_eps;
+        src.acc = p->iter_acc; src.ev = ev; src.roll_sums = e->d.roll_sums; src.roll_eps = e->d.roll_eps;
         src.stop = p->stop_flag; src.p2p_err = c->p2p_enabled ? c->p2p.err : nullptr; src.ring = e->ring;
         src.has_ring = e->d.monitor ? 1 : 0;
         Span sp(c, DRIL_K_MONITOR);

@@ -88,6 +88,8 @@ struct EnvDev {
     float* ret_stats;           // [2] mean, var
     long long* counts;          // [2] obs_count, ret_count
     double* partials;           // [2 parity][max_blocks][2*obs_dim + 2]
+    double* roll_moments;       // [2 * (obs_dim + 1) + 2]: this rollout's sums / sums of squares per normalised column
+                                // (obs dims, discounted return) and the obs / return sample counts (data-parallel merge)
     float* tobs;                // [n][obs_dim] raw terminal observations scratch
     float* old_obs;             // [n][obs_dim] raw obs of the last observe (compat path)
     float* old_rewards;         // [n]

@@ -91,6 +91,54 @@ __device__ __forceinline__ void rms_merge(float& mean, float& var, long long cou
     }
 }
 
+// Data-parallel normaliser merge after a rollout: xr holds, summed over ranks, [roll return sum, roll length sum,
+// roll episodes | per column (obs dims, return): sum, sum of squares | obs samples, return samples] of this rollout; the running
+// statistics become snap (+) global batch with the Chan merge of normalizeWrapperEnv.jl:28-50, identically on every rank.
+__global__ void norm_monitor_merge_kernel(EnvDev env, const double* __restrict__ xr, const float* __restrict__ snap, const long long* __restrict__ snap_cnt,
+                                          int do_norm) {
+    const int D = env.obs_dim, t = threadIdx.x;
+    if (t == 0) {
+        env.roll_sums[0] = xr[0]; env.roll_sums[1] = xr[1];
+        *env.roll_eps = (unsigned long long)(xr[2] + 0.5);
+    }
+    if (!do_norm) return;
+    const double* mom = xr + 3;
+    const double n_obs = mom[2 * (D + 1)], n_ret = mom[2 * (D + 1) + 1];
+    for (int d = t; d < D; d += blockDim.x) {
+        if (n_obs > 0.0) {
+            const double bm = mom[2 * d] / n_obs;
+            double bv = mom[2 * d + 1] / n_obs - bm * bm;
+            if (bv < 0.0) bv = 0.0;
+            float m = snap[d], v = snap[D + d];
+            rms_merge(m, v, snap_cnt[0], (float)bm, (float)bv, (long long)(n_obs + 0.5));
+            env.obs_mean[d] = m; env.obs_var[d] = v;
+        }
+    }
+    if (t == 0) {
+        if (n_ret > 0.0) {
+            const double bm = mom[2 * D] / n_ret;
+            double bv = mom[2 * D + 1] / n_ret - bm * bm;
+            if (bv < 0.0) bv = 0.0;
+            float m = snap[2 * D], v = snap[2 * D + 1];
+            rms_merge(m, v, snap_cnt[1], (float)bm, (float)bv, (long long)(n_ret + 0.5));
+            env.ret_stats[0] = m; env.ret_stats[1] = v;
+        }
+        env.counts[0] = snap_cnt[0] + (long long)(n_obs + 0.5);
+        env.counts[1] = snap_cnt[1] + (long long)(n_ret + 0.5);
+    }
+}
+__global__ void norm_monitor_pack_kernel(EnvDev env, double* __restrict__ xr, float* __restrict__ snap, long long* __restrict__ snap_cnt, int n_mom) {
+    const int t = threadIdx.x;
+    if (t == 0) { xr[0] = env.roll_sums[0]; xr[1] = env.roll_sums[1]; xr[2] = (double)*env.roll_eps; }
+    for (int i = t; i < n_mom; i += blockDim.x) xr[3 + i] = env.roll_moments ? env.roll_moments[i] : 0.0;
+}
+__global__ void norm_snapshot_kernel(EnvDev env, float* __restrict__ snap, long long* __restrict__ snap_cnt) {
+    const int D = env.obs_dim, t = threadIdx.x;
+    for (int d = t; d < D; d += blockDim.x) { snap[d] = env.obs_mean[d]; snap[D + d] = env.obs_var[d]; }
+    if (t == 0) { snap[2 * D] = env.ret_stats[0]; snap[2 * D + 1] = env.ret_stats[1]; snap_cnt[0] = env.counts[0]; snap_cnt[1] = env.counts[1]; }
+    for (int i = t; i < 2 * (D + 1) + 2; i += blockDim.x) env.roll_moments[i] = 0.0;
+}
+
 __device__ __forceinline__ float normalize_obs_val(float x, float mean, float var, float eps, float clip) {
     float v = __fdiv_rn(__fsub_rn(x, mean), __fsqrt_rn(__fadd_rn(var, eps)));
     return fminf(fmaxf(v, -clip), clip);
@@ -181,6 +229,18 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
             if (lane == 0) sAcc[c] = s;
         }
         __syncthreads();
+        // data-parallel runs: this rollout's batch moments are also accumulated on their own, so that after the rollout the ranks
+        // can merge (count, mean, M2) of the GLOBAL batch into the statistics they all started the rollout with
+        if (env.roll_moments && blockIdx.x == 0) {
+            for (int c = tid; c < 2 * ncol; c += blockDim.x) {
+                const bool is_ret = (c >> 1) == D;
+                if (is_ret ? do_ret : do_obs) env.roll_moments[c] += sAcc[c];
+            }
+            if (tid == 0) {
+                if (do_obs) env.roll_moments[2 * ncol] += (double)N;
+                if (do_ret) env.roll_moments[2 * ncol + 1] += (double)N;
+            }
+        }
         double dn = (double)N;
         if (do_obs) {
             for (int d = tid; d < D; d += blockDim.x) {
