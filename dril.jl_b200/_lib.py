@@ -104,7 +104,7 @@ PROTOTYPES = {
     "dril_iteration_result": [P, C.POINTER(IterStats)],
     "dril_explained_variance": [P, C.POINTER(c_f32)],
 }
-SPECIAL_RESTYPE = {"dril_last_error": C.c_char_p, "dril_version": c_i32}
+SPECIAL_RESTYPE = {"dril_last_error": C.c_char_p, "dril_version": c_i32, "dril_source_hash": C.c_char_p}
 
 BUF_FIELDS = dict(obs=0, actions=1, rewards=2, values=3, logprobs=4, advantages=5, returns=6, flags=7, boot=8,
                   last_values=9, episode_r=10, episode_l=11)
@@ -130,6 +130,8 @@ def load(require_device=True):
         lib.dril_last_error.argtypes = []
         lib.dril_version.restype = c_i32
         lib.dril_version.argtypes = []
+        lib.dril_source_hash.restype = C.c_char_p
+        lib.dril_source_hash.argtypes = []
         _lib = lib
     if require_device:
         n = c_i32(0)

@@ -31,7 +31,13 @@ void dril_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 extern "C" const char* dril_last_error(void) { return g_err; }
-extern "C" int32_t dril_version(void) { return 100; }
+extern "C" int32_t dril_version(void) { return 200; }
+#ifndef DRIL_SOURCE_HASH
+#define DRIL_SOURCE_HASH "unknown"
+#endif
+/* SHA-256 prefix of the sources + flags this library was compiled from (dril.jl_b200/build.py decides staleness with it) */
+static const char g_source_hash_marker[] = "DRIL_SOURCE_HASH=" DRIL_SOURCE_HASH;      // build.py finds the marker in the file (no dlopen)
+extern "C" const char* dril_source_hash(void) { return g_source_hash_marker + 17; }
 // ---------------------------------------------------------------------------------------
 // options
 // ---------------------------------------------------------------------------------------

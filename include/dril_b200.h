@@ -119,6 +119,8 @@ enum {
 
 const char* dril_last_error(void);
 int32_t dril_version(void);
+/* SHA-256 prefix of the sources + compiler flags the library was built from (build.py rebuilds when it differs from the tree) */
+const char* dril_source_hash(void);
 /* 0 if a CUDA device is usable, else an error (used by hosts to fail loudly, never to fall back) */
 int32_t dril_device_count(int32_t* count);
 /* process-wide kernel-path switches (all default 1; every combination meets the same parity bounds, tests/

@@ -226,7 +226,9 @@ def _mk(D, kind, n, seed, ms, monitor, norm):
     ("cartpole", 64, 16, 500, True, False), ("cartpole", 333, 64, 20, True, False), ("cartpole", 4096, 32, 25, False, False),
     ("pendulum", 100, 40, 15, True, True), ("pendulum", 1000, 24, 10, True, True), ("cartpole", 200, 48, 18, True, True),
     ("pendulum", 50, 30, 12, False, False),
-    ("pendulum", 10240, 5, 3, True, True)])     # >= 64 envs per SM with a wide net: 64-env tiles, wide layers on mma.sync tiles
+    ("pendulum", 10240, 5, 3, True, True),      # >= 64 envs per SM with a wide net: 64-env tiles, wide layers on mma.sync tiles
+    ("pendulum", 16384, 4, 3, True, True),      # BASELINE config C3's env count (Pendulum + NormalizeWrapperEnv), truncation every 3 steps
+    ("cartpole", 65536, 6, 4, True, False)])    # BASELINE config C4's env count: 2048 tiles on the tensor-core rollout, truncation list at scale
 def test_fused_rollout_replay(D, kind, n, T, ms, monitor, norm):
     env, oenv, spec = _mk(D, kind, n, 9, ms, monitor, norm)
     rng = np.random.default_rng(4)
@@ -273,9 +275,11 @@ def test_fused_rollout_replay(D, kind, n, T, ms, monitor, norm):
             np.testing.assert_allclose(s["obs_var"], oenv.obs_rms.var, rtol=1e-5, atol=1e-6)
             np.testing.assert_allclose([s["ret_mean"], s["ret_var"]], [oenv.ret_rms.mean, oenv.ret_rms.var], rtol=1e-5, atol=1e-6)
         assert (te | tr).any()
-        # reference buffer order (rollout_buffer.jl:70-74) is a permutation of the device order
-        order = buf.reference_order()
-        assert sorted(order.tolist()) == list(range(T * n))
+        # reference buffer order (rollout_buffer.jl:70-74): the permutation of the device order, element for element
+        if T * n <= 40000:
+            order = buf.reference_order()
+            np.testing.assert_array_equal(order, OO.reference_order(ob["term"], ob["trunc"]))
+            assert sorted(order.tolist()) == list(range(T * n))
         buf.close()
 
 
@@ -444,19 +448,45 @@ def test_ppo_update_vs_oracle(D, kind, batch):
 
 
 def test_target_kl_stop(D):
-    """ppo.jl:235-238: stop before applying; grad_norm still recorded."""
+    """ppo.jl:235-238: the KL check comes before the step is applied and stops ALL remaining epochs; grad_norm of the stopping
+    minibatch is still recorded; means over the applied minibatches (NaN when none was applied, ppo.jl:257-263).  Stop step,
+    parameters and statistics against oracle.ppo.ppo_update on the same buffer."""
+    import ctypes as C
+    from dril_b200 import _lib as L
     n, T = 32, 16
-    env, oenv, spec = _mk(D, "cartpole", n, 1, 500, False, False)
-    flat = OP.init_params(spec, seed=1)
-    layer = D.ActorCriticLayer(env.observation_space(), env.action_space(), hidden_dims=spec.hidden)
-    alg = D.PPO(n_steps=T, batch_size=128, epochs=5, target_kl=1e-9, learning_rate=1e-2)
-    agent = D.Agent(layer, alg, rng=np.random.default_rng(0))
-    agent.set_parameters(flat)
-    out = D.train(agent, env, alg, n * T)
-    assert out is not None
-    # first minibatch has kl == 0 -> applied; the second one trips the stop
-    assert agent.stats.gradient_updates < 5 * (n * T // 128)
-    assert np.isfinite(out[0]["grad_norms"]).all()
+    for case, target_kl, lr in (("later", 1e-4, 3e-2), ("first", 1e-4, 1e-2)):   # stops after a few applied steps / on the very first minibatch
+        env, oenv, spec = _mk(D, "cartpole", n, 1, 500, False, False)
+        flat = OP.init_params(spec, seed=1)
+        layer = D.ActorCriticLayer(env.observation_space(), env.action_space(), hidden_dims=spec.hidden)
+        alg = D.PPO(n_steps=T, batch_size=128, epochs=5, target_kl=target_kl, learning_rate=lr)
+        agent = D.Agent(layer, alg, rng=np.random.default_rng(0))
+        agent.set_parameters(flat)
+        buf = D.RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, T, n)
+        D.collect_rollout(buf, agent, alg, env)
+        ob = {k: buf.download(k) for k in ("obs", "actions", "rewards", "values", "logprobs", "advantages", "returns")}
+        st = D.IterStats()
+        h = alg.hyper()
+        if case == "first":       # parameters moved away from the ones the rollout was collected with: the first minibatch trips the stop
+            flat = (flat + np.random.default_rng(3).normal(size=flat.size).astype(f32) * 0.05).astype(f32)
+            agent.set_parameters(flat)
+        L.check(agent.ctx.lib.dril_ppo_update(agent.device.h, buf.h, C.byref(h), alg.epochs, alg.batch_size, 11, 0, C.byref(st)))
+        cfg = OO.PPOConfig(n_steps=T, batch_size=128, epochs=5, target_kl=target_kl, learning_rate=lr)
+        opt = OO.Adam(flat.size, lr=lr)
+        new_flat, means, epochs_run = OO.ppo_update(spec, flat, opt, ob, cfg, shuffle_seed=11, epoch_counter0=0)
+        assert st.kl_stopped == 1
+        assert st.n_minibatch_steps == opt.t, (st.n_minibatch_steps, opt.t)
+        assert st.n_minibatch_steps < 5 * (n * T // 128)
+        np.testing.assert_allclose(agent.device.get_params(), new_flat, rtol=2e-4, atol=5e-6)
+        for k in ("policy_loss", "value_loss", "approx_kl_div", "loss", "grad_norm"):
+            got, exp = getattr(st, k), means[k]
+            if np.isnan(exp):
+                assert np.isnan(got), (k, got)
+            else:
+                assert abs(got - exp) <= 5e-4 * max(1.0, abs(exp)), (k, got, exp)
+        if case == "first":
+            assert opt.t == 0 and np.isnan(st.policy_loss) and np.isfinite(st.grad_norm)   # empty means are NaN, the norm was recorded
+            np.testing.assert_array_equal(agent.device.get_params(), flat)
+        buf.close()
 
 
 # ------------------------------------------------------------------------------------------
