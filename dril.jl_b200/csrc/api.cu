@@ -14,6 +14,7 @@
 #include "update.cuh"
 #include "update_tc.cuh"
 #include "update_ft.cuh"
+#include "update_ftg.cuh"
 #include "rollout_tc.cuh"
 
 #define DRIL_SMEM_MAX 232448  // 227 KB opt-in per CTA on sm_100
@@ -44,6 +45,7 @@ extern "C" const char* dril_source_hash(void) { return g_source_hash_marker + 17
 static int g_opt_tc = getenv("DRIL_TC") ? atoi(getenv("DRIL_TC")) : 1;
 // features-on-lanes tcgen05 loss/grad kernel (update_ft.cuh) instead of the samples-on-lanes one (update_tc.cuh)
 static int g_opt_ft = getenv("DRIL_FT") ? atoi(getenv("DRIL_FT")) : 1;
+static int g_opt_ftg = getenv("DRIL_FTG") ? atoi(getenv("DRIL_FTG")) : 1;   // general-shape features-on-lanes kernel (update_ftg.cuh); 2: also where update_ft.cuh applies
 static int g_opt_tc_rollout = getenv("DRIL_TC_ROLLOUT") ? atoi(getenv("DRIL_TC_ROLLOUT")) : 1;   // tensor-core rollout (CartPole, [64,64])
 static int g_opt_tail = getenv("DRIL_TAIL") ? atoi(getenv("DRIL_TAIL")) : 1;   // fused reduce/clip/Adam tail of the TC kernel
 // fp32 loss/grad kernel, wide nets: one net per pass with shared activation rows (fixed per policy at creation)
@@ -54,6 +56,7 @@ extern "C" int32_t dril_set_option(const char* key, int32_t value) {
     DRIL_REQUIRE(key, "key is NULL");
     if (!strcmp(key, "tc")) { g_opt_tc = value; return DRIL_OK; }
     if (!strcmp(key, "ft")) { g_opt_ft = value; return DRIL_OK; }
+    if (!strcmp(key, "ftg")) { g_opt_ftg = value; return DRIL_OK; }
     if (!strcmp(key, "fused_tail")) { g_opt_tail = value; return DRIL_OK; }
     if (!strcmp(key, "tc_rollout")) { g_opt_tc_rollout = value; return DRIL_OK; }
     if (!strcmp(key, "single_net")) { g_opt_single_net = value; return DRIL_OK; }   // policies created afterwards
@@ -63,6 +66,17 @@ extern "C" int32_t dril_set_option(const char* key, int32_t value) {
 }
 // the tensor-core loss/grad kernel covers the reference's default layer: hidden_dims = [64, 64], obs_dim <= 4,
 // Discrete(n <= 2)
+// the general-shape features-on-lanes kernel (update_ftg.cuh): 2 or 3 hidden layers of width 64 / 128 (same in both nets),
+// obs_dim <= 15, Discrete(n <= 2) or Box of dimension <= 2, and everything resident in shared memory
+static bool ftg_eligible(const PolicyDesc& pd) {
+    const int L = pd.n_layers - 1;
+    if (L < 2 || L > 3 || pd.obs_dim > FTG_MAX_OBS || pd.act_n > 2) return false;
+    for (int l = 0; l < L; ++l) {
+        if (pd.L[0][l].N != pd.L[1][l].N) return false;
+        if (pd.L[0][l].N != 64 && pd.L[0][l].N != 128) return false;
+    }
+    return ftg_layout(pd).total <= DRIL_SMEM_MAX - 2048;
+}
 static bool tc_eligible(const PolicyDesc& pd) {
     if (pd.n_layers != 3 || pd.obs_dim > 4 || pd.act_kind != DRIL_ACT_DISCRETE || pd.act_n > 2) return false;
     for (int net = 0; net < 2; ++net) {
@@ -314,6 +328,13 @@ extern "C" int32_t dril_ctx_create(int32_t device, uint64_t seed, dril_ctx** out
     DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_ft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
     DRIL_CUDA(cudaFuncSetAttribute(ppo_loss_grad_ft_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
+    {
+        const void* fns[] = {(const void*)ppo_loss_grad_ftg_kernel<2, 0, 1>, (const void*)ppo_loss_grad_ftg_kernel<2, 0, 2>,
+                             (const void*)ppo_loss_grad_ftg_kernel<2, 1, 1>, (const void*)ppo_loss_grad_ftg_kernel<2, 1, 2>,
+                             (const void*)ppo_loss_grad_ftg_kernel<3, 0, 1>, (const void*)ppo_loss_grad_ftg_kernel<3, 0, 2>,
+                             (const void*)ppo_loss_grad_ftg_kernel<3, 1, 1>, (const void*)ppo_loss_grad_ftg_kernel<3, 1, 2>};
+        for (const void* fn : fns) DRIL_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX - 2048));   // 1 KB of static shared memory
+    }
     DRIL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM_BYTES));
     *out = c;
     return DRIL_OK;
@@ -598,6 +619,7 @@ extern "C" int32_t dril_buffer_upload(dril_buffer* b, int32_t field, const void*
 static inline int pad4(int x) { return (x + 3) & ~3; }
 struct LossLaunch { int M4; bool ws; size_t smem; int grid_cap; int splits; bool single; bool mma; bool thin; };
 static int32_t plan_loss(dril_policy* p, LossLaunch* out);
+static bool ftg_active(const dril_policy* p);
 
 extern "C" int32_t dril_policy_create(dril_ctx* c, int32_t obs_dim, int32_t n_hidden, const int32_t* hidden,
                                       int32_t act_kind, int32_t act_n, int32_t act_start, const float* act_low,
@@ -740,7 +762,7 @@ extern "C" int32_t dril_policy_num_params(dril_policy* p, int64_t* n) {
 extern "C" int32_t dril_policy_update_path(dril_policy* p, int32_t* out) {
     DRIL_REQUIRE(p && out, "NULL argument");
     *out = 0;
-    if (g_opt_tc && tc_eligible(p->pd)) { *out = 1; return DRIL_OK; }
+    if (ftg_active(p) || (g_opt_tc && tc_eligible(p->pd))) { *out = 1; return DRIL_OK; }
     if (p->plan_mma == 1)
         for (int net = 0; net < 2; ++net)
             for (int l = 0; l < p->pd.n_layers; ++l) {
@@ -1631,7 +1653,44 @@ static int32_t plan_loss(dril_policy* p, LossLaunch* out) {
 }
 
 // update_ft.cuh path: the samples of one epoch (all its minibatches) as shuffled, contiguous tile records
-static bool ft_active(const dril_policy* p) { return g_opt_tc && g_opt_ft && tc_eligible(p->pd); }
+static bool ft_active(const dril_policy* p) { return g_opt_tc && g_opt_ft && tc_eligible(p->pd) && !(g_opt_ftg == 2 && ftg_eligible(p->pd)); }
+// update_ftg.cuh path (general shapes); option "ftg" = 2 prefers it over update_ft.cuh where both apply
+static bool ftg_active(const dril_policy* p) {
+    if (!g_opt_ftg || !ftg_eligible(p->pd)) return false;
+    if (g_opt_ftg == 2) return true;
+    return !(g_opt_tc && tc_eligible(p->pd));
+}
+static const void* ftg_kernel(const PolicyDesc& pd) {
+    const int L = pd.n_layers - 1, cont = pd.act_kind == DRIL_ACT_CONTINUOUS ? 1 : 0, n = pd.act_n;
+    if (L == 2) {
+        if (cont) return n == 1 ? (const void*)ppo_loss_grad_ftg_kernel<2, 1, 1> : (const void*)ppo_loss_grad_ftg_kernel<2, 1, 2>;
+        return n == 1 ? (const void*)ppo_loss_grad_ftg_kernel<2, 0, 1> : (const void*)ppo_loss_grad_ftg_kernel<2, 0, 2>;
+    }
+    if (cont) return n == 1 ? (const void*)ppo_loss_grad_ftg_kernel<3, 1, 1> : (const void*)ppo_loss_grad_ftg_kernel<3, 1, 2>;
+    return n == 1 ? (const void*)ppo_loss_grad_ftg_kernel<3, 0, 1> : (const void*)ppo_loss_grad_ftg_kernel<3, 0, 2>;
+}
+static int32_t ftg_stage_epoch(dril_policy* p, const BufDev& bd, const FeistelKey& fk, long long n_total, long long batch_size, int identity) {
+    dril_ctx* c = p->ctx;
+    const int n_mb = (int)((n_total + batch_size - 1) / batch_size);
+    const int tpm = (int)((std::min<long long>(batch_size, n_total) + 63) / 64);
+    const int cont = p->pd.act_kind == DRIL_ACT_CONTINUOUS ? 1 : 0;
+    const int rf = ftg_rec_floats(p->pd.obs_dim, cont, p->pd.act_n);
+    const size_t bytes = (size_t)n_mb * tpm * rf * 4;
+    if (p->ft_tiles_bytes < bytes) {
+        if (p->ft_tiles) { DRIL_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(p->ft_tiles); }
+        p->ft_tiles = nullptr; p->ft_tiles_bytes = 0;
+        DRIL_CUDA(cudaMalloc((void**)&p->ft_tiles, bytes));
+        p->ft_tiles_bytes = bytes;
+    }
+    p->ft_tiles_per_mb = tpm; p->ft_batch = batch_size;
+    const long long slots = (long long)n_mb * tpm * 64;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((slots + 255) / 256, (long long)c->sm_count * 8));
+    Span sp(c, DRIL_K_PERMUTE);
+    ftg_permute_kernel<<<grid, 256, 0, c->stream>>>(bd, fk, n_total, batch_size, n_mb, tpm, identity, p->pd.act_start, p->pd.act_n, cont, rf,
+                                                    reinterpret_cast<float*>(p->ft_tiles));
+    DRIL_CUDA(cudaGetLastError());
+    return DRIL_OK;
+}
 static int32_t ft_stage_epoch(dril_policy* p, const BufDev& bd, const FeistelKey& fk, long long n_total, long long batch_size, int identity) {
     dril_ctx* c = p->ctx;
     const int n_mb = (int)((n_total + batch_size - 1) / batch_size);
@@ -1663,9 +1722,10 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
     a.stop_flag = p->stop_flag; a.mb = mb; a.hp = hp; a.M4 = ll.M4; a.weights_smem = ll.ws;
     a.half_stride = p->gpart_ctas; a.small_splits = ll.splits; a.single_net = ll.single ? 1 : 0;
     a.use_mma = ll.mma ? 1 : 0; a.stage_thin = ll.thin ? 1 : 0;
-    const bool tc = g_opt_tc && tc_eligible(pd);
-    const bool ft = tc && g_opt_ft;
-    const int tile_m = ft ? FT_TS : (tc ? TC_M : ll.M4);
+    const bool ftg = ftg_active(p);
+    const bool tc = ftg || (g_opt_tc && tc_eligible(pd));
+    const bool ft = !ftg && tc && g_opt_ft;
+    const int tile_m = (ft || ftg) ? FT_TS : (tc ? TC_M : ll.M4);
     long long tiles = (mb.count + tile_m - 1) / tile_m;
     int grid = (int)std::max<long long>(1, std::min<long long>(tiles, tc ? std::min(c->sm_count, p->gpart_ctas) : ll.grid_cap));
     const unsigned char* planes_dev = tc ? p->f2planes_one : p->f2planes;
@@ -1688,7 +1748,16 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
             tl.flat2g = p->flat2g; tl.f2planes = planes_dev; tl.stats_off = pd.pack_fwd + pd.act_n; tl.sq_part = p->sq_part;
             tl.adam = aa;
             if (p2p) tl.pp = c->p2p;
-            if (ft) {
+            if (ftg) {
+                FtgArgs fa;
+                fa.tiles = p->ft_tiles;
+                fa.tile0 = (mb.start / std::max<long long>(1, p->ft_batch)) * p->ft_tiles_per_mb;
+                fa.lay = ftg_layout(pd);
+                const void* fn = ftg_kernel(pd);
+                void* args[] = {(void*)&a, (void*)&tl, (void*)&fa};
+                if (tail) DRIL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FTG_THREADS), args, (size_t)fa.lay.total, c->stream));
+                else DRIL_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(FTG_THREADS), args, (size_t)fa.lay.total, c->stream));
+            } else if (ft) {
                 // tile records of this minibatch: written by ft_stage_epoch before the epoch's first step
                 FtArgs fa;
                 fa.tiles = p->ft_tiles;
@@ -1786,7 +1855,8 @@ static int32_t update_async(dril_policy* p, dril_buffer* b, const dril_ppo_hyper
             n_extra = 0;
         }
         for (int e = 0; e < ne; ++e) {
-            if (ft_active(p)) DRIL_TRY(ft_stage_epoch(p, b->d, fks.k[e], n_total, batch_size, 0));
+            if (ftg_active(p)) DRIL_TRY(ftg_stage_epoch(p, b->d, fks.k[e], n_total, batch_size, 0));
+            else if (ft_active(p)) DRIL_TRY(ft_stage_epoch(p, b->d, fks.k[e], n_total, batch_size, 0));
             for (int i = 0; i < n_mb; ++i) {
                 Minibatch mb;
                 mb.n_total = n_total; mb.start = (long long)i * batch_size;
@@ -2021,7 +2091,8 @@ extern "C" int32_t dril_ppo_loss_grad(dril_policy* p, const float* obs, const vo
         c->launches += 2;
         Minibatch mb;
         mb.n_total = B; mb.start = 0; mb.count = B; mb.global_count = (double)B; mb.fk = fk; mb.identity = 1;
-        if (ft_active(p) && (st = ft_stage_epoch(p, b->d, fk, B, B, 1))) break;
+        if (ftg_active(p)) { if ((st = ftg_stage_epoch(p, b->d, fk, B, B, 1))) break; }
+        else if (ft_active(p) && (st = ft_stage_epoch(p, b->d, fk, B, B, 1))) break;
         if ((st = minibatch_step(p, b->d, mb, p->mbstats, hp, ll, false, 0))) break;
         std::vector<float> g((size_t)pd.n_params + 6);
         cudaMemcpyAsync(g.data(), p->g, g.size() * 4, cudaMemcpyDeviceToHost, c->stream);

@@ -658,7 +658,7 @@ def test_wide_net_single_net_passes(D, name, single, mma):
     spec = WIDE[name]()
     rng = np.random.default_rng(11)
     flat = (OP.init_params(spec, seed=4) + rng.normal(size=spec.n_params()).astype(f32) * 0.05).astype(f32)
-    D.set_option("single_net", single); D.set_option("mma", mma); D.set_option("tc", 0)
+    D.set_option("single_net", single); D.set_option("mma", mma); D.set_option("tc", 0); D.set_option("ftg", 0)
     try:
         p = _device_policy(D, spec, flat)
         assert p.update_path() != "tensor"
@@ -675,7 +675,7 @@ def test_wide_net_single_net_passes(D, name, single, mma):
             print(name, single, mma, B, "grad relerr", _relerr(g, eg))
         p.close()
     finally:
-        D.set_option("single_net", 1); D.set_option("mma", 1); D.set_option("tc", 1)
+        D.set_option("single_net", 1); D.set_option("mma", 1); D.set_option("tc", 1); D.set_option("ftg", 1)
 
 
 # ------------------------------------------------------------------------------------------
@@ -770,3 +770,76 @@ def test_tcgen05_kernels_vs_oracle(D, ft, B):
             p.close()
     finally:
         D.set_option("ft", 1)
+
+
+FTG = {
+    "pendulum": lambda: SPECS["pendulum"](),                                                        # [128,128,64], Box(1): BASELINE config C3
+    "cartpole64": lambda: SPECS["cartpole"](),                                                      # [64,64] through the general kernel (option ftg = 2)
+    "wide_discrete": lambda: OP.PolicySpec(10, [128, 128], "discrete", 2, act_start=0),
+    "mixed_box2": lambda: OP.PolicySpec(6, [64, 128, 64], "continuous", 2, act_low=[-1, -1], act_high=[1, 1]),
+    "narrow_then_wide": lambda: OP.PolicySpec(15, [64, 128], "discrete", 1, act_start=3),
+    "three_64": lambda: OP.PolicySpec(3, [64, 64, 64], "continuous", 1, act_low=[-2], act_high=[2]),
+}
+
+
+@pytest.mark.parametrize("name", list(FTG))
+def test_general_tcgen05_kernel_vs_oracle(D, name):
+    """update_ftg.cuh: the features-on-lanes tcgen05 kernel for two or three hidden layers of width 64 / 128, Discrete(<= 2) or
+    Box(<= 2) actions: loss, statistics and gradients against the oracle on ragged tile counts, many tiles per CTA, large
+    return scales (the per-pass delta scale) and both loss configurations."""
+    spec = FTG[name]()
+    D.set_option("ftg", 2)
+    try:
+        rng = np.random.default_rng(5)
+        flat = (OP.init_params(spec, seed=4) + rng.normal(size=spec.n_params()).astype(f32) * 0.05).astype(f32)
+        p = _device_policy(D, spec, flat)
+        assert p.update_path() == "tensor"
+        for B, scale in ((1, 1.0), (63, 1.0), (64, 1.0), (200, 1.0), (1000, 3e4), (148 * 64 * 2 + 17, 1.0)):
+            obs, actions, adv, ret, old_lp, old_v = _minibatch(spec, flat, B, rng)
+            ret = (ret * scale).astype(f32)
+            old_v = (old_v * scale).astype(f32)
+            for alg in (D.PPO(ent_coef=0.01, clip_range_vf=0.3 * scale), D.PPO(ent_coef=0.0, normalize_advantage=False, vf_coef=0.7)):
+                if B == 1 and alg.normalize_advantage:
+                    continue
+                cfg = OO.PPOConfig(ent_coef=alg.ent_coef, clip_range_vf=alg.clip_range_vf, normalize_advantage=alg.normalize_advantage,
+                                   vf_coef=alg.vf_coef)
+                loss, stats, g = p.loss_grad(obs, actions, adv, ret, old_lp, old_v, alg.hyper())
+                eloss, estats, eg = OO.ppo_loss_and_grads(spec, flat, obs, actions, adv, ret, old_lp, old_v, cfg)
+                assert abs(loss - eloss) <= 1e-4 * max(1.0, abs(eloss)), (name, B, loss, eloss)
+                for k in estats:
+                    assert abs(stats[k] - estats[k]) <= 1e-4 * max(1.0, abs(estats[k])), (name, B, k, stats[k], estats[k])
+                assert _relerr(g, eg) < 1e-4, (name, B, scale, _relerr(g, eg))
+        p.close()
+    finally:
+        D.set_option("ftg", 1)
+
+
+def test_c3_shape_update_vs_oracle(D):
+    """BASELINE config C3 at reduced env count (Pendulum, [128,128,64], NormalizeWrapperEnv): one epoch of the update through the
+    general tcgen05 kernel + fused tail against the oracle on the same buffer and the same Feistel minibatches."""
+    n, T = 1024, 32
+    env, oenv, spec = _mk(D, "pendulum", n, 5, 200, False, True)
+    flat = OP.init_params(spec, seed=2)
+    layer = D.ActorCriticLayer(env.observation_space(), env.action_space(), hidden_dims=spec.hidden)
+    alg = D.PPO(n_steps=T, batch_size=T * n // 4, epochs=2, ent_coef=0.01)
+    agent = D.Agent(layer, alg, rng=np.random.default_rng(0))
+    agent.set_parameters(flat)
+    assert agent.device.update_path() == "tensor"
+    buf = D.RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, T, n)
+    D.collect_rollout(buf, agent, alg, env)
+    ob = {k: buf.download(k) for k in ("obs", "actions", "rewards", "values", "logprobs", "advantages", "returns")}
+    import ctypes as C
+    from dril_b200 import _lib as L
+    st = D.IterStats()
+    h = alg.hyper()
+    L.check(agent.ctx.lib.dril_ppo_update(agent.device.h, buf.h, C.byref(h), alg.epochs, alg.batch_size, 41, 2, C.byref(st)))
+    cfg = OO.PPOConfig(n_steps=T, batch_size=T * n // 4, epochs=2, ent_coef=0.01)
+    opt = OO.Adam(flat.size, lr=cfg.learning_rate)
+    new_flat, means, _ = OO.ppo_update(spec, flat, opt, ob, cfg, shuffle_seed=41, epoch_counter0=2)
+    got = agent.device.get_params()
+    assert st.n_minibatch_steps == 8
+    assert _relerr(got - flat, new_flat - flat) < 2e-3, _relerr(got - flat, new_flat - flat)
+    np.testing.assert_allclose(got, new_flat, rtol=1e-4, atol=2e-6)
+    for k in ("policy_loss", "value_loss", "entropy_loss", "approx_kl_div", "clip_fraction", "loss", "grad_norm"):
+        assert abs(getattr(st, k) - means[k]) <= 2e-4 * max(1.0, abs(means[k])), (k, getattr(st, k), means[k])
+    buf.close()
