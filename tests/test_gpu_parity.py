@@ -524,7 +524,7 @@ def test_full_size_properties(D):
 def test_kernel_paths_vs_oracle(D, tc, tail, tc_rollout):
     """The tensor-core loss/grad kernel (with and without its fused reduce/clip/Adam tail), the fp32 CUDA-core kernel,
     the tensor-core rollout and the general rollout are interchangeable: same buffer, same updated parameters."""
-    opts = {"tc": tc, "fused_tail": tail, "tc_rollout": tc_rollout}
+    opts = {"tc": tc, "fused_tail": tail, "tc_rollout": tc_rollout, "ftg": 1 if tc else 0}   # tc = 0: the general mma.sync kernel
     try:
         for k, v in opts.items():
             D.set_option(k, v)
