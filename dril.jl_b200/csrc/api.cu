@@ -238,7 +238,11 @@ struct dril_policy {
     // scratch for the host-pointer entry points
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
-    // update_ft.cuh: the current epoch's samples as shuffled tile records
+    // update_ft.cuh / update_ftg.cuh: per-sample records of the buffer (packed once per update) and the current epoch's
+    // samples as shuffled tile records
+    float* ft_recs = nullptr;
+    size_t ft_recs_floats = 0;
+    int ft_rec_stride = 0;
     unsigned char* ft_tiles = nullptr;
     size_t ft_tiles_bytes = 0;
     int ft_tiles_per_mb = 0;
@@ -741,7 +745,7 @@ extern "C" int32_t dril_policy_destroy(dril_policy* p) {
     }
     void* ps[] = {p->flat, p->pack, p->m, p->v, p->g, p->gpart, p->flat2pack, p->flat2packT, p->flat2g, p->step,
                   p->iter_acc, p->ev_acc, p->mbstats, p->adv_partial, p->stop_flag, p->scratch, p->f2planes, p->f2planes_one, p->sq_part,
-                  p->ticket, p->ft_tiles};
+                  p->ticket, p->ft_tiles, p->ft_recs};
     for (void* q : ps) if (q) cudaFree(q);
     for (int i = 0; i < 3; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
     for (auto& sl : p->slots) {
@@ -1652,6 +1656,24 @@ static int32_t plan_loss(dril_policy* p, LossLaunch* out) {
     return DRIL_OK;
 }
 
+// per-sample records of the whole buffer (update_ft.cuh): one streaming pass per update, read by every epoch's permute kernel
+static int32_t ft_pack_records(dril_policy* p, const BufDev& bd, long long n_total) {
+    dril_ctx* c = p->ctx;
+    const int stride = ft_rec_stride(bd.obs_dim, bd.act_dim);
+    const size_t need = (size_t)n_total * stride;
+    if (p->ft_recs_floats < need) {
+        if (p->ft_recs) { DRIL_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(p->ft_recs); }
+        p->ft_recs = nullptr; p->ft_recs_floats = 0;
+        DRIL_CUDA(cudaMalloc((void**)&p->ft_recs, need * 4));
+        p->ft_recs_floats = need;
+    }
+    p->ft_rec_stride = stride;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n_total + 255) / 256, (long long)c->sm_count * 8));
+    Span sp(c, DRIL_K_PERMUTE);
+    ft_pack_records_kernel<<<grid, 256, 0, c->stream>>>(bd, n_total, stride, p->ft_recs);
+    DRIL_CUDA(cudaGetLastError());
+    return DRIL_OK;
+}
 // update_ft.cuh path: the samples of one epoch (all its minibatches) as shuffled, contiguous tile records
 static bool ft_active(const dril_policy* p) { return g_opt_tc && g_opt_ft && tc_eligible(p->pd) && !(g_opt_ftg == 2 && ftg_eligible(p->pd)); }
 // update_ftg.cuh path (general shapes); option "ftg" = 2 prefers it over update_ft.cuh where both apply
@@ -1686,8 +1708,8 @@ static int32_t ftg_stage_epoch(dril_policy* p, const BufDev& bd, const FeistelKe
     const long long slots = (long long)n_mb * tpm * 64;
     const int grid = (int)std::max<long long>(1, std::min<long long>((slots + 255) / 256, (long long)c->sm_count * 8));
     Span sp(c, DRIL_K_PERMUTE);
-    ftg_permute_kernel<<<grid, 256, 0, c->stream>>>(bd, fk, n_total, batch_size, n_mb, tpm, identity, p->pd.act_start, p->pd.act_n, cont, rf,
-                                                    reinterpret_cast<float*>(p->ft_tiles));
+    ftg_permute_kernel<<<grid, 256, 0, c->stream>>>(p->ft_recs, p->ft_rec_stride, bd.obs_dim, fk, n_total, batch_size, n_mb, tpm, identity,
+                                                    p->pd.act_start, p->pd.act_n, cont, rf, reinterpret_cast<float*>(p->ft_tiles));
     DRIL_CUDA(cudaGetLastError());
     return DRIL_OK;
 }
@@ -1706,7 +1728,8 @@ static int32_t ft_stage_epoch(dril_policy* p, const BufDev& bd, const FeistelKey
     const long long slots = (long long)n_mb * tpm * FT_TS;
     const int grid = (int)std::max<long long>(1, std::min<long long>((slots + 255) / 256, (long long)c->sm_count * 8));
     Span sp(c, DRIL_K_PERMUTE);
-    ft_permute_kernel<<<grid, 256, 0, c->stream>>>(bd, fk, n_total, batch_size, n_mb, tpm, identity, p->pd.act_start, p->pd.act_n, p->ft_tiles);
+    ft_permute_kernel<<<grid, 256, 0, c->stream>>>(p->ft_recs, p->ft_rec_stride, fk, n_total, batch_size, n_mb, tpm, identity, p->pd.act_start,
+                                                   p->pd.act_n, p->ft_tiles);
     DRIL_CUDA(cudaGetLastError());
     return DRIL_OK;
 }
@@ -1831,6 +1854,7 @@ static int32_t update_async(dril_policy* p, dril_buffer* b, const dril_ppo_hyper
     LossLaunch ll;
     DRIL_TRY(plan_loss(p, &ll));
     const int bpm = (int)std::max<long long>(1, std::min<long long>(64, (std::min<long long>(batch_size, n_total) + 2047) / 2048));
+    if (ftg_active(p) || ft_active(p)) DRIL_TRY(ft_pack_records(p, b->d, n_total));
     DRIL_CUDA(cudaMemsetAsync(p->iter_acc, 0, 12 * 8, c->stream));   // [12],[13] carry beta^t across iterations
     DRIL_CUDA(cudaMemsetAsync(p->stop_flag, 0, 4, c->stream));
     // minibatch advantage moments of up to DRIL_MAX_EPOCHS_BATCHED epochs per launch / allreduce
@@ -2091,6 +2115,7 @@ extern "C" int32_t dril_ppo_loss_grad(dril_policy* p, const float* obs, const vo
         c->launches += 2;
         Minibatch mb;
         mb.n_total = B; mb.start = 0; mb.count = B; mb.global_count = (double)B; mb.fk = fk; mb.identity = 1;
+        if ((ftg_active(p) || ft_active(p)) && (st = ft_pack_records(p, b->d, B))) break;
         if (ftg_active(p)) { if ((st = ftg_stage_epoch(p, b->d, fk, B, B, 1))) break; }
         else if (ft_active(p) && (st = ft_stage_epoch(p, b->d, fk, B, B, 1))) break;
         if ((st = minibatch_step(p, b->d, mb, p->mbstats, hp, ll, false, 0))) break;

@@ -15,9 +15,10 @@
 //
 // Precision: fp16 hi/lo split on kind::f16 (x = hi + lo, hi = fp16(x), lo = fp16(x - hi); products hi*hi + lo*hi +
 // hi*lo, fp32 accumulation): 22 significant bits like 3xTF32 at half the instructions and half the operand bytes.
-// H0/H1 are tanh outputs and W1 is a weight matrix (bounded); the deltas dZ1 are not, so every tile scales them by a
-// power of two S chosen from the tile's own max |dL/dout| and the net's max |W2| row sum such that |S dZ1| < 2^12
-// (no overflow possible, exact rescaling); dW1 is therefore flushed from TMEM into fp32 register accumulators per tile.
+// H0/H1 are tanh outputs and W1 is a weight matrix (bounded); the deltas dZ1 are not, so every group scales them by a
+// power of two S chosen from a tile's max |dL/dout| and the net's max |W2| row sum such that |S dZ1|
+// is below 2^4 on the tile that fixes it (the first tile of a group with a non-zero gradient; later tiles may be 2^12 times
+// larger before fp16 overflows), so dW1 stays in TMEM over all tiles of a group and everything is unscaled exactly at the end.
 //
 // M = 64 accumulators use 16 lanes of every TMEM lane quadrant; the actor's sit at lane offset 0 and the critic's at
 // lane offset 16 of the same columns, so warp q, lane l is feature 16 q + l % 16 of net l / 16 and both nets run in ONE
@@ -79,33 +80,49 @@ struct FtArgs {
     long long tile0;               // first record of this minibatch
 };
 
+// Sample records: the update gathers minibatches in shuffled order, and a gather from the time-major field arrays costs one
+// 32-byte sector per 4-byte field (nine sectors per sample).  Once per iteration the fields of every sample are therefore
+// packed into one contiguous record [obs (Dp) | action (A) | advantage | old log-prob | return | old value | pad] (stride a
+// multiple of 4 floats) by a streaming kernel; the per-epoch permute kernels then read two sectors per sample.
+__host__ __device__ inline int ft_rec_stride(int obs_dim, int act_elems) { return ((((obs_dim + 3) & ~3) + act_elems + 4) + 3) & ~3; }
+__global__ void __launch_bounds__(256) ft_pack_records_kernel(const BufDev buf, long long n_total, int stride, float* __restrict__ recs) {
+    const int D = buf.obs_dim, Dp = (D + 3) & ~3, A = buf.act_dim;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += (long long)gridDim.x * blockDim.x) {
+        auto val = [&](int k) -> float {
+            if (k < Dp) return k < D ? buf.obs[i * D + k] : 0.f;
+            k -= Dp;
+            if (k < A) return reinterpret_cast<const float*>(buf.actions)[i * A + k];      // int32 bits for discrete actions
+            k -= A;
+            return k == 0 ? buf.advantages[i] : (k == 1 ? buf.logprobs[i] : (k == 2 ? buf.returns[i] : (k == 3 ? buf.values[i] : 0.f)));
+        };
+        float4* r = reinterpret_cast<float4*>(recs + i * stride);
+        for (int k = 0; k < stride; k += 4) r[k >> 2] = make_float4(val(k), val(k + 1), val(k + 2), val(k + 3));
+    }
+}
+
 // The epoch's samples in shuffled order as contiguous tile records (one launch per epoch; padding slots are zero).
-__global__ void __launch_bounds__(256) ft_permute_kernel(const BufDev buf, const FeistelKey fk, long long n_total, long long batch_size, int n_mb,
-                                                         int tiles_per_mb, int identity, int act_start, int nout, unsigned char* __restrict__ out) {
+__global__ void __launch_bounds__(256) ft_permute_kernel(const float* __restrict__ recs, int stride, const FeistelKey fk, long long n_total,
+                                                         long long batch_size, int n_mb, int tiles_per_mb, int identity, int act_start, int nout,
+                                                         unsigned char* __restrict__ out) {
     const long long per = (long long)tiles_per_mb * FT_TS;
     const long long slots = per * n_mb;
-    const int D = buf.obs_dim;
     for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (long long)gridDim.x * blockDim.x) {
         const long long mb = s / per, r = s - mb * per;
         const long long pos = mb * batch_size + r;
         const bool valid = r < batch_size && pos < n_total;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        float adv = 0.f, olp = 0.f, ret = 0.f, ov = 0.f;
-        int ai = 0;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), u = x, w = x;
         if (valid) {
             const long long sidx = identity ? pos : feistel_permute(pos, n_total, fk);
-            const float* xo = buf.obs + sidx * D;
-            if (D == 4) x = *reinterpret_cast<const float4*>(xo);
-            else { x.x = xo[0]; if (D > 1) x.y = xo[1]; if (D > 2) x.z = xo[2]; }
-            adv = buf.advantages[sidx]; olp = buf.logprobs[sidx]; ret = buf.returns[sidx]; ov = buf.values[sidx];
-            ai = reinterpret_cast<const int*>(buf.actions)[sidx] - act_start;
-            ai = ai < 0 ? 0 : (ai >= nout ? nout - 1 : ai);
+            const float4* rp = reinterpret_cast<const float4*>(recs + sidx * stride);      // obs (4) | action, adv, logp, ret | val
+            x = rp[0]; u = rp[1]; w = rp[2];
         }
+        int ai = valid ? __float_as_int(u.x) - act_start : 0;
+        ai = ai < 0 ? 0 : (ai >= nout ? nout - 1 : ai);
         float* blk = reinterpret_cast<float*>(out + (s >> 6) * FT_TILE_BYTES);
         const int j = (int)(s & 63);
         reinterpret_cast<float4*>(blk)[j] = x;
-        blk[FT_R_ADV + j] = adv; blk[FT_R_OLP + j] = olp; reinterpret_cast<int*>(blk)[FT_R_ACT + j] = ai;
-        blk[FT_R_RET + j] = ret; blk[FT_R_OVAL + j] = ov;
+        blk[FT_R_ADV + j] = u.y; blk[FT_R_OLP + j] = u.z; reinterpret_cast<int*>(blk)[FT_R_ACT + j] = ai;
+        blk[FT_R_RET + j] = u.w; blk[FT_R_OVAL + j] = w.x;
     }
 }
 
@@ -116,12 +133,13 @@ __device__ __forceinline__ void ft_mma(uint32_t d, uint64_t da, uint64_t db, uin
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
                  "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
-// x = hi + lo of two values, packed as half2 pairs
+// x = hi + lo of two values, packed as half2 pairs; |x| > 65504 saturates instead of becoming inf
 __device__ __forceinline__ void ft_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(a, b);
-    const float2 hf = __half22float2(h);
+    uint32_t h;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));      // upper half <- first source, lower half <- second
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
     const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
+    hi = h;
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 __device__ __forceinline__ void ft_st32(uint32_t taddr, const float* r) {
@@ -293,9 +311,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
     const float invB = (float)(1.0 / a.mb.global_count);
     float stats[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float accb2_0 = 0.f, accb2_1 = 0.f;                               // head threads: sums of dL/dout (output-layer bias gradients)
-    float accW1[32];                                                  // dW1[f][m0 .. m0 + 31] of this thread's net
-#pragma unroll
-    for (int j = 0; j < 32; ++j) accW1[j] = 0.f;
+    // delta scale of this thread's net in this group: a power of two fixed at the group's first tile with a non-zero gradient, so
+    // that dW1 can stay in TMEM over all the group's tiles; the scaled sums below are unscaled once at the end
+    float S = 1.0f, invS = 1.0f;
+    bool s_fixed = false;
     float accb1 = 0.f, accW2_0 = 0.f, accW2_1 = 0.f, accb0 = 0.f, accW0_0 = 0.f, accW0_1 = 0.f, accW0_2 = 0.f, accW0_3 = 0.f;
 
     // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0 .. nt-1; group g takes j = g, g + 2, ...
@@ -518,14 +537,17 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
         tc_group_sync(g);
         FT_MARK(10);
         // ---- B2: dZ1 = (W2 dout) .* (1 - H1^2), scaled by the tile's power of two -> dZ1 images; db1, dW2 sums -------------------
-        float invS;
         {
-            const float bound = fmaxf(sMax[net * 2], sMax[net * 2 + 1]) * w2bound;
-            int E = ((__float_as_int(bound) >> 23) & 255) - 127;                  // bound < 2^(E + 1)
-            E = E < -100 ? -100 : (E > 100 ? 100 : E);
-            if (!(bound > 0.f)) E = 11;
-            const float S = __int_as_float((11 - E + 127) << 23);                 // |S dZ1| < 2^12
-            invS = __int_as_float((E - 11 + 127) << 23);
+            if (!s_fixed) {
+                const float bound = fmaxf(sMax[net * 2], sMax[net * 2 + 1]) * w2bound;
+                if (bound > 0.f && bound < 3.0e38f) {
+                    int E = ((__float_as_int(bound) >> 23) & 255) - 127;          // bound < 2^(E + 1)
+                    E = E < -100 ? -100 : (E > 100 ? 100 : E);
+                    S = __int_as_float((3 - E + 127) << 23);                      // |S dZ1| < 2^4 on this tile: later tiles may grow 2^12-fold
+                    invS = __int_as_float((E - 3 + 127) << 23);
+                    s_fixed = true;
+                }
+            }
             const float ws0 = w2_0 * S, ws1 = w2_1 * S;
             float z[32];
             tc_ld32(my + FT_COL_D + m0, z);                                       // H1
@@ -542,7 +564,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
                 z[j] = u * fmaf(-h, h, 1.0f);
                 sb += z[j];
             }
-            accb1 = fmaf(sb, invS, accb1);
+            accb1 += sb;
             accW2_0 += sw0; accW2_1 += sw1;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -587,7 +609,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
                         ft_mma(gcol + FT_COL_D3 + ((uint32_t)wn << 20), tc_desc(ai + kk * 256, 128, 1024, 0), tc_desc(bi + kk * 256, 128, 1024, 0),
-                               idesc_g3, (ps | kk) ? 1u : 0u);
+                               idesc_g3, (it | ps | kk) ? 1u : 0u);          // accumulates over all tiles of the group
                 }
             tc_commit(bar3);
             if (it + 1 < n_own) issue_g0();
@@ -613,23 +635,31 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
                     s0 = fmaf(zz, x.x, s0); s1 = fmaf(zz, x.y, s1); s2 = fmaf(zz, x.z, s2); s3 = fmaf(zz, x.w, s3);
                 }
             }
-            const float cz = invS * (1.0f / FT_C2);
-            accb0 = fmaf(sb, cz, accb0);
-            accW0_0 = fmaf(s0, cz, accW0_0); accW0_1 = fmaf(s1, cz, accW0_1); accW0_2 = fmaf(s2, cz, accW0_2); accW0_3 = fmaf(s3, cz, accW0_3);
+            accb0 += sb;
+            accW0_0 += s0; accW0_1 += s1; accW0_2 += s2; accW0_3 += s3;
         }
-        // ---- flush this tile's dW1 (scaled by S) into the register accumulators ----------------------------------------------
+        // ---- G3 reads the H0 / dZ1 images: it must be done before the next tile overwrites them ----------------------------------
         FT_MARK(14);
         tc_wait(bar3, ph);
         FT_MARK(15);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        {
-            float d3[32];
-            tc_ld32(my + FT_COL_D3 + m0, d3);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) accW1[j] = fmaf(d3[j], invS, accW1[j]);
-        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         tc_group_sync(g);
+    }
+    // unscale the sums that were accumulated from scaled deltas; this group's dW1 from TMEM
+    accb1 *= invS;
+    {
+        const float cz = invS * (1.0f / FT_C2);
+        accb0 *= cz; accW0_0 *= cz; accW0_1 *= cz; accW0_2 *= cz; accW0_3 *= cz;
+    }
+    float accW1[32];                                                  // dW1[f][m0 .. m0 + 31] of this thread's net
+    if (n_own > 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tc_ld32(my + FT_COL_D3 + m0, accW1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) accW1[j] *= invS;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) accW1[j] = 0.f;
     }
 
     // ---- end of the minibatch: combine sample halves and groups, write this CTA's partial plane -------------------------------

@@ -74,12 +74,12 @@ __host__ inline FtgLayout ftg_layout(const PolicyDesc& pd) {
 
 // The epoch's samples in shuffled order as contiguous records of 64: x [64][Dp] | advantage | old log-prob | return | old value |
 // action (index int / act_n floats, [j][64]).
-__global__ void __launch_bounds__(256) ftg_permute_kernel(const BufDev buf, const FeistelKey fk, long long n_total, long long batch_size, int n_mb,
-                                                          int tiles_per_mb, int identity, int act_start, int act_n, int cont, int rec_floats,
-                                                          float* __restrict__ out) {
+__global__ void __launch_bounds__(256) ftg_permute_kernel(const float* __restrict__ recs, int stride, int D, const FeistelKey fk, long long n_total,
+                                                          long long batch_size, int n_mb, int tiles_per_mb, int identity, int act_start, int act_n,
+                                                          int cont, int rec_floats, float* __restrict__ out) {
     const long long per = (long long)tiles_per_mb * 64;
     const long long slots = per * n_mb;
-    const int D = buf.obs_dim, Dp = (D + 3) & ~3;
+    const int Dp = (D + 3) & ~3, A = cont ? act_n : 1;
     for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (long long)gridDim.x * blockDim.x) {
         const long long mb = s / per, r = s - mb * per;
         const long long pos = mb * batch_size + r;
@@ -88,32 +88,24 @@ __global__ void __launch_bounds__(256) ftg_permute_kernel(const BufDev buf, cons
         const int j = (int)(s & 63);
         long long sidx = 0;
         if (valid) sidx = identity ? pos : feistel_permute(pos, n_total, fk);
-        for (int d = 0; d < Dp; ++d) blk[j * Dp + d] = (valid && d < D) ? buf.obs[sidx * D + d] : 0.f;
+        const float* rp = recs + sidx * stride;                       // obs (Dp) | action (A) | adv, logp, ret, val: sample record (update_ft.cuh)
+        for (int d4 = 0; d4 < Dp; d4 += 4)
+            *reinterpret_cast<float4*>(blk + j * Dp + d4) = valid ? *reinterpret_cast<const float4*>(rp + d4) : make_float4(0.f, 0.f, 0.f, 0.f);
         float* sc = blk + 64 * Dp;
-        sc[j] = valid ? buf.advantages[sidx] : 0.f;
-        sc[64 + j] = valid ? buf.logprobs[sidx] : 0.f;
-        sc[128 + j] = valid ? buf.returns[sidx] : 0.f;
-        sc[192 + j] = valid ? buf.values[sidx] : 0.f;
+        sc[j] = valid ? rp[Dp + A] : 0.f;
+        sc[64 + j] = valid ? rp[Dp + A + 1] : 0.f;
+        sc[128 + j] = valid ? rp[Dp + A + 2] : 0.f;
+        sc[192 + j] = valid ? rp[Dp + A + 3] : 0.f;
         if (cont) {
-            for (int a = 0; a < act_n; ++a) sc[256 + a * 64 + j] = valid ? reinterpret_cast<const float*>(buf.actions)[sidx * act_n + a] : 0.f;
+            for (int a = 0; a < act_n; ++a) sc[256 + a * 64 + j] = valid ? rp[Dp + a] : 0.f;
         } else {
-            int ai = valid ? reinterpret_cast<const int*>(buf.actions)[sidx] - act_start : 0;
+            int ai = valid ? __float_as_int(rp[Dp]) - act_start : 0;
             ai = ai < 0 ? 0 : (ai >= act_n ? act_n - 1 : ai);
             reinterpret_cast<int*>(sc)[256 + j] = ai;
         }
     }
 }
 
-// saturating split: x = hi + lo as packed half2 pairs, |x| > 65504 clamps instead of becoming inf
-__device__ __forceinline__ void ftg_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    uint32_t h;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));      // d = {hi half: first source, lo half: second}
-    const __half2 hh = *reinterpret_cast<const __half2*>(&h);
-    const float2 hf = __half22float2(hh);
-    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-    hi = h;
-    lo = *reinterpret_cast<const uint32_t*>(&l);
-}
 __device__ __forceinline__ void ftg_st16(uint32_t taddr, const float* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
                  "r"(__float_as_uint(r[0])), "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])), "r"(__float_as_uint(r[3])),
@@ -326,8 +318,8 @@ __device__ __forceinline__ void ftg_pass(const LossArgs& a, const FtgArgs& fa, u
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         uint4 vh, vl;
-                        ftg_split2(v[8 * c], v[8 * c + 1], vh.x, vl.x); ftg_split2(v[8 * c + 2], v[8 * c + 3], vh.y, vl.y);
-                        ftg_split2(v[8 * c + 4], v[8 * c + 5], vh.z, vl.z); ftg_split2(v[8 * c + 6], v[8 * c + 7], vh.w, vl.w);
+                        ft_split2(v[8 * c], v[8 * c + 1], vh.x, vl.x); ft_split2(v[8 * c + 2], v[8 * c + 3], vh.y, vl.y);
+                        ft_split2(v[8 * c + 4], v[8 * c + 5], vh.z, vl.z); ft_split2(v[8 * c + 6], v[8 * c + 7], vh.w, vl.w);
                         const uint32_t off = ft_row_off(fl[l], m0 + 8 * c);
                         *reinterpret_cast<uint4*>(ph + off) = vh;
                         *reinterpret_cast<uint4*>(ph + wd[l] * 128 + off) = vl;
@@ -494,8 +486,8 @@ __device__ __forceinline__ void ftg_pass(const LossArgs& a, const FtgArgs& fa, u
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint4 vh, vl;
-                    ftg_split2(z[8 * c], z[8 * c + 1], vh.x, vl.x); ftg_split2(z[8 * c + 2], z[8 * c + 3], vh.y, vl.y);
-                    ftg_split2(z[8 * c + 4], z[8 * c + 5], vh.z, vl.z); ftg_split2(z[8 * c + 6], z[8 * c + 7], vh.w, vl.w);
+                    ft_split2(z[8 * c], z[8 * c + 1], vh.x, vl.x); ft_split2(z[8 * c + 2], z[8 * c + 3], vh.y, vl.y);
+                    ft_split2(z[8 * c + 4], z[8 * c + 5], vh.z, vl.z); ft_split2(z[8 * c + 6], z[8 * c + 7], vh.w, vl.w);
                     const uint32_t off = ft_row_off(flast, m0 + 8 * c);
                     *reinterpret_cast<uint4*>(pz + off) = vh;
                     *reinterpret_cast<uint4*>(pz + wd[L - 1] * 128 + off) = vl;
@@ -540,8 +532,8 @@ __device__ __forceinline__ void ftg_pass(const LossArgs& a, const FtgArgs& fa, u
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         uint4 vh, vl;
-                        ftg_split2(dz[8 * c], dz[8 * c + 1], vh.x, vl.x); ftg_split2(dz[8 * c + 2], dz[8 * c + 3], vh.y, vl.y);
-                        ftg_split2(dz[8 * c + 4], dz[8 * c + 5], vh.z, vl.z); ftg_split2(dz[8 * c + 6], dz[8 * c + 7], vh.w, vl.w);
+                        ft_split2(dz[8 * c], dz[8 * c + 1], vh.x, vl.x); ft_split2(dz[8 * c + 2], dz[8 * c + 3], vh.y, vl.y);
+                        ft_split2(dz[8 * c + 4], dz[8 * c + 5], vh.z, vl.z); ft_split2(dz[8 * c + 6], dz[8 * c + 7], vh.w, vl.w);
                         const uint32_t off = ft_row_off(fl[l - 1], m0 + 8 * c);
                         *reinterpret_cast<uint4*>(pz + off) = vh;
                         *reinterpret_cast<uint4*>(pz + wd[l - 1] * 128 + off) = vl;
