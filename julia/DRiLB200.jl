@@ -8,6 +8,9 @@
 #   CudaBatchedEnv <: AbstractParallelEnv      src/interfaces/environments.jl:39-157
 #   train!(agent, env::CudaBatchedEnv, alg::PPO, max_steps; callbacks)   src/algorithms/ppo.jl:100-325
 #   collect_rollout!(buf::DeviceRolloutBuffer, agent, alg, env::CudaBatchedEnv)  src/buffers/rollout_buffer.jl:46-90
+#   evaluate_agent(agent, env::CudaBatchedEnv; ...)                              src/evaluation.jl:54-143
+#   save_normalization_stats / load_normalization_stats! / sync_normalization_stats!   src/environment_wrappers/normalizeWrapperEnv.jl:261-309
+#   extract_policy(agent, norm_env::CudaBatchedEnv)                              src/deployment/deployment_policy.jl:50-71
 # Agent.train_state.parameters stays the source of truth: parameters are flattened in
 # ComponentVector order on the way in and copied back after train! so extract_policy,
 # predict_actions and save_policy_params_and_state keep working unchanged.
@@ -224,25 +227,34 @@ function DeviceRolloutBuffer(ctx::Context, env::CudaBatchedEnv, n_steps::Integer
 end
 Base.length(b::DeviceRolloutBuffer) = b.n_steps * b.n_envs
 
-"""
-on_step of collect_trajectories (src/buffers/trajectory.jl:34-39): one call per env step i = 1..n_steps; the first
-`false` aborts.  The fused rollout cannot be interrupted, so the n_steps hooks of a rollout run before it is launched
-(same step counter, abort decision and `steps_taken`, which moves once per rollout: test/test_callbacks.jl:92-99).
-"""
-function on_step_hooks(callbacks, agent, env, alg, n_steps)
-    isnothing(callbacks) && return true
-    n_envs = env.n_envs
-    for i in 1:n_steps
-        all(c -> DRiL.on_step(c, Base.@locals), callbacks) || return false
-    end
-    return true
-end
+"Callbacks that override `on_step` (src/buffers/trajectory.jl:34-39); the others keep the fused rollout."
+on_step_callbacks(callbacks) = isnothing(callbacks) ? AbstractCallback[] :
+    [c for c in callbacks if which(DRiL.on_step, (typeof(c), Dict)) != which(DRiL.on_step, (AbstractCallback, Dict))]
 
-"collect_rollout!(buffer, agent, alg, env) -> (fps, success)  (src/buffers/rollout_buffer.jl:46-90)"
-function DRiL.collect_rollout!(buf::DeviceRolloutBuffer, agent::Agent, alg::PPO, env::CudaBatchedEnv; callbacks = nothing)
-    on_step_hooks(callbacks, agent, env, alg, buf.n_steps) || return 0.0f0, false
+"""
+collect_rollout!(buffer, agent, alg, env) -> (fps, success)  (src/buffers/rollout_buffer.jl:46-90).
+When a callback overrides `on_step` the rollout runs in chunks of one step (`dril_rollout_collect_steps`): the observe()
+before the loop (trajectory.jl:32) precedes the first hook, hook i sees the env after i - 1 steps, and a `false` stops the
+collection there; otherwise one fused launch.
+"""
+function DRiL.collect_rollout!(buf::DeviceRolloutBuffer, agent::Agent, alg::PPO, env::CudaBatchedEnv; callbacks = nothing,
+        push = true)
     p = device_policy(agent, env.ctx)
-    push_params!(p, agent)
+    push && push_params!(p, agent)
+    active = on_step_callbacks(callbacks)
+    if !isempty(active)
+        n_steps, n_envs = buf.n_steps, buf.n_envs
+        t0 = time()
+        check(ccall((:dril_rollout_collect_steps, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Cvoid}),
+            env.h, p.h, buf.h, 0, 0, 1, C_NULL))
+        for i in 1:n_steps
+            all(c -> DRiL.on_step(c, Base.@locals), active) || return 0.0f0, false
+            check(ccall((:dril_rollout_collect_steps, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Cvoid}),
+                env.h, p.h, buf.h, i - 1, 1, 0, C_NULL))
+        end
+        check(ccall((:dril_gae, LIB), Int32, (Ptr{Cvoid}, Float32, Float32), buf.h, alg.gamma, alg.gae_lambda))
+        return Float32(n_steps * n_envs / max(time() - t0, 1e-12)), true
+    end
     fps = Ref{Float32}(0)
     check(ccall((:dril_rollout_collect, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Float32}),
         env.h, p.h, buf.h, C_NULL, fps))
@@ -257,11 +269,21 @@ Same contract as src/algorithms/ppo.jl:100-325: returns the 10-field `learn_stat
 TimerOutput; callbacks get a `Dict{Symbol,Any}` with the keys pinned by test/test_callbacks.jl:24-38;
 a callback returning `false` aborts and `train!` returns `nothing`; `add_step!` once per rollout.
 """
+const BUFFERS = IdDict{Any, DeviceRolloutBuffer}()      # one device buffer per agent, reused while its shape fits (allocation is the expensive part)
+function cached_buffer(agent::Agent, env::CudaBatchedEnv, n_steps::Integer)
+    b = get(BUFFERS, agent, nothing)
+    if b === nothing || b.n_steps != n_steps || b.n_envs != env.n_envs
+        b = DeviceRolloutBuffer(env.ctx, env, n_steps)
+        BUFFERS[agent] = b
+    end
+    return b
+end
+
 function DRiL.train!(agent::Agent, env::CudaBatchedEnv, alg::PPO{T}, max_steps::Int;
         ad_type = nothing, callbacks::Union{Vector{<:AbstractCallback}, Nothing} = nothing) where {T}
     to = DRiL.TimerOutput()
     n_steps, n_envs = alg.n_steps, env.n_envs
-    roll_buffer = DeviceRolloutBuffer(env.ctx, env, n_steps)
+    roll_buffer = cached_buffer(agent, env, n_steps)
     iterations = max_steps ÷ (n_steps * n_envs)
     total_steps = iterations * n_steps * n_envs
     p = device_policy(agent, env.ctx)
@@ -274,48 +296,142 @@ function DRiL.train!(agent::Agent, env::CudaBatchedEnv, alg::PPO{T}, max_steps::
     epoch_counter = UInt64(0)
     hook(f, loc) = isnothing(callbacks) || all(c -> f(c, loc), callbacks)
     hook(DRiL.on_training_start, Base.@locals) || return nothing
-    for i in 1:iterations
-        learning_rate = alg.learning_rate
-        hook(DRiL.on_rollout_start, Base.@locals) || return nothing
-        on_step_hooks(callbacks, agent, env, alg, n_steps) || return nothing
+    # without callbacks nothing on the host can influence the next iteration: iteration i + 1 is enqueued before the record of
+    # iteration i is read (FIFO of 4 slots in the library), so the device never waits for the host
+    pipelined = isnothing(callbacks)
+    enqueue() = begin
         hyper = Ref(PPOHyper(alg))
         check(ccall((:dril_ppo_iteration_async, LIB), Int32,
             (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{PPOHyper}, Int32, Int64, UInt64, UInt64),
             env.h, p.h, roll_buffer.h, hyper, alg.epochs, alg.batch_size, shuffle_seed, epoch_counter))
         epoch_counter += alg.epochs
-        st = Ref{IterStats}()
-        check(ccall((:dril_iteration_result, LIB), Int32, (Ptr{Cvoid}, Ref{IterStats}), p.h, st))
-        s = st[]
-        fps = Float32(n_steps * n_envs / (s.rollout_ms * 1.0f-3))
-        push!(total_fps, fps)
-        DRiL.add_step!(agent, n_steps * n_envs)
-        DRiL.increment_step!(agent.logger, n_steps * n_envs)
-        DRiL.log_scalar!(agent.logger, "env/fps", fps)
-        DRiL.log_stats(env, agent.logger)
-        hook(DRiL.on_rollout_end, Base.@locals) || return nothing
-        push!(stats[:learning_rates], learning_rate); push!(stats[:explained_variances], s.explained_variance)
-        push!(stats[:entropy_losses], s.entropy_loss); push!(stats[:policy_losses], s.policy_loss)
-        push!(stats[:value_losses], s.value_loss); push!(stats[:approx_kl_divs], s.approx_kl_div)
-        push!(stats[:clip_fractions], s.clip_fraction); push!(stats[:losses], s.loss); push!(stats[:grad_norms], s.grad_norm)
-        for (k, v) in ("train/entropy_loss" => s.entropy_loss, "train/explained_variance" => s.explained_variance,
-            "train/policy_loss" => s.policy_loss, "train/value_loss" => s.value_loss, "train/approx_kl_div" => s.approx_kl_div,
-            "train/clip_fraction" => s.clip_fraction, "train/loss" => s.loss, "train/grad_norm" => s.grad_norm,
-            "train/learning_rate" => learning_rate)
-            DRiL.log_scalar!(agent.logger, k, v)
-        end
     end
-    pull_params!(agent, p)
+    completed = false
+    try
+        for i in 1:iterations
+            learning_rate = alg.learning_rate
+            hook(DRiL.on_rollout_start, Base.@locals) || return nothing
+            st = Ref{IterStats}()
+            local fps::Float32
+            if pipelined
+                i == 1 && enqueue()
+                i < iterations && enqueue()
+                check(ccall((:dril_iteration_result, LIB), Int32, (Ptr{Cvoid}, Ref{IterStats}), p.h, st))
+                fps = Float32(n_steps * n_envs / (st[].rollout_ms * 1.0f-3))
+            else
+                # split like src/algorithms/ppo.jl:160-186: collect_rollout! (on_step hooks inside), bookkeeping, on_rollout_end,
+                # then the update: a hook returning false skips the update, every hook sees the rollout's parameters
+                fps, ok = DRiL.collect_rollout!(roll_buffer, agent, alg, env; callbacks, push = false)
+                ok || return nothing
+            end
+            push!(total_fps, fps)
+            DRiL.add_step!(agent, n_steps * n_envs)
+            DRiL.increment_step!(agent.logger, n_steps * n_envs)
+            DRiL.log_scalar!(agent.logger, "env/fps", fps)
+            DRiL.log_stats(env, agent.logger)
+            hook(DRiL.on_rollout_end, Base.@locals) || return nothing
+            if !pipelined
+                hyper = Ref(PPOHyper(alg))
+                check(ccall((:dril_ppo_update, LIB), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ref{PPOHyper}, Int32, Int64, UInt64, UInt64, Ref{IterStats}),
+                    p.h, roll_buffer.h, hyper, alg.epochs, alg.batch_size, shuffle_seed, epoch_counter, st))
+                epoch_counter += alg.epochs
+            end
+            s = st[]
+            push!(stats[:learning_rates], learning_rate); push!(stats[:explained_variances], s.explained_variance)
+            push!(stats[:entropy_losses], s.entropy_loss); push!(stats[:policy_losses], s.policy_loss)
+            push!(stats[:value_losses], s.value_loss); push!(stats[:approx_kl_divs], s.approx_kl_div)
+            push!(stats[:clip_fractions], s.clip_fraction); push!(stats[:losses], s.loss); push!(stats[:grad_norms], s.grad_norm)
+            for (k, v) in ("train/entropy_loss" => s.entropy_loss, "train/explained_variance" => s.explained_variance,
+                "train/policy_loss" => s.policy_loss, "train/value_loss" => s.value_loss, "train/approx_kl_div" => s.approx_kl_div,
+                "train/clip_fraction" => s.clip_fraction, "train/loss" => s.loss, "train/grad_norm" => s.grad_norm,
+                "train/learning_rate" => learning_rate)
+                DRiL.log_scalar!(agent.logger, k, v)
+            end
+        end
+        completed = true
+    finally
+        if !completed          # drain unread pipelined results
+            st = Ref{IterStats}()
+            while ccall((:dril_iteration_result, LIB), Int32, (Ptr{Cvoid}, Ref{IterStats}), p.h, st) == 0 end
+        end
+        pull_params!(agent, p)  # an aborted train! keeps the parameters it updated in place (ppo.jl:179-186)
+    end
     learn_stats = NamedTuple{keys10}(Tuple(stats[k] for k in keys10))
     hook(DRiL.on_training_end, Base.@locals) || return nothing
     return learn_stats, to
 end
 
+# ---- evaluation on the device (src/evaluation.jl:54-143) -------------------------------------------------------------------------
+"""
+    evaluate_agent(agent, env::CudaBatchedEnv; n_eval_episodes, deterministic, reward_threshold, return_stats)
+
+Same contract as src/evaluation.jl:54-143; the episode loop runs on the device (`dril_evaluate`: fused policy + env steps in
+chunks, one device -> host copy of the episode records per chunk, episodes appended in (step, env) order).
+"""
+function DRiL.evaluate_agent(agent::Agent, env::CudaBatchedEnv; n_eval_episodes::Int = 10, deterministic::Bool = true,
+        reward_threshold = nothing, return_stats::Bool = true, warn::Bool = true, rng = agent.rng, show_progress::Bool = false,
+        chunk_steps::Integer = 64)
+    p = device_policy(agent, env.ctx)
+    push_params!(p, agent)
+    er = Vector{Float32}(undef, n_eval_episodes); el = Vector{Int64}(undef, n_eval_episodes)
+    got = Ref{Int64}(0); steps = Ref{Int64}(0)
+    check(ccall((:dril_evaluate, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Int32, Ptr{Float32}, Ptr{Int64}, Ref{Int64}, Ref{Int64}),
+        env.h, p.h, n_eval_episodes, Int32(deterministic), Int32(chunk_steps), er, el, got, steps))
+    mean_reward = DRiL.mean(er)
+    if reward_threshold !== nothing && mean_reward < reward_threshold
+        error("Mean reward below threshold: $(round(mean_reward, digits = 2)) < $(reward_threshold)")
+    end
+    return_stats || return er, Int.(el)
+    return (; mean_reward, std_reward = DRiL.std(er), mean_length = DRiL.mean(el), std_length = DRiL.std(el))
+end
+
+# ---- normaliser statistics (src/environment_wrappers/normalizeWrapperEnv.jl:261-309) and deployment ------------------------------
+function norm_stats(env::CudaBatchedEnv)
+    D = size(env.obs_space)[1]
+    m = Vector{Float32}(undef, D); v = Vector{Float32}(undef, D)
+    oc = Ref{Int64}(0); rc = Ref{Int64}(0); rm = Ref{Float32}(0); rv = Ref{Float32}(0)
+    check(ccall((:dril_env_get_norm_stats, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ref{Int64}, Ref{Float32}, Ref{Float32}, Ref{Int64}), env.h, m, v, oc, rm, rv, rc))
+    return (; obs_mean = m, obs_var = v, obs_count = oc[], ret_mean = rm[], ret_var = rv[], ret_count = rc[])
+end
+set_norm_stats!(env::CudaBatchedEnv, s) = check(ccall((:dril_env_set_norm_stats, LIB), Int32,
+    (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int64, Float32, Float32, Int64),
+    env.h, Float32.(s.obs_mean), Float32.(s.obs_var), s.obs_count, s.ret_mean, s.ret_var, s.ret_count))
+
+"save_normalization_stats(env, filepath): the ten keys of normalizeWrapperEnv.jl:261-277, through DRiL's own JLD2 `save`."
+function DRiL.save_normalization_stats(env::CudaBatchedEnv, filepath::String)
+    s, c = norm_stats(env), env.normalize
+    return DRiL.save(filepath, Dict("obs_mean" => s.obs_mean, "obs_var" => s.obs_var, "obs_count" => s.obs_count,
+        "ret_mean" => [s.ret_mean], "ret_var" => [s.ret_var], "ret_count" => s.ret_count, "clip_obs" => c.clip_obs,
+        "clip_reward" => c.clip_reward, "gamma" => c.gamma, "epsilon" => c.epsilon))
+end
+function DRiL.load_normalization_stats!(env::CudaBatchedEnv, filepath::String)
+    d = DRiL.load(filepath)
+    set_norm_stats!(env, (; obs_mean = d["obs_mean"], obs_var = d["obs_var"], obs_count = d["obs_count"],
+        ret_mean = first(d["ret_mean"]), ret_var = first(d["ret_var"]), ret_count = d["ret_count"]))
+    return env
+end
+"sync_normalization_stats!(eval_env, train_env): statistics copied, the eval env's discounted returns zeroed (normalizeWrapperEnv.jl:299-309)"
+function DRiL.sync_normalization_stats!(eval_env::CudaBatchedEnv, train_env::CudaBatchedEnv)
+    set_norm_stats!(eval_env, norm_stats(train_env))
+    check(ccall((:dril_env_zero_returns, LIB), Int32, (Ptr{Cvoid},), eval_env.h))
+    return nothing
+end
+"extract_policy(agent, norm_env) -> NormWrapperPolicy (src/deployment/deployment_policy.jl:50-71) with the device env's obs statistics"
+function DRiL.extract_policy(agent::Agent, norm_env::CudaBatchedEnv)
+    s = norm_stats(norm_env)
+    rms = DRiL.RunningMeanStd{Float32}(s.obs_mean, s.obs_var, s.obs_count)
+    return DRiL.NormWrapperPolicy(DRiL.extract_policy(agent), rms, norm_env.normalize.epsilon, norm_env.normalize.clip_obs)
+end
+
 # ---- kernel-path switches and data-parallel setup (include/dril_b200.h) --------------------------------------------
-"`set_option(\"tc\" | \"fused_tail\" | \"tc_rollout\" | \"single_net\" | \"mma\", 0/1)`: process-wide kernel-path switches (all default on;\nthe last two apply to policies created afterwards)."
+"`set_option(\"tc\" | \"ft\" | \"ftg\" | \"fused_tail\" | \"tc_rollout\" | \"single_net\" | \"mma\", 0/1)`: process-wide kernel-path switches (all default on;\nthe last two apply to policies created afterwards)."
 set_option(key::AbstractString, value::Integer) =
     check(ccall((:dril_set_option, LIB), Int32, (Cstring, Int32), key, value))
 
-"`:tensor`: the update of this policy runs the tcgen05 (3xTF32) loss/grad kernel; `:mma`: the general-shape kernel with its
+"`:tensor`: the update of this policy runs a tcgen05 loss/grad kernel (update_ft.cuh / update_ftg.cuh / update_tc.cuh); `:mma`: the general-shape kernel with its
 wide layers on mma.sync 3xTF32 tiles; `:fp32`: the general-shape kernel on FMA tiles only."
 function update_path(p::DevicePolicy)
     out = Ref{Int32}(0)

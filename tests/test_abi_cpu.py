@@ -72,3 +72,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_julia_shim_binds_declared_symbols(lib):
+    """julia/DRiLB200.jl cannot be executed here (no Julia toolchain): at least every symbol it `ccall`s must be declared in
+    include/dril_b200.h and exported by the built library."""
+    import re
+    src = open(os.path.join(ROOT, "julia", "DRiLB200.jl")).read()
+    header = open(os.path.join(ROOT, "include", "dril_b200.h")).read()
+    syms = sorted(set(re.findall(r"ccall\(\(:(\w+), LIB\)", src)))
+    assert len(syms) >= 25
+    for s in syms:
+        assert re.search(r"\b%s\s*\(" % s, header), f"{s} is not declared in include/dril_b200.h"
+        assert hasattr(lib, s), f"{s} is not exported by libdril_b200.so"
