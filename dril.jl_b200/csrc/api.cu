@@ -45,6 +45,8 @@ extern "C" const char* dril_source_hash(void) { return g_source_hash_marker + 17
 static int g_opt_tc = getenv("DRIL_TC") ? atoi(getenv("DRIL_TC")) : 1;
 // features-on-lanes tcgen05 loss/grad kernel (update_ft.cuh) instead of the samples-on-lanes one (update_tc.cuh)
 static int g_opt_ft = getenv("DRIL_FT") ? atoi(getenv("DRIL_FT")) : 1;
+// general rollout kernel: actor only in the step loop, values by one batched tcgen05 critic pass afterwards (shapes of update_ftg.cuh)
+static int g_opt_defer_critic = getenv("DRIL_DEFER_CRITIC") ? atoi(getenv("DRIL_DEFER_CRITIC")) : 1;
 static int g_opt_ftg = getenv("DRIL_FTG") ? atoi(getenv("DRIL_FTG")) : 1;   // general-shape features-on-lanes kernel (update_ftg.cuh); 2: also where update_ft.cuh applies
 static int g_opt_tc_rollout = getenv("DRIL_TC_ROLLOUT") ? atoi(getenv("DRIL_TC_ROLLOUT")) : 1;   // tensor-core rollout (CartPole, [64,64])
 static int g_opt_tail = getenv("DRIL_TAIL") ? atoi(getenv("DRIL_TAIL")) : 1;   // fused reduce/clip/Adam tail of the TC kernel
@@ -57,6 +59,7 @@ extern "C" int32_t dril_set_option(const char* key, int32_t value) {
     if (!strcmp(key, "tc")) { g_opt_tc = value; return DRIL_OK; }
     if (!strcmp(key, "ft")) { g_opt_ft = value; return DRIL_OK; }
     if (!strcmp(key, "ftg")) { g_opt_ftg = value; return DRIL_OK; }
+    if (!strcmp(key, "defer_critic")) { g_opt_defer_critic = value; return DRIL_OK; }
     if (!strcmp(key, "fused_tail")) { g_opt_tail = value; return DRIL_OK; }
     if (!strcmp(key, "tc_rollout")) { g_opt_tc_rollout = value; return DRIL_OK; }
     if (!strcmp(key, "single_net")) { g_opt_single_net = value; return DRIL_OK; }   // policies created afterwards
@@ -178,6 +181,8 @@ struct dril_buffer {
     int act_elems;  // per-sample action elements
     TcRolloutScratch tcs = {nullptr, nullptr, nullptr, nullptr, 0};   // tensor-core rollout: inputs of the batched critic pass
     void* tcs_slab = nullptr;
+    DeferredCritic dcs = {nullptr, nullptr, nullptr, nullptr, 0};      // general rollout with the critic deferred to a batched pass
+    void* dcs_slab = nullptr;
     bool is_view = false;   // rows [t0, t0 + T) of another buffer (chunked collection): no tensor-core rollout scratch
 };
 
@@ -338,6 +343,8 @@ extern "C" int32_t dril_ctx_create(int32_t device, uint64_t seed, dril_ctx** out
                              (const void*)ppo_loss_grad_ftg_kernel<3, 0, 1>, (const void*)ppo_loss_grad_ftg_kernel<3, 0, 2>,
                              (const void*)ppo_loss_grad_ftg_kernel<3, 1, 1>, (const void*)ppo_loss_grad_ftg_kernel<3, 1, 2>};
         for (const void* fn : fns) DRIL_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX - 2048));   // 1 KB of static shared memory
+        DRIL_CUDA(cudaFuncSetAttribute(critic_values_ftg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX - 2048));
+        DRIL_CUDA(cudaFuncSetAttribute(critic_values_ftg_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX - 2048));
     }
     DRIL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM_BYTES));
     *out = c;
@@ -569,6 +576,7 @@ extern "C" int32_t dril_buffer_destroy(dril_buffer* b) {
     cudaStreamSynchronize(b->ctx->stream);
     cudaFree(b->slab);
     if (b->tcs_slab) cudaFree(b->tcs_slab);
+    if (b->dcs_slab) cudaFree(b->dcs_slab);
     delete b;
     return DRIL_OK;
 }
@@ -1159,6 +1167,25 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
             }
         if (any) { M4 = 64; flags |= RO_MMA; }
     }
+    // shapes the general tcgen05 kernels cover (update_ftg.cuh): only the actor runs inside the step loop; V(s_t), V(terminal_obs)
+    // and V(new_obs) come from one batched critic pass over the stored (normalised) observations afterwards
+    const bool defer = has_policy && g_opt_defer_critic && g_opt_ftg && ftg_eligible(a.pd) && !b->is_view && T == b->d.T && T > 0 &&
+                       !(base_flags & RO_DETERMINISTIC);
+    if (defer) {
+        if (!b->dcs_slab) {
+            const size_t cap = (size_t)b->d.T * b->d.N, Db = (size_t)d.obs_dim * 4;
+            auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+            const size_t o_last = 0, o_tobs = o_last + al((size_t)N * Db), o_tidx = o_tobs + al(cap * Db), o_cnt = o_tidx + al(cap * 8);
+            DRIL_CUDA(cudaMalloc(&b->dcs_slab, o_cnt + 256));
+            char* base = (char*)b->dcs_slab;
+            b->dcs.last_obs = (float*)(base + o_last); b->dcs.trunc_obs = (float*)(base + o_tobs);
+            b->dcs.trunc_idx = (long long*)(base + o_tidx); b->dcs.trunc_count = (unsigned int*)(base + o_cnt);
+            b->dcs.cap = (unsigned int)std::min<size_t>(cap, 0x7fffffffu);
+        }
+        DRIL_CUDA(cudaMemsetAsync(b->dcs.trunc_count, 0, 4, c->stream));
+        a.dc = b->dcs;
+        flags |= RO_DEFER_CRITIC;
+    }
     if (ws) flags |= RO_WEIGHTS_SMEM;
     a.M4 = M4; a.flags = flags;
     a.n_tiles = (int)((N + M4 - 1) / M4);
@@ -1187,6 +1214,15 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
     } else {
         if (ws) rollout_kernel<true><<<grid, threads, smem, c->stream>>>(a);
         else rollout_kernel<false><<<grid, threads, smem, c->stream>>>(a);
+        DRIL_CUDA(cudaGetLastError());
+    }
+    if (defer) {
+        Span sp2(c, DRIL_K_ROLLOUT);
+        const FtgLayout lay = ftg_layout(a.pd);
+        const long long tiles = ((long long)b->d.T * N + N + 63) / 64 + 8;
+        const int cgrid = (int)std::min<long long>(tiles, (long long)c->sm_count);
+        if (a.pd.n_layers - 1 == 2) critic_values_ftg_kernel<2><<<cgrid, FTG_THREADS, (size_t)lay.total, c->stream>>>(a.pd, a.pack, b->d, b->dcs, lay);
+        else critic_values_ftg_kernel<3><<<cgrid, FTG_THREADS, (size_t)lay.total, c->stream>>>(a.pd, a.pack, b->d, b->dcs, lay);
         DRIL_CUDA(cudaGetLastError());
     }
     return DRIL_OK;
@@ -1432,7 +1468,7 @@ static dril_buffer buffer_view(dril_buffer* b, long long t0, long long tc) {
     v.d.actions = (char*)b->d.actions + r0 * b->act_elems * 4;
     v.d.rewards += r0; v.d.values += r0; v.d.logprobs += r0; v.d.advantages += r0; v.d.returns += r0; v.d.boot += r0;
     v.d.episode_r += r0; v.d.episode_l += r0; v.d.flags += r0; v.d.done_count += t0;
-    v.is_view = true; v.tcs_slab = nullptr;
+    v.is_view = true; v.tcs_slab = nullptr; v.dcs_slab = nullptr;
     return v;
 }
 

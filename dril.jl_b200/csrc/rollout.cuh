@@ -31,7 +31,18 @@ enum {
     RO_WRITE_OBS_OUT = 32,    // compat observe: write normalised obs to obs_out
     RO_TILES_8X8 = 64,        // throughput mode (many envs per SM): 8x8 register tiles in the hidden layers
     RO_MMA = 128,             // general kernel, tile width multiple of 16: wide layers on mma.sync 3xTF32 tiles
-    RO_DETERMINISTIC = 256    // general kernel: mode of the distribution instead of a sample (evaluate_agent, evaluation.jl:54-143)
+    RO_DETERMINISTIC = 256,   // general kernel: mode of the distribution instead of a sample (evaluate_agent, evaluation.jl:54-143)
+    RO_DEFER_CRITIC = 512     // general kernel: only the actor runs in the step loop; V(s_t), V(terminal_obs) and V(new_obs) are
+                              // evaluated afterwards by one batched critic pass over the (normalised) observations it stored
+};
+
+// observations whose values are evaluated after the rollout (RO_DEFER_CRITIC): what the policy saw, i.e. already normalised
+struct DeferredCritic {
+    float* last_obs;          // [N][D] observation after the final step
+    float* trunc_obs;         // [cap][D] terminal observations of truncated steps
+    long long* trunc_idx;     // [cap] buffer sample index of each entry
+    unsigned int* trunc_count;
+    unsigned int cap;
 };
 
 struct RolloutArgs {
@@ -45,6 +56,7 @@ struct RolloutArgs {
     unsigned long long pseed;
     unsigned int step0;
     int T, M4, n_tiles, flags;
+    DeferredCritic dc;
 };
 
 struct RolloutSmem {
@@ -168,6 +180,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
     const BufDev& buf = a.buf;
     const PolicyDesc& pd = a.pd;
     const bool has_policy = a.flags & RO_HAS_POLICY;
+    const bool defer = (a.flags & RO_DEFER_CRITIC) != 0;
     const bool grid_sync = a.flags & RO_GRID_SYNC;
     const bool use_mma = (a.flags & RO_MMA) != 0;
     const int D = env.obs_dim, Dp = (D + 3) & ~3;
@@ -356,8 +369,8 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
                     int e = i / D, d = i - e * D;
                     buf.obs[(row + n0) * D + i] = sX[(size_t)d * ld + e];
                 }
-                // actor + critic forward
-                fin = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, 3, use_mma);
+                // actor + critic forward (critic deferred: actor only)
+                fin = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, defer ? 1 : 3, use_mma);
             }
             // sample / replay action, log-prob, value; hand the env-space action to the step
             int a_disc = 0;
@@ -365,7 +378,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
                 const uint32_t gid = (uint32_t)(env.gid_offset + n);
                 if (has_policy) {
                     const float* z = sActA + (size_t)fin * pd.max_np * ld + tid;
-                    float value = sActC[(size_t)fin * pd.max_np * ld + tid];
+                    float value = defer ? 0.f : sActC[(size_t)fin * pd.max_np * ld + tid];
                     float logp;
                     if (pd.act_kind == DRIL_ACT_DISCRETE) {
                         int mode = 0, forced_v = 0;
@@ -399,7 +412,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
                         }
                         logp = -0.5f * (2.0f * ls_sum + dss + (float)A * DRIL_LOG2PI);
                     }
-                    buf.values[row + n] = value;
+                    if (!defer) buf.values[row + n] = value;
                     buf.logprobs[row + n] = logp;
                 } else {  // compat act!: actions are given in env space
                     if (env.act_dim == 0) a_disc = reinterpret_cast<const int*>(a.forced)[row + n];
@@ -516,7 +529,16 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
                     sX[(size_t)d * ld + e] = x;
                 }
                 __syncthreads();
-                if (has_policy) {                               // V(terminal_obs), trajectory.jl:57-61
+                if (has_policy && defer) {                      // V(terminal_obs) later: keep the normalised terminal observation
+                    if (mine && trunc) {
+                        const unsigned int k = atomicAdd(a.dc.trunc_count, 1u);
+                        if (k < a.dc.cap) {
+                            for (int d = 0; d < D; ++d) a.dc.trunc_obs[(size_t)k * D + d] = sX[(size_t)d * ld + tid];
+                            a.dc.trunc_idx[k] = (long long)(row + n);
+                        }
+                    }
+                    __syncthreads();
+                } else if (has_policy) {                        // V(terminal_obs), trajectory.jl:57-61
                     int f = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, 2, use_mma);
                     if (mine && trunc) buf.boot[row + n] = sActC[(size_t)f * pd.max_np * ld + tid];
                     __syncthreads();
@@ -533,6 +555,14 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
             int nvalid = (int)min((long long)M4, N - n0);
             tile_raw_obs(n0, nvalid);
             tile_normalize(sMean, sVar, nvalid);
+            if (defer) {
+                for (int i = tid; i < nvalid * D; i += blockDim.x) {
+                    int e = i / D, d = i - e * D;
+                    a.dc.last_obs[(size_t)n0 * D + i] = sX[(size_t)d * ld + e];
+                }
+                __syncthreads();
+                continue;
+            }
             int f = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, 2, use_mma);
             if (tid < nvalid) buf.last_values[n0 + tid] = sActC[(size_t)f * pd.max_np * ld + tid];
             __syncthreads();

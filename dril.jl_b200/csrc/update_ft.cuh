@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
     float* sWmax = sSmall + 208;                                   // [4 warps][2 nets]
     float* Hs = reinterpret_cast<float*>(smg + FT_G_Q);
     float4* sPart = reinterpret_cast<float4*>(smg + FT_G_PART);
-    float2* sDout = reinterpret_cast<float2*>(smg + FT_G_DOUT);
+    float* sDout = reinterpret_cast<float*>(smg + FT_G_DOUT);     // [net][64 samples]: the sample's dL/dout scalar (see the loss head)
     float* sMax = reinterpret_cast<float*>(smg + FT_G_MAX);
     uint64_t* barL = &bars[g][0];
     uint64_t* bar1 = &bars[g][2];
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
     // that dW1 can stay in TMEM over all the group's tiles; the scaled sums below are unscaled once at the end
     float S = 1.0f, invS = 1.0f;
     bool s_fixed = false;
-    float accb1 = 0.f, accW2_0 = 0.f, accW2_1 = 0.f, accb0 = 0.f, accW0_0 = 0.f, accW0_1 = 0.f, accW0_2 = 0.f, accW0_3 = 0.f;
+    float accb1 = 0.f, accW2_0 = 0.f, accb0 = 0.f, accW0_0 = 0.f, accW0_1 = 0.f, accW0_2 = 0.f, accW0_3 = 0.f;
 
     // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0 .. nt-1; group g takes j = g, g + 2, ...
     const long long n_tiles = (a.mb.count + FT_TS - 1) / FT_TS;
@@ -509,7 +509,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
                 }
                 accb2_0 += dout[0];
                 if (NOUT > 1) accb2_1 += dout[NOUT > 1 ? 1 : 0];
-                sDout[ms] = make_float2(dout[0], NOUT > 1 ? dout[NOUT > 1 ? 1 : 0] : 0.f);
+                // two logits: the softmax gradient sums to zero (dL/dout_1 = -dL/dout_0 up to rounding), so ONE scalar per sample
+                // goes to the feature threads (half the broadcast loads of the delta phase); their mean cancels the rounding
+                sDout[ms] = NOUT > 1 ? 0.5f * (dout[0] - dout[NOUT > 1 ? 1 : 0]) : dout[0];
                 dmax = fabsf(dout[0]);
                 if (NOUT > 1) dmax = fmaxf(dmax, fabsf(dout[NOUT > 1 ? 1 : 0]));
             } else {
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
                 const float dc = (valid && v_pass) ? a.hp.vf_coef * 2.0f * verr * invB : 0.f;
                 if (valid) stats[1] += verr * verr;
                 accb2_0 += dc;
-                sDout[64 + ms] = make_float2(dc, 0.f);
+                sDout[64 + ms] = dc;
                 dmax = fabsf(dc);
             }
 #pragma unroll
@@ -548,24 +550,21 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
                     s_fixed = true;
                 }
             }
-            const float ws0 = w2_0 * S, ws1 = w2_1 * S;
+            const float wsd = (w2_0 - w2_1) * S;                                  // actor, two logits: W2[f][0] - W2[f][1]; else W2[f][0] (w2_1 = 0)
             float z[32];
             tc_ld32(my + FT_COL_D + m0, z);                                       // H1
-            const float2* dd = sDout + net * 64 + m0;
-            float sb = 0.f, sw0 = 0.f, sw1 = 0.f;
+            const float* dd = sDout + net * 64 + m0;
+            float sb = 0.f, sw0 = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float2 d = dd[j];
+                const float d = dd[j];
                 const float h = z[j];
-                sw0 = fmaf(h, d.x, sw0);
-                if (NOUT > 1) sw1 = fmaf(h, d.y, sw1);
-                float u = d.x * ws0;
-                if (NOUT > 1) u = fmaf(d.y, ws1, u);
-                z[j] = u * fmaf(-h, h, 1.0f);
+                sw0 = fmaf(h, d, sw0);
+                z[j] = (d * wsd) * fmaf(-h, h, 1.0f);
                 sb += z[j];
             }
             accb1 += sb;
-            accW2_0 += sw0; accW2_1 += sw1;
+            accW2_0 += sw0;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint4 vh, vl;
@@ -680,7 +679,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
     }
     {
         float* r = sRed + ((g * 2 + sh) * 8) * 128 + net * 64 + f;
-        r[0] = accW0_0; r[128] = accW0_1; r[256] = accW0_2; r[384] = accW0_3; r[512] = accb0; r[640] = accb1; r[768] = accW2_0; r[896] = accW2_1;
+        r[0] = accW0_0; r[128] = accW0_1; r[256] = accW0_2; r[384] = accW0_3; r[512] = accb0; r[640] = accb1; r[768] = accW2_0; r[896] = -accW2_0;     // dW2[f][1] = -dW2[f][0] (two logits)
     }
     if (q < 2) {
         // head warps: output-layer bias gradients and the six statistic sums (warp sums, then 8 warp slots in fixed order)

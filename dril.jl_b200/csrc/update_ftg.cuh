@@ -702,3 +702,197 @@ __global__ void __launch_bounds__(FTG_THREADS, 1) ppo_loss_grad_ftg_kernel(const
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(FTG_TMEM_COLS));
     if (tl.mode) tc_fused_tail(a, tl, reinterpret_cast<float*>(sm + fa.lay.part), scratch, s_f2);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Batched critic for the general rollout (rollout.cuh, RO_DEFER_CRITIC): V of all T*N buffer observations, of the N final
+// observations (bootstrap of trajectories cut by the rollout end, trajectory.jl:65-70) and of the terminal observations of
+// truncated steps (trajectory.jl:57-61), all already normalised as the policy saw them.  Forward half of ftg_pass for the
+// critic net: 64 observations per tile, G0 -> tanh -> G1 -> tanh [-> G2 -> tanh] on tcgen05, output layer on CUDA cores.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(FTG_THREADS, 1) critic_values_ftg_kernel(const __grid_constant__ PolicyDesc pd, const float* __restrict__ pack,
+                                                                           const BufDev buf, const DeferredCritic dc,
+                                                                           const __grid_constant__ FtgLayout ly) {
+    extern __shared__ __align__(1024) unsigned char ftg_smem_raw[];
+    __shared__ __align__(8) uint64_t barM;
+    __shared__ uint32_t tmem_base_s;
+    constexpr int net = 1;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int lane = tid & 31, q = warp & 3, sg = warp >> 2;
+    const int m0 = 16 * sg, ms = tid & 63, slice = tid >> 6;
+    const bool issuer = warp == 0;
+    const uint32_t raw = tc_smem_u32(ftg_smem_raw);
+    const uint32_t sm_base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = ftg_smem_raw + (sm_base - raw);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_s)), "r"(64));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&barM)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    int wd[L], fl[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        wd[l] = pd.L[net][l].N;
+        fl[l] = wd[l] == 128 ? 32 * q + lane : (lane < 16 ? 16 * q + lane : -1);
+    }
+    const int D = pd.obs_dim;
+    float* sSmall = reinterpret_cast<float*>(sm + ly.small);
+    float2* sWout = reinterpret_cast<float2*>(sSmall);
+    float* sMisc = sSmall + 256;
+    float* Hs = reinterpret_cast<float*>(sm + ly.last);
+    float4* sPart = reinterpret_cast<float4*>(sm + ly.part);
+    __half* sXimg = reinterpret_cast<__half*>(sm + ly.ximg);
+    const LayerDesc& Lout = pd.L[net][L];
+    // ---- the critic's weights: images of C2 * W_l (l >= 1), of C2 * [W_0; b_0]^T, output layer in fp32 -------------------------
+#pragma unroll
+    for (int l = 1; l < L; ++l) {
+        const LayerDesc& Ll = pd.L[net][l];
+        const int K = wd[l - 1], N = wd[l], KB = K >> 3;
+        __half* hi = reinterpret_cast<__half*>(sm + ly.w[l - 1]);
+        __half* lo = hi + N * K;
+        for (int i0 = tid * 4; i0 < K * N; i0 += FTG_THREADS * 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(pack + Ll.pw_off + i0);
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+            const int k = i0 / N, nb = i0 - k * N;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = nb + j;
+                const float w = fminf(fmaxf(wv[j] * FT_C2, -65504.f), 65504.f);
+                const __half h = __float2half_rn(w);
+                const int idx = ((n >> 3) * KB + (k >> 3)) * 64 + (n & 7) * 8 + (k & 7);
+                hi[idx] = h;
+                lo[idx] = __float2half_rn(w - __half2float(h));
+            }
+        }
+    }
+    {
+        const LayerDesc& L0 = pd.L[net][0];
+        __half* hi = reinterpret_cast<__half*>(sm + ly.w0a);
+        __half* lo = hi + wd[0] * 16;
+        for (int i = tid; i < wd[0] * 16; i += FTG_THREADS) {
+            const int k = i >> 4, d = i & 15;
+            float w = d < D ? pack[L0.pw_off + d * L0.Np + k] : (d == D ? pack[L0.pb_off + k] : 0.f);
+            w = fminf(fmaxf(w * FT_C2, -65504.f), 65504.f);
+            const __half h = __float2half_rn(w);
+            const int idx = ((k >> 3) * 2 + (d >> 3)) * 64 + (k & 7) * 8 + (d & 7);
+            hi[idx] = h;
+            lo[idx] = __float2half_rn(w - __half2float(h));
+        }
+    }
+    for (int i = tid; i < wd[L - 1]; i += FTG_THREADS) sWout[i] = make_float2(pack[Lout.pw_off + i * Lout.Np], 0.f);
+    if (tid == 0) sMisc[0] = pack[Lout.pb_off];
+    for (int i = tid; i < 2 * 1024; i += FTG_THREADS) {
+        const int e = i & 1023, d = ((e >> 9) << 3) + ((e >> 3) & 7);
+        sXimg[i] = __float2half_rn((i < 1024 && d == D) ? 1.0f : 0.f);
+    }
+    float bsc[L];
+#pragma unroll
+    for (int l = 1; l < L; ++l) bsc[l] = fl[l] >= 0 ? pack[pd.L[net][l].pb_off + fl[l]] * FT_C2 : 0.f;
+    bsc[0] = 0.f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+    const uint32_t my = tb + ((uint32_t)(q * 32) << 16);
+    const long long TN = buf.T * buf.N;
+    const unsigned int ntr = min(*dc.trunc_count, dc.cap);
+    const long long total = TN + buf.N + (long long)ntr;
+    const long long n_tiles = (total + 63) / 64;
+    uint32_t n_mma = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // ---- x of the tile's 64 observations -> fp16 hi / lo rows of the x images ---------------------------------------------
+        for (int i = tid; i < 64 * D; i += FTG_THREADS) {
+            const int m = i & 63, d = i >> 6;
+            const long long v = tile * 64 + m;
+            float x = 0.f;
+            if (v < TN) x = buf.obs[v * D + d];
+            else if (v < TN + buf.N) x = dc.last_obs[(v - TN) * D + d];
+            else if (v < total) x = dc.trunc_obs[(v - TN - buf.N) * D + d];
+            x = fminf(fmaxf(x, -65504.f), 65504.f);
+            const __half h = __float2half_rn(x);
+            const int idx = ((d >> 3) * 8 + (m >> 3)) * 64 + (d & 7) * 8 + (m & 7);
+            sXimg[idx] = h;
+            sXimg[1024 + idx] = __float2half_rn(x - __half2float(h));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            if (issuer && tc_elect_one()) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (l == 0) {
+                    const uint32_t id = ft_idesc(wd[0], 64, 0, 1);
+#pragma unroll
+                    for (int ps = 0; ps < 3; ++ps)
+                        ft_mma(tb, tc_desc(sm_base + ly.w0a + (ps == 1 ? wd[0] * 32 : 0), 128, 256, 0),
+                               tc_desc(sm_base + ly.ximg + (ps == 2 ? 2048 : 0), 1024, 128, 0), id, ps ? 1u : 0u);
+                } else {
+                    const int K = wd[l - 1], N = wd[l];
+                    const uint32_t id = ft_idesc(N, 64, 0, 1);
+#pragma unroll
+                    for (int ps = 0; ps < 3; ++ps) {
+                        const uint32_t ai = sm_base + ly.w[l - 1] + (ps == 1 ? N * K * 2 : 0), bi = sm_base + ly.h[l - 1] + (ps == 2 ? K * 128 : 0);
+                        for (int kk = 0; kk < (K >> 4); ++kk)
+                            ft_mma(tb, tc_desc(ai + kk * 256, 128, (K >> 3) * 128, 0), tc_desc(bi + kk * 2048, 1024, 128, 0), id, (ps || kk) ? 1u : 0u);
+                    }
+                }
+                tc_commit(&barM);
+            }
+            tc_wait(&barM, n_mma & 1u); ++n_mma;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float v[16];
+            ft_ld16(my + m0, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = ft_tanh_scaled(v[j] + bsc[l]);
+            if (l + 1 < L) {
+                if (fl[l] >= 0) {
+                    unsigned char* ph = sm + ly.h[l];
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint4 vh, vl;
+                        ft_split2(v[8 * c], v[8 * c + 1], vh.x, vl.x); ft_split2(v[8 * c + 2], v[8 * c + 3], vh.y, vl.y);
+                        ft_split2(v[8 * c + 4], v[8 * c + 5], vh.z, vl.z); ft_split2(v[8 * c + 6], v[8 * c + 7], vh.w, vl.w);
+                        const uint32_t off = ft_row_off(fl[l], m0 + 8 * c);
+                        *reinterpret_cast<uint4*>(ph + off) = vh;
+                        *reinterpret_cast<uint4*>(ph + wd[l] * 128 + off) = vl;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            } else if (fl[l] >= 0) {
+                float* hr = Hs + fl[l] * FT_HS_LD + m0;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(hr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+        }
+        {
+            const int per = wd[L - 1] >> 3;
+            float p0 = 0.f;
+            const float* hp = Hs + (slice * per) * FT_HS_LD + ms;
+            for (int n = 0; n < per; ++n) p0 = fmaf(hp[n * FT_HS_LD], sWout[slice * per + n].x, p0);
+            sPart[slice * 64 + ms] = make_float4(p0, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+        if (tid < 64) {
+            float val = sMisc[0];
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl) val += sPart[sl * 64 + ms].x;
+            const long long v = tile * 64 + ms;
+            if (v < TN) buf.values[v] = val;
+            else if (v < TN + buf.N) buf.last_values[v - TN] = val;
+            else if (v < total) buf.boot[dc.trunc_idx[v - TN - buf.N]] = val;
+        }
+        __syncthreads();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(64));
+}
