@@ -1144,29 +1144,6 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
     // tile width: the per-step critical path (state load -> forward -> sample -> dynamics) is latency
     // bound, so small batches are cut into ~4 CTAs per SM that overlap each other's phases; at most
     // 64 envs per tile, shrink until shared memory fits
-    static const int env_ctas = getenv("DRIL_ROLLOUT_CTAS_PER_SM") ? atoi(getenv("DRIL_ROLLOUT_CTAS_PER_SM")) : 4;
-    static const int env_threads = getenv("DRIL_ROLLOUT_THREADS") ? atoi(getenv("DRIL_ROLLOUT_THREADS")) : 0;
-    const long long want_ctas = (long long)c->sm_count * std::max(env_ctas, 1);
-    int M4 = (int)std::min<long long>(64, ((N + want_ctas - 1) / want_ctas + 3) & ~3ll);
-    M4 = std::max(M4, 4);
-    bool ws = has_policy;
-    auto total = [&](int m4, bool w) { return rollout_smem_layout(a.pd, d.obs_dim, d.act_dim, m4, w, has_policy).total; };
-    while (M4 > 4 && total(M4, ws) > DRIL_SMEM_MAX && total(M4, false) > DRIL_SMEM_MAX) M4 -= 4;
-    if (total(M4, ws) > DRIL_SMEM_MAX) ws = false;
-    if (total(M4, ws) > DRIL_SMEM_MAX) { dril_set_error("network too wide for the rollout kernel's shared memory"); return DRIL_ERR_UNSUPPORTED; }
-    // weights that leave no room for a reasonable tile are streamed from L2 instead
-    if (ws && M4 < 32 && N >= 32ll * c->sm_count && total(64, false) <= DRIL_SMEM_MAX) { ws = false; M4 = 64; }
-    // wide nets whose weights stream from L2 anyway: 64-env tiles with the wide layers on mma.sync 3xTF32 tiles
-    // (mma_tiles.cuh) once there are enough envs to give every SM such a tile
-    if (has_policy && !ws && g_opt_mma && N >= 64ll * c->sm_count && total(64, false) <= DRIL_SMEM_MAX) {
-        bool any = false;
-        for (int net = 0; net < 2; ++net)
-            for (int l = 0; l < a.pd.n_layers; ++l) {
-                const LayerDesc& L = a.pd.L[net][l];
-                any = any || mma_layer_ok(L.Kp, L.Np);
-            }
-        if (any) { M4 = 64; flags |= RO_MMA; }
-    }
     // shapes the general tcgen05 kernels cover (update_ftg.cuh): only the actor runs inside the step loop; V(s_t), V(terminal_obs)
     // and V(new_obs) come from one batched critic pass over the stored (normalised) observations afterwards
     const bool defer = has_policy && g_opt_defer_critic && g_opt_ftg && ftg_eligible(a.pd) && !b->is_view && T == b->d.T && T > 0 &&
@@ -1185,6 +1162,32 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
         DRIL_CUDA(cudaMemsetAsync(b->dcs.trunc_count, 0, 4, c->stream));
         a.dc = b->dcs;
         flags |= RO_DEFER_CRITIC;
+    }
+    static const int env_ctas = getenv("DRIL_ROLLOUT_CTAS_PER_SM") ? atoi(getenv("DRIL_ROLLOUT_CTAS_PER_SM")) : 4;
+    static const int env_threads = getenv("DRIL_ROLLOUT_THREADS") ? atoi(getenv("DRIL_ROLLOUT_THREADS")) : 0;
+    const long long want_ctas = (long long)c->sm_count * std::max(env_ctas, 1);
+    int M4 = (int)std::min<long long>(64, ((N + want_ctas - 1) / want_ctas + 3) & ~3ll);
+    M4 = std::max(M4, 4);
+    bool ws = has_policy;
+    auto total = [&](int m4, bool w) { return rollout_smem_layout(a.pd, d.obs_dim, d.act_dim, m4, w, has_policy, !defer).total; };
+    while (M4 > 4 && total(M4, ws) > DRIL_SMEM_MAX && total(M4, false) > DRIL_SMEM_MAX) M4 -= 4;
+    if (total(M4, ws) > DRIL_SMEM_MAX) ws = false;
+    if (total(M4, ws) > DRIL_SMEM_MAX) { dril_set_error("network too wide for the rollout kernel's shared memory"); return DRIL_ERR_UNSUPPORTED; }
+    // weights that leave no room for a reasonable tile are streamed from L2 instead
+    if (ws && M4 < 32 && N >= 32ll * c->sm_count && total(64, false) <= DRIL_SMEM_MAX) { ws = false; M4 = 64; }
+    // wide nets whose weights stream from L2 anyway: 64-env tiles with the wide layers on mma.sync 3xTF32 tiles
+    // (mma_tiles.cuh) once there are enough envs to give every SM such a tile
+    if (has_policy && !ws && g_opt_mma && N >= 64ll * c->sm_count && total(64, false) <= DRIL_SMEM_MAX) {
+        bool any = false;
+        for (int net = 0; net < 2; ++net)
+            for (int l = 0; l < a.pd.n_layers; ++l) {
+                const LayerDesc& L = a.pd.L[net][l];
+                any = any || mma_layer_ok(L.Kp, L.Np);
+            }
+        if (any) { M4 = 64; flags |= RO_MMA; }
+        // critic deferred: the actor's activations alone leave room for 128-env tiles, i.e. one tile per SM and step at C3's
+        // 16 384 envs instead of two 64-env tiles in sequence (the per-step env / statistics phases are per tile)
+        if (any && defer && N >= 96ll * c->sm_count && total(128, false) <= DRIL_SMEM_MAX) M4 = 128;
     }
     if (ws) flags |= RO_WEIGHTS_SMEM;
     a.M4 = M4; a.flags = flags;

@@ -64,8 +64,9 @@ struct RolloutSmem {
     size_t w, raw, x, acta, actc, envact, stat, part, total;  // float offsets (part: bytes offset for doubles)
 };
 
+// critic = false (RO_DEFER_CRITIC): no critic activations, which leaves room for 128-env tiles with wide nets
 __host__ __device__ inline RolloutSmem rollout_smem_layout(const PolicyDesc& pd, int obs_dim, int act_dim, int M4,
-                                                           bool weights_smem, bool has_policy) {
+                                                           bool weights_smem, bool has_policy, bool critic = true) {
     RolloutSmem s;
     s.ld = M4 + 4;
     int Dp = (obs_dim + 3) & ~3;
@@ -75,7 +76,7 @@ __host__ __device__ inline RolloutSmem rollout_smem_layout(const PolicyDesc& pd,
     s.raw = o; o += (size_t)s.raw_rows * s.ld;
     s.x = o; o += (size_t)Dp * s.ld;
     s.acta = o; o += has_policy ? (size_t)2 * pd.max_np * s.ld : 0;
-    s.actc = o; o += has_policy ? (size_t)2 * pd.max_np * s.ld : 0;
+    s.actc = o; o += (has_policy && critic) ? (size_t)2 * pd.max_np * s.ld : 0;
     int adp = act_dim < 1 ? 1 : act_dim;
     s.envact = o; o += (size_t)adp * s.ld;
     s.stat = o; o += (size_t)4 * Dp + 8;
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
     const int D = env.obs_dim, Dp = (D + 3) & ~3;
     const int M4 = a.M4;
     const long long N = env.n_envs;
-    const RolloutSmem L = rollout_smem_layout(pd, D, env.act_dim, M4, WS, has_policy);
+    const RolloutSmem L = rollout_smem_layout(pd, D, env.act_dim, M4, WS, has_policy, !(a.flags & RO_DEFER_CRITIC));
     const int ld = L.ld;
     float* sRaw = smem + L.raw;
     float* sX = smem + L.x;
