@@ -16,6 +16,7 @@
 #include "update_ft.cuh"
 #include "update_ftg.cuh"
 #include "rollout_tc.cuh"
+#include "rollout_syn.cuh"
 
 #define DRIL_SMEM_MAX 232448  // 227 KB opt-in per CTA on sm_100
 #define DRIL_RESULT_SLOTS 4   // iterations that may be enqueued before their results are read
@@ -49,6 +50,7 @@ static int g_opt_ft = getenv("DRIL_FT") ? atoi(getenv("DRIL_FT")) : 1;
 static int g_opt_defer_critic = getenv("DRIL_DEFER_CRITIC") ? atoi(getenv("DRIL_DEFER_CRITIC")) : 1;
 static int g_opt_ftg = getenv("DRIL_FTG") ? atoi(getenv("DRIL_FTG")) : 1;   // general-shape features-on-lanes kernel (update_ftg.cuh); 2: also where update_ft.cuh applies
 static int g_opt_tc_rollout = getenv("DRIL_TC_ROLLOUT") ? atoi(getenv("DRIL_TC_ROLLOUT")) : 1;   // tensor-core rollout (CartPole, [64,64])
+static int g_opt_syn_rollout = getenv("DRIL_SYN_ROLLOUT") ? atoi(getenv("DRIL_SYN_ROLLOUT")) : 1;   // thread-per-env rollout (synthetic env, small policy)
 static int g_opt_tail = getenv("DRIL_TAIL") ? atoi(getenv("DRIL_TAIL")) : 1;   // fused reduce/clip/Adam tail of the TC kernel
 // fp32 loss/grad kernel, wide nets: one net per pass with shared activation rows (fixed per policy at creation)
 static int g_opt_single_net = getenv("DRIL_SINGLE_NET") ? atoi(getenv("DRIL_SINGLE_NET")) : 1;
@@ -62,6 +64,7 @@ extern "C" int32_t dril_set_option(const char* key, int32_t value) {
     if (!strcmp(key, "defer_critic")) { g_opt_defer_critic = value; return DRIL_OK; }
     if (!strcmp(key, "fused_tail")) { g_opt_tail = value; return DRIL_OK; }
     if (!strcmp(key, "tc_rollout")) { g_opt_tc_rollout = value; return DRIL_OK; }
+    if (!strcmp(key, "syn_rollout")) { g_opt_syn_rollout = value; return DRIL_OK; }
     if (!strcmp(key, "single_net")) { g_opt_single_net = value; return DRIL_OK; }   // policies created afterwards
     if (!strcmp(key, "mma")) { g_opt_mma = value; return DRIL_OK; }                 // policies created afterwards
     dril_set_error("unknown option '%s'", key);
@@ -1105,6 +1108,24 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
             critic_values_tc_kernel<<<grid, CV_THREADS, CV_SMEM_BYTES, c->stream>>>(a.pd, a.pack, b->d, b->tcs);
             DRIL_CUDA(cudaGetLastError());
         }
+        return DRIL_OK;
+    }
+    if (has_policy && g_opt_syn_rollout && !b->is_view && T > 0 && syn_rollout_eligible(a.pd, d)) {
+        // synthetic env + small policy: one thread per env, everything in registers (rollout_syn.cuh)
+        int hp = 0;
+        for (int net = 0; net < 2; ++net)
+            for (int l = 0; l + 1 < a.pd.n_layers; ++l) hp = std::max(hp, a.pd.L[net][l].Np);
+        const int HP = hp <= 8 ? 8 : 16, NH = a.pd.n_layers - 1;
+        const int threads = N >= 512ll * c->sm_count ? 128 : (N >= 64ll * c->sm_count ? 64 : 32);
+        const int grid = (int)((N + threads - 1) / threads);
+        const size_t smem = (size_t)syn_smem_layout((d.obs_dim + 3) & ~3, HP, NH).total * sizeof(float);
+        a.flags = flags; a.M4 = threads; a.n_tiles = grid;
+        Span sp(c, DRIL_K_ROLLOUT);
+        if (HP == 8 && NH == 1) rollout_syn_kernel<8, 1><<<grid, threads, smem, c->stream>>>(a);
+        else if (HP == 8) rollout_syn_kernel<8, 2><<<grid, threads, smem, c->stream>>>(a);
+        else if (NH == 1) rollout_syn_kernel<16, 1><<<grid, threads, smem, c->stream>>>(a);
+        else rollout_syn_kernel<16, 2><<<grid, threads, smem, c->stream>>>(a);
+        DRIL_CUDA(cudaGetLastError());
         return DRIL_OK;
     }
     static const int env_nofast = getenv("DRIL_ROLLOUT_NO_FAST") ? atoi(getenv("DRIL_ROLLOUT_NO_FAST")) : 0;

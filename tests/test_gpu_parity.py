@@ -316,6 +316,80 @@ def test_fused_rollout_synthetic_env(D, obs_dim, n, T, norm):
     buf.close()
 
 
+@pytest.mark.parametrize("obs_dim,hidden,n,T", [(4, [8], 700, 24), (10, [16, 12], 333, 18), (64, [8, 8], 130, 12), (16, [6], 5000, 9)])
+def test_syn_rollout_kernel_vs_oracle(D, obs_dim, hidden, n, T):
+    """Thread-per-env rollout of the synthetic env with a small policy (rollout_syn.cuh) against the oracle:
+    two consecutive rollouts (the state written back by the first feeds the second) with replayed actions are bit-exact on
+    flags / observations / rewards, 3e-5 on values, log-probs and both kinds of bootstrap values; Monitor statistics agree;
+    a third, SAMPLED rollout follows the Philox stream and matches the general kernel element for element."""
+    ms = 7
+    mk = lambda: D.CudaBatchedEnv("synthetic", n, obs_dim=obs_dim, max_steps=ms, seed=4, monitor_window=100)
+    env = mk()
+    oenv = OE.MonitorWrapper(OE.ParallelEnv(OE.SyntheticBatch(n, obs_dim, seed=4, max_steps=ms)))
+    n_a = env.action_space().n
+    spec = OP.PolicySpec(obs_dim, hidden, "discrete", n_a, act_start=1)
+    rng = np.random.default_rng(2)
+    flat = (OP.init_params(spec, seed=1) + rng.normal(size=spec.n_params()).astype(f32) * 0.3).astype(f32)
+    layer = D.ActorCriticLayer(env.observation_space(), env.action_space(), hidden_dims=hidden)
+    alg = D.PPO(n_steps=T)
+    agent = D.Agent(layer, alg, rng=np.random.default_rng(0))
+    agent.set_parameters(flat)
+    buf = D.RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, T, n)
+    tol = dict(rtol=3e-5, atol=3e-5)
+    for it in range(2):
+        forced = rng.integers(1, 1 + n_a, (T, n))
+        D.collect_rollout(buf, agent, alg, env, forced_actions=forced)
+        ob = OO.collect_rollout_timemajor(oenv, spec, flat, T, forced_actions=forced)
+        te, tr = _flags(buf)
+        np.testing.assert_array_equal(te, ob["term"])
+        np.testing.assert_array_equal(tr, ob["trunc"])
+        np.testing.assert_array_equal(buf.download("obs"), ob["obs"])
+        np.testing.assert_array_equal(buf.download("rewards"), ob["rewards"])
+        np.testing.assert_array_equal(buf.download("actions").reshape(T, n), forced)
+        np.testing.assert_allclose(buf.download("values"), ob["values"], **tol)
+        np.testing.assert_allclose(buf.download("logprobs"), ob["logprobs"], **tol)
+        np.testing.assert_allclose(np.where(tr, buf.download("boot"), 0), ob["boot"], **tol)
+        np.testing.assert_allclose(buf.download("last_values"), ob["last_values"], **tol)
+        assert tr.any()
+        s = env.monitor_stats()
+        mon = oenv
+        assert s["total_episodes"] == mon.total_episodes
+        done = te | tr
+        np.testing.assert_array_equal(np.where(done, buf.download("episode_l"), 0), np.where(done, ob["episode_l"], 0))
+        np.testing.assert_allclose(np.where(done, buf.download("episode_r"), 0), np.where(done, ob["episode_r"], 0), rtol=1e-6)
+    # sampled rollout: the same env state through both kernels
+    env2 = mk()
+    outs = []
+    for e, opt in ((env, 1), (env2, 0)):
+        if e is env2:       # bring env2 to the state of env: replaying is cheaper than copying state
+            D.set_option("syn_rollout", 1)
+            e2buf = D.RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, 2 * T, n)
+            alg2 = D.PPO(n_steps=2 * T)
+            D.collect_rollout(e2buf, agent, alg2, env2, forced_actions=rng.integers(1, 1 + n_a, (2 * T, n)))
+            e2buf.close()
+        D.set_option("syn_rollout", opt)
+        try:
+            agent.device.seed(99, 5)
+            D.collect_rollout(buf, agent, alg, e)
+        finally:
+            D.set_option("syn_rollout", 1)
+        outs.append({k: buf.download(k) for k in ("obs", "actions", "rewards", "values", "logprobs", "boot", "last_values", "flags")})
+    a, b = outs
+    for k in ("obs", "actions", "rewards", "flags"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    tr = (a["flags"] & 2) != 0
+    for k in ("values", "logprobs", "last_values"):
+        np.testing.assert_allclose(a[k], b[k], rtol=1e-5, atol=1e-6, err_msg=k)
+    np.testing.assert_allclose(np.where(tr, a["boot"], 0), np.where(tr, b["boot"], 0), rtol=1e-5, atol=1e-6)
+    obs, act = a["obs"].reshape(T * n, -1), a["actions"].reshape(T * n)
+    probs = OP.softmax(OP.mlp_forward(OP.unflatten(spec, flat)["actor"], obs))
+    u = OPH.sample_uniform64(np.tile(np.arange(n), T), 5 + np.repeat(np.arange(T), n), 99)
+    ea = OP.categorical_sample(probs, u, spec.act_start)
+    margin = np.abs(np.cumsum(probs, axis=1) - u[:, None]).min(axis=1)
+    assert ((act == ea) | (margin < 1e-5)).all()
+    buf.close()
+
+
 def test_fused_rollout_sampling_consistency(D):
     """Sampling mode: stored logprobs/values equal evaluate_actions on the stored (obs, actions)
     (test/test_buffers.jl:3-27,166-214) and actions follow the Philox stream."""
