@@ -405,8 +405,11 @@ def run_c5(args, D, ctx, dist, rank, world, local):
     hidden = [int(x) for x in os.environ.get("C5_HIDDEN", "8").split(",") if x]
     points = []
     n_steps = 128
-    for obs_dim in (4, 16, 64):
-        for lg_n in (10, 14, 17, 20):
+    grid = [(o, l) for o in (4, 16, 64) for l in (10, 14, 17, 20)]
+    if os.environ.get("C5_POINTS"):                      # e.g. "16:17,64:17" (obs_dim:log2 n_envs): profiling single points
+        grid = [tuple(int(v) for v in q.split(":")) for q in os.environ["C5_POINTS"].split(",")]
+    for obs_dim, lg_n in grid:
+        if True:
             n_envs = 1 << lg_n
             env = D.CudaBatchedEnv("synthetic", n_envs, obs_dim=obs_dim, seed=0, ctx=ctx, monitor_window=0, gid_offset=rank * n_envs)
             layer = D.ActorCriticLayer(env.observation_space(), env.action_space(), hidden_dims=hidden)

@@ -1116,15 +1116,18 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
         for (int net = 0; net < 2; ++net)
             for (int l = 0; l + 1 < a.pd.n_layers; ++l) hp = std::max(hp, a.pd.L[net][l].Np);
         const int HP = hp <= 8 ? 8 : 16, NH = a.pd.n_layers - 1;
+        const int E = (HP == 8 && g_opt_syn_rollout == 2) ? 2 : 1;          // envs per thread: two only on request (measured slower: registers halve the occupancy)
         const int threads = N >= 512ll * c->sm_count ? 128 : (N >= 64ll * c->sm_count ? 64 : 32);
-        const int grid = (int)((N + threads - 1) / threads);
+        const int grid = (int)((N + (long long)threads * E - 1) / ((long long)threads * E));
         const size_t smem = (size_t)syn_smem_layout((d.obs_dim + 3) & ~3, HP, NH).total * sizeof(float);
         a.flags = flags; a.M4 = threads; a.n_tiles = grid;
         Span sp(c, DRIL_K_ROLLOUT);
-        if (HP == 8 && NH == 1) rollout_syn_kernel<8, 1><<<grid, threads, smem, c->stream>>>(a);
-        else if (HP == 8) rollout_syn_kernel<8, 2><<<grid, threads, smem, c->stream>>>(a);
-        else if (NH == 1) rollout_syn_kernel<16, 1><<<grid, threads, smem, c->stream>>>(a);
-        else rollout_syn_kernel<16, 2><<<grid, threads, smem, c->stream>>>(a);
+        if (HP == 8 && NH == 1 && E == 2) rollout_syn_kernel<8, 1, 2><<<grid, threads, smem, c->stream>>>(a);
+        else if (HP == 8 && E == 2) rollout_syn_kernel<8, 2, 2><<<grid, threads, smem, c->stream>>>(a);
+        else if (HP == 8 && NH == 1) rollout_syn_kernel<8, 1, 1><<<grid, threads, smem, c->stream>>>(a);
+        else if (HP == 8) rollout_syn_kernel<8, 2, 1><<<grid, threads, smem, c->stream>>>(a);
+        else if (NH == 1) rollout_syn_kernel<16, 1, 1><<<grid, threads, smem, c->stream>>>(a);
+        else rollout_syn_kernel<16, 2, 1><<<grid, threads, smem, c->stream>>>(a);
         DRIL_CUDA(cudaGetLastError());
         return DRIL_OK;
     }

@@ -13,8 +13,9 @@
 //     registers; there is no barrier in the step loop;
 //   * V(terminal_obs) of a truncated step is a rare divergent critic evaluation; Monitor totals are accumulated per thread
 //     and reduced once per CTA at the end (one atomic per CTA instead of one per finished episode).
-// Eligibility (host: syn_rollout_eligible): synthetic env, no NormalizeWrapperEnv, discrete head with <= 4 actions, one or
-// two hidden layers of width <= 16, obs_dim <= 256.
+// Eligibility (host: syn_rollout_eligible): synthetic env (two actions), no NormalizeWrapperEnv, one or two hidden layers of
+// width <= 16, obs_dim <= 256.  Narrow nets (<= 8) run two envs per thread: every weight read feeds both, and the two Philox /
+// tanh chains interleave.
 #pragma once
 #include "rollout.cuh"
 
@@ -41,7 +42,7 @@ __host__ __device__ inline SynSmem syn_smem_layout(int Dp, int HP, int NH) {
 
 inline bool syn_rollout_eligible(const PolicyDesc& pd, const EnvDev& d) {
     if (d.kind != DRIL_ENV_SYNTHETIC || d.normalize) return false;
-    if (pd.act_kind != DRIL_ACT_DISCRETE || pd.act_n > SYN_MAX_A) return false;
+    if (pd.act_kind != DRIL_ACT_DISCRETE || pd.act_n != 2) return false;    // the synthetic env's Discrete(2)
     if (pd.n_layers < 2 || pd.n_layers > 3 || d.obs_dim > 256) return false;
     for (int net = 0; net < 2; ++net)
         for (int l = 0; l + 1 < pd.n_layers; ++l)
@@ -49,26 +50,53 @@ inline bool syn_rollout_eligible(const PolicyDesc& pd, const EnvDev& d) {
     return true;
 }
 
-// hidden layers of the nets in MASK (1 actor, 2 critic) on the observation of (gid, life); the observation row is stored to
-// `obs_row` when non-null.  h[net][*] returns the last hidden activation.
-template <int HP, int NH, int MASK>
-__device__ __forceinline__ void syn_hidden(const float* __restrict__ sW, const SynSmem& L, int D, int Dp, uint32_t gid, uint32_t life,
-                                           unsigned long long seed, float* __restrict__ obs_row, float (&h)[2][HP]) {
+// tanh of a pre-activation that already carries the factor 2·log2(e) (folded into the staged weights and biases):
+// tanh(x) = 1 - 2 / (1 + 2^(x · 2 log2 e)), the same evaluation as fast_tanh (common.cuh) without its multiply
+#define SYN_TANH_SCALE 2.8853900817779268f
+__device__ __forceinline__ float syn_tanh_prescaled(float z) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+
+// observation block b of lifetime step `life`: the values of synthetic_obs_block (env.cuh) — (float)(x >> 8) · 2^-24 is exact and
+// so is its double, hence -1 + 2u rounds once, exactly like this single fma
+__device__ __forceinline__ void syn_obs_block(uint32_t gid, uint32_t life, int b, unsigned long long seed, float o[4]) {
+    uint32_t x[4];
+    philox4x32(gid, life, (uint32_t)b, DRIL_TAG_SYN_OBS, seed, x);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = fmaf((float)(x[j] >> 8), 1.1920928955078125e-07f, -1.0f);
+}
+
+// hidden layers of the nets in MASK (1 actor, 2 critic) for E envs at once (every weight read from shared memory feeds E envs);
+// the observation rows are stored to obs_row[e] when non-null.  h[e][net][*] returns the last hidden activation.
+template <int HP, int NH, int MASK, int E>
+__device__ __forceinline__ void syn_hidden(const float* __restrict__ sW, const SynSmem& L, int D, int Dp, const uint32_t (&gid)[E],
+                                           const uint32_t (&life)[E], unsigned long long seed, float* const (&obs_row)[E],
+                                           float (&h)[E][2][HP]) {
 #pragma unroll
     for (int net = 0; net < 2; ++net)
         if (MASK & (1 << net)) {
 #pragma unroll
-            for (int n = 0; n < HP; ++n) h[net][n] = sW[L.b0 + net * HP + n];
+            for (int n = 0; n < HP; ++n) {
+                const float bv = sW[L.b0 + net * HP + n];
+#pragma unroll
+                for (int e = 0; e < E; ++e) h[e][net][n] = bv;
+            }
         }
     const int nb = Dp >> 2;
     for (int b = 0; b < nb; ++b) {
-        float o[4];
-        synthetic_obs_block(gid, life, b, seed, o);
-        if (obs_row) {
-            if ((D & 3) == 0) *reinterpret_cast<float4*>(obs_row + 4 * b) = make_float4(o[0], o[1], o[2], o[3]);
-            else {
+        float o[E][4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (4 * b + j < D) obs_row[4 * b + j] = o[j];
+        for (int e = 0; e < E; ++e) {
+            syn_obs_block(gid[e], life[e], b, seed, o[e]);
+            if (obs_row[e]) {
+                if ((D & 3) == 0) *reinterpret_cast<float4*>(obs_row[e] + 4 * b) = make_float4(o[e][0], o[e][1], o[e][2], o[e][3]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (4 * b + j < D) obs_row[e][4 * b + j] = o[e][j];
+                }
             }
         }
 #pragma unroll
@@ -80,41 +108,55 @@ __device__ __forceinline__ void syn_hidden(const float* __restrict__ sW, const S
 #pragma unroll
                     for (int q = 0; q < HP / 4; ++q) {
                         const float4 v = w[q];
-                        h[net][4 * q + 0] = fmaf(o[j], v.x, h[net][4 * q + 0]);
-                        h[net][4 * q + 1] = fmaf(o[j], v.y, h[net][4 * q + 1]);
-                        h[net][4 * q + 2] = fmaf(o[j], v.z, h[net][4 * q + 2]);
-                        h[net][4 * q + 3] = fmaf(o[j], v.w, h[net][4 * q + 3]);
+#pragma unroll
+                        for (int e = 0; e < E; ++e) {
+                            h[e][net][4 * q + 0] = fmaf(o[e][j], v.x, h[e][net][4 * q + 0]);
+                            h[e][net][4 * q + 1] = fmaf(o[e][j], v.y, h[e][net][4 * q + 1]);
+                            h[e][net][4 * q + 2] = fmaf(o[e][j], v.z, h[e][net][4 * q + 2]);
+                            h[e][net][4 * q + 3] = fmaf(o[e][j], v.w, h[e][net][4 * q + 3]);
+                        }
                     }
                 }
         }
     }
 #pragma unroll
-    for (int net = 0; net < 2; ++net)
-        if (MASK & (1 << net)) {
+    for (int e = 0; e < E; ++e)
 #pragma unroll
-            for (int n = 0; n < HP; ++n) h[net][n] = fast_tanh(h[net][n]);
-        }
+        for (int net = 0; net < 2; ++net)
+            if (MASK & (1 << net)) {
+#pragma unroll
+                for (int n = 0; n < HP; ++n) h[e][net][n] = syn_tanh_prescaled(h[e][net][n]);
+            }
     if (NH == 2) {
 #pragma unroll
         for (int net = 0; net < 2; ++net)
             if (MASK & (1 << net)) {
-                float g[HP];
+                float g[E][HP];
 #pragma unroll
-                for (int n = 0; n < HP; ++n) g[n] = sW[L.b1 + net * HP + n];
+                for (int n = 0; n < HP; ++n) {
+                    const float bv = sW[L.b1 + net * HP + n];
+#pragma unroll
+                    for (int e = 0; e < E; ++e) g[e][n] = bv;
+                }
 #pragma unroll
                 for (int k = 0; k < HP; ++k) {
                     const float4* w = reinterpret_cast<const float4*>(sW + L.w1 + ((size_t)net * HP + k) * HP);
 #pragma unroll
                     for (int q = 0; q < HP / 4; ++q) {
                         const float4 v = w[q];
-                        g[4 * q + 0] = fmaf(h[net][k], v.x, g[4 * q + 0]);
-                        g[4 * q + 1] = fmaf(h[net][k], v.y, g[4 * q + 1]);
-                        g[4 * q + 2] = fmaf(h[net][k], v.z, g[4 * q + 2]);
-                        g[4 * q + 3] = fmaf(h[net][k], v.w, g[4 * q + 3]);
+#pragma unroll
+                        for (int e = 0; e < E; ++e) {
+                            g[e][4 * q + 0] = fmaf(h[e][net][k], v.x, g[e][4 * q + 0]);
+                            g[e][4 * q + 1] = fmaf(h[e][net][k], v.y, g[e][4 * q + 1]);
+                            g[e][4 * q + 2] = fmaf(h[e][net][k], v.z, g[e][4 * q + 2]);
+                            g[e][4 * q + 3] = fmaf(h[e][net][k], v.w, g[e][4 * q + 3]);
+                        }
                     }
                 }
 #pragma unroll
-                for (int n = 0; n < HP; ++n) h[net][n] = fast_tanh(g[n]);
+                for (int e = 0; e < E; ++e)
+#pragma unroll
+                    for (int n = 0; n < HP; ++n) h[e][net][n] = syn_tanh_prescaled(g[e][n]);
             }
     }
 }
@@ -131,12 +173,15 @@ __device__ __forceinline__ float syn_value(const float* __restrict__ sW, const S
 template <int HP, int NH>
 __device__ __noinline__ float syn_critic_only(const float* __restrict__ sW, SynSmem L, int D, int Dp, uint32_t gid, uint32_t life,
                                               unsigned long long seed) {
-    float h[2][HP];
-    syn_hidden<HP, NH, 2>(sW, L, D, Dp, gid, life, seed, nullptr, h);
-    return syn_value<HP>(sW, L, h[1]);
+    float h[1][2][HP];
+    const uint32_t g1[1] = {gid}, l1[1] = {life};
+    float* const none[1] = {nullptr};
+    syn_hidden<HP, NH, 2, 1>(sW, L, D, Dp, g1, l1, seed, none, h);
+    return syn_value<HP>(sW, L, h[0][1]);
 }
 
-template <int HP, int NH>
+// E envs per thread: env e of thread tid in CTA c is c·E·blockDim + e·blockDim + tid (per-step rows stay coalesced per e)
+template <int HP, int NH, int E>
 __global__ void __launch_bounds__(128) rollout_syn_kernel(const __grid_constant__ RolloutArgs a) {
     extern __shared__ float4 smem4[];
     float* sW = reinterpret_cast<float*>(smem4);
@@ -144,27 +189,29 @@ __global__ void __launch_bounds__(128) rollout_syn_kernel(const __grid_constant_
     const EnvDev& env = a.env;
     const BufDev& buf = a.buf;
     const PolicyDesc& pd = a.pd;
-    const int D = env.obs_dim, Dp = (D + 3) & ~3, A = pd.act_n;
+    const int D = env.obs_dim, Dp = (D + 3) & ~3;
+    constexpr int A = 2;                                       // the synthetic env's Discrete(2)
     const long long N = env.n_envs;
     const SynSmem L = syn_smem_layout(Dp, HP, NH);
     const int tid = threadIdx.x;
-    // ---- weights: packed [Kp][Np] (zero padded) -> own layout padded to HP (padding columns zero: tanh(0) = 0 feeds nothing) ----
+    // ---- weights: packed [Kp][Np] (zero padded) -> own layout padded to HP (padding columns zero: tanh(0) = 0 feeds nothing);
+    //      hidden layers carry tanh's 2·log2(e) ------------------------------------------------------------------------------
     for (int i = tid; i < L.total; i += blockDim.x) sW[i] = 0.f;
     __syncthreads();
     for (int net = 0; net < 2; ++net) {
         const LayerDesc& l0 = pd.L[net][0];
         for (int i = tid; i < l0.K * l0.N; i += blockDim.x) {
             const int k = i / l0.N, n = i - k * l0.N;
-            sW[L.w0 + ((size_t)net * Dp + k) * HP + n] = a.pack[l0.pw_off + k * l0.Np + n];
+            sW[L.w0 + ((size_t)net * Dp + k) * HP + n] = a.pack[l0.pw_off + k * l0.Np + n] * SYN_TANH_SCALE;
         }
-        for (int n = tid; n < l0.N; n += blockDim.x) sW[L.b0 + net * HP + n] = a.pack[l0.pb_off + n];
+        for (int n = tid; n < l0.N; n += blockDim.x) sW[L.b0 + net * HP + n] = a.pack[l0.pb_off + n] * SYN_TANH_SCALE;
         if (NH == 2) {
             const LayerDesc& l1 = pd.L[net][1];
             for (int i = tid; i < l1.K * l1.N; i += blockDim.x) {
                 const int k = i / l1.N, n = i - k * l1.N;
-                sW[L.w1 + ((size_t)net * HP + k) * HP + n] = a.pack[l1.pw_off + k * l1.Np + n];
+                sW[L.w1 + ((size_t)net * HP + k) * HP + n] = a.pack[l1.pw_off + k * l1.Np + n] * SYN_TANH_SCALE;
             }
-            for (int n = tid; n < l1.N; n += blockDim.x) sW[L.b1 + net * HP + n] = a.pack[l1.pb_off + n];
+            for (int n = tid; n < l1.N; n += blockDim.x) sW[L.b1 + net * HP + n] = a.pack[l1.pb_off + n] * SYN_TANH_SCALE;
         }
     }
     {
@@ -180,105 +227,113 @@ __global__ void __launch_bounds__(128) rollout_syn_kernel(const __grid_constant_
     }
     __syncthreads();
 
-    const long long n = (long long)blockIdx.x * blockDim.x + tid;
-    const bool mine = n < N;
-    const uint32_t gid = (uint32_t)(env.gid_offset + n);
-    uint32_t life = 0, episode = 0;
-    int steps = 0, ep_len = 0;
-    float ep_ret = 0.f;
+    long long n[E];
+    bool mine[E];
+    uint32_t gid[E], life[E], episode[E];
+    int steps[E], ep_len[E];
+    float ep_ret[E];
     double sum_r = 0.0, sum_l = 0.0, sum_e = 0.0;
-    if (mine) {
-        life = env.life[n]; steps = env.steps[n]; episode = env.episode[n];
-        if (env.monitor) { ep_ret = env.ep_ret[n]; ep_len = env.ep_len[n]; }
-    }
+    const int monitor = env.monitor, max_steps = env.max_steps, act_start = pd.act_start;
+    const unsigned long long eseed = env.seed, pseed = a.pseed;
+    const int* __restrict__ forced = reinterpret_cast<const int*>(a.forced);
     const bool deterministic = (a.flags & RO_DETERMINISTIC) != 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        n[e] = ((long long)blockIdx.x * E + e) * blockDim.x + tid;
+        mine[e] = n[e] < N;
+        gid[e] = (uint32_t)(env.gid_offset + n[e]);
+        life[e] = 0; episode[e] = 0; steps[e] = 0; ep_len[e] = 0; ep_ret[e] = 0.f;
+        if (mine[e]) {
+            life[e] = env.life[n[e]]; steps[e] = env.steps[n[e]]; episode[e] = env.episode[n[e]];
+            if (monitor) { ep_ret[e] = env.ep_ret[n[e]]; ep_len[e] = env.ep_len[n[e]]; }
+        }
+    }
     for (int t = 0; t < a.T; ++t) {
         const size_t row = (size_t)t * N;
-        int done_i = 0;
-        if (mine) {
-            float h[2][HP];
-            syn_hidden<HP, NH, 3>(sW, L, D, Dp, gid, life, env.seed, buf.obs + (row + n) * D, h);
-            const float value = syn_value<HP>(sW, L, h[1]);
-            float z[SYN_MAX_A];
+        float h[E][2][HP];
+        float* orow[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) orow[e] = mine[e] ? buf.obs + (row + n[e]) * D : nullptr;
+        // (threads past the end compute on gid garbage and store nothing)
+        syn_hidden<HP, NH, 3, E>(sW, L, D, Dp, gid, life, eseed, orow, h);
+        int done_any = 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const float value = syn_value<HP>(sW, L, h[e][1]);
+            float z0, z1;
             {
-                const float4 bo = *reinterpret_cast<const float4*>(sW + L.bo);
-                z[0] = bo.x; z[1] = bo.y; z[2] = bo.z; z[3] = bo.w;
+                const float2 bo = *reinterpret_cast<const float2*>(sW + L.bo);
+                z0 = bo.x; z1 = bo.y;
 #pragma unroll
                 for (int k = 0; k < HP; ++k) {
-                    const float4 w = *reinterpret_cast<const float4*>(sW + L.wo + k * SYN_MAX_A);
-                    z[0] = fmaf(h[0][k], w.x, z[0]); z[1] = fmaf(h[0][k], w.y, z[1]);
-                    z[2] = fmaf(h[0][k], w.z, z[2]); z[3] = fmaf(h[0][k], w.w, z[3]);
+                    const float2 w = *reinterpret_cast<const float2*>(sW + L.wo + k * SYN_MAX_A);
+                    z0 = fmaf(h[e][0][k], w.x, z0); z1 = fmaf(h[e][0][k], w.y, z1);
                 }
             }
-            // categorical head in registers: the operations of categorical_head (mlp.cuh; categorical.jl:20-52)
-            float m = z[0];
-#pragma unroll
-            for (int j = 1; j < SYN_MAX_A; ++j) if (j < A) m = fmaxf(m, z[j]);
-            float ex[SYN_MAX_A], s = 0.f;
-#pragma unroll
-            for (int j = 0; j < SYN_MAX_A; ++j) { ex[j] = j < A ? expf(z[j] - m) : 0.f; if (j < A) s += ex[j]; }
+            // categorical head in registers: the operations of categorical_head (mlp.cuh; categorical.jl:20-52) for two logits
+            const float m = fmaxf(z0, z1);
+            const float e0 = expf(z0 - m), e1 = expf(z1 - m);
+            const float s = e0 + e1;
             int idx = A - 1;
-            if (a.forced) {
-                idx = reinterpret_cast<const int*>(a.forced)[row + n] - pd.act_start;
+            if (forced) {
+                idx = mine[e] ? forced[row + n[e]] - act_start : 0;
                 idx = idx < 0 ? 0 : (idx >= A ? A - 1 : idx);
             } else if (deterministic) {
-                float best = -1.f;
-#pragma unroll
-                for (int j = 0; j < SYN_MAX_A; ++j) if (j < A) { const float p = ex[j] / s; if (p > best) { best = p; idx = j; } }
+                idx = (e1 / s > e0 / s) ? 1 : 0;
             } else {
                 uint32_t x[4];
-                philox4x32(gid, a.step0 + (uint32_t)t, 0u, DRIL_TAG_SAMPLE, a.pseed, x);
+                philox4x32(gid[e], a.step0 + (uint32_t)t, 0u, DRIL_TAG_SAMPLE, pseed, x);
                 const double u = u01_f64(x[0], x[1]);
-                float cum = 0.f;
-                bool found = false;
-#pragma unroll
-                for (int j = 0; j < SYN_MAX_A; ++j)
-                    if (j < A) {
-                        cum += ex[j] / s;                            // fp32 cumsum vs Float64 u (categorical.jl:45-47)
-                        if (!found && (double)cum >= u) { idx = j; found = true; }
-                    }
+                const float c0 = 0.f + e0 / s;                       // fp32 cumsum vs Float64 u (categorical.jl:45-47)
+                const float c1 = c0 + e1 / s;
+                idx = (double)c0 >= u ? 0 : ((double)c1 >= u ? 1 : A - 1);
             }
-            float pe = ex[0];
-#pragma unroll
-            for (int j = 1; j < SYN_MAX_A; ++j) if (j == idx) pe = ex[j];
-            reinterpret_cast<int*>(buf.actions)[row + n] = idx + pd.act_start;
-            buf.values[row + n] = value;
-            buf.logprobs[row + n] = logf(pe / s);
+            const float logp = logf((idx == 0 ? e0 : e1) / s);
             // env step (the action is ignored by this env), Monitor, auto-reset
             bool term = false;
-            const float r = synthetic_step(gid, life, env.seed, &term);
-            life += 1;
-            steps += 1;
-            const bool trunc = steps >= env.max_steps;
+            const float r = synthetic_step(gid[e], life[e], eseed, &term);
+            life[e] += 1;
+            steps[e] += 1;
+            const bool trunc = steps[e] >= max_steps;
             const bool done = term || trunc;
-            buf.flags[row + n] = (unsigned char)((term ? 1 : 0) | (trunc ? 2 : 0));
-            buf.rewards[row + n] = r;
-            if (env.monitor) {
-                ep_ret = __fadd_rn(ep_ret, r);
-                ep_len += 1;
-                if (done) {
-                    buf.episode_r[row + n] = ep_ret;
-                    buf.episode_l[row + n] = ep_len;
-                    sum_r += (double)ep_ret; sum_l += (double)ep_len; sum_e += 1.0;
-                    done_i = 1;
-                    ep_ret = 0.f; ep_len = 0;
+            if (mine[e]) {
+                const size_t sidx = row + n[e];
+                reinterpret_cast<int*>(buf.actions)[sidx] = idx + act_start;
+                buf.values[sidx] = value;
+                buf.logprobs[sidx] = logp;
+                buf.flags[sidx] = (unsigned char)((term ? 1 : 0) | (trunc ? 2 : 0));
+                buf.rewards[sidx] = r;
+                if (monitor) {
+                    ep_ret[e] = __fadd_rn(ep_ret[e], r);
+                    ep_len[e] += 1;
+                    if (done) {
+                        buf.episode_r[sidx] = ep_ret[e];
+                        buf.episode_l[sidx] = ep_len[e];
+                        sum_r += (double)ep_ret[e]; sum_l += (double)ep_len[e]; sum_e += 1.0;
+                        done_any += 1;
+                        ep_ret[e] = 0.f; ep_len[e] = 0;
+                    }
                 }
+                // terminal_observation = observe() of the stepped env (lifetime counter already advanced), trajectory.jl:57-61
+                if (trunc) buf.boot[sidx] = syn_critic_only<HP, NH>(sW, L, D, Dp, gid[e], life[e], eseed);
             }
-            // terminal_observation = observe() of the stepped env (lifetime counter already advanced), trajectory.jl:57-61
-            if (trunc) buf.boot[row + n] = syn_critic_only<HP, NH>(sW, L, D, Dp, gid, life, env.seed);
-            if (done) { episode += 1; steps = 0; }
+            if (done) { episode[e] += 1; steps[e] = 0; }
         }
-        if (env.monitor) {
-            const unsigned int bal = __ballot_sync(0xffffffffu, done_i);
-            if (bal && (tid & 31) == 0) atomicAdd(&buf.done_count[t], __popc(bal));
+        if (monitor) {
+            int c = done_any;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (c && (tid & 31) == 0) atomicAdd(&buf.done_count[t], c);
         }
     }
-    if (mine && a.T > 0) buf.last_values[n] = syn_critic_only<HP, NH>(sW, L, D, Dp, gid, life, env.seed);   // trajectory.jl:65-70
-    if (mine) {
-        env.life[n] = life; env.steps[n] = steps; env.episode[n] = episode;
-        if (env.monitor) { env.ep_ret[n] = ep_ret; env.ep_len[n] = ep_len; }
-    }
-    if (env.monitor) {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if (mine[e]) {
+            if (a.T > 0) buf.last_values[n[e]] = syn_critic_only<HP, NH>(sW, L, D, Dp, gid[e], life[e], eseed);   // trajectory.jl:65-70
+            env.life[n[e]] = life[e]; env.steps[n[e]] = steps[e]; env.episode[n[e]] = episode[e];
+            if (monitor) { env.ep_ret[n[e]] = ep_ret[e]; env.ep_len[n[e]] = ep_len[e]; }
+        }
+    if (monitor) {
         sum_r = warp_sum(sum_r); sum_l = warp_sum(sum_l); sum_e = warp_sum(sum_e);
         if ((tid & 31) == 0) { s_red[0][tid >> 5] = sum_r; s_red[1][tid >> 5] = sum_l; s_red[2][tid >> 5] = sum_e; }
         __syncthreads();

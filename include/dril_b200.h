@@ -125,7 +125,13 @@ const char* dril_source_hash(void);
 int32_t dril_device_count(int32_t* count);
 /* process-wide kernel-path switches (all default 1; every combination meets the same parity bounds, tests/
  * test_gpu_parity.py::test_kernel_paths_vs_oracle).  Unknown keys are an error.
- *   "tc"          tensor-core (tcgen05, 3xTF32) loss/grad kernel for hidden_dims = [64, 64], obs_dim <= 4, Discrete(<= 2)
+ *   "ft"          features-on-lanes tcgen05 loss/grad kernel (fp16 hi/lo split, actor + critic merged) for hidden_dims = [64, 64],
+ *                 obs_dim <= 4, Discrete(<= 2): the default for such policies
+ *   "ftg"         general-shape features-on-lanes tcgen05 loss/grad kernel (1-3 hidden layers of width <= 128, discrete or
+ *                 Gaussian head); 2 = also prefer it where "ft" applies
+ *   "tc"          round-1 samples-on-lanes tcgen05 (3xTF32) loss/grad kernel for the "ft" shapes (used when "ft" is 0)
+ *   "defer_critic" general rollout kernel: actor-only step loop, values from one batched tcgen05 critic pass afterwards
+ *   "syn_rollout" thread-per-env rollout kernel for the synthetic env with a small policy (2 = always two envs per thread)
  *   "fused_tail"  partial reduction + (peer-memory allreduce) + clip + KL stop + Adam inside that kernel (cooperative launch)
  *   "tc_rollout"  tensor-core rollout for CartPole with such a policy (actor-only step loop + batched critic pass)
  *   "single_net"  fp32 loss/grad kernel, networks too wide for a 128-sample tile of both nets: one net per pass over the

@@ -316,13 +316,16 @@ def test_fused_rollout_synthetic_env(D, obs_dim, n, T, norm):
     buf.close()
 
 
-@pytest.mark.parametrize("obs_dim,hidden,n,T", [(4, [8], 700, 24), (10, [16, 12], 333, 18), (64, [8, 8], 130, 12), (16, [6], 5000, 9)])
-def test_syn_rollout_kernel_vs_oracle(D, obs_dim, hidden, n, T):
+@pytest.mark.parametrize("obs_dim,hidden,n,T,per_thread", [(4, [8], 700, 24, 1), (4, [8], 700, 24, 2), (10, [16, 12], 333, 18, 1),
+                                                           (64, [8, 8], 130, 12, 2), (16, [6], 5000, 9, 2), (7, [5, 8], 257, 9, 1)])
+def test_syn_rollout_kernel_vs_oracle(D, obs_dim, hidden, n, T, per_thread):
     """Thread-per-env rollout of the synthetic env with a small policy (rollout_syn.cuh) against the oracle:
     two consecutive rollouts (the state written back by the first feeds the second) with replayed actions are bit-exact on
     flags / observations / rewards, 3e-5 on values, log-probs and both kinds of bootstrap values; Monitor statistics agree;
-    a third, SAMPLED rollout follows the Philox stream and matches the general kernel element for element."""
+    a third, SAMPLED rollout follows the Philox stream and matches the general kernel element for element.  `per_thread` = 2
+    forces the two-envs-per-thread variant that large batches of narrow nets use."""
     ms = 7
+    D.set_option("syn_rollout", per_thread)
     mk = lambda: D.CudaBatchedEnv("synthetic", n, obs_dim=obs_dim, max_steps=ms, seed=4, monitor_window=100)
     env = mk()
     oenv = OE.MonitorWrapper(OE.ParallelEnv(OE.SyntheticBatch(n, obs_dim, seed=4, max_steps=ms)))
@@ -362,12 +365,12 @@ def test_syn_rollout_kernel_vs_oracle(D, obs_dim, hidden, n, T):
     outs = []
     for e, opt in ((env, 1), (env2, 0)):
         if e is env2:       # bring env2 to the state of env: replaying is cheaper than copying state
-            D.set_option("syn_rollout", 1)
+            D.set_option("syn_rollout", per_thread)
             e2buf = D.RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, 2 * T, n)
             alg2 = D.PPO(n_steps=2 * T)
             D.collect_rollout(e2buf, agent, alg2, env2, forced_actions=rng.integers(1, 1 + n_a, (2 * T, n)))
             e2buf.close()
-        D.set_option("syn_rollout", opt)
+        D.set_option("syn_rollout", per_thread if opt else 0)
         try:
             agent.device.seed(99, 5)
             D.collect_rollout(buf, agent, alg, e)
