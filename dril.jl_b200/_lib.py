@@ -72,6 +72,7 @@ PROTOTYPES = {
     "dril_env_get_norm_stats": [P, P, P, C.POINTER(c_i64), C.POINTER(c_f32), C.POINTER(c_f32), C.POINTER(c_i64)],
     "dril_env_set_norm_stats": [P, P, P, c_i64, c_f32, c_f32, c_i64],
     "dril_env_set_training": [P, c_i32],
+    "dril_env_set_scaling": [P, c_i32, P, P, P, P],
     "dril_env_get_original": [P, P, P],
     "dril_env_monitor_stats": [P, C.POINTER(c_f32), C.POINTER(c_f32), C.POINTER(c_i64), C.POINTER(c_i64)],
     "dril_policy_create": [P, c_i32, c_i32, P, c_i32, c_i32, c_i32, P, P, C.POINTER(P)],

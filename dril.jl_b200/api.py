@@ -25,7 +25,7 @@ BroadcastedParallelEnv = MultiThreadedParallelEnv
 def _rewrap(env, **over):
     args = dict(kind=env.kind, n_envs=env.n_envs, max_steps=env.max_steps, obs_dim=env.obs_dim,
                 act_start=env.act_start, ctx=env.ctx, monitor_window=env.monitor_window,
-                normalize=env.normalize, gid_offset=env.gid_offset,
+                normalize=env.normalize, gid_offset=env.gid_offset, scaling=env.scaling,
                 obs_shape=env.obs_shape if len(env.obs_shape) > 1 else None)
     args.update(over)
     kind, n = args.pop("kind"), args.pop("n_envs")
@@ -39,6 +39,12 @@ def _rewrap(env, **over):
 def MonitorWrapperEnv(env, stats_window=100):
     """monitorWrapperEnv.jl:16-24."""
     return _rewrap(env, monitor_window=stats_window)
+
+
+def ScalingWrapperEnv(env):
+    """scalingWrapperEnv.jl:14-49: observations and actions of a Box/Box env mapped to [-1, 1]; applied per env, i.e. below
+    Monitor / Normalize whatever the order of the calls."""
+    return _rewrap(env, scaling=True)
 
 
 def NormalizeWrapperEnv(env, **kw):

@@ -116,7 +116,7 @@ class CudaBatchedEnv:
     path used by evaluate_agent and callbacks; training uses the fused device rollout."""
 
     def __init__(self, kind, n_envs, max_steps=0, obs_dim=0, act_start=1, seed=None, ctx=None,
-                 monitor_window=0, normalize=None, gid_offset=0, obs_shape=None):
+                 monitor_window=0, normalize=None, gid_offset=0, obs_shape=None, scaling=False):
         self.kind = kind.lower()
         assert self.kind in ENV_KINDS, f"unknown env kind {kind}"
         self.ctx = ctx or Context.default()
@@ -150,6 +150,16 @@ class CudaBatchedEnv:
                                     self.act_start, self.gid_offset, C.byref(cfg) if cfg is not None else None,
                                     self.monitor_window, C.byref(h)))
         self.h = h
+        self.scaling = bool(scaling)
+        if self.scaling:
+            # ScalingWrapperEnv around every env (scalingWrapperEnv.jl:14-49): spaces become [-1, 1] boxes, the originals are kept
+            assert isinstance(self._obs_space, Box) and isinstance(self._act_space, Box), "ScalingWrapperEnv needs Box spaces"
+            self.orig_observation_space, self.orig_action_space = self._obs_space, self._act_space
+            ol, oh = L.f32(self._obs_space.low).ravel(), L.f32(self._obs_space.high).ravel()
+            al, ah = L.f32(self._act_space.low).ravel(), L.f32(self._act_space.high).ravel()
+            L.check(lib.dril_env_set_scaling(self.h, 1, L.ptr(ol), L.ptr(oh), L.ptr(al), L.ptr(ah)))
+            self._obs_space = Box(-np.ones_like(ol).reshape(self._obs_space.low.shape), np.ones_like(oh).reshape(self._obs_space.low.shape))
+            self._act_space = Box(-np.ones_like(al), np.ones_like(ah))
         self._term = np.zeros(self.n_envs, dtype=bool)
         self._trunc = np.zeros(self.n_envs, dtype=bool)
         if seed is not None:

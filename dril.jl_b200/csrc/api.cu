@@ -1361,6 +1361,23 @@ extern "C" int32_t dril_env_set_training(dril_env* e, int32_t training) {
     e->d.training = training ? 1 : 0;
     return DRIL_OK;
 }
+extern "C" int32_t dril_env_set_scaling(dril_env* e, int32_t on, const float* obs_low, const float* obs_high, const float* act_low,
+                                        const float* act_high) {
+    DRIL_REQUIRE(e, "NULL argument");
+    if (!on) { e->d.scaling = 0; return DRIL_OK; }
+    DRIL_REQUIRE(obs_low && obs_high && act_low && act_high, "NULL bounds");
+    // ScalingWrapperEnv needs Box observation and action spaces (scalingWrapperEnv.jl:22): of the built-in envs that is Pendulum
+    DRIL_REQUIRE(e->d.kind == DRIL_ENV_PENDULUM, "ScalingWrapperEnv: Box observation and action spaces required (pendulum)");
+    DRIL_REQUIRE(e->d.obs_dim <= 4 && e->d.act_dim == 1, "ScalingWrapperEnv: obs_dim <= 4, act_dim == 1");
+    for (int j = 0; j < e->d.obs_dim; ++j) {
+        e->d.sc_obs_f[j] = 2.0f / (obs_high[j] - obs_low[j]);                     // :37-39
+        e->d.sc_obs_o[j] = obs_low[j];
+    }
+    e->d.sc_act_f = 2.0f / (act_high[0] - act_low[0]);                            // :42-44
+    e->d.sc_act_o = act_low[0];
+    e->d.scaling = 1;
+    return DRIL_OK;
+}
 extern "C" int32_t dril_env_get_original(dril_env* e, float* obs_out, float* rewards_out) {
     DRIL_REQUIRE(e, "NULL argument");
     dril_ctx* c = e->ctx;

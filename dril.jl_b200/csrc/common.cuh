@@ -90,6 +90,10 @@ struct EnvDev {
     double* partials;           // [2 parity][max_blocks][2*obs_dim + 2]
     double* roll_moments;       // [2 * (obs_dim + 1) + 2]: this rollout's sums / sums of squares per normalised column
                                 // (obs dims, discounted return) and the obs / return sample counts (data-parallel merge)
+    // ScalingWrapperEnv (scalingWrapperEnv.jl:14-49): per-env wrapper BELOW Monitor / Normalize; factors pre-computed on the host
+    int scaling;
+    float sc_obs_f[4], sc_obs_o[4];   // obs' = (obs - offset) * factor - 1
+    float sc_act_f, sc_act_o;         // env action = (a + 1) / factor + offset
     float* tobs;                // [n][obs_dim] raw terminal observations scratch
     float* old_obs;             // [n][obs_dim] raw obs of the last observe (compat path)
     float* old_rewards;         // [n]

@@ -29,6 +29,21 @@ __device__ __forceinline__ void env_raw_obs(int kind, const float* st, float* o)
     }
 }
 
+// observation as the wrappers above the env see it: raw, or mapped to [-1, 1] by ScalingWrapperEnv.observe
+// (scalingWrapperEnv.jl:72-75,94-99: `(x - offset) * scale - 1`, three separate fp32 roundings)
+__device__ __forceinline__ void env_obs(const EnvDev& env, const float* st, float* o) {
+    env_raw_obs(env.kind, st, o);
+    if (env.scaling) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < env.obs_dim) o[j] = __fsub_rn(__fmul_rn(__fsub_rn(o[j], env.sc_obs_o[j]), env.sc_obs_f[j]), 1.0f);
+    }
+}
+// ScalingWrapperEnv.act! (scalingWrapperEnv.jl:77-80,112-115): `(a + 1) / scale + offset` before the wrapped env's act!
+__device__ __forceinline__ float env_unscale_action(const EnvDev& env, float a) {
+    return env.scaling ? __fadd_rn(__fdiv_rn(__fadd_rn(a, 1.0f), env.sc_act_f), env.sc_act_o) : a;
+}
+
 __device__ __forceinline__ void env_reset_state(int kind, uint32_t gid, uint32_t episode, unsigned long long seed,
                                                 float* st) {
     uint32_t x[4];

@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
                     float st[ENV_MAX_STATE] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int k = 0; k < ENV_MAX_STATE; ++k) if (k < env.state_dim) st[k] = env.state[(size_t)k * N + n0 + tid];
-                    env_raw_obs(env.kind, st, o);
+                    env_obs(env, st, o);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) if (j < Dp) sRaw[(size_t)j * ld + tid] = o[j];
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
                 float r;
                 uint32_t life = 0;
                 if (env.kind == DRIL_ENV_CARTPOLE) r = cartpole_step(st, a_disc - env.act_start, &term);
-                else if (env.kind == DRIL_ENV_PENDULUM) r = pendulum_step(st, sEnvAct[tid]);
+                else if (env.kind == DRIL_ENV_PENDULUM) r = pendulum_step(st, env_unscale_action(env, sEnvAct[tid]));
                 else { life = env.life[n]; r = synthetic_step(gid, life, env.seed, &term); life += 1; env.life[n] = life; }
                 steps += 1;
                 const bool trunc = steps >= env.max_steps;
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
                         }
                     } else {
                         float o[4];
-                        env_raw_obs(env.kind, st, o);
+                        env_obs(env, st, o);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) if (j < D) env.tobs[(size_t)n * D + j] = o[j];
                     }
@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_fast_kernel(const __grid
         if (tid < M4) {
             float o[4] = {0.f, 0.f, 0.f, 0.f};
             if (mine) {
-                env_raw_obs(env.kind, st, o);
+                env_obs(env, st, o);
                 if (norm_obs) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) if (j < D) o[j] = normalize_obs_val(o[j], sMean[j], sVar[j], env.eps, env.clip_obs);
@@ -819,7 +819,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_fast_kernel(const __grid
             bool term = false;
             float r;
             if (env.kind == DRIL_ENV_CARTPOLE) r = cartpole_step(st, a_disc - env.act_start, &term);
-            else r = pendulum_step(st, a_cont);
+            else r = pendulum_step(st, env_unscale_action(env, a_cont));
             steps += 1;
             const bool trunc = steps >= env.max_steps;
             const bool done = term || trunc;
@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_fast_kernel(const __grid
             }
             if (trunc) {
                 trunc_i = 1;
-                env_raw_obs(env.kind, st, tobs);
+                env_obs(env, st, tobs);
                 if (norm_obs) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) if (j < D) tobs[j] = normalize_obs_val(tobs[j], sMean[j], sVar[j], env.eps, env.clip_obs);

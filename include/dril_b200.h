@@ -200,6 +200,11 @@ int32_t dril_env_get_norm_stats(dril_env* env, float* obs_mean, float* obs_var, 
 int32_t dril_env_set_norm_stats(dril_env* env, const float* obs_mean, const float* obs_var, int64_t obs_count,
                                 float ret_mean, float ret_var, int64_t ret_count);
 int32_t dril_env_set_training(dril_env* env, int32_t training);
+/* ScalingWrapperEnv(env) around every env of the batch (environment_wrappers/scalingWrapperEnv.jl:14-49): observations are
+ * mapped from the ORIGINAL Box [obs_low, obs_high] to [-1, 1] (observe, :94-99), actions arrive in [-1, 1] and are mapped back
+ * to [act_low, act_high] before act! (:112-115).  The wrapper sits below Monitor / Normalize.  Box/Box envs only (pendulum). */
+int32_t dril_env_set_scaling(dril_env* env, int32_t on, const float* obs_low, const float* obs_high,
+                             const float* act_low, const float* act_high);
 /* original (un-normalised) obs / rewards of the last observe/act (old_obs, old_rewards) */
 int32_t dril_env_get_original(dril_env* env, float* obs_out, float* rewards_out);
 /* the zeroing of `returns` in sync_normalization_stats! (normalizeWrapperEnv.jl:299-309) */

@@ -89,7 +89,7 @@ mutable struct CudaBatchedEnv <: AbstractParallelEnv
 end
 
 function CudaBatchedEnv(kind::Symbol, n_envs::Integer; ctx = default_ctx(), max_steps = 0, obs_dim = 0, act_start = 1,
-        monitor_window = 0, normalize::Union{Nothing, NormCfg} = nothing, gid_offset = 0)
+        monitor_window = 0, normalize::Union{Nothing, NormCfg} = nothing, gid_offset = 0, scaling::Bool = false)
     obs_space, act_space = if kind == :cartpole
         hi = Float32[4.8, Inf32, 0.41887903, Inf32]
         Box(-hi, hi), Discrete(2, act_start)
@@ -104,6 +104,15 @@ function CudaBatchedEnv(kind::Symbol, n_envs::Integer; ctx = default_ctx(), max_
         (Ptr{Cvoid}, Int32, Int64, Int32, Int32, Int32, Int64, Ptr{NormCfg}, Int32, Ref{Ptr{Cvoid}}),
         ctx.h, ENV_KINDS[kind], n_envs, max_steps, size(obs_space)[1], act_start, gid_offset,
         isnothing(normalize) ? C_NULL : Base.unsafe_convert(Ptr{NormCfg}, normptr), monitor_window, out))
+    if scaling
+        # ScalingWrapperEnv around every env of the batch (scalingWrapperEnv.jl:14-49): Box/Box envs only; the device maps
+        # observations to [-1, 1] and actions back from [-1, 1], so the spaces the agent sees are the scaled ones
+        obs_space isa Box && act_space isa Box || error("ScalingWrapperEnv needs Box observation and action spaces")
+        check(ccall((:dril_env_set_scaling, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
+            out[], 1, vec(obs_space.low), vec(obs_space.high), vec(act_space.low), vec(act_space.high)))
+        obs_space = Box(-ones(Float32, size(obs_space.low)), ones(Float32, size(obs_space.high)))
+        act_space = Box(-ones(Float32, size(act_space.low)), ones(Float32, size(act_space.high)))
+    end
     env = CudaBatchedEnv(ctx, out[], kind, n_envs, obs_space, act_space, monitor_window, normalize,
         falses(n_envs), falses(n_envs))
     finalizer(e -> ccall((:dril_env_destroy, LIB), Int32, (Ptr{Cvoid},), e.h), env)

@@ -204,6 +204,51 @@ class SyntheticBatch:
         return r
 
 
+class ScalingBatch:
+    """ScalingWrapperEnv (environment_wrappers/scalingWrapperEnv.jl:14-49,72-120) around every env of a batch: observations
+    of a Box space are mapped to [-1, 1] with the pre-computed factors `scale = 2 / (high - low)`, `offset = low` as
+    `(x - offset) * scale - 1` (:72-75), actions come in [-1, 1] and are mapped back with `(a + 1) / scale + offset` (:77-80)
+    before the wrapped env's act!.  Everything else is forwarded (:122-132).  fp32 like the spaces' eltype."""
+
+    def __init__(self, batch, obs_low, obs_high, act_low=None, act_high=None):
+        self.b = batch
+        self.orig_obs_low, self.orig_obs_high = np.asarray(obs_low, dtype=f32), np.asarray(obs_high, dtype=f32)
+        self.orig_act_low = np.asarray(batch.act_low if act_low is None else act_low, dtype=f32)
+        self.orig_act_high = np.asarray(batch.act_high if act_high is None else act_high, dtype=f32)
+        with np.errstate(divide="ignore"):
+            self.obs_scale = (f32(2.0) / (self.orig_obs_high - self.orig_obs_low)).astype(f32)       # :37-38
+            self.act_scale = (f32(2.0) / (self.orig_act_high - self.orig_act_low)).astype(f32)       # :42-43
+        self.obs_offset, self.act_offset = self.orig_obs_low, self.orig_act_low
+        self.act_low = -np.ones_like(self.orig_act_low)                                               # :30-34
+        self.act_high = np.ones_like(self.orig_act_high)
+
+    def __getattr__(self, name):            # n, kind, obs_dim, act_kind, act_dim, steps, terminated, truncated, ...
+        return getattr(self.b, name)
+
+    def scale_obs(self, x):
+        return (((np.asarray(x, dtype=f32) - self.obs_offset).astype(f32) * self.obs_scale).astype(f32) - f32(1.0)).astype(f32)
+
+    def unscale_action(self, a):
+        a = np.asarray(a, dtype=f32).reshape(self.b.n, -1)
+        return (((a + f32(1.0)).astype(f32) / self.act_scale).astype(f32) + self.act_offset).astype(f32)
+
+    def obs(self):
+        return self.scale_obs(self.b.obs())
+
+    def step(self, actions):
+        return self.b.step(self.unscale_action(actions))
+
+    def reset_idx(self, idx):
+        self.b.reset_idx(idx)
+
+    def reset_all(self):
+        self.b.reset_all()
+
+
+PENDULUM_OBS_LOW = np.array([-1.0, -1.0, -8.0], dtype=f32)       # Pendulum-v1 observation space (cos, sin, angular velocity)
+PENDULUM_OBS_HIGH = np.array([1.0, 1.0, 8.0], dtype=f32)
+
+
 class ParallelEnv:
     """Vector env with auto-reset. environment_wrappers/multithreadedParallelEnv.jl:47-74:
     reward; flags read BEFORE reset; terminal_observation stored iff truncated; reset iff

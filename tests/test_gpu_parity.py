@@ -28,7 +28,8 @@ def _flags(buf):
 # (a) env replay through the compat act!/observe path
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind,n,steps,max_steps", [("cartpole", 300, 120, 40), ("pendulum", 257, 90, 30),
-                                                     ("synthetic", 130, 60, 25), ("cartpole", 1, 30, 500)])
+                                                     ("synthetic", 130, 60, 25), ("cartpole", 1, 30, 500),
+                                                     ("pendulum_scaled", 200, 70, 30)])
 def test_env_replay_bit_exact_flags(D, kind, n, steps, max_steps):
     rng = np.random.default_rng(0)
     if kind == "cartpole":
@@ -39,6 +40,11 @@ def test_env_replay_bit_exact_flags(D, kind, n, steps, max_steps):
         ob = OE.PendulumBatch(n, seed=5, max_steps=max_steps)
         env = D.CudaBatchedEnv("pendulum", n, max_steps=max_steps, seed=5)
         act = lambda: rng.uniform(-2.5, 2.5, (n, 1)).astype(f32)
+    elif kind == "pendulum_scaled":      # ScalingWrapperEnv (scalingWrapperEnv.jl:94-115) through observe / act!
+        ob = OE.ScalingBatch(OE.PendulumBatch(n, seed=5, max_steps=max_steps), OE.PENDULUM_OBS_LOW, OE.PENDULUM_OBS_HIGH)
+        env = D.ScalingWrapperEnv(D.MultiThreadedParallelEnv("pendulum", n, max_steps=max_steps))
+        env.seed(5); env.reset()
+        act = lambda: rng.uniform(-1.0, 1.0, (n, 1)).astype(f32)
     else:
         ob = OE.SyntheticBatch(n, 10, seed=5, max_steps=max_steps)
         env = D.CudaBatchedEnv("synthetic", n, obs_dim=10, max_steps=max_steps, seed=5)
@@ -60,7 +66,7 @@ def test_env_replay_bit_exact_flags(D, kind, n, steps, max_steps):
             np.testing.assert_allclose(infos[i]["terminal_observation"], info["terminal_observation"][i], rtol=1e-6)
         assert all(("terminal_observation" in infos[i]) == bool(tro[i]) for i in range(n))
         n_term += teo.sum(); n_trunc += tro.sum()
-    assert n == 1 or (n_trunc > 0 and (kind == "pendulum" or n_term > 0))
+    assert n == 1 or (n_trunc > 0 and (kind.startswith("pendulum") or n_term > 0))
     st, steps_dev = env.get_state()
     np.testing.assert_array_equal(steps_dev, ob.steps)
 
@@ -211,6 +217,14 @@ def _mk(D, kind, n, seed, ms, monitor, norm):
         env = D.CudaBatchedEnv("cartpole", n, max_steps=ms, seed=seed, monitor_window=100 if monitor else 0,
                                normalize=D.NormalizeConfig() if norm else None)
         o = OE.ParallelEnv(OE.CartPoleBatch(n, seed=seed, max_steps=ms)); spec = SPECS["cartpole"]()
+    elif kind == "pendulum_scaled":
+        # ScalingWrapperEnv around every Pendulum env (scalingWrapperEnv.jl): obs and actions in [-1, 1], below Monitor / Normalize
+        env = D.CudaBatchedEnv("pendulum", n, max_steps=ms, seed=seed, monitor_window=100 if monitor else 0,
+                               normalize=D.NormalizeConfig() if norm else None, scaling=True)
+        assert np.array_equal(env.observation_space().low, -np.ones(3, f32)) and np.array_equal(env.action_space().high, np.ones(1, f32))
+        assert np.array_equal(env.orig_action_space.low, [-2.0])
+        o = OE.ParallelEnv(OE.ScalingBatch(OE.PendulumBatch(n, seed=seed, max_steps=ms), OE.PENDULUM_OBS_LOW, OE.PENDULUM_OBS_HIGH))
+        spec = OP.PolicySpec(3, [64, 32], "continuous", 1, act_low=[-1], act_high=[1])
     else:
         env = D.CudaBatchedEnv("pendulum", n, max_steps=ms, seed=seed, monitor_window=100 if monitor else 0,
                                normalize=D.NormalizeConfig() if norm else None)
@@ -226,6 +240,7 @@ def _mk(D, kind, n, seed, ms, monitor, norm):
     ("cartpole", 64, 16, 500, True, False), ("cartpole", 333, 64, 20, True, False), ("cartpole", 4096, 32, 25, False, False),
     ("pendulum", 100, 40, 15, True, True), ("pendulum", 1000, 24, 10, True, True), ("cartpole", 200, 48, 18, True, True),
     ("pendulum", 50, 30, 12, False, False),
+    ("pendulum_scaled", 300, 30, 12, True, False), ("pendulum_scaled", 700, 20, 9, True, True),     # fast kernel / cooperative kernel
     ("pendulum", 10240, 5, 3, True, True),      # >= 64 envs per SM with a wide net: 64-env tiles, wide layers on mma.sync tiles
     ("pendulum", 16384, 4, 3, True, True),      # BASELINE config C3's env count (Pendulum + NormalizeWrapperEnv), truncation every 3 steps
     ("cartpole", 65536, 6, 4, True, False)])    # BASELINE config C4's env count: 2048 tiles on the tensor-core rollout, truncation list at scale

@@ -177,6 +177,56 @@ def test_normalize_wrapper_semantics():
     np.testing.assert_allclose(back, raw, atol=1e-5)
 
 
+class _FixedBatch:
+    """One env with a fixed observation that records the last action it received (the ObsTestEnv / ActionTestEnv /
+    LargeRangeEnv fixtures of test/test_scaling_wrapper.jl)."""
+    n = 1
+
+    def __init__(self, obs, act_low, act_high):
+        self._obs = np.asarray(obs, dtype=f32)[None]
+        self.act_low, self.act_high = np.asarray(act_low, dtype=f32), np.asarray(act_high, dtype=f32)
+        self.last_action = None
+
+    def obs(self):
+        return self._obs.copy()
+
+    def step(self, actions):
+        self.last_action = np.asarray(actions, dtype=f32).reshape(-1)
+        return self.last_action[:1].copy()
+
+
+def test_scaling_wrapper_reference_scenarios():
+    """ScalingWrapperEnv pinned by the reference's own closed-form tests (test/test_scaling_wrapper.jl:42-81 observation
+    scaling, :83-129 action scaling, :208-238 large ranges, :178-206 zero-width ranges do not raise)."""
+    lo, hi = [0.0, -10.0, 5.0], [10.0, 10.0, 25.0]
+    for obs, want in (([5.0, 0.0, 15.0], [0, 0, 0]), (lo, [-1, -1, -1]), (hi, [1, 1, 1])):
+        w = E.ScalingBatch(_FixedBatch(obs, [-1.0], [1.0]), lo, hi)
+        assert np.abs(w.obs()[0] - np.asarray(want, f32)).max() < 1e-6
+        assert w.obs().dtype == f32
+    b = _FixedBatch([0.0], [2.0, -5.0, 0.0], [8.0, 15.0, 10.0])
+    w = E.ScalingBatch(b, [-1.0], [1.0])
+    np.testing.assert_array_equal(w.act_low, [-1, -1, -1]); np.testing.assert_array_equal(w.act_high, [1, 1, 1])
+    for a, want in (([0, 0, 0], [5, 5, 5]), ([-1, -1, -1], [2, -5, 0]), ([1, 1, 1], [8, 15, 10])):
+        w.step(np.asarray(a, f32))
+        assert np.abs(b.last_action - np.asarray(want, f32)).max() < 1e-6
+    b = _FixedBatch([500.0, 500.0], [-100.0], [300.0])
+    w = E.ScalingBatch(b, [-1000.0, -500.0], [2000.0, 1500.0])
+    assert np.abs(w.obs()[0]).max() < 1e-5
+    assert abs(float(w.step(np.asarray([0.5], f32))[0]) - 200.0) < 1e-5
+    w = E.ScalingBatch(_FixedBatch([0.0, -1.0], [5.0], [5.0]), [0.0, -1.0], [0.0, -1.0])       # zero-width ranges: no exception
+    with np.errstate(invalid="ignore", divide="ignore"):
+        assert w.obs().shape == (1, 2)
+        w.step(np.asarray([0.0], f32))
+    # Pendulum through the wrapper: scaled obs in [-1, 1]; a scaled action a reaches the env as the torque 2 a
+    pb = E.PendulumBatch(6, seed=3)
+    w = E.ScalingBatch(pb, E.PENDULUM_OBS_LOW, E.PENDULUM_OBS_HIGH)
+    o = w.obs()
+    assert (np.abs(o) <= 1 + 1e-6).all() and np.abs(o[:, 2] * 8 - pb.obs()[:, 2]).max() < 1e-5
+    pb2 = E.PendulumBatch(6, seed=3)
+    a = np.linspace(-1, 1, 6, dtype=f32)[:, None]
+    np.testing.assert_allclose(w.step(a), pb2.step(2 * a), rtol=1e-6)
+
+
 def test_monitor_wrapper():
     """environment_wrappers/monitorWrapperEnv.jl:44-60 — episode r/l on done, 100-deep window."""
     env = E.MonitorWrapper(E.ParallelEnv(E.PendulumBatch(3, seed=1, max_steps=4)), stats_window=5)
