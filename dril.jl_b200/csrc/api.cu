@@ -17,6 +17,7 @@
 #include "update_ftg.cuh"
 #include "rollout_tc.cuh"
 #include "rollout_syn.cuh"
+#include "rollout_gtc.cuh"
 
 #define DRIL_SMEM_MAX 232448  // 227 KB opt-in per CTA on sm_100
 #define DRIL_RESULT_SLOTS 4   // iterations that may be enqueued before their results are read
@@ -50,6 +51,7 @@ static int g_opt_ft = getenv("DRIL_FT") ? atoi(getenv("DRIL_FT")) : 1;
 static int g_opt_defer_critic = getenv("DRIL_DEFER_CRITIC") ? atoi(getenv("DRIL_DEFER_CRITIC")) : 1;
 static int g_opt_ftg = getenv("DRIL_FTG") ? atoi(getenv("DRIL_FTG")) : 1;   // general-shape features-on-lanes kernel (update_ftg.cuh); 2: also where update_ft.cuh applies
 static int g_opt_tc_rollout = getenv("DRIL_TC_ROLLOUT") ? atoi(getenv("DRIL_TC_ROLLOUT")) : 1;   // tensor-core rollout (CartPole, [64,64])
+static int g_opt_tc_actor = getenv("DRIL_TC_ACTOR") ? atoi(getenv("DRIL_TC_ACTOR")) : 1;   // general rollout: actor forward on tcgen05 (rollout_gtc.cuh)
 static int g_opt_syn_rollout = getenv("DRIL_SYN_ROLLOUT") ? atoi(getenv("DRIL_SYN_ROLLOUT")) : 1;   // thread-per-env rollout (synthetic env, small policy)
 static int g_opt_tail = getenv("DRIL_TAIL") ? atoi(getenv("DRIL_TAIL")) : 1;   // fused reduce/clip/Adam tail of the TC kernel
 // fp32 loss/grad kernel, wide nets: one net per pass with shared activation rows (fixed per policy at creation)
@@ -65,6 +67,7 @@ extern "C" int32_t dril_set_option(const char* key, int32_t value) {
     if (!strcmp(key, "fused_tail")) { g_opt_tail = value; return DRIL_OK; }
     if (!strcmp(key, "tc_rollout")) { g_opt_tc_rollout = value; return DRIL_OK; }
     if (!strcmp(key, "syn_rollout")) { g_opt_syn_rollout = value; return DRIL_OK; }
+    if (!strcmp(key, "tc_actor")) { g_opt_tc_actor = value; return DRIL_OK; }
     if (!strcmp(key, "single_net")) { g_opt_single_net = value; return DRIL_OK; }   // policies created afterwards
     if (!strcmp(key, "mma")) { g_opt_mma = value; return DRIL_OK; }                 // policies created afterwards
     dril_set_error("unknown option '%s'", key);
@@ -346,6 +349,8 @@ extern "C" int32_t dril_ctx_create(int32_t device, uint64_t seed, dril_ctx** out
                              (const void*)ppo_loss_grad_ftg_kernel<3, 0, 1>, (const void*)ppo_loss_grad_ftg_kernel<3, 0, 2>,
                              (const void*)ppo_loss_grad_ftg_kernel<3, 1, 1>, (const void*)ppo_loss_grad_ftg_kernel<3, 1, 2>};
         for (const void* fn : fns) DRIL_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX - 2048));   // 1 KB of static shared memory
+        DRIL_CUDA(cudaFuncSetAttribute(rollout_gtc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX - 2048));
+        DRIL_CUDA(cudaFuncSetAttribute(rollout_gtc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX - 2048));
         DRIL_CUDA(cudaFuncSetAttribute(critic_values_ftg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX - 2048));
         DRIL_CUDA(cudaFuncSetAttribute(critic_values_ftg_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX - 2048));
     }
@@ -1187,6 +1192,44 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
         a.dc = b->dcs;
         flags |= RO_DEFER_CRITIC;
     }
+    // the batched critic pass behind a deferred-critic step loop
+    auto launch_critic = [&]() -> int32_t {
+        Span sp2(c, DRIL_K_ROLLOUT);
+        const FtgLayout lay = ftg_layout(a.pd);
+        const long long tiles = ((long long)b->d.T * N + N + 63) / 64 + 8;
+        const int cgrid = (int)std::min<long long>(tiles, (long long)c->sm_count);
+        if (a.pd.n_layers - 1 == 2) critic_values_ftg_kernel<2><<<cgrid, FTG_THREADS, (size_t)lay.total, c->stream>>>(a.pd, a.pack, b->d, b->dcs, lay);
+        else critic_values_ftg_kernel<3><<<cgrid, FTG_THREADS, (size_t)lay.total, c->stream>>>(a.pd, a.pack, b->d, b->dcs, lay);
+        DRIL_CUDA(cudaGetLastError());
+        return DRIL_OK;
+    };
+    // enough envs for a 128-env tile per SM: the actor's layers on tcgen05 inside the step loop (rollout_gtc.cuh)
+    if (defer && g_opt_tc_actor && N >= 64ll * c->sm_count) {
+        const size_t body = rollout_smem_layout(a.pd, d.obs_dim, d.act_dim, GTC_ENVS, false, true, false, true).total;
+        const GtcLayout gl = gtc_layout(a.pd);
+        const size_t smem_g = body + (size_t)gl.total;
+        if (smem_g <= (size_t)DRIL_SMEM_MAX - 2048) {
+            a.M4 = GTC_ENVS; a.flags = flags;
+            a.n_tiles = (int)((N + GTC_ENVS - 1) / GTC_ENVS);
+            int grid = a.n_tiles, body_i = (int)body;
+            void* fn = a.pd.n_layers - 1 == 2 ? (void*)rollout_gtc_kernel<2> : (void*)rollout_gtc_kernel<3>;
+            void* args[] = {(void*)&a, (void*)&gl, (void*)&body_i};
+            {
+                Span sp(c, DRIL_K_ROLLOUT);
+                if (flags & RO_GRID_SYNC) {
+                    int per_sm = 0;
+                    DRIL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, DRIL_THREADS, smem_g));
+                    DRIL_REQUIRE(per_sm >= 1, "rollout kernel does not fit on an SM");
+                    grid = std::min(grid, std::min(per_sm * c->sm_count, e->max_blocks));
+                    DRIL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(DRIL_THREADS), args, smem_g, c->stream));
+                } else {
+                    grid = std::min(grid, 4 * c->sm_count);
+                    DRIL_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(DRIL_THREADS), args, smem_g, c->stream));
+                }
+            }
+            return launch_critic();
+        }
+    }
     static const int env_ctas = getenv("DRIL_ROLLOUT_CTAS_PER_SM") ? atoi(getenv("DRIL_ROLLOUT_CTAS_PER_SM")) : 4;
     static const int env_threads = getenv("DRIL_ROLLOUT_THREADS") ? atoi(getenv("DRIL_ROLLOUT_THREADS")) : 0;
     const long long want_ctas = (long long)c->sm_count * std::max(env_ctas, 1);
@@ -1243,15 +1286,7 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
         else rollout_kernel<false><<<grid, threads, smem, c->stream>>>(a);
         DRIL_CUDA(cudaGetLastError());
     }
-    if (defer) {
-        Span sp2(c, DRIL_K_ROLLOUT);
-        const FtgLayout lay = ftg_layout(a.pd);
-        const long long tiles = ((long long)b->d.T * N + N + 63) / 64 + 8;
-        const int cgrid = (int)std::min<long long>(tiles, (long long)c->sm_count);
-        if (a.pd.n_layers - 1 == 2) critic_values_ftg_kernel<2><<<cgrid, FTG_THREADS, (size_t)lay.total, c->stream>>>(a.pd, a.pack, b->d, b->dcs, lay);
-        else critic_values_ftg_kernel<3><<<cgrid, FTG_THREADS, (size_t)lay.total, c->stream>>>(a.pd, a.pack, b->d, b->dcs, lay);
-        DRIL_CUDA(cudaGetLastError());
-    }
+    if (defer) return launch_critic();
     return DRIL_OK;
 }
 

@@ -65,8 +65,10 @@ struct RolloutSmem {
 };
 
 // critic = false (RO_DEFER_CRITIC): no critic activations, which leaves room for 128-env tiles with wide nets
+// tca (rollout_gtc.cuh): the actor's layers run on tcgen05 out of their own image region behind `total`; only the output rows
+// (<= 8 actions / action dims) are kept here
 __host__ __device__ inline RolloutSmem rollout_smem_layout(const PolicyDesc& pd, int obs_dim, int act_dim, int M4,
-                                                           bool weights_smem, bool has_policy, bool critic = true) {
+                                                           bool weights_smem, bool has_policy, bool critic = true, bool tca = false) {
     RolloutSmem s;
     s.ld = M4 + 4;
     int Dp = (obs_dim + 3) & ~3;
@@ -75,7 +77,7 @@ __host__ __device__ inline RolloutSmem rollout_smem_layout(const PolicyDesc& pd,
     s.w = o; o += (weights_smem && has_policy) ? (size_t)pd.pack_fwd : 0;
     s.raw = o; o += (size_t)s.raw_rows * s.ld;
     s.x = o; o += (size_t)Dp * s.ld;
-    s.acta = o; o += has_policy ? (size_t)2 * pd.max_np * s.ld : 0;
+    s.acta = o; o += has_policy ? (tca ? (size_t)8 * s.ld : (size_t)2 * pd.max_np * s.ld) : 0;
     s.actc = o; o += (has_policy && critic) ? (size_t)2 * pd.max_np * s.ld : 0;
     int adp = act_dim < 1 ? 1 : act_dim;
     s.envact = o; o += (size_t)adp * s.ld;
@@ -173,10 +175,17 @@ __device__ __forceinline__ void tile_column_sums(const float* sRaw, int ld, int 
     }
 }
 
-template <bool WS>
-__global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_constant__ RolloutArgs a) {
-    extern __shared__ float4 smem4[];
-    float* smem = reinterpret_cast<float*>(smem4);
+// the layer forward of the step loop: fp32 FMA / mma.sync tiles out of the ping-pong activation buffers (mlp.cuh); the tcgen05
+// actor of rollout_gtc.cuh is the other implementation of this call
+struct MlpForward {
+    __device__ __forceinline__ int operator()(const PolicyDesc& pd, const float* __restrict__ Wbase, const float* sX, float* sActA, float* sActC,
+                                              int M4, int ld, int net_mask, bool use_mma) const {
+        return mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, net_mask, use_mma);
+    }
+};
+
+template <bool WS, bool TCA, class Fwd>
+__device__ __forceinline__ void rollout_body(const RolloutArgs& a, float* smem, Fwd& fwd) {
     const EnvDev& env = a.env;
     const BufDev& buf = a.buf;
     const PolicyDesc& pd = a.pd;
@@ -187,7 +196,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
     const int D = env.obs_dim, Dp = (D + 3) & ~3;
     const int M4 = a.M4;
     const long long N = env.n_envs;
-    const RolloutSmem L = rollout_smem_layout(pd, D, env.act_dim, M4, WS, has_policy, !(a.flags & RO_DEFER_CRITIC));
+    const RolloutSmem L = rollout_smem_layout(pd, D, env.act_dim, M4, WS, has_policy, !(a.flags & RO_DEFER_CRITIC), TCA);
     const int ld = L.ld;
     float* sRaw = smem + L.raw;
     float* sX = smem + L.x;
@@ -371,7 +380,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
                     buf.obs[(row + n0) * D + i] = sX[(size_t)d * ld + e];
                 }
                 // actor + critic forward (critic deferred: actor only)
-                fin = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, defer ? 1 : 3, use_mma);
+                fin = fwd(pd, Wbase, sX, sActA, sActC, M4, ld, defer ? 1 : 3, use_mma);
             }
             // sample / replay action, log-prob, value; hand the env-space action to the step
             int a_disc = 0;
@@ -540,7 +549,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
                     }
                     __syncthreads();
                 } else if (has_policy) {                        // V(terminal_obs), trajectory.jl:57-61
-                    int f = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, 2, use_mma);
+                    int f = fwd(pd, Wbase, sX, sActA, sActC, M4, ld, 2, use_mma);
                     if (mine && trunc) buf.boot[row + n] = sActC[(size_t)f * pd.max_np * ld + tid];
                     __syncthreads();
                 }
@@ -564,7 +573,7 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
                 __syncthreads();
                 continue;
             }
-            int f = mlp_forward_pingpong(pd, Wbase, sX, sActA, sActC, M4, ld, 2, use_mma);
+            int f = fwd(pd, Wbase, sX, sActA, sActC, M4, ld, 2, use_mma);
             if (tid < nvalid) buf.last_values[n0 + tid] = sActC[(size_t)f * pd.max_np * ld + tid];
             __syncthreads();
         }
@@ -573,6 +582,13 @@ __global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_cons
         for (int d = tid; d < D; d += blockDim.x) { env.obs_mean[d] = sMean[d]; env.obs_var[d] = sVar[d]; }
         if (tid == 0) { env.ret_stats[0] = sRet[0]; env.ret_stats[1] = sRet[1]; env.counts[0] = sCnt[0]; env.counts[1] = sCnt[1]; }
     }
+}
+
+template <bool WS>
+__global__ void __launch_bounds__(DRIL_THREADS) rollout_kernel(const __grid_constant__ RolloutArgs a) {
+    extern __shared__ float4 smem4[];
+    MlpForward fwd;
+    rollout_body<WS, false>(a, reinterpret_cast<float*>(smem4), fwd);
 }
 
 // ---------------------------------------------------------------------------------------

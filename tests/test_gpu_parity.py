@@ -243,6 +243,7 @@ def _mk(D, kind, n, seed, ms, monitor, norm):
     ("pendulum_scaled", 300, 30, 12, True, False), ("pendulum_scaled", 700, 20, 9, True, True),     # fast kernel / cooperative kernel
     ("pendulum", 10240, 5, 3, True, True),      # >= 64 envs per SM with a wide net: 64-env tiles, wide layers on mma.sync tiles
     ("pendulum", 16384, 4, 3, True, True),      # BASELINE config C3's env count (Pendulum + NormalizeWrapperEnv), truncation every 3 steps
+    ("cartpole", 14400, 5, 4, True, True),      # general kernel with a [64,64] discrete actor on tcgen05 (rollout_gtc.cuh, two hidden layers)
     ("cartpole", 65536, 6, 4, True, False)])    # BASELINE config C4's env count: 2048 tiles on the tensor-core rollout, truncation list at scale
 def test_fused_rollout_replay(D, kind, n, T, ms, monitor, norm):
     env, oenv, spec = _mk(D, kind, n, 9, ms, monitor, norm)
