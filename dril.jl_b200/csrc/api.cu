@@ -258,6 +258,7 @@ struct dril_policy {
     size_t ft_tiles_bytes = 0;
     int ft_tiles_per_mb = 0;
     long long ft_batch = 1;
+    long long ft_epoch_tile0 = 0;      // first tile of the current epoch when all epochs of an update were staged at once
     // Adam betas of the most recent update (dril_ppo_hyper carries them per call); Optimisers.Adam defaults until then
     double beta1 = 0.9, beta2 = 0.999;
 };
@@ -1849,6 +1850,41 @@ static int32_t ft_stage_epoch(dril_policy* p, const BufDev& bd, const FeistelKey
     return DRIL_OK;
 }
 
+// ALL epochs of an update staged by one launch (both tcgen05 paths), which also leaves the per-minibatch advantage moments in
+// p->adv_partial (layout of adv_stats_kernel with `bpm` blocks per minibatch).  *staged = false (nothing launched) when the tile
+// records of all epochs would not fit the memory budget: the caller then stages epoch by epoch.
+static int32_t ft_stage_epochs(dril_policy* p, const BufDev& bd, const FeistelKeys& fks, int ne, long long n_total, long long batch_size, int bpm,
+                               bool* staged) {
+    dril_ctx* c = p->ctx;
+    *staged = false;
+    const bool ftg = ftg_active(p);
+    const int n_mb = (int)((n_total + batch_size - 1) / batch_size);
+    const int tpm = (int)((std::min<long long>(batch_size, n_total) + 63) / 64);
+    const int cont = p->pd.act_kind == DRIL_ACT_CONTINUOUS ? 1 : 0;
+    const int rf = ftg_rec_floats(p->pd.obs_dim, cont, p->pd.act_n);
+    const size_t tile_bytes = ftg ? (size_t)rf * 4 : (size_t)FT_TILE_BYTES;
+    const long long epoch_tiles = (long long)n_mb * tpm;
+    const size_t bytes = (size_t)ne * epoch_tiles * tile_bytes;
+    static const size_t budget = (getenv("DRIL_STAGE_ALL_MB") ? (size_t)atoll(getenv("DRIL_STAGE_ALL_MB")) : 8192) << 20;
+    if (bytes > budget) return DRIL_OK;
+    if (p->ft_tiles_bytes < bytes) {
+        if (p->ft_tiles) { DRIL_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(p->ft_tiles); }
+        p->ft_tiles = nullptr; p->ft_tiles_bytes = 0;
+        DRIL_CUDA(cudaMalloc((void**)&p->ft_tiles, bytes));
+        p->ft_tiles_bytes = bytes;
+    }
+    p->ft_tiles_per_mb = tpm; p->ft_batch = batch_size;
+    Span sp(c, DRIL_K_PERMUTE);
+    const dim3 grid(bpm, n_mb, ne);
+    if (ftg) ftg_permute_epochs_kernel<<<grid, 256, 0, c->stream>>>(p->ft_recs, p->ft_rec_stride, bd.obs_dim, fks, n_total, batch_size, tpm, p->pd.act_start,
+                                                                   p->pd.act_n, cont, rf, reinterpret_cast<float*>(p->ft_tiles), epoch_tiles, p->adv_partial);
+    else ft_permute_epochs_kernel<<<grid, 256, 0, c->stream>>>(p->ft_recs, p->ft_rec_stride, fks, n_total, batch_size, tpm, p->pd.act_start, p->pd.act_n,
+                                                               p->ft_tiles, epoch_tiles, p->adv_partial);
+    DRIL_CUDA(cudaGetLastError());
+    *staged = true;
+    return DRIL_OK;
+}
+
 // one minibatch: loss/grad kernel -> reduce -> (allreduce) -> clip + Adam
 static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch& mb, const double* mbstats_dev,
                               const UpdateHyper& hp, const LossLaunch& ll, bool apply, int apply_stats) {
@@ -1889,7 +1925,7 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
             if (ftg) {
                 FtgArgs fa;
                 fa.tiles = p->ft_tiles;
-                fa.tile0 = (mb.start / std::max<long long>(1, p->ft_batch)) * p->ft_tiles_per_mb;
+                fa.tile0 = p->ft_epoch_tile0 + (mb.start / std::max<long long>(1, p->ft_batch)) * p->ft_tiles_per_mb;
                 fa.lay = ftg_layout(pd);
                 const void* fn = ftg_kernel(pd);
                 void* args[] = {(void*)&a, (void*)&tl, (void*)&fa};
@@ -1899,7 +1935,7 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
                 // tile records of this minibatch: written by ft_stage_epoch before the epoch's first step
                 FtArgs fa;
                 fa.tiles = p->ft_tiles;
-                fa.tile0 = (mb.start / std::max<long long>(1, p->ft_batch)) * p->ft_tiles_per_mb;
+                fa.tile0 = p->ft_epoch_tile0 + (mb.start / std::max<long long>(1, p->ft_batch)) * p->ft_tiles_per_mb;
                 const void* fn = pd.act_n == 1 ? (const void*)ppo_loss_grad_ft_kernel<1> : (const void*)ppo_loss_grad_ft_kernel<2>;
                 void* args[] = {(void*)&a, (void*)&tl, (void*)&fa};
                 if (tail) DRIL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FT_THREADS), args, FT_SMEM_BYTES, c->stream));
@@ -1979,8 +2015,11 @@ static int32_t update_async(dril_policy* p, dril_buffer* b, const dril_ppo_hyper
         FeistelKeys fks;
         for (int e = 0; e < ne; ++e) fks.k[e] = make_feistel(n_total, epoch_counter + e0 + e, c->rank, shuffle_seed);
         for (int e = ne; e < DRIL_MAX_EPOCHS_BATCHED; ++e) fks.k[e] = fks.k[0];
+        // tcgen05 paths: the tile records of all `ne` epochs and the advantage moments come from one launch
+        bool staged_all = false;
+        if (ftg_active(p) || ft_active(p)) DRIL_TRY(ft_stage_epochs(p, b->d, fks, ne, n_total, batch_size, bpm, &staged_all));
         if (hp.normalize_advantage) {
-            {
+            if (!staged_all) {
                 Span sp(c, DRIL_K_ADV_STATS);
                 adv_stats_kernel<<<dim3(bpm, n_mb, ne), 256, 0, c->stream>>>(b->d.advantages, n_total, batch_size, fks, 0, p->adv_partial);
                 DRIL_CUDA(cudaGetLastError());
@@ -1994,8 +2033,12 @@ static int32_t update_async(dril_policy* p, dril_buffer* b, const dril_ppo_hyper
             n_extra = 0;
         }
         for (int e = 0; e < ne; ++e) {
-            if (ftg_active(p)) DRIL_TRY(ftg_stage_epoch(p, b->d, fks.k[e], n_total, batch_size, 0));
-            else if (ft_active(p)) DRIL_TRY(ft_stage_epoch(p, b->d, fks.k[e], n_total, batch_size, 0));
+            if (staged_all) p->ft_epoch_tile0 = (long long)e * n_mb * p->ft_tiles_per_mb;
+            else {
+                p->ft_epoch_tile0 = 0;
+                if (ftg_active(p)) DRIL_TRY(ftg_stage_epoch(p, b->d, fks.k[e], n_total, batch_size, 0));
+                else if (ft_active(p)) DRIL_TRY(ft_stage_epoch(p, b->d, fks.k[e], n_total, batch_size, 0));
+            }
             for (int i = 0; i < n_mb; ++i) {
                 Minibatch mb;
                 mb.n_total = n_total; mb.start = (long long)i * batch_size;
@@ -2006,6 +2049,7 @@ static int32_t update_async(dril_policy* p, dril_buffer* b, const dril_ppo_hyper
             }
         }
     }
+    p->ft_epoch_tile0 = 0;
     if (n_extra) DRIL_TRY(allreduce_small(c, nullptr, 0, extra, n_extra));   // no advantage moments were exchanged
     return DRIL_OK;
 }

@@ -100,29 +100,60 @@ __global__ void __launch_bounds__(256) ft_pack_records_kernel(const BufDev buf, 
     }
 }
 
-// The epoch's samples in shuffled order as contiguous tile records (one launch per epoch; padding slots are zero).
+// slot r of minibatch mb of an epoch -> its place in the tile records (padding slots are zero); returns the sample's advantage
+__device__ __forceinline__ float ft_permute_slot(const float* __restrict__ recs, int stride, const FeistelKey& fk, long long n_total,
+                                                 long long batch_size, long long per, long long mb, long long r, int identity, int act_start,
+                                                 int nout, unsigned char* __restrict__ out, bool& valid) {
+    const long long pos = mb * batch_size + r, s = mb * per + r;
+    valid = r < batch_size && pos < n_total;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f), u = x, w = x;
+    if (valid) {
+        const long long sidx = identity ? pos : feistel_permute(pos, n_total, fk);
+        const float4* rp = reinterpret_cast<const float4*>(recs + sidx * stride);      // obs (4) | action, adv, logp, ret | val
+        x = rp[0]; u = rp[1]; w = rp[2];
+    }
+    int ai = valid ? __float_as_int(u.x) - act_start : 0;
+    ai = ai < 0 ? 0 : (ai >= nout ? nout - 1 : ai);
+    float* blk = reinterpret_cast<float*>(out + (s >> 6) * FT_TILE_BYTES);
+    const int j = (int)(s & 63);
+    reinterpret_cast<float4*>(blk)[j] = x;
+    blk[FT_R_ADV + j] = u.y; blk[FT_R_OLP + j] = u.z; reinterpret_cast<int*>(blk)[FT_R_ACT + j] = ai;
+    blk[FT_R_RET + j] = u.w; blk[FT_R_OVAL + j] = w.x;
+    return u.y;
+}
+// The epoch's samples in shuffled order as contiguous tile records (one launch per epoch).
 __global__ void __launch_bounds__(256) ft_permute_kernel(const float* __restrict__ recs, int stride, const FeistelKey fk, long long n_total,
                                                          long long batch_size, int n_mb, int tiles_per_mb, int identity, int act_start, int nout,
                                                          unsigned char* __restrict__ out) {
     const long long per = (long long)tiles_per_mb * FT_TS;
     const long long slots = per * n_mb;
     for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (long long)gridDim.x * blockDim.x) {
-        const long long mb = s / per, r = s - mb * per;
-        const long long pos = mb * batch_size + r;
-        const bool valid = r < batch_size && pos < n_total;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), u = x, w = x;
-        if (valid) {
-            const long long sidx = identity ? pos : feistel_permute(pos, n_total, fk);
-            const float4* rp = reinterpret_cast<const float4*>(recs + sidx * stride);      // obs (4) | action, adv, logp, ret | val
-            x = rp[0]; u = rp[1]; w = rp[2];
-        }
-        int ai = valid ? __float_as_int(u.x) - act_start : 0;
-        ai = ai < 0 ? 0 : (ai >= nout ? nout - 1 : ai);
-        float* blk = reinterpret_cast<float*>(out + (s >> 6) * FT_TILE_BYTES);
-        const int j = (int)(s & 63);
-        reinterpret_cast<float4*>(blk)[j] = x;
-        blk[FT_R_ADV + j] = u.y; blk[FT_R_OLP + j] = u.z; reinterpret_cast<int*>(blk)[FT_R_ACT + j] = ai;
-        blk[FT_R_RET + j] = u.w; blk[FT_R_OVAL + j] = w.x;
+        const long long mb = s / per;
+        bool valid;
+        ft_permute_slot(recs, stride, fk, n_total, batch_size, per, mb, s - mb * per, identity, act_start, nout, out, valid);
+    }
+}
+// ALL epochs of an update in one launch, grid (blocks per minibatch, minibatches, epochs): epoch e's records start at tile
+// e * epoch_tiles; the same pass accumulates the minibatch's advantage moments (what adv_stats_kernel computes for the other
+// loss/grad kernels, same partial layout: fixed-order sums => deterministic)
+__global__ void __launch_bounds__(256) ft_permute_epochs_kernel(const float* __restrict__ recs, int stride, const __grid_constant__ FeistelKeys fks,
+                                                                long long n_total, long long batch_size, int tiles_per_mb, int act_start,
+                                                                int nout, unsigned char* __restrict__ out, long long epoch_tiles,
+                                                                double* __restrict__ partial) {
+    __shared__ double scratch[32];
+    const FeistelKey& fk = fks.k[blockIdx.z];
+    const long long per = (long long)tiles_per_mb * FT_TS, mb = blockIdx.y;
+    unsigned char* o = out + (size_t)blockIdx.z * epoch_tiles * FT_TILE_BYTES;
+    double sm = 0, sq = 0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < per; r += (long long)gridDim.x * blockDim.x) {
+        bool valid;
+        const float adv = ft_permute_slot(recs, stride, fk, n_total, batch_size, per, mb, r, 0, act_start, nout, o, valid);
+        if (valid) { sm += (double)adv; sq += (double)adv * (double)adv; }
+    }
+    sm = block_sum(sm, scratch); sq = block_sum(sq, scratch);
+    if (threadIdx.x == 0) {
+        double* pp = partial + (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 2;
+        pp[0] = sm; pp[1] = sq;
     }
 }
 

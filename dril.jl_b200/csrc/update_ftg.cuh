@@ -73,36 +73,65 @@ __host__ inline FtgLayout ftg_layout(const PolicyDesc& pd) {
 }
 
 // The epoch's samples in shuffled order as contiguous records of 64: x [64][Dp] | advantage | old log-prob | return | old value |
-// action (index int / act_n floats, [j][64]).
+// action (index int / act_n floats, [j][64]).  Slot r of minibatch mb; returns the sample's advantage.
+__device__ __forceinline__ float ftg_permute_slot(const float* __restrict__ recs, int stride, int D, const FeistelKey& fk, long long n_total,
+                                                  long long batch_size, long long per, long long mb, long long r, int identity, int act_start,
+                                                  int act_n, int cont, int rec_floats, float* __restrict__ out, bool& valid) {
+    const int Dp = (D + 3) & ~3, A = cont ? act_n : 1;
+    const long long pos = mb * batch_size + r, s = mb * per + r;
+    valid = r < batch_size && pos < n_total;
+    float* blk = out + (s >> 6) * rec_floats;
+    const int j = (int)(s & 63);
+    long long sidx = 0;
+    if (valid) sidx = identity ? pos : feistel_permute(pos, n_total, fk);
+    const float* rp = recs + sidx * stride;                       // obs (Dp) | action (A) | adv, logp, ret, val: sample record (update_ft.cuh)
+    for (int d4 = 0; d4 < Dp; d4 += 4)
+        *reinterpret_cast<float4*>(blk + j * Dp + d4) = valid ? *reinterpret_cast<const float4*>(rp + d4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float* sc = blk + 64 * Dp;
+    const float adv = valid ? rp[Dp + A] : 0.f;
+    sc[j] = adv;
+    sc[64 + j] = valid ? rp[Dp + A + 1] : 0.f;
+    sc[128 + j] = valid ? rp[Dp + A + 2] : 0.f;
+    sc[192 + j] = valid ? rp[Dp + A + 3] : 0.f;
+    if (cont) {
+        for (int a = 0; a < act_n; ++a) sc[256 + a * 64 + j] = valid ? rp[Dp + a] : 0.f;
+    } else {
+        int ai = valid ? __float_as_int(rp[Dp]) - act_start : 0;
+        ai = ai < 0 ? 0 : (ai >= act_n ? act_n - 1 : ai);
+        reinterpret_cast<int*>(sc)[256 + j] = ai;
+    }
+    return adv;
+}
 __global__ void __launch_bounds__(256) ftg_permute_kernel(const float* __restrict__ recs, int stride, int D, const FeistelKey fk, long long n_total,
                                                           long long batch_size, int n_mb, int tiles_per_mb, int identity, int act_start, int act_n,
                                                           int cont, int rec_floats, float* __restrict__ out) {
     const long long per = (long long)tiles_per_mb * 64;
     const long long slots = per * n_mb;
-    const int Dp = (D + 3) & ~3, A = cont ? act_n : 1;
     for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (long long)gridDim.x * blockDim.x) {
-        const long long mb = s / per, r = s - mb * per;
-        const long long pos = mb * batch_size + r;
-        const bool valid = r < batch_size && pos < n_total;
-        float* blk = out + (s >> 6) * rec_floats;
-        const int j = (int)(s & 63);
-        long long sidx = 0;
-        if (valid) sidx = identity ? pos : feistel_permute(pos, n_total, fk);
-        const float* rp = recs + sidx * stride;                       // obs (Dp) | action (A) | adv, logp, ret, val: sample record (update_ft.cuh)
-        for (int d4 = 0; d4 < Dp; d4 += 4)
-            *reinterpret_cast<float4*>(blk + j * Dp + d4) = valid ? *reinterpret_cast<const float4*>(rp + d4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float* sc = blk + 64 * Dp;
-        sc[j] = valid ? rp[Dp + A] : 0.f;
-        sc[64 + j] = valid ? rp[Dp + A + 1] : 0.f;
-        sc[128 + j] = valid ? rp[Dp + A + 2] : 0.f;
-        sc[192 + j] = valid ? rp[Dp + A + 3] : 0.f;
-        if (cont) {
-            for (int a = 0; a < act_n; ++a) sc[256 + a * 64 + j] = valid ? rp[Dp + a] : 0.f;
-        } else {
-            int ai = valid ? __float_as_int(rp[Dp]) - act_start : 0;
-            ai = ai < 0 ? 0 : (ai >= act_n ? act_n - 1 : ai);
-            reinterpret_cast<int*>(sc)[256 + j] = ai;
-        }
+        const long long mb = s / per;
+        bool valid;
+        ftg_permute_slot(recs, stride, D, fk, n_total, batch_size, per, mb, s - mb * per, identity, act_start, act_n, cont, rec_floats, out, valid);
+    }
+}
+// all epochs of an update in one launch + the minibatch advantage moments (see ft_permute_epochs_kernel, update_ft.cuh)
+__global__ void __launch_bounds__(256) ftg_permute_epochs_kernel(const float* __restrict__ recs, int stride, int D, const __grid_constant__ FeistelKeys fks,
+                                                                 long long n_total, long long batch_size, int tiles_per_mb, int act_start, int act_n,
+                                                                 int cont, int rec_floats, float* __restrict__ out, long long epoch_tiles,
+                                                                 double* __restrict__ partial) {
+    __shared__ double scratch[32];
+    const FeistelKey& fk = fks.k[blockIdx.z];
+    const long long per = (long long)tiles_per_mb * 64, mb = blockIdx.y;
+    float* o = out + (size_t)blockIdx.z * epoch_tiles * rec_floats;
+    double sm = 0, sq = 0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < per; r += (long long)gridDim.x * blockDim.x) {
+        bool valid;
+        const float adv = ftg_permute_slot(recs, stride, D, fk, n_total, batch_size, per, mb, r, 0, act_start, act_n, cont, rec_floats, o, valid);
+        if (valid) { sm += (double)adv; sq += (double)adv * (double)adv; }
+    }
+    sm = block_sum(sm, scratch); sq = block_sum(sq, scratch);
+    if (threadIdx.x == 0) {
+        double* pp = partial + (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 2;
+        pp[0] = sm; pp[1] = sq;
     }
 }
 
