@@ -53,6 +53,7 @@ static int g_opt_ftg = getenv("DRIL_FTG") ? atoi(getenv("DRIL_FTG")) : 1;   // g
 static int g_opt_tc_rollout = getenv("DRIL_TC_ROLLOUT") ? atoi(getenv("DRIL_TC_ROLLOUT")) : 1;   // tensor-core rollout (CartPole, [64,64])
 static int g_opt_tc_actor = getenv("DRIL_TC_ACTOR") ? atoi(getenv("DRIL_TC_ACTOR")) : 1;   // general rollout: actor forward on tcgen05 (rollout_gtc.cuh)
 static int g_opt_syn_rollout = getenv("DRIL_SYN_ROLLOUT") ? atoi(getenv("DRIL_SYN_ROLLOUT")) : 1;   // thread-per-env rollout (synthetic env, small policy)
+static int g_opt_persistent = getenv("DRIL_PERSISTENT") ? atoi(getenv("DRIL_PERSISTENT")) : 1;   // [64,64] tcgen05 update: all minibatch steps of an update in one cooperative launch
 static int g_opt_tail = getenv("DRIL_TAIL") ? atoi(getenv("DRIL_TAIL")) : 1;   // fused reduce/clip/Adam tail of the TC kernel
 // fp32 loss/grad kernel, wide nets: one net per pass with shared activation rows (fixed per policy at creation)
 static int g_opt_single_net = getenv("DRIL_SINGLE_NET") ? atoi(getenv("DRIL_SINGLE_NET")) : 1;
@@ -68,6 +69,7 @@ extern "C" int32_t dril_set_option(const char* key, int32_t value) {
     if (!strcmp(key, "tc_rollout")) { g_opt_tc_rollout = value; return DRIL_OK; }
     if (!strcmp(key, "syn_rollout")) { g_opt_syn_rollout = value; return DRIL_OK; }
     if (!strcmp(key, "tc_actor")) { g_opt_tc_actor = value; return DRIL_OK; }
+    if (!strcmp(key, "persistent")) { g_opt_persistent = value; return DRIL_OK; }
     if (!strcmp(key, "single_net")) { g_opt_single_net = value; return DRIL_OK; }   // policies created afterwards
     if (!strcmp(key, "mma")) { g_opt_mma = value; return DRIL_OK; }                 // policies created afterwards
     dril_set_error("unknown option '%s'", key);
@@ -1934,6 +1936,7 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
             } else if (ft) {
                 // tile records of this minibatch: written by ft_stage_epoch before the epoch's first step
                 FtArgs fa;
+                memset(&fa, 0, sizeof(fa));
                 fa.tiles = p->ft_tiles;
                 fa.tile0 = p->ft_epoch_tile0 + (mb.start / std::max<long long>(1, p->ft_batch)) * p->ft_tiles_per_mb;
                 const void* fn = pd.act_n == 1 ? (const void*)ppo_loss_grad_ft_kernel<1> : (const void*)ppo_loss_grad_ft_kernel<2>;
@@ -1978,6 +1981,51 @@ static int32_t minibatch_step(dril_policy* p, const BufDev& bd, const Minibatch&
         adam_finalize_kernel<<<1, 1024, 0, c->stream>>>(aa);
         DRIL_CUDA(cudaGetLastError());
     }
+    return DRIL_OK;
+}
+
+// update_ft.cuh, persistent mode: the n_mb * ne minibatch steps of `ne` staged epochs in ONE cooperative launch (reduction, peer
+// exchange, clip, KL stop and Adam in the kernel's tail; a grid barrier between steps).  *done = false when the conditions of the
+// fused tail do not hold (the caller then steps minibatch by minibatch).
+static int32_t ft_persistent_update(dril_policy* p, const BufDev& bd, const UpdateHyper& hp, const LossLaunch& ll, int n_mb, int ne, long long n_total,
+                                    long long batch_size, bool* done) {
+    dril_ctx* c = p->ctx;
+    const PolicyDesc& pd = p->pd;
+    *done = false;
+    const int n = pd.n_params + 6;
+    const bool fused = c->nranks == 1;
+    const bool p2p = c->nranks > 1 && c->p2p_enabled && n <= c->p2p.n_slots;
+    const long long tiles = (std::min<long long>(batch_size, n_total) + FT_TS - 1) / FT_TS;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, std::min(c->sm_count, p->gpart_ctas)));
+    if (!g_opt_persistent || !g_opt_tail || !(fused || p2p) || grid > c->sm_count || grid > P2P_MAX_CTA || n_mb * ne < 2) return DRIL_OK;
+    LossArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pd = pd; a.buf = bd; a.pack = p->pack; a.flat = p->flat; a.mbstats = p->mbstats; a.gpart = p->gpart;
+    a.stop_flag = p->stop_flag; a.hp = hp; a.M4 = ll.M4; a.weights_smem = ll.ws;
+    a.half_stride = p->gpart_ctas; a.small_splits = ll.splits; a.single_net = ll.single ? 1 : 0;
+    a.use_mma = ll.mma ? 1 : 0; a.stage_thin = ll.thin ? 1 : 0;
+    a.mb.n_total = n_total; a.mb.start = 0; a.mb.count = std::min<long long>(batch_size, n_total);
+    a.mb.global_count = (double)a.mb.count * c->nranks; a.mb.identity = 0;
+    AdamArgs aa;
+    aa.g = p->g; aa.flat = p->flat; aa.m = p->m; aa.v = p->v; aa.pack = p->pack; aa.flat2pack = p->flat2pack;
+    aa.flat2packT = p->flat2packT; aa.step = p->step; aa.iter_acc = p->iter_acc; aa.stop_flag = p->stop_flag;
+    aa.global_count = a.mb.global_count; aa.hp = hp; aa.n_params = pd.n_params; aa.apply_stats = 1;
+    TailArgs tl;
+    memset(&tl, 0, sizeof(tl));
+    tl.mode = fused ? 1 : 2;
+    tl.flat2g = p->flat2g; tl.f2planes = p->f2planes_one; tl.stats_off = pd.pack_fwd + pd.act_n; tl.sq_part = p->sq_part;
+    tl.adam = aa;
+    if (p2p) tl.pp = c->p2p;
+    FtArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.tiles = p->ft_tiles; fa.tile0 = 0;
+    fa.n_steps = n_mb * ne; fa.n_mb = n_mb; fa.tpm = p->ft_tiles_per_mb; fa.nranks = c->nranks;
+    fa.batch = batch_size; fa.n_total = n_total; fa.epoch_tiles = (long long)n_mb * p->ft_tiles_per_mb; fa.mbstats0 = p->mbstats;
+    const void* fn = pd.act_n == 1 ? (const void*)ppo_loss_grad_ft_kernel<1> : (const void*)ppo_loss_grad_ft_kernel<2>;
+    void* args[] = {(void*)&a, (void*)&tl, (void*)&fa};
+    Span sp(c, DRIL_K_LOSS_GRAD);
+    DRIL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FT_THREADS), args, FT_SMEM_BYTES, c->stream));
+    *done = true;
     return DRIL_OK;
 }
 
@@ -2031,6 +2079,11 @@ static int32_t update_async(dril_policy* p, dril_buffer* b, const dril_ppo_hyper
             }
             DRIL_TRY(allreduce_small(c, p->mbstats, n_mb * ne * 2, extra, n_extra));
             n_extra = 0;
+        }
+        if (staged_all && ft_active(p)) {
+            bool done = false;
+            DRIL_TRY(ft_persistent_update(p, b->d, hp, ll, n_mb, ne, n_total, batch_size, &done));
+            if (done) continue;
         }
         for (int e = 0; e < ne; ++e) {
             if (staged_all) p->ft_epoch_tile0 = (long long)e * n_mb * p->ft_tiles_per_mb;

@@ -638,10 +638,11 @@ struct AdamArgs {
 };
 
 // KL early stop of ppo.jl:235-238, decided BEFORE the step is applied, from the reduced statistics in g[n_params..]
-__device__ __forceinline__ int adam_stop(const AdamArgs& a) {
-    const float kl = a.g[a.n_params + 4] * (float)(1.0 / a.global_count);
+__device__ __forceinline__ int adam_stop(const AdamArgs& a, double global_count) {
+    const float kl = a.g[a.n_params + 4] * (float)(1.0 / global_count);
     return (a.apply_stats && a.hp.target_kl >= 0.f && kl > 1.5f * a.hp.target_kl) ? 1 : 0;
 }
+__device__ __forceinline__ int adam_stop(const AdamArgs& a) { return adam_stop(a, a.global_count); }
 // The per-iteration accumulators (learn_stats sums, applied-step count, running beta^t, step counter, stop flag):
 // threads 0..15 of ONE CTA, independent global round trips.  s_f[0..1] receive the Adam bias corrections 1 - beta^t.
 // `old` = iter_acc[tid] and invB = 1 / global_count may be fetched / computed by the caller ahead of time (they do not depend on

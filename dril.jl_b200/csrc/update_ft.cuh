@@ -78,6 +78,12 @@ static_assert(FT_G_XIMG + 2 * FT_XIMG <= FT_GROUP_BYTES, "group region too small
 struct FtArgs {
     const unsigned char* tiles;    // records of this epoch, [minibatch][tiles_per_mb]
     long long tile0;               // first record of this minibatch
+    // persistent mode (n_steps > 0, cooperative launch with the fused tail): ONE launch runs the minibatch steps 0 .. n_steps-1 of
+    // an update — step s is minibatch s % n_mb of staged epoch s / n_mb — separated by grid barriers; tile0 / LossArgs::mb /
+    // LossArgs::mbstats then describe nothing and are derived per step from the fields below
+    int n_steps, n_mb, tpm, nranks;
+    long long batch, n_total, epoch_tiles;
+    const double* mbstats0;        // advantage moments [epoch][minibatch][2]
 };
 
 // Sample records: the update gathers minibatches in shuffled order, and a gather from the time-major field arrays costs one
@@ -262,9 +268,28 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_s)), "r"(FT_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    const int n_steps = fa.n_steps > 0 ? fa.n_steps : 1;
+    uint32_t tb = 0;
+    for (int step = 0; step < n_steps; ++step) {
+    // this step's minibatch
+    long long mb_count = a.mb.count, tile0 = fa.tile0;
+    double gcount = a.mb.global_count;
+    const double* mbst = a.mbstats;
+    if (fa.n_steps > 0) {
+        const int e = step / fa.n_mb, i = step - e * fa.n_mb;
+        mb_count = min(fa.batch, fa.n_total - (long long)i * fa.batch);
+        tile0 = (long long)e * fa.epoch_tiles + (long long)i * fa.tpm;
+        gcount = (double)mb_count * fa.nranks;
+        mbst = fa.mbstats0 + 2 * ((size_t)e * fa.n_mb + i);
+    }
     if (tid == 0) {
+        // (every phase of the previous step's barriers has completed: its last MMAs were waited for before the end-of-pass)
 #pragma unroll
-        for (int i = 0; i < 12; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[0][0] + i)));
+        for (int i = 0; i < 12; ++i) {
+            if (step > 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&bars[0][0] + i)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[0][0] + i)));
+        }
+        if (step > 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&bar_stagger)));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bar_stagger)));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
@@ -322,7 +347,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+    tb = __shfl_sync(0xffffffffu, tmem_base_s, 0);
 #ifdef TC_TRACE
     if (tid == 0 && blockIdx.x == 0) g_tc_trace[0][30][1] = clock64();
 #endif
@@ -332,14 +357,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
 
     float adv_mean = 0.f, adv_den = 1.f;
     if (a.hp.normalize_advantage) {
-        const double n = a.mb.global_count;
-        const double mean = a.mbstats[0] / n;
-        double var = (a.mbstats[1] - n * mean * mean) / (n - 1.0);
+        const double n = gcount;
+        const double mean = mbst[0] / n;
+        double var = (mbst[1] - n * mean * mean) / (n - 1.0);
         if (var < 0.0) var = 0.0;
         adv_mean = (float)mean;
         adv_den = (float)sqrt(var) + 1e-8f;
     }
-    const float invB = (float)(1.0 / a.mb.global_count);
+    const float invB = (float)(1.0 / gcount);
     float stats[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float accb2_0 = 0.f, accb2_1 = 0.f;                               // head threads: sums of dL/dout (output-layer bias gradients)
     // delta scale of this thread's net in this group: a power of two fixed at the group's first tile with a non-zero gradient, so
@@ -349,10 +374,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
     float accb1 = 0.f, accW2_0 = 0.f, accb0 = 0.f, accW0_0 = 0.f, accW0_1 = 0.f, accW0_2 = 0.f, accW0_3 = 0.f;
 
     // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0 .. nt-1; group g takes j = g, g + 2, ...
-    const long long n_tiles = (a.mb.count + FT_TS - 1) / FT_TS;
+    const long long n_tiles = (mb_count + FT_TS - 1) / FT_TS;
     const int nt = (long long)blockIdx.x < n_tiles ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
     const int n_own = g ? nt / 2 : (nt + 1) / 2;
-    const unsigned char* rec0 = fa.tiles + (size_t)fa.tile0 * FT_TILE_BYTES;
+    const unsigned char* rec0 = fa.tiles + (size_t)tile0 * FT_TILE_BYTES;
     auto load_tile = [&](int it) {                                    // one thread: bulk copy of tile `it` of this group into record buffer it & 1
         const long long tile = (long long)blockIdx.x + (long long)(2 * it + g) * gridDim.x;
         const uint32_t dst = smg_base + FT_G_IN + (uint32_t)(it & 1) * FT_TILE_BYTES;
@@ -497,7 +522,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
         if (q < 2) {
             const float4 p0 = sPart[ms], p1 = sPart[64 + ms], p2 = sPart[128 + ms], p3 = sPart[192 + ms];
             const long long tile = (long long)blockIdx.x + (long long)(2 * it + g) * gridDim.x;
-            const bool valid = tile * FT_TS + ms < a.mb.count;
+            const bool valid = tile * FT_TS + ms < mb_count;
             float dmax;
             if (q == 0) {
                 float out[NOUT], dout[NOUT];
@@ -771,11 +796,21 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
 #ifdef TC_TRACE
     if (tid == 0 && blockIdx.x == 0) g_tc_trace[0][30][10] = clock64();
 #endif
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(FT_TMEM_COLS));
 #ifdef TC_TRACE
     if (tid == 0 && blockIdx.x == 0) g_tc_trace[0][30][3] = clock64();
 #endif
-    if (tl.mode) tc_fused_tail(a, tl, reinterpret_cast<float*>(sm + FT_OFF_GROUP + FT_G_P), scratch, s_f2);
+    bool stop = false;
+    if (tl.mode) stop = tc_fused_tail(a, tl, reinterpret_cast<float*>(sm + FT_OFF_GROUP + FT_G_P), scratch, s_f2, gcount);
+    if (stop) break;                                                  // target-KL stop: identical in every CTA (ppo.jl:235-238)
+    if (step + 1 < n_steps) {
+        // the next step builds its weight images from the parameters every CTA's Adam slice just wrote
+        __threadfence();
+        cooperative_groups::this_grid().sync();
+    }
+    }   // minibatch steps
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(FT_TMEM_COLS));
 #ifdef TC_TRACE
     if (tid == 0 && blockIdx.x == 0) {
         unsigned long long gt;

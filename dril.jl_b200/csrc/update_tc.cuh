@@ -622,11 +622,13 @@ struct TailArgs {
     P2PDev pp;
 };
 
-__device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs& tl, float* s_red /* [8][64] */, double* scratch,
-                                              float* s_f) {
+// Returns the target-KL stop flag (identical in every CTA).  global_count < 0: the minibatch size over all ranks is tl.adam's.
+__device__ __forceinline__ bool tc_fused_tail(const LossArgs& a, const TailArgs& tl, float* s_red /* [8][64] */, double* scratch,
+                                              float* s_f, double global_count = -1.0) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     const AdamArgs& ad = tl.adam;
+    const double gcount = global_count > 0.0 ? global_count : ad.global_count;
     const int tid = threadIdx.x, nb = (int)gridDim.x;
     const int n = ad.n_params + 6;
     const int per = (n + nb - 1) / nb;
@@ -736,7 +738,7 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
     // CTA 0's statistic accumulators do not depend on the other CTAs either
     double acc_old = 0.0;
     float acc_invB = 0.f;
-    if (blockIdx.x == 0 && tid < 16) { acc_old = ad.iter_acc[tid]; acc_invB = (float)(1.0 / ad.global_count); }
+    if (blockIdx.x == 0 && tid < 16) { acc_old = ad.iter_acc[tid]; acc_invB = (float)(1.0 / gcount); }
     sq = block_sum(sq, scratch);
     if (tid == 0) tl.sq_part[blockIdx.x] = sq;
     __threadfence();
@@ -747,12 +749,12 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
     q = block_sum(q, scratch);
     TAIL_MARK(8);
     const float norm = (float)sqrt(q);
-    const int stop = adam_stop(ad);
+    const int stop = adam_stop(ad, gcount);
     TAIL_MARK(9);
     if (blockIdx.x == 0) adam_accumulate_pre(ad, norm, stop, tid, s_f, acc_old, acc_invB);
     TAIL_MARK(10);
     if (tl.mode == 2 && blockIdx.x == 0 && tid == 32) *tl.pp.local_seq = seq;       // every CTA read the old value before the barrier
-    if (stop) return;
+    if (stop) return true;
     float scale = 1.f;
     if (ad.hp.max_grad_norm >= 0.f && norm > ad.hp.max_grad_norm) scale = ad.hp.max_grad_norm / norm;
     const float c1 = (float)(1.0 - bp1 * (double)ad.hp.beta1), c2 = (float)(1.0 - bp2 * (double)ad.hp.beta2);
@@ -769,6 +771,7 @@ __device__ __forceinline__ void tc_fused_tail(const LossArgs& a, const TailArgs&
     }
     for (int p = p_lo + 64 + tid; p < min(p_hi, ad.n_params); p += blockDim.x) adam_param(ad, p, scale, c1, c2);   // slices wider than 64
     TAIL_MARK(4);
+    return false;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) ppo_loss_grad_tc_kernel(const __grid_constant__ LossArgs a, const __grid_constant__ TailArgs tl) {

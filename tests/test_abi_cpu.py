@@ -48,7 +48,7 @@ def test_struct_layouts_match_header():
 def test_kernel_path_options(lib):
     """dril_set_option needs no device: every documented switch is accepted, unknown keys are an error with a message."""
     import dril_b200
-    for key in ("tc", "ft", "ftg", "defer_critic", "syn_rollout", "tc_actor", "fused_tail", "tc_rollout", "single_net", "mma"):
+    for key in ("tc", "ft", "ftg", "defer_critic", "syn_rollout", "tc_actor", "persistent", "fused_tail", "tc_rollout", "single_net", "mma"):
         dril_b200.set_option(key, 1)
     with pytest.raises(dril_b200.DrilError):
         dril_b200.set_option("no_such_switch", 1)

@@ -613,11 +613,12 @@ def test_full_size_properties(D):
 # ------------------------------------------------------------------------------------------
 # kernel-path switches: every combination must agree with the oracle (and hence with each other)
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("tc,tail,tc_rollout", [(1, 1, 1), (1, 0, 1), (0, 0, 0), (1, 1, 0), (0, 0, 1)])
-def test_kernel_paths_vs_oracle(D, tc, tail, tc_rollout):
-    """The tensor-core loss/grad kernel (with and without its fused reduce/clip/Adam tail), the fp32 CUDA-core kernel,
-    the tensor-core rollout and the general rollout are interchangeable: same buffer, same updated parameters."""
-    opts = {"tc": tc, "fused_tail": tail, "tc_rollout": tc_rollout, "ftg": 1 if tc else 0}   # tc = 0: the general mma.sync kernel
+@pytest.mark.parametrize("tc,tail,tc_rollout,persistent", [(1, 1, 1, 1), (1, 1, 1, 0), (1, 0, 1, 1), (0, 0, 0, 1), (1, 1, 0, 1), (0, 0, 1, 1)])
+def test_kernel_paths_vs_oracle(D, tc, tail, tc_rollout, persistent):
+    """The tensor-core loss/grad kernel (all minibatch steps in one persistent launch, one launch per step with the fused
+    reduce/clip/Adam tail, and without the tail), the fp32 CUDA-core kernel, the tensor-core rollout and the general rollout are
+    interchangeable: same buffer, same updated parameters."""
+    opts = {"tc": tc, "fused_tail": tail, "tc_rollout": tc_rollout, "ftg": 1 if tc else 0, "persistent": persistent}   # tc = 0: the general mma.sync kernel
     try:
         for k, v in opts.items():
             D.set_option(k, v)
