@@ -344,7 +344,8 @@ def run_ours(args):
                 "kind::f16 with the fp16 hi/lo split (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM, 22 significant bits, gradient "
                 "error ~1e-6 vs the oracle), deltas rescaled per tile by a power of two; achieved = fp32-equivalent algorithmic FLOPs "
                 "(fwd + 2x bwd) / time, peak = measured dense bf16 by contract; tensor_issued_tflops counts the three issued products; "
-                "the kernel is co-limited by CUDA-core issue, MUFU (tanh) and shared-memory wavefronts, see DESIGN.md")
+                "one persistent cooperative launch runs all minibatch steps of the iteration (Adam and the gradient exchange in its tail); "
+                "the kernel is bound by the shared-memory pipe (UMMA operand reads + LDS/STS of the CUDA-core phases), see DESIGN.md")
     elif lg_path == "mma":
         note = ("general-shape loss_grad kernel: hidden GEMMs on warp-level tensor-core tiles (mma.sync m16n8k8 TF32, 3xTF32 split, "
                 "fp32-level accuracy), thin layers and loss head on CUDA cores; achieved = fp32-equivalent algorithmic FLOPs / time, "
@@ -353,7 +354,9 @@ def run_ours(args):
         note = ("fp32 CUDA-core kernels; frac is against the tensor peak by contract, frac_of_fp32_fma_peak is the pipe it actually runs on")
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of workload C2
     # (profiles/r02_lossgrad_ft_summary.txt, profiles/r01_rollout_tc_final_summary.txt); null for other workloads
-    traffic_c2 = {"loss_grad": 5.41e6 + 0.0, "rollout": 192.3e3} if (main_w == "c2" and lg_path == "tensor") else {}
+    # (the loss/grad launch is the persistent kernel: one launch = the 16 minibatch steps of an iteration, 76.2 MB read + 3.7 MB written
+    # against 75.5 MB of algorithmic record bytes)
+    traffic_c2 = {"loss_grad": 76.2e6 + 3.7e6, "rollout": 192.3e3} if (main_w == "c2" and lg_path == "tensor") else {}
     roof.update({"kernel": dominant, "traffic": traffic_c2.get(dominant),
                  "peak_source": pk["source"] + (" sustained bf16" if roof["bound"] == "tensor" else " copy"), "note": note})
     w = WORKLOADS[main_w]
