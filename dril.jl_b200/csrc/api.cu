@@ -357,7 +357,8 @@ extern "C" int32_t dril_ctx_create(int32_t device, uint64_t seed, dril_ctx** out
         DRIL_CUDA(cudaFuncSetAttribute(critic_values_ftg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX - 2048));
         DRIL_CUDA(cudaFuncSetAttribute(critic_values_ftg_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DRIL_SMEM_MAX - 2048));
     }
-    DRIL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM_BYTES));
+    DRIL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM_BYTES));
+    DRIL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM_BYTES));
     *out = c;
     return DRIL_OK;
 }
@@ -1100,13 +1101,12 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
         a.n_tiles = (int)((N + RT_ENVS - 1) / RT_ENVS);
         {
             Span sp(c, DRIL_K_ROLLOUT);
-            static int per_sm = 0;                                       // registers allow one 512-thread CTA per SM today
-            if (!per_sm) {
-                DRIL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_tc_kernel, RT_THREADS, RT_SMEM_BYTES));
-                per_sm = std::max(per_sm, 1);
-            }
-            const int grid = std::min(a.n_tiles, per_sm * c->sm_count);
-            rollout_tc_kernel<<<grid, RT_THREADS, RT_SMEM_BYTES, c->stream>>>(a, b->tcs);
+            // at least two tiles per SM: the two-CTAs-per-SM build (64 registers) overlaps two per-step chains
+            static const int two_opt = getenv("DRIL_TC_ROLLOUT_2CTA") ? atoi(getenv("DRIL_TC_ROLLOUT_2CTA")) : 1;
+            const bool two = two_opt && a.n_tiles >= 2 * c->sm_count;
+            const int grid = std::min(a.n_tiles, (two ? 2 : 1) * c->sm_count);
+            if (two) rollout_tc_kernel<2><<<grid, RT_THREADS, RT_SMEM_BYTES, c->stream>>>(a, b->tcs);
+            else rollout_tc_kernel<1><<<grid, RT_THREADS, RT_SMEM_BYTES, c->stream>>>(a, b->tcs);
             DRIL_CUDA(cudaGetLastError());
         }
         {

@@ -96,7 +96,10 @@ __device__ __forceinline__ void rt_mma_f16_ss(uint32_t d, uint64_t da, uint64_t 
                  "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
 
-__global__ void __launch_bounds__(RT_THREADS, 1) rollout_tc_kernel(const __grid_constant__ RolloutArgs a, const TcRolloutScratch sc) {
+// MINB = 2: register budget of two resident CTAs per SM (64 registers per thread): used when every SM has at least two tiles, so
+// that two per-step latency chains overlap (throughput regime, C4); MINB = 1 keeps the shortest chain for one tile per SM (C2)
+template <int MINB>
+__global__ void __launch_bounds__(RT_THREADS, MINB) rollout_tc_kernel(const __grid_constant__ RolloutArgs a, const TcRolloutScratch sc) {
     extern __shared__ __align__(1024) unsigned char rt_smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base_s;
