@@ -198,6 +198,9 @@ def measure(D, ctx, dist, rank, world, local, wname, steps, repeats, warmup, p2p
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # every allocation up front, then all ranks together: no rank sits in a cudaMalloc while a peer's GPU already spins in an exchange
+    L.check(lib.dril_iteration_prepare(env.h, agent.device.h, buf.h, int(alg.epochs), int(alg.batch_size)))
+    barrier()
     # ---- warm-up: at least W (>= 3) iterations and at least 0.3 s of work (sustained clocks, steady-state enqueue path) ----
     t_w = time.perf_counter()
     n_w = 0

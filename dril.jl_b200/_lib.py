@@ -101,6 +101,7 @@ PROTOTYPES = {
     "dril_ppo_loss_grad": [P, P, P, P, P, P, P, c_i64, C.POINTER(PPOHyper), C.POINTER(c_f32), P, P],
     "dril_optimizer_step": [P, P, c_i64, C.POINTER(PPOHyper), C.POINTER(c_f32)],
     "dril_ppo_update": [P, P, C.POINTER(PPOHyper), c_i32, c_i64, c_u64, c_u64, C.POINTER(IterStats)],
+    "dril_iteration_prepare": [P, P, P, c_i32, c_i64],
     "dril_ppo_iteration_async": [P, P, P, C.POINTER(PPOHyper), c_i32, c_i64, c_u64, c_u64],
     "dril_iteration_result": [P, C.POINTER(IterStats)],
     "dril_explained_variance": [P, C.POINTER(c_f32)],

@@ -364,6 +364,8 @@ def train(agent, env, alg, max_steps, callbacks=None, sync_every_iteration=True)
     total_fps = learn["fps"]
     agent.device.set_params(agent.train_state.parameters)     # host parameters are the source of truth
     lib = agent.ctx.lib
+    # all lazily made allocations up front (data-parallel callers synchronise their ranks after this: `on_training_start` is the hook)
+    L.check(lib.dril_iteration_prepare(env.h, agent.device.h, roll_buffer.h, int(alg.epochs), int(alg.batch_size)))
     to["setup"] = time.time() - t_setup
     if not _hook(callbacks, "on_training_start", dict(locals())):
         return None

@@ -1064,6 +1064,32 @@ extern "C" int32_t dril_env_num_envs(dril_env* e, int64_t* n) {
 }
 
 // Launch the rollout engine. policy may be NULL (compat paths).
+// scratch of the deferred-critic rollouts (final observations + the compact list of truncated terminal observations)
+static int32_t ensure_tcs(dril_buffer* b) {
+    if (b->tcs_slab) return DRIL_OK;
+    const size_t cap = (size_t)b->d.T * b->d.N, N = (size_t)b->d.N;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_last = 0, o_tobs = o_last + al(N * 16), o_tidx = o_tobs + al(cap * 16), o_cnt = o_tidx + al(cap * 8);
+    DRIL_CUDA(cudaMalloc(&b->tcs_slab, o_cnt + 256));
+    char* base = (char*)b->tcs_slab;
+    b->tcs.last_obs = (float*)(base + o_last); b->tcs.trunc_obs = (float*)(base + o_tobs);
+    b->tcs.trunc_idx = (long long*)(base + o_tidx); b->tcs.trunc_count = (unsigned int*)(base + o_cnt);
+    b->tcs.cap = (unsigned int)std::min<size_t>(cap, 0x7fffffffu);
+    return DRIL_OK;
+}
+static int32_t ensure_dcs(dril_buffer* b) {
+    if (b->dcs_slab) return DRIL_OK;
+    const size_t cap = (size_t)b->d.T * b->d.N, Db = (size_t)b->d.obs_dim * 4, N = (size_t)b->d.N;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_last = 0, o_tobs = o_last + al(N * Db), o_tidx = o_tobs + al(cap * Db), o_cnt = o_tidx + al(cap * 8);
+    DRIL_CUDA(cudaMalloc(&b->dcs_slab, o_cnt + 256));
+    char* base = (char*)b->dcs_slab;
+    b->dcs.last_obs = (float*)(base + o_last); b->dcs.trunc_obs = (float*)(base + o_tobs);
+    b->dcs.trunc_idx = (long long*)(base + o_tidx); b->dcs.trunc_count = (unsigned int*)(base + o_cnt);
+    b->dcs.cap = (unsigned int)std::min<size_t>(cap, 0x7fffffffu);
+    return DRIL_OK;
+}
+
 static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const void* forced_dev, float* obs_out_dev,
                               int T, int base_flags) {
     dril_ctx* c = e->ctx;
@@ -1086,16 +1112,7 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
     if (has_policy && !general_only && g_opt_tc_rollout && !d.normalize && d.kind == DRIL_ENV_CARTPOLE && d.obs_dim == 4 && T > 0 && tc_eligible(a.pd) &&
         T == b->d.T) {
         // tensor-core path: actor-only step loop (64 envs per CTA) + one batched critic pass for values / bootstrap values
-        if (!b->tcs_slab) {
-            const size_t cap = (size_t)b->d.T * b->d.N;
-            auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-            const size_t o_last = 0, o_tobs = o_last + al((size_t)N * 16), o_tidx = o_tobs + al(cap * 16), o_cnt = o_tidx + al(cap * 8);
-            DRIL_CUDA(cudaMalloc(&b->tcs_slab, o_cnt + 256));
-            char* base = (char*)b->tcs_slab;
-            b->tcs.last_obs = (float*)(base + o_last); b->tcs.trunc_obs = (float*)(base + o_tobs);
-            b->tcs.trunc_idx = (long long*)(base + o_tidx); b->tcs.trunc_count = (unsigned int*)(base + o_cnt);
-            b->tcs.cap = (unsigned int)std::min<size_t>(cap, 0x7fffffffu);
-        }
+        DRIL_TRY(ensure_tcs(b));
         DRIL_CUDA(cudaMemsetAsync(b->tcs.trunc_count, 0, 4, c->stream));
         a.flags = flags; a.M4 = RT_ENVS;
         a.n_tiles = (int)((N + RT_ENVS - 1) / RT_ENVS);
@@ -1181,16 +1198,7 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
     const bool defer = has_policy && g_opt_defer_critic && g_opt_ftg && ftg_eligible(a.pd) && !b->is_view && T == b->d.T && T > 0 &&
                        !(base_flags & RO_DETERMINISTIC);
     if (defer) {
-        if (!b->dcs_slab) {
-            const size_t cap = (size_t)b->d.T * b->d.N, Db = (size_t)d.obs_dim * 4;
-            auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-            const size_t o_last = 0, o_tobs = o_last + al((size_t)N * Db), o_tidx = o_tobs + al(cap * Db), o_cnt = o_tidx + al(cap * 8);
-            DRIL_CUDA(cudaMalloc(&b->dcs_slab, o_cnt + 256));
-            char* base = (char*)b->dcs_slab;
-            b->dcs.last_obs = (float*)(base + o_last); b->dcs.trunc_obs = (float*)(base + o_tobs);
-            b->dcs.trunc_idx = (long long*)(base + o_tidx); b->dcs.trunc_count = (unsigned int*)(base + o_cnt);
-            b->dcs.cap = (unsigned int)std::min<size_t>(cap, 0x7fffffffu);
-        }
+        DRIL_TRY(ensure_dcs(b));
         DRIL_CUDA(cudaMemsetAsync(b->dcs.trunc_count, 0, 4, c->stream));
         a.dc = b->dcs;
         flags |= RO_DEFER_CRITIC;
@@ -1775,7 +1783,7 @@ static int32_t plan_loss(dril_policy* p, LossLaunch* out) {
 }
 
 // per-sample records of the whole buffer (update_ft.cuh): one streaming pass per update, read by every epoch's permute kernel
-static int32_t ft_pack_records(dril_policy* p, const BufDev& bd, long long n_total) {
+static int32_t ensure_ft_recs(dril_policy* p, const BufDev& bd, long long n_total) {
     dril_ctx* c = p->ctx;
     const int stride = ft_rec_stride(bd.obs_dim, bd.act_dim);
     const size_t need = (size_t)n_total * stride;
@@ -1786,6 +1794,22 @@ static int32_t ft_pack_records(dril_policy* p, const BufDev& bd, long long n_tot
         p->ft_recs_floats = need;
     }
     p->ft_rec_stride = stride;
+    return DRIL_OK;
+}
+static int32_t ensure_ft_tiles(dril_policy* p, size_t bytes) {
+    dril_ctx* c = p->ctx;
+    if (p->ft_tiles_bytes < bytes) {
+        if (p->ft_tiles) { DRIL_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(p->ft_tiles); }
+        p->ft_tiles = nullptr; p->ft_tiles_bytes = 0;
+        DRIL_CUDA(cudaMalloc((void**)&p->ft_tiles, bytes));
+        p->ft_tiles_bytes = bytes;
+    }
+    return DRIL_OK;
+}
+static int32_t ft_pack_records(dril_policy* p, const BufDev& bd, long long n_total) {
+    dril_ctx* c = p->ctx;
+    DRIL_TRY(ensure_ft_recs(p, bd, n_total));
+    const int stride = p->ft_rec_stride;
     const int grid = (int)std::max<long long>(1, std::min<long long>((n_total + 255) / 256, (long long)c->sm_count * 8));
     Span sp(c, DRIL_K_PERMUTE);
     ft_pack_records_kernel<<<grid, 256, 0, c->stream>>>(bd, n_total, stride, p->ft_recs);
@@ -1816,12 +1840,7 @@ static int32_t ftg_stage_epoch(dril_policy* p, const BufDev& bd, const FeistelKe
     const int cont = p->pd.act_kind == DRIL_ACT_CONTINUOUS ? 1 : 0;
     const int rf = ftg_rec_floats(p->pd.obs_dim, cont, p->pd.act_n);
     const size_t bytes = (size_t)n_mb * tpm * rf * 4;
-    if (p->ft_tiles_bytes < bytes) {
-        if (p->ft_tiles) { DRIL_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(p->ft_tiles); }
-        p->ft_tiles = nullptr; p->ft_tiles_bytes = 0;
-        DRIL_CUDA(cudaMalloc((void**)&p->ft_tiles, bytes));
-        p->ft_tiles_bytes = bytes;
-    }
+    DRIL_TRY(ensure_ft_tiles(p, bytes));
     p->ft_tiles_per_mb = tpm; p->ft_batch = batch_size;
     const long long slots = (long long)n_mb * tpm * 64;
     const int grid = (int)std::max<long long>(1, std::min<long long>((slots + 255) / 256, (long long)c->sm_count * 8));
@@ -1836,12 +1855,7 @@ static int32_t ft_stage_epoch(dril_policy* p, const BufDev& bd, const FeistelKey
     const int n_mb = (int)((n_total + batch_size - 1) / batch_size);
     const int tpm = (int)((std::min<long long>(batch_size, n_total) + FT_TS - 1) / FT_TS);
     const size_t bytes = (size_t)n_mb * tpm * FT_TILE_BYTES;
-    if (p->ft_tiles_bytes < bytes) {
-        if (p->ft_tiles) { DRIL_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(p->ft_tiles); }
-        p->ft_tiles = nullptr; p->ft_tiles_bytes = 0;
-        DRIL_CUDA(cudaMalloc((void**)&p->ft_tiles, bytes));
-        p->ft_tiles_bytes = bytes;
-    }
+    DRIL_TRY(ensure_ft_tiles(p, bytes));
     p->ft_tiles_per_mb = tpm; p->ft_batch = batch_size;
     const long long slots = (long long)n_mb * tpm * FT_TS;
     const int grid = (int)std::max<long long>(1, std::min<long long>((slots + 255) / 256, (long long)c->sm_count * 8));
@@ -1869,12 +1883,7 @@ static int32_t ft_stage_epochs(dril_policy* p, const BufDev& bd, const FeistelKe
     const size_t bytes = (size_t)ne * epoch_tiles * tile_bytes;
     static const size_t budget = (getenv("DRIL_STAGE_ALL_MB") ? (size_t)atoll(getenv("DRIL_STAGE_ALL_MB")) : 8192) << 20;
     if (bytes > budget) return DRIL_OK;
-    if (p->ft_tiles_bytes < bytes) {
-        if (p->ft_tiles) { DRIL_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(p->ft_tiles); }
-        p->ft_tiles = nullptr; p->ft_tiles_bytes = 0;
-        DRIL_CUDA(cudaMalloc((void**)&p->ft_tiles, bytes));
-        p->ft_tiles_bytes = bytes;
-    }
+    DRIL_TRY(ensure_ft_tiles(p, bytes));
     p->ft_tiles_per_mb = tpm; p->ft_batch = batch_size;
     Span sp(c, DRIL_K_PERMUTE);
     const dim3 grid(bpm, n_mb, ne);
@@ -1997,7 +2006,10 @@ static int32_t ft_persistent_update(dril_policy* p, const BufDev& bd, const Upda
     const bool p2p = c->nranks > 1 && c->p2p_enabled && n <= c->p2p.n_slots;
     const long long tiles = (std::min<long long>(batch_size, n_total) + FT_TS - 1) / FT_TS;
     const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, std::min(c->sm_count, p->gpart_ctas)));
-    if (!g_opt_persistent || !g_opt_tail || !(fused || p2p) || grid > c->sm_count || grid > P2P_MAX_CTA || n_mb * ne < 2) return DRIL_OK;
+    // single GPU only by default: with the peer exchange inside the step loop an 8-GPU run stopped making progress (2 and 4 GPUs
+    // pass; not understood yet), so data-parallel updates keep one launch per minibatch step unless "persistent" is 2
+    if (!g_opt_persistent || (c->nranks > 1 && g_opt_persistent < 2) || !g_opt_tail || !(fused || p2p) || grid > c->sm_count ||
+        grid > P2P_MAX_CTA || n_mb * ne < 2) return DRIL_OK;
     LossArgs a;
     memset(&a, 0, sizeof(a));
     a.pd = pd; a.buf = bd; a.pack = p->pack; a.flat = p->flat; a.mbstats = p->mbstats; a.gpart = p->gpart;
@@ -2203,6 +2215,43 @@ extern "C" int32_t dril_ppo_update(dril_policy* p, dril_buffer* b, const dril_pp
     DRIL_CUDA(cudaEventElapsedTime(&ms, p->ev[1], p->ev[2]));
     s.update_ms = ms;
     if (stats_out) *stats_out = s;
+    return DRIL_OK;
+}
+
+// Every allocation the first iterations would otherwise make lazily (result slots, pinned records, sample / tile records,
+// advantage-moment buffers, deferred-critic scratch).  Data-parallel hosts call it on every rank and then synchronise the ranks
+// BEFORE the first iteration: a rank that is still inside cudaMalloc / cudaMallocHost while a peer's GPU already spins in a
+// peer-memory exchange waiting for it can stall for a long time (driver calls may need every peer-mapped device).
+extern "C" int32_t dril_iteration_prepare(dril_env* e, dril_policy* p, dril_buffer* b, int32_t epochs, int64_t batch_size) {
+    DRIL_TRY(check_compat(e, p, b));
+    DRIL_REQUIRE(batch_size >= 1 && epochs >= 0, "bad prepare arguments");
+    dril_ctx* c = e->ctx;
+    DRIL_CUDA(cudaSetDevice(c->device));
+    for (int si = 0; si < DRIL_RESULT_SLOTS; ++si) {
+        dril_policy::Slot& sl = p->slots[si];
+        if (!sl.host) {
+            DRIL_CUDA(cudaMallocHost(&sl.host, sizeof(IterRecord)));
+            for (int i = 0; i < 4; ++i) DRIL_CUDA(cudaEventCreate(&sl.ev[i]));
+        }
+    }
+    if (!p->rec_dev) DRIL_CUDA(cudaMalloc(&p->rec_dev, sizeof(IterRecord) * DRIL_RESULT_SLOTS));
+    const long long n_total = b->d.T * b->d.N;
+    const int n_mb = (int)((n_total + batch_size - 1) / batch_size);
+    const int ne = std::max(1, std::min<int>(DRIL_MAX_EPOCHS_BATCHED, epochs));
+    const int bpm = (int)std::max<long long>(1, std::min<long long>(64, (std::min<long long>(batch_size, n_total) + 2047) / 2048));
+    DRIL_TRY(ensure_mbstats(p, n_mb * ne, bpm));
+    if (ftg_active(p) || ft_active(p)) {
+        DRIL_TRY(ensure_ft_recs(p, b->d, n_total));
+        const int tpm = (int)((std::min<long long>(batch_size, n_total) + 63) / 64);
+        const int cont = p->pd.act_kind == DRIL_ACT_CONTINUOUS ? 1 : 0;
+        const size_t tile_bytes = ftg_active(p) ? (size_t)ftg_rec_floats(p->pd.obs_dim, cont, p->pd.act_n) * 4 : (size_t)FT_TILE_BYTES;
+        const size_t budget = (getenv("DRIL_STAGE_ALL_MB") ? (size_t)atoll(getenv("DRIL_STAGE_ALL_MB")) : 8192) << 20;
+        const size_t all = (size_t)ne * n_mb * tpm * tile_bytes;
+        DRIL_TRY(ensure_ft_tiles(p, all <= budget ? all : (size_t)n_mb * tpm * tile_bytes));
+    }
+    if (!e->d.normalize && e->d.kind == DRIL_ENV_CARTPOLE && tc_eligible(p->pd)) DRIL_TRY(ensure_tcs(b));
+    if (ftg_eligible(p->pd)) DRIL_TRY(ensure_dcs(b));
+    DRIL_CUDA(cudaStreamSynchronize(c->stream));
     return DRIL_OK;
 }
 

@@ -295,6 +295,10 @@ int32_t dril_optimizer_step(dril_policy* p, const float* grads, int64_t n, const
 int32_t dril_ppo_update(dril_policy* p, dril_buffer* buf, const dril_ppo_hyper* hyper, int32_t epochs,
                         int64_t batch_size, uint64_t shuffle_seed, uint64_t epoch_counter,
                         dril_iter_stats* stats_out);
+/* Makes every allocation the first iterations would otherwise make lazily (result slots, sample / tile records, moment buffers,
+ * deferred-critic scratch).  Optional on one GPU; data-parallel hosts call it on every rank and synchronise the ranks before the
+ * first iteration, so that no rank is inside a cudaMalloc while a peer's GPU already spins in a peer-memory exchange. */
+int32_t dril_iteration_prepare(dril_env* env, dril_policy* policy, dril_buffer* buf, int32_t epochs, int64_t batch_size);
 /* one train! iteration (ppo.jl:154-297): rollout + GAE + update + explained variance.
  * The _async form only enqueues; dril_iteration_result waits for the OLDEST enqueued iteration whose result has not
  * been read yet and returns its statistics (one pinned device->host record per iteration).  Up to 4 iterations may

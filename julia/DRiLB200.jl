@@ -304,6 +304,9 @@ function DRiL.train!(agent::Agent, env::CudaBatchedEnv, alg::PPO{T}, max_steps::
     shuffle_seed = rand(agent.rng, UInt64)
     epoch_counter = UInt64(0)
     hook(f, loc) = isnothing(callbacks) || all(c -> f(c, loc), callbacks)
+    # all lazily made allocations up front (data-parallel hosts synchronise their ranks after this, e.g. in on_training_start)
+    check(ccall((:dril_iteration_prepare, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64),
+        env.h, p.h, roll_buffer.h, alg.epochs, alg.batch_size))
     hook(DRiL.on_training_start, Base.@locals) || return nothing
     # without callbacks nothing on the host can influence the next iteration: iteration i + 1 is enqueued before the record of
     # iteration i is read (FIFO of 4 slots in the library), so the device never waits for the host
