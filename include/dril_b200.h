@@ -132,7 +132,8 @@ int32_t dril_device_count(int32_t* count);
  *   "tc"          round-1 samples-on-lanes tcgen05 (3xTF32) loss/grad kernel for the "ft" shapes (used when "ft" is 0)
  *   "defer_critic" general rollout kernel: actor-only step loop, values from one batched tcgen05 critic pass afterwards
  *   "persistent"  "ft" kernel with the fused tail: all minibatch steps of an update (epochs x minibatches, tile records of all
- *                 epochs staged up front) run in ONE cooperative launch, a grid barrier between steps
+ *                 epochs staged up front) run in ONE cooperative launch, a grid barrier between steps; 1 = on a single GPU
+ *                 (default), 2 = also data parallel (peer exchange inside the loop: verified on 2 and 4 GPUs only)
  *   "tc_actor"    general rollout kernel with a deferred critic and >= 96 envs per SM: the actor's layers on tcgen05 inside the
  *                 step loop (128-env tiles, rollout_gtc.cuh) instead of mma.sync / FMA tiles
  *   "syn_rollout" thread-per-env rollout kernel for the synthetic env with a small policy (2 = always two envs per thread)
