@@ -45,7 +45,9 @@ def _worker(rank, world, port, out):
         return o
 
     res = {}
-    for path in ("nccl", "p2p"):
+    for path in ("nccl", "p2p", "p2p_persistent"):
+        # "p2p_persistent": the exchange inside the persistent step loop (option "persistent" = 2; off by default in data-parallel runs)
+        D.set_option("persistent", 2 if path == "p2p_persistent" else 1)
         ctx = D.Context(device=rank, seed=0)
         uid = [D.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -57,7 +59,7 @@ def _worker(rank, world, port, out):
         alg = D.PPO(n_steps=T, batch_size=T * N_LOCAL // 2, epochs=EPOCHS, ent_coef=0.01)
         agent = D.Agent(layer, alg, rng=np.random.default_rng(0), ctx=ctx)
         agent.set_parameters(flat)
-        if path == "p2p":
+        if path != "nccl":
             ctx.comm_p2p_setup(all_gather, agent.device.n_params + 8)
         forced = np.random.default_rng(100 + rank).integers(1, 3, (T, N_LOCAL))
         buf = D.RolloutBuffer(env.observation_space(), env.action_space(), alg.gae_lambda, alg.gamma, T, N_LOCAL, ctx=ctx)
@@ -68,6 +70,7 @@ def _worker(rank, world, port, out):
         L.check(ctx.lib.dril_ppo_update(agent.device.h, buf.h, C.byref(h), alg.epochs, alg.batch_size, SEED, 3, C.byref(st)))
         res[path] = dict(params=agent.device.get_params(), shard=shard, stats=st.as_dict(), monitor=env.monitor_stats())
         buf.close(); env.close(); agent.device.close()
+    D.set_option("persistent", 1)
     # ---- data-parallel Pendulum + NormalizeWrapperEnv: one rollout with replayed actions, then the merged statistics --------
     ctx = D.Context(device=rank, seed=0)
     uid = [D.Context.comm_unique_id() if rank == 0 else None]
@@ -106,7 +109,7 @@ def test_dp_cuda_paths_vs_oracle(tmp_path):
     R = [np.load(out + f".rank{r}.npy", allow_pickle=True).item() for r in range(2)]
     spec = OP.PolicySpec(4, [64, 64], "discrete", 2, act_start=1)
     flat = OP.init_params(spec, seed=6)
-    for path in ("nccl", "p2p"):
+    for path in ("nccl", "p2p", "p2p_persistent"):
         np.testing.assert_array_equal(R[0][path]["params"], R[1][path]["params"], err_msg=f"{path}: ranks differ")
         shards = [R[r][path]["shard"] for r in range(2)]
         n_tot = T * N_LOCAL
@@ -135,6 +138,7 @@ def test_dp_cuda_paths_vs_oracle(tmp_path):
             m = float(np.mean(np.asarray(v, np.float32)))
             assert abs(st[k] - m) <= 2e-4 * max(1.0, abs(m)), (path, k, st[k], m)
     assert np.abs(R[0]["nccl"]["params"] - R[0]["p2p"]["params"]).max() <= 1e-6
+    np.testing.assert_array_equal(R[0]["p2p"]["params"], R[0]["p2p_persistent"]["params"])     # same kernel, same order of sums
     # ---- normaliser merge: both ranks hold the Chan merge over all shards ------------------------------------------------------
     s0, s1 = R[0]["norm"]["stats"], R[1]["norm"]["stats"]
     for k in ("obs_mean", "obs_var"):
