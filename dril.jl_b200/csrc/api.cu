@@ -1129,7 +1129,7 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
         {
             Span sp(c, DRIL_K_ROLLOUT);
             const long long tiles = ((long long)b->d.T * N + N + 127) / 128 + 8;
-            const int grid = (int)std::min<long long>(tiles, 2ll * c->sm_count);
+            const int grid = (int)std::min<long long>(tiles, 3ll * c->sm_count);
             critic_values_tc_kernel<<<grid, CV_THREADS, CV_SMEM_BYTES, c->stream>>>(a.pd, a.pack, b->d, b->tcs);
             DRIL_CUDA(cudaGetLastError());
         }

@@ -401,11 +401,13 @@ __global__ void __launch_bounds__(RT_THREADS, MINB) rollout_tc_kernel(const __gr
 // ---------------------------------------------------------------------------------------------------------
 // Batched critic: values of all T*N buffer observations, of the N final observations (bootstrap, trajectory.jl:65-70)
 // and of the terminal observations of truncated steps (trajectory.jl:57-61).  128 samples per tile, two threads per
-// sample (32 hidden features each), hidden layer on tcgen05 (3xTF32).  2 CTAs per SM (256 TMEM columns each).
+// sample (32 hidden features each), hidden layer on tcgen05 (fp16 hi/lo).  3 CTAs per SM (128 TMEM columns each).
 // ---------------------------------------------------------------------------------------------------------
 #define CV_THREADS 256
-#define CV_TMEM_COLS 256
-__global__ void __launch_bounds__(CV_THREADS, 2) critic_values_tc_kernel(const PolicyDesc pd, const float* __restrict__ pack, BufDev buf,
+#define CV_TMEM_COLS 128         // D 0..63 | packed hi operand 64..95 | packed lo operand 96..127: three CTAs per SM (registers: 85)
+#define CV_COL_HI 64
+#define CV_COL_LO 96
+__global__ void __launch_bounds__(CV_THREADS, 3) critic_values_tc_kernel(const PolicyDesc pd, const float* __restrict__ pack, BufDev buf,
                                                                         const TcRolloutScratch sc) {
     extern __shared__ __align__(1024) unsigned char rt_smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -477,7 +479,7 @@ __global__ void __launch_bounds__(CV_THREADS, 2) critic_values_tc_kernel(const P
                 h[4] = fmaf(xd, w1.x, h[4]); h[5] = fmaf(xd, w1.y, h[5]); h[6] = fmaf(xd, w1.z, h[6]); h[7] = fmaf(xd, w1.w, h[7]);
             }
             // fp16 hi/lo split (bounded operands, see rt_split_f16); A operand in TMEM: two consecutive K elements per 32-bit
-            // column, each thread inside its own 32 columns [f0, f0 + 32)
+            // column, feature k of the hi / lo operand in packed column k / 2
             uint32_t ph[4], pl[4];
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
@@ -488,9 +490,9 @@ __global__ void __launch_bounds__(CV_THREADS, 2) critic_values_tc_kernel(const P
                 ph[j >> 1] = *reinterpret_cast<const uint32_t*>(&vh);
                 pl[j >> 1] = *reinterpret_cast<const uint32_t*>(&vl);
             }
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my + RT_COL_HI + f0 + (c0 >> 1)), "r"(ph[0]), "r"(ph[1]),
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my + CV_COL_HI + ((f0 + c0) >> 1)), "r"(ph[0]), "r"(ph[1]),
                          "r"(ph[2]), "r"(ph[3]) : "memory");
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my + RT_COL_LO + f0 + (c0 >> 1)), "r"(pl[0]), "r"(pl[1]),
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my + CV_COL_LO + ((f0 + c0) >> 1)), "r"(pl[0]), "r"(pl[1]),
                          "r"(pl[2]), "r"(pl[3]) : "memory");
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -500,13 +502,13 @@ __global__ void __launch_bounds__(CV_THREADS, 2) critic_values_tc_kernel(const P
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int ps = 0; ps < 3; ++ps) {
-                const uint32_t acol = tb + (ps == 1 ? RT_COL_LO : RT_COL_HI);
+                const uint32_t acol = tb + (ps == 1 ? CV_COL_LO : CV_COL_HI);
                 const uint32_t bimg = sm_base + (ps == 2 ? RT_OFF_WT_LO : RT_OFF_WT_HI);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)          // K = 16: features 16 kk .. 16 kk + 15 = 8 packed columns
                     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(
                                      tb + RT_COL_D),
-                                 "r"(acol + (kk >> 1) * 32 + (kk & 1) * 8), "l"(tc_desc(bimg + kk * 256, 128, 1024, 0)), "r"(idesc),
+                                 "r"(acol + kk * 8), "l"(tc_desc(bimg + kk * 256, 128, 1024, 0)), "r"(idesc),
                                  "r"((ps | kk) ? 1u : 0u) : "memory");
             }
             tc_commit(&bar);
