@@ -292,6 +292,21 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
         if (step > 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&bar_stagger)));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bar_stagger)));
         asm volatile("fence.mbarrier_init.release.cluster;");
+        // first tile record of both groups: in flight while the weight images are (re)built (records do not depend on the parameters)
+        const long long n_tiles0 = (mb_count + FT_TS - 1) / FT_TS;
+        const int nt0 = (long long)blockIdx.x < n_tiles0 ? (int)((n_tiles0 - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+#pragma unroll
+        for (int gg = 0; gg < 2; ++gg) {
+            if ((gg ? nt0 / 2 : (nt0 + 1) / 2) > 0) {
+                const long long tile = (long long)blockIdx.x + (long long)gg * gridDim.x;
+                const uint32_t dst = sm_base + FT_OFF_GROUP + (uint32_t)gg * FT_GROUP_BYTES + FT_G_IN;
+                const uint32_t bar = tc_smem_u32(&bars[gg][0]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(FT_TILE_BYTES) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                             "l"(fa.tiles + ((size_t)tile0 + (size_t)tile) * FT_TILE_BYTES), "r"(FT_TILE_BYTES), "r"(bar) : "memory");
+            }
+        }
     }
     {
         // 16 elements per thread, loads issued together (one L2 round trip)
@@ -387,7 +402,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ppo_loss_grad_ft_kernel(const _
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                      "l"(rec0 + (size_t)tile * FT_TILE_BYTES), "r"(FT_TILE_BYTES), "r"(bar) : "memory");
     };
-    if (t == 0 && n_own > 0) load_tile(0);
+    // (tile 0 of both groups was requested by thread 0 right after the barrier initialisation)
 
     const uint32_t idesc_g1 = ft_idesc(64, 64, 0, 1), idesc_g2 = ft_idesc(64, 64, 1, 1), idesc_g3 = ft_idesc(64, 64, 0, 0);
     const uint32_t imgP = smg_base + FT_G_P, imgQ = smg_base + FT_G_Q, imgW = sm_base + FT_OFF_W;
