@@ -24,9 +24,11 @@
 // lane offset 16 of the same columns, so warp q, lane l is feature 16 q + l % 16 of net l / 16 and both nets run in ONE
 // pass over the minibatch.  Two groups of 8 warps work on alternate 64-sample tiles with private images and TMEM
 // columns (no hand-over between the groups); within a group warps w and w + 4 share a lane quadrant and split the
-// tile's samples.  Tiles arrive as contiguous 2304-byte records written once per epoch by ft_permute_kernel (the
-// DataLoader shuffle of ppo.jl:188-195) and are prefetched with cp.async.bulk + mbarrier one tile ahead.
-// The kernel ends with the cooperative tail of update_tc.cuh (reduction, peer exchange, clip, KL stop, Adam).
+// tile's samples.  Tiles arrive as contiguous 2304-byte records written for ALL epochs of the update by one launch of
+// ft_permute_epochs_kernel (the DataLoader shuffle of ppo.jl:188-195, plus the minibatch advantage moments) and are
+// prefetched with cp.async.bulk + mbarrier one tile ahead.
+// A minibatch step ends with the cooperative tail of update_tc.cuh (reduction, peer exchange, clip, KL stop, Adam); in
+// persistent mode (FtArgs::n_steps > 0) the kernel then crosses a grid barrier and runs the next step of the update.
 #pragma once
 #include <cuda_fp16.h>
 #include "update_tc.cuh"
@@ -89,7 +91,7 @@ struct FtArgs {
 // Sample records: the update gathers minibatches in shuffled order, and a gather from the time-major field arrays costs one
 // 32-byte sector per 4-byte field (nine sectors per sample).  Once per iteration the fields of every sample are therefore
 // packed into one contiguous record [obs (Dp) | action (A) | advantage | old log-prob | return | old value | pad] (stride a
-// multiple of 4 floats) by a streaming kernel; the per-epoch permute kernels then read two sectors per sample.
+// multiple of 4 floats) by a streaming kernel; the permute kernels then read two sectors per sample.
 __host__ __device__ inline int ft_rec_stride(int obs_dim, int act_elems) { return ((((obs_dim + 3) & ~3) + act_elems + 4) + 3) & ~3; }
 __global__ void __launch_bounds__(256) ft_pack_records_kernel(const BufDev buf, long long n_total, int stride, float* __restrict__ recs) {
     const int D = buf.obs_dim, Dp = (D + 3) & ~3, A = buf.act_dim;
@@ -127,7 +129,8 @@ __device__ __forceinline__ float ft_permute_slot(const float* __restrict__ recs,
     blk[FT_R_RET + j] = u.w; blk[FT_R_OVAL + j] = w.x;
     return u.y;
 }
-// The epoch's samples in shuffled order as contiguous tile records (one launch per epoch).
+// One epoch's samples in shuffled order as contiguous tile records (fallback when all epochs exceed the staging budget, and the
+// single-minibatch parity entry).
 __global__ void __launch_bounds__(256) ft_permute_kernel(const float* __restrict__ recs, int stride, const FeistelKey fk, long long n_total,
                                                          long long batch_size, int n_mb, int tiles_per_mb, int identity, int act_start, int nout,
                                                          unsigned char* __restrict__ out) {

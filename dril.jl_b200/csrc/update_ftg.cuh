@@ -16,8 +16,9 @@
 //     unscaled exactly when the partial plane is written;
 //   * shared memory: weight images of the pass (W_1.., W_0 with the bias row), one image buffer per hidden layer but
 //     the last (H_l, later reused for dZ_l), one buffer for the last layer's fp32 tile / delta image, two tile records.
-// The kernel ends with the cooperative tail of update_tc.cuh.  Tile records are written once per epoch by
-// ftg_permute_kernel (DataLoader shuffle, ppo.jl:188-195) and fetched with cp.async.bulk one tile ahead.
+// The kernel ends with the cooperative tail of update_tc.cuh.  Tile records of all epochs are written by one launch of
+// ftg_permute_epochs_kernel (DataLoader shuffle, ppo.jl:188-195, + minibatch advantage moments) and fetched with
+// cp.async.bulk one tile ahead.
 #pragma once
 #include "update_ft.cuh"
 
