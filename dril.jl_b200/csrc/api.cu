@@ -1135,7 +1135,7 @@ static int32_t launch_rollout(dril_env* e, dril_policy* p, dril_buffer* b, const
         }
         return DRIL_OK;
     }
-    if (has_policy && g_opt_syn_rollout && !b->is_view && T > 0 && syn_rollout_eligible(a.pd, d)) {
+    if (has_policy && g_opt_syn_rollout && !general_only && T > 0 && syn_rollout_eligible(a.pd, d)) {      // (evaluation / chunked collection: general kernel)
         // synthetic env + small policy: one thread per env, everything in registers (rollout_syn.cuh)
         int hp = 0;
         for (int net = 0; net < 2; ++net)
